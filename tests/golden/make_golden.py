@@ -15,6 +15,9 @@ What it writes (all small; committed):
   precision = 6 significant digits) from it.
 * ``charge_density_0.txt`` -- verbatim copy of the reference's only data file
   Diagnostics/Charge_Density-0.txt (36 rows ``z n``), the known-answer vector.
+* ``fixture_rings_r0.npz`` -- the r=0 rings (z only) of ``loadDensityFile(electrons, 150 K,
+  100000)`` whose deposit IS that data file (lets the plain-C oracle be pinned to the
+  fixture on a box without the reference).
 * ``trap_kat.json`` -- scalar known answers of the default trap (hz, hr, length,
   phi_trap samples, well limits, nnz).
 * ``c1_step_kat.npz`` -- C1 (4001 e- + 4001 pbar) state before/after steps of the
@@ -83,6 +86,9 @@ def main():
     mine = rhs[275:311] * ref.EPSILON0 / ref.E_POS
     kat["fixture_rel_l2"] = float(np.linalg.norm(mine - fixture[:, 1]) / np.linalg.norm(fixture[:, 1]))
     kat["fixture_count_100000"] = int(el.count())
+    r100k, z100k, _ = el.rings()
+    np.savez_compressed(os.path.join(HERE, "fixture_rings_r0.npz"), z=z100k[r100k == 0],
+                        macroChargeDensity=el.params()["macroChargeDensity"], chargeMacro=el.params()["chargeMacro"])
     print("fixture rel-L2", kat["fixture_rel_l2"])
     trap.close()
 
