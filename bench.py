@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the PIC step (PenningTrap::movePlasmas: push + deposit + all-reduce + solve).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0. Metric: particle-steps/s, whole job. Default workload "c4" =
+BASELINE.json configs[3]: single-species 100 M macro-rings on the default (driver-A) trap, fp64,
+sharded over the N GPUs (strong scaling, one rho all-reduce per step, solve replicated).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (species list [(name, mass key, share)], total macro-rings, description)
+    "c4": ([("Antiprotons", "massP", 1.0)], 100_000_000, "single-species 100M macro-rings, default trap 585x128 (BASELINE configs[3])"),
+    "c2": ([("Antiprotons", "massP", 1.0)], 1_000_000, "antiproton plasma, 1M macro-rings, default trap (BASELINE configs[1]; L2-resident)"),
+    "c3": ([("Electrons", "massE", 0.5), ("Antiprotons", "massP", 0.5)], 10_000_000, "e- + pbar co-trapped, 10M macro-rings (BASELINE configs[2])"),
+}
+DT = 2e-8 / 35            # Diagnostics/C) Visualise Evolution.txt:34-36
+TEMPERATURE = 150.0
+
+
+def expected_density():
+    d = np.load(os.path.join(ROOT, "tests", "golden", "expected_density_nonzero.npz"))
+    dens = np.zeros(int(d["G"]))
+    dens[d["index"]] = d["value"]
+    return dens
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def build_load(ptp, loaders, workload, rank, n_ranks, hz, hr):
+    species, total, _ = WORKLOADS[workload]
+    dens = expected_density()
+    out = []
+    for si, (name, mkey, share) in enumerate(species):
+        mass = getattr(ptp, mkey)
+        r, z, charge_macro, _ = loaders.place_rings(dens * share, 585, 128, hz, hr, int(total * share), rank, n_ranks)
+        v = loaders.maxwellian_speeds(len(r), TEMPERATURE, mass, seed=1000 * si + rank)
+        out.append((name, mass, r, z, v, charge_macro))
+    return out
+
+
+def cpu_reference_run(workload, steps, warmup, sample_rings):
+    """The reference's own CPU implementation (oracle/_ref: its .cpp files compiled unmodified) on a bounded
+    sample of the workload: every m-th ring of the same load, same trap, same dt; single thread (the
+    reference has no threading)."""
+    ptp = importlib.import_module("pic-trapped-plasma_b200")
+    loaders = importlib.import_module("pic-trapped-plasma_b200.loaders")
+    from oracle import port, ref
+    kind = "reference" if ref.available() else "port"
+    species, total, _ = WORKLOADS[workload]
+    stride = max(1, total // sample_rings)
+    trap = ref.default_trap() if kind == "reference" else port.default_trap()
+    load = build_load(ptp, loaders, workload, 0, stride, trap.hz, trap.hr)   # ring i % stride == 0 of every row
+    n = 0
+    plasmas = []
+    for name, mass, r, z, v, cm in load:
+        p = trap.plasma(name, mass, -ptp.ePos)
+        p.set_rings(r, z, v, cm * stride)
+        p.solve_poisson()
+        plasmas.append(p)
+        n += len(r)
+    if kind == "reference":
+        trap.timed_steps(DT, warmup)
+        ring_steps, sec = trap.timed_steps(DT, steps)
+    else:
+        trap.move_plasmas(DT, warmup)
+        t0 = time.perf_counter()
+        ring_steps = 0
+        for _ in range(steps):
+            ring_steps += sum(p.count() for p in plasmas)
+            trap.move_plasmas(DT, 1)
+        sec = [0, 0, 0, time.perf_counter() - t0]
+    trap.close()
+    value = ring_steps / sec[3]
+    info = {"value": value, "unit": "particle-steps/s", "cores": 1, "kind": kind,
+            "sample": "%d of %d rings (every %d-th ring of each row), %d steps of movePlasmas on the same trap; "
+                      "1 thread of %d cores (the reference is single-threaded); solve = direct banded LU stand-in for Eigen::SparseLU"
+                      % (n, total, stride, steps, os.cpu_count()),
+            "phases_s": {"moveRings": sec[0], "updateRHS": sec[1], "solve": sec[2], "whole": sec[3]},
+            "push_deposit_particle_steps_per_s": (ring_steps / (sec[0] + sec[1])) if sec[0] + sec[1] > 0 else None}
+    return info, sec[3] / steps * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--deposit", default="fp64", choices=["fp64", "fixed"])
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=-1)
+    ap.add_argument("--sort-interval", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=10_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    species, total, desc = WORKLOADS[args.workload]
+    config = {"workload": "%s: %s" % (args.workload, desc), "grid": "Nz=585 Nr=128", "dt_s": DT, "species": len(species),
+              "rings_total": total, "deposit": args.deposit,
+              "l2": "ring arrays %d MB per GPU vs 126 MB L2 (no flush needed)" % (total // world * 16 // 2**20) if total // world * 16 > 200e6
+              else "ring arrays %d MB per GPU: L2-resident, NOT an HBM-bound measurement" % (total // world * 16 // 2**20)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        info, ms = cpu_reference_run(args.workload, args.steps, max(args.warmup, 1), min(args.cpu_sample, total))
+        line = {"impl": "reference", "metric": "particle-steps/s (push+deposit+solve)", "value": info["value"], "unit": "particle-steps/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": info, "gpu_launches": 0,
+                "e2e": {"value": info["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    ptp = importlib.import_module("pic-trapped-plasma_b200")
+    loaders = importlib.import_module("pic-trapped-plasma_b200.loaders")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    trap = ptp.default_trap(device=local_rank)
+    if world > 1:
+        uid = [ptp.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        trap.comm_init(uid[0], world, rank)
+    trap.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64 if args.deposit == "fixed" else ptp.PTP_DEPOSIT_FP64)
+    if args.threads or args.window or args.ctas >= 0:
+        trap.set_tuning(args.threads, args.window, args.ctas)
+    trap.set_sort_interval(args.sort_interval)
+
+    load = build_load(ptp, loaders, args.workload, rank, world, trap.hz, trap.hr)
+    # pinned host staging (the e2e leg copies from / to these)
+    pinned = []
+    for name, mass, r, z, v, cm in load:
+        pr = torch.from_numpy(r).pin_memory().numpy()
+        pz = torch.from_numpy(z).pin_memory().numpy()
+        pv = torch.from_numpy(v).pin_memory().numpy()
+        pinned.append((name, mass, pr, pz, pv, cm * world))
+    n_local = sum(len(x[2]) for x in pinned)
+    plasmas = []
+    for name, mass, pr, pz, pv, cm in pinned:
+        p = ptp.Plasma(trap, name, mass, -ptp.ePos)
+        p.upload(pr, pz, pv, cm)
+        plasmas.append(p)
+    for p in plasmas:
+        p.solvePoisson()
+
+    # ---- device-resident leg: W warm-up steps, then exactly K timed steps ----------------------------
+    trap.movePlasmas(DT, args.warmup)
+    trap.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    alive_before = sum_over_ranks(sum(p.getNumMacro() for p in plasmas))
+    barrier()
+    trap.movePlasmas(DT, args.steps)
+    trap.sync()
+    barrier()
+    times = trap.last_times()
+    launches = trap.last_launches()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(float(times[0]))
+    ms_push = max_over_ranks(float(times[1]))
+    alive_after = sum_over_ranks(sum(p.getNumMacro() for p in plasmas))
+    ring_steps = 0.5 * (alive_before + alive_after) * args.steps
+    value = ring_steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (K1: 32 B per ring-step) -------------------------------------
+    peak, peak_kind = peaks()
+    k1_ms = ms_push / args.steps
+    achieved = 32.0 * n_local / (k1_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_push_deposit", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "bytes_per_unit": 32, "units_per_launch": n_local, "k1_ms_per_launch": k1_ms,
+                "k1_share_of_step": ms_push / ms_total}
+    prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(args.workload)
+        except Exception:
+            pass
+
+    # ---- end-to-end leg through the C ABI with host buffers ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        h2d = 0
+        for p, (name, mass, pr, pz, pv, cm) in zip(plasmas, pinned):
+            p.upload(pr, pz, pv, cm)                       # H2D from pinned host memory
+            h2d += pr.nbytes + pz.nbytes + pv.nbytes
+        for p in plasmas:
+            p.solvePoisson()
+        d2h = 0
+        e2e_steps = args.steps
+        for _ in range(e2e_steps):
+            trap.movePlasmas(DT, 1)
+        counts = [p.getNumMacro() for p in plasmas]        # D2H: the step's metric
+        d2h += 8 * len(plasmas)
+        rhs = plasmas[0].rhs()                             # D2H: density grid (the diagnostics' input)
+        d2h += rhs.nbytes
+        trap.sync()
+        barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": sum_over_ranks(float(sum(counts))) * e2e_steps / sec, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
+               "protocol": "upload rings from pinned host (H2D, %d B/ring) + first deposit/solve + %d x movePlasmas + read back alive counts and the density grid; "
+                           "rings stay resident between steps as in the reference's API (movePlasmas(dt) takes no ring data)" % (20, e2e_steps)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_reference_run(args.workload, 3, 1, min(args.cpu_sample, total))
+
+    if rank == 0:
+        line = {"metric": "particle-steps/s (push+deposit+solve)", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "phases_ms_per_step": {"push_deposit": ms_push / args.steps, "allreduce": float(times[2]) / args.steps,
+                                       "solve_node_field": float(times[3]) / args.steps},
+                "tuning": {"threads": args.threads or 256, "window": args.window or 64, "ctas": args.ctas}}
+        print(json.dumps(line))
+    trap.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/* ptp.h -- C ABI of the B200-native PIC step for a Penning-Malmberg trapped plasma.
+ *
+ * Drop-in boundary for ONE hot path of Daniel32Duque/PIC-Trapped-Plasma:
+ * PenningTrap::movePlasmas(dt) (reference Source/PenningTrap.cpp:352-363) and the
+ * private phases below it. The reference has no FFI layer; its boundary is the
+ * C++ class surface (Source/PenningTrap.hpp:54-98, Source/Plasma.hpp:139-197).
+ * The host-side classes in pic-trapped-plasma_b200/host keep that surface and
+ * call the functions below; every function names the reference member it
+ * replaces. Plain pointers and sizes only; all host buffers are caller-owned,
+ * all device memory is library-owned unless a function says "device pointer".
+ *
+ * Conventions
+ *   - return 0 on success, a PTP_E* code otherwise; ptp_last_error() gives text.
+ *   - grids are r-major, z fastest: node (r=j, z=k) -> (Nz+1)*j + k, G=(Nz+1)*Nr
+ *     doubles (reference layout, Source/PenningTrap.hpp:51).
+ *   - one host thread per trap; calls are synchronous w.r.t. returned host data.
+ *   - there is NO CPU fallback: every entry point fails with PTP_ECUDA when no
+ *     CUDA device is usable.
+ */
+#ifndef PTP_H
+#define PTP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ptp_trap ptp_trap;     /* device twin of PenningTrap (Source/PenningTrap.hpp:54-98) */
+typedef struct ptp_plasma ptp_plasma; /* device twin of Plasma      (Source/Plasma.hpp:139-197)   */
+
+enum {
+	PTP_OK = 0,
+	PTP_EINVAL = 1,   /* bad argument (the host classes turn these into std::logic_error) */
+	PTP_ECUDA = 2,    /* CUDA runtime error / no device */
+	PTP_ENOMEM = 3,
+	PTP_ECOMM = 4,    /* NCCL error or NCCL not loadable */
+	PTP_ESTATE = 5    /* call made in the wrong state (e.g. step before upload) */
+};
+
+/* deposit accumulator (north_star: fp64 default, fixed-point = deterministic) */
+enum { PTP_DEPOSIT_FP64 = 0, PTP_DEPOSIT_FIXED64 = 1 };
+/* PTP_ARITH_FAST: reciprocal multiplies for /hz, /mass (cell index still bit-exact).
+ * PTP_ARITH_EXACT: IEEE divisions in the reference's expression order -> per-ring
+ * z, v bit-identical to the reference for identical node fields. */
+enum { PTP_ARITH_FAST = 0, PTP_ARITH_EXACT = 1 };
+/* Poisson solver: direct separable (DCT-I in z + Thomas in r), or red-black SOR (cross-check). */
+enum { PTP_SOLVER_DIRECT = 0, PTP_SOLVER_SOR = 1 };
+
+const char* ptp_last_error(void);
+int ptp_version(void);
+int ptp_device_count(void);
+
+/* ---- trap ------------------------------------------------------------------------------- */
+
+/* PenningTrap::PenningTrap + generateSparse + analyzePattern/factorize
+ * (Source/PenningTrap.cpp:36-58, 94-162): builds the device operator for the
+ * 5-point cylindrical stencil. hz = length/Nz and hr = radius/Nr are passed as
+ * the host class computed them (Source/PenningTrap.cpp:51-52). `device` is the
+ * CUDA ordinal. phi_trap starts at zero: call ptp_trap_set_wall next. */
+int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double length, double radius, int device);
+int ptp_trap_destroy(ptp_trap* t);
+
+/* PenningTrap::updateRHS + solveLaplace (Source/PenningTrap.cpp:163-203), also what
+ * setPotential (Source/PenningTrap.cpp:313-317) triggers. vWall[k], k=0..Nz, is the
+ * wall potential per axial node (the `boundary` values of :169-197; the host class
+ * keeps that electrode->node loop). Sets RHS(last row) = -(hr^-2 + 1/(2(R-hr)hr))*vWall
+ * and solves for phi_trap. */
+int ptp_trap_set_wall(ptp_trap* t, const double* vWall);
+
+/* solver.solve(b) (Source/PenningTrap.cpp:202, Source/Plasma.cpp:98,389,412): phi = A^-1 rhs, host buffers of G. */
+int ptp_trap_solve(ptp_trap* t, const double* rhs, double* phi);
+/* y = A x with the assembled operator (coefficients * vector, Source/PenningTrap.cpp:250). */
+int ptp_trap_apply(ptp_trap* t, const double* x, double* y);
+
+int ptp_trap_get_phi(ptp_trap* t, double* phi);        /* potentialsVector (Source/PenningTrap.hpp:51) */
+int ptp_trap_set_phi(ptp_trap* t, const double* phi);  /* parity hook: inject phi_trap */
+/* PenningTrap::getEField(int,int) on every node (Source/PenningTrap.cpp:208-236), for the current potentials. */
+int ptp_trap_get_enodes(ptp_trap* t, double* eNodes);
+
+/* PenningTrap::movePlasmas(dt) x nSteps (Source/PenningTrap.cpp:352-363): every plasma pushed with the
+ * pre-step field, then every plasma deposited and solved. */
+int ptp_trap_step(ptp_trap* t, double dt, int nSteps);
+/* The two halves of a step, separately (parity and timing): Plasma::moveRings + Plasma::updateRHS of all
+ * plasmas (Source/Plasma.cpp:100-120, 77-94) ... */
+int ptp_trap_push_deposit(ptp_trap* t, double dt);
+/* ... and solver.solve of every plasma's RHS plus the node field (Source/Plasma.cpp:98; PenningTrap.cpp:208-236). */
+int ptp_trap_solve_fields(ptp_trap* t);
+/* Block until all queued work of this trap has finished. */
+int ptp_trap_sync(ptp_trap* t);
+/* Device time in milliseconds of the last ptp_trap_step call: [0]=whole call; summed over its steps: [1]=push+deposit kernels,
+ * [2]=all-reduce, [3]=solve + node field (CUDA events on the trap's stream). */
+int ptp_trap_last_times(ptp_trap* t, double* ms4);
+/* Number of kernels the last ptp_trap_step / push_deposit / solve_fields call launched. */
+int64_t ptp_trap_last_launches(ptp_trap* t);
+
+/* Maintenance (K5): per-row counting sort of every plasma's rings by axial cell and compaction of lost rings. */
+int ptp_trap_sort(ptp_trap* t);
+/* sort every `interval` steps inside ptp_trap_step (0 = only when the tile windows overflow). */
+int ptp_trap_set_sort_interval(ptp_trap* t, int interval);
+
+int ptp_trap_set_deposit_mode(ptp_trap* t, int mode);
+int ptp_trap_set_arith_mode(ptp_trap* t, int mode);
+int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMaxIterations);
+/* Tuning: threads per CTA (256/512), bins per thread-private tile window, CTAs (0 = one per SM). */
+int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas);
+
+/* ---- multi-GPU (one process per GPU; rings sharded, rho all-reduced, solve replicated) --- */
+
+/* 128-byte NCCL unique id; rank 0 creates it, the launcher broadcasts it (torch.distributed / MPI / file). */
+int ptp_comm_unique_id(void* id128);
+int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank);
+/* 0: NCCL all-reduce, 1: one-shot peer-memory all-reduce kernel (needs ptp_trap_comm_init). */
+int ptp_trap_set_allreduce(ptp_trap* t, int kind);
+
+/* ---- plasma ------------------------------------------------------------------------------- */
+
+/* Plasma::Plasma (Source/Plasma.cpp:68-72): registers with the trap; registration order is the
+ * summation order of the species' potentials in the node field (Source/PenningTrap.cpp:228-232). */
+int ptp_plasma_create(ptp_trap* t, ptp_plasma** out, double mass, double charge);
+int ptp_plasma_destroy(ptp_plasma* p);
+
+/* Replace the rings (what both loaders end with, Source/Plasma.cpp:504-526 / 598-620): n rings
+ * {r[i] in [0,Nr), z[i], v[i]} in any order; ring i keeps id i. macroChargeDensity as in
+ * Source/Plasma.cpp:494. Does not deposit or solve. */
+int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* z, const double* v, double macroChargeDensity);
+/* Plasma::solvePoisson (Source/Plasma.cpp:95-99): deposit this plasma's RHS and solve its self potential. */
+int ptp_plasma_deposit_solve(ptp_plasma* p);
+/* Plasma::updateRHS alone (Source/Plasma.cpp:77-94). */
+int ptp_plasma_deposit(ptp_plasma* p);
+
+int ptp_plasma_count(ptp_plasma* p, int64_t* nAlive);   /* Plasma::getNumMacro (Source/Plasma.cpp:147-150) */
+/* Live rings, row-bucketed order; buffers of at least ptp_plasma_count entries; id = index at upload. Any pointer may be NULL. */
+int ptp_plasma_download(ptp_plasma* p, int32_t* r, double* z, double* v, int64_t* id);
+/* The integer keys of the step for the live rings, same order as ptp_plasma_download:
+ * k = (int)floor(z/hz), idx = (Nz+1)*r + k (Source/Plasma.cpp:87-88). */
+int ptp_plasma_cell_index(ptp_plasma* p, int32_t* k, int32_t* idx);
+
+int ptp_plasma_get_rhs(ptp_plasma* p, double* rhs);                 /* Plasma::RHS (Source/Plasma.hpp:53) */
+int ptp_plasma_get_self_potential(ptp_plasma* p, double* phi);      /* Plasma::selfPotential (:52) */
+int ptp_plasma_set_self_potential(ptp_plasma* p, const double* phi);/* parity hook / loaders */
+
+/* Diagnostics reductions on device ("next" row 2 of SURVEY 8f):
+ * getPotentialEnergy (Source/Plasma.cpp:244-252), sum of ring mass*v^2 terms for getTemperature (:212-228),
+ * getNumMacroCentralWell (:151-162; limits = per-row [left,right] node indices, Source/PenningTrap.cpp:63-90). */
+int ptp_plasma_potential_energy(ptp_plasma* p, double chargeMacro, double* pe);
+int ptp_plasma_count_central_well(ptp_plasma* p, const int32_t* limitLeft, const int32_t* limitRight, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTP_H */

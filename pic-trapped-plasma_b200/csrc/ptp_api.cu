@@ -1,0 +1,469 @@
+// C ABI (include/ptp.h): handles, grids, and the orchestration of PenningTrap::movePlasmas
+// (reference Source/PenningTrap.cpp:352-363) on one CUDA stream per trap.
+#include "ptp_internal.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace {
+thread_local std::string g_error;
+}
+
+void ptp_set_error(const std::string& msg) { g_error = msg; }
+
+int ptp_cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+	g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")";
+	return e == cudaErrorMemoryAllocation ? PTP_ENOMEM : PTP_ECUDA;
+}
+
+namespace {
+
+// (Re)size the per-species grids so that species s owns slice s of each [capS][G] array.
+int ensure_species_capacity(ptp_trap* t, int need)
+{
+	if (need <= t->capS) return PTP_OK;
+	int cap = t->capS ? t->capS : 2;
+	while (cap < need) cap *= 2;
+	const size_t bytes = (size_t)cap * t->G * sizeof(double), old = (size_t)t->capS * t->G * sizeof(double);
+	double *rho = nullptr, *phi = nullptr, *spec = nullptr, *scale = nullptr;
+	PTP_CUDA(cudaMalloc(&rho, bytes));
+	PTP_CUDA(cudaMalloc(&phi, bytes));
+	PTP_CUDA(cudaMalloc(&spec, bytes));
+	PTP_CUDA(cudaMalloc(&scale, cap * sizeof(double)));
+	PTP_CUDA(cudaMemset(rho, 0, bytes));
+	PTP_CUDA(cudaMemset(phi, 0, bytes));
+	PTP_CUDA(cudaMemset(scale, 0, cap * sizeof(double)));
+	if (t->capS) {
+		PTP_CUDA(cudaMemcpy(rho, t->rhoAll, old, cudaMemcpyDeviceToDevice));
+		PTP_CUDA(cudaMemcpy(phi, t->phiSelfAll, old, cudaMemcpyDeviceToDevice));
+		PTP_CUDA(cudaMemcpy(scale, t->dScale, t->capS * sizeof(double), cudaMemcpyDeviceToDevice));
+	}
+	cudaFree(t->rhoAll); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
+	t->rhoAll = rho; t->phiSelfAll = phi; t->specAll = spec; t->dScale = scale;
+	t->capS = cap;
+	return PTP_OK;
+}
+
+int solve_species(ptp_trap* t, int first, int count)
+{
+	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64;
+	const double* rho = t->rhoAll + (size_t)first * t->G;
+	double* phi = t->phiSelfAll + (size_t)first * t->G;
+	if (t->solver == PTP_SOLVER_SOR) return ptp_sor_run(t, rho, fixed, t->dScale + first, count, phi);
+	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi);
+}
+
+// Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
+int push_deposit_all(ptp_trap* t, double dt)
+{
+	const int nS = (int)t->plasmas.size();
+	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
+	PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, (size_t)nS * t->G * sizeof(double), t->stream));
+	for (ptp_plasma* p : t->plasmas) {
+		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+		PTP_TRY(ptp_push_launch(t, p, dt, true));
+	}
+	return PTP_OK;
+}
+
+int reduce_rho(ptp_trap* t)
+{
+	const int nS = (int)t->plasmas.size();
+	return ptp_comm_allreduce(t, t->rhoAll, (size_t)nS * t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
+}
+
+int solve_all(ptp_trap* t)
+{
+	PTP_TRY(solve_species(t, 0, (int)t->plasmas.size()));
+	return ptp_node_field(t);
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ptp_last_error(void) { return g_error.c_str(); }
+int ptp_version(void) { return PTP_VERSION; }
+
+int ptp_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double length, double radius, int device)
+{
+	if (!out) { ptp_set_error("ptp_trap_create: null output"); return PTP_EINVAL; }
+	*out = nullptr;
+	if (Nz < 4 || Nr < 2 || !(hz > 0) || !(hr > 0) || !(length > 0) || !(radius > 0)) {
+		ptp_set_error("ptp_trap_create: need Nz >= 4, Nr >= 2 and positive hz, hr, length, radius");
+		return PTP_EINVAL;
+	}
+	int nDev = 0;
+	cudaError_t e = cudaGetDeviceCount(&nDev);
+	if (e != cudaSuccess || nDev == 0) {
+		cudaGetLastError();
+		ptp_set_error("no CUDA device available (this library has no CPU fallback)");
+		return PTP_ECUDA;
+	}
+	if (device < 0 || device >= nDev) { ptp_set_error("ptp_trap_create: bad device ordinal"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(device));
+	ptp_trap* t = new ptp_trap;
+	t->device = device;
+	t->Nz = Nz; t->Nr = Nr; t->G = (long long)(Nz + 1) * Nr;
+	t->hz = hz; t->hr = hr; t->length = length; t->radius = radius;
+	cudaDeviceProp prop;
+	PTP_CUDA(cudaGetDeviceProperties(&prop, device));
+	t->smCount = prop.multiProcessorCount;
+	t->smemMax = prop.sharedMemPerBlockOptin;
+	PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+	for (auto& ev : t->ev) PTP_CUDA(cudaEventCreate(&ev));
+	const size_t gb = (size_t)t->G * sizeof(double);
+	PTP_CUDA(cudaMalloc(&t->phiTrap, gb));
+	PTP_CUDA(cudaMalloc(&t->eNodes, gb));
+	PTP_CUDA(cudaMalloc(&t->tmpA, gb));
+	PTP_CUDA(cudaMalloc(&t->tmpB, gb));
+	PTP_CUDA(cudaMalloc(&t->tmpSpec, gb));
+	PTP_CUDA(cudaMemset(t->phiTrap, 0, gb));
+	PTP_CUDA(cudaMemset(t->eNodes, 0, gb));
+	int rc = ptp_solver_build(t);
+	if (rc != PTP_OK) { ptp_trap_destroy(t); return rc; }
+	rc = ensure_species_capacity(t, 2);
+	if (rc != PTP_OK) { ptp_trap_destroy(t); return rc; }
+	*out = t;
+	return PTP_OK;
+}
+
+int ptp_trap_destroy(ptp_trap* t)
+{
+	if (!t) return PTP_OK;
+	cudaSetDevice(t->device);
+	if (t->stream) cudaStreamSynchronize(t->stream);
+	while (!t->plasmas.empty()) ptp_plasma_destroy(t->plasmas.back());
+	ptp_comm_free(t);
+	ptp_solver_free(t);
+	cudaFree(t->phiTrap); cudaFree(t->eNodes); cudaFree(t->tmpA); cudaFree(t->tmpB); cudaFree(t->tmpSpec);
+	cudaFree(t->rhoAll); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
+	for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
+	for (auto& ev : t->evPool) cudaEventDestroy(ev);
+	if (t->stream) cudaStreamDestroy(t->stream);
+	delete t;
+	return PTP_OK;
+}
+
+int ptp_trap_solve(ptp_trap* t, const double* rhs, double* phi)
+{
+	if (!t || !rhs || !phi) { ptp_set_error("ptp_trap_solve: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	const size_t gb = (size_t)t->G * sizeof(double);
+	PTP_CUDA(cudaMemcpyAsync(t->tmpA, rhs, gb, cudaMemcpyHostToDevice, t->stream));
+	if (t->solver == PTP_SOLVER_SOR) {
+		PTP_CUDA(cudaMemsetAsync(t->tmpB, 0, gb, t->stream));
+		PTP_TRY(ptp_sor_run(t, t->tmpA, false, nullptr, 1, t->tmpB));
+	}
+	else PTP_TRY(ptp_solver_run(t, t->tmpA, false, nullptr, 1, t->tmpSpec, t->tmpB));
+	PTP_CUDA(cudaMemcpyAsync(phi, t->tmpB, gb, cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_apply(ptp_trap* t, const double* x, double* y)
+{
+	if (!t || !x || !y) { ptp_set_error("ptp_trap_apply: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	const size_t gb = (size_t)t->G * sizeof(double);
+	PTP_CUDA(cudaMemcpyAsync(t->tmpA, x, gb, cudaMemcpyHostToDevice, t->stream));
+	PTP_TRY(ptp_solver_apply(t, t->tmpA, t->tmpB));
+	PTP_CUDA(cudaMemcpyAsync(y, t->tmpB, gb, cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_set_wall(ptp_trap* t, const double* vWall)
+{
+	if (!t || !vWall) { ptp_set_error("ptp_trap_set_wall: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	PTP_CUDA(cudaMemcpyAsync(t->tmpSpec, vWall, (size_t)(t->Nz + 1) * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+	PTP_TRY(ptp_wall_rhs(t, t->tmpSpec, t->tmpA));
+	if (t->solver == PTP_SOLVER_SOR) PTP_TRY(ptp_sor_run(t, t->tmpA, false, nullptr, 1, t->phiTrap));
+	else PTP_TRY(ptp_solver_run(t, t->tmpA, false, nullptr, 1, t->tmpSpec, t->phiTrap));
+	t->eNodesValid = false;
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_get_phi(ptp_trap* t, double* phi)
+{
+	if (!t || !phi) { ptp_set_error("ptp_trap_get_phi: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaMemcpyAsync(phi, t->phiTrap, (size_t)t->G * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_set_phi(ptp_trap* t, const double* phi)
+{
+	if (!t || !phi) { ptp_set_error("ptp_trap_set_phi: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaMemcpyAsync(t->phiTrap, phi, (size_t)t->G * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	t->eNodesValid = false;
+	return PTP_OK;
+}
+
+int ptp_trap_get_enodes(ptp_trap* t, double* eNodes)
+{
+	if (!t || !eNodes) { ptp_set_error("ptp_trap_get_enodes: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
+	PTP_CUDA(cudaMemcpyAsync(eNodes, t->eNodes, (size_t)t->G * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_push_deposit(ptp_trap* t, double dt)
+{
+	if (!t) { ptp_set_error("ptp_trap_push_deposit: null trap"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	PTP_TRY(push_deposit_all(t, dt));
+	PTP_TRY(reduce_rho(t));
+	return PTP_OK;
+}
+
+int ptp_trap_solve_fields(ptp_trap* t)
+{
+	if (!t) { ptp_set_error("ptp_trap_solve_fields: null trap"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	return solve_all(t);
+}
+
+int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
+{
+	if (!t || nSteps < 0) { ptp_set_error("ptp_trap_step: bad arguments"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	// phase events for every step (up to a bound), so that callers can report the mean kernel time
+	const int timed = nSteps <= 4096 ? nSteps : 0;
+	while ((int)t->evPool.size() < 4 * timed) {
+		cudaEvent_t e;
+		PTP_CUDA(cudaEventCreate(&e));
+		t->evPool.push_back(e);
+	}
+	t->evSteps = timed;
+	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
+	for (int s = 0; s < nSteps; ++s) {
+		cudaEvent_t* e = s < timed ? &t->evPool[4 * s] : nullptr;
+		if (e) PTP_CUDA(cudaEventRecord(e[0], t->stream));
+		PTP_TRY(push_deposit_all(t, dt));
+		if (e) PTP_CUDA(cudaEventRecord(e[1], t->stream));
+		PTP_TRY(reduce_rho(t));
+		if (e) PTP_CUDA(cudaEventRecord(e[2], t->stream));
+		PTP_TRY(solve_all(t));
+		if (e) PTP_CUDA(cudaEventRecord(e[3], t->stream));
+		++t->stepCount;
+		if (t->sortInterval > 0 && t->stepCount % t->sortInterval == 0)
+			for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
+	}
+	PTP_CUDA(cudaEventRecord(t->ev[4], t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_sync(ptp_trap* t)
+{
+	if (!t) { ptp_set_error("ptp_trap_sync: null trap"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_last_times(ptp_trap* t, double* ms4)
+{
+	if (!t || !ms4) { ptp_set_error("ptp_trap_last_times: null argument"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	float whole = 0;
+	if (cudaEventElapsedTime(&whole, t->ev[0], t->ev[4]) != cudaSuccess) { cudaGetLastError(); whole = 0; }
+	double sum[3] = { 0, 0, 0 };
+	for (int s = 0; s < t->evSteps; ++s)
+		for (int ph = 0; ph < 3; ++ph) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, t->evPool[4 * s + ph], t->evPool[4 * s + ph + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+			sum[ph] += ms;
+		}
+	ms4[0] = whole; ms4[1] = sum[0]; ms4[2] = sum[1]; ms4[3] = sum[2];
+	return PTP_OK;
+}
+
+int64_t ptp_trap_last_launches(ptp_trap* t) { return t ? t->lastLaunches : 0; }
+
+int ptp_trap_sort(ptp_trap* t)
+{
+	if (!t) { ptp_set_error("ptp_trap_sort: null trap"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
+	return PTP_OK;
+}
+
+int ptp_trap_set_sort_interval(ptp_trap* t, int interval)
+{
+	if (!t || interval < 0) { ptp_set_error("ptp_trap_set_sort_interval: bad arguments"); return PTP_EINVAL; }
+	t->sortInterval = interval;
+	return PTP_OK;
+}
+
+int ptp_trap_set_deposit_mode(ptp_trap* t, int mode)
+{
+	if (!t || (mode != PTP_DEPOSIT_FP64 && mode != PTP_DEPOSIT_FIXED64)) { ptp_set_error("ptp_trap_set_deposit_mode: bad mode"); return PTP_EINVAL; }
+	const int old = t->depositMode;
+	t->depositMode = mode;
+	if (ptp_push_configure(t) != PTP_OK) { t->depositMode = old; return PTP_EINVAL; }
+	return PTP_OK;
+}
+
+int ptp_trap_set_arith_mode(ptp_trap* t, int mode)
+{
+	if (!t || (mode != PTP_ARITH_FAST && mode != PTP_ARITH_EXACT)) { ptp_set_error("ptp_trap_set_arith_mode: bad mode"); return PTP_EINVAL; }
+	t->arithMode = mode;
+	return PTP_OK;
+}
+
+int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMaxIterations)
+{
+	if (!t || (solver != PTP_SOLVER_DIRECT && solver != PTP_SOLVER_SOR)) { ptp_set_error("ptp_trap_set_solver: bad solver"); return PTP_EINVAL; }
+	t->solver = solver;
+	if (sorTolerance > 0) t->sorTol = sorTolerance;
+	if (sorMaxIterations > 0) t->sorMaxIter = sorMaxIterations;
+	return PTP_OK;
+}
+
+int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas)
+{
+	if (!t) { ptp_set_error("ptp_trap_set_tuning: null trap"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	const int oT = t->threads, oW = t->window, oC = t->ctas;
+	if (threads > 0) t->threads = threads;
+	if (window > 0) t->window = window;
+	if (ctas >= 0) t->ctas = ctas;
+	if (ptp_push_configure(t) != PTP_OK) { t->threads = oT; t->window = oW; t->ctas = oC; return PTP_EINVAL; }
+	for (ptp_plasma* p : t->plasmas)
+		if (p->cap) { PTP_TRY(ptp_build_segments(t, p)); PTP_TRY(ptp_bounds_launch(t, p)); }
+	return PTP_OK;
+}
+
+int ptp_plasma_create(ptp_trap* t, ptp_plasma** out, double mass, double charge)
+{
+	if (!t || !out || !(mass > 0) || charge == 0) { ptp_set_error("ptp_plasma_create: bad arguments"); return PTP_EINVAL; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	PTP_TRY(ensure_species_capacity(t, (int)t->plasmas.size() + 1));
+	ptp_plasma* p = new ptp_plasma;
+	p->trap = t;
+	p->index = (int)t->plasmas.size();
+	p->mass = mass;
+	p->charge = charge;
+	p->rowOff.assign(t->Nr + 1, 0);
+	p->rowLive.assign(t->Nr, 0);
+	PTP_CUDA(cudaMalloc(&p->dLost, sizeof(unsigned long long)));
+	PTP_CUDA(cudaMemset(p->dLost, 0, sizeof(unsigned long long)));
+	const size_t gb = (size_t)t->G * sizeof(double);
+	PTP_CUDA(cudaMemset(t->rhoAll + (size_t)p->index * t->G, 0, gb));
+	PTP_CUDA(cudaMemset(t->phiSelfAll + (size_t)p->index * t->G, 0, gb));
+	t->plasmas.push_back(p);
+	t->eNodesValid = false;
+	*out = p;
+	return PTP_OK;
+}
+
+int ptp_plasma_destroy(ptp_plasma* p)
+{
+	if (!p) return PTP_OK;
+	ptp_trap* t = p->trap;
+	cudaSetDevice(t->device);
+	cudaStreamSynchronize(t->stream);
+	// later species move down one slice so that slices stay contiguous and in registration order
+	const size_t gb = (size_t)t->G * sizeof(double);
+	for (size_t s = p->index + 1; s < t->plasmas.size(); ++s) {
+		cudaMemcpy(t->rhoAll + (s - 1) * t->G, t->rhoAll + s * t->G, gb, cudaMemcpyDeviceToDevice);
+		cudaMemcpy(t->phiSelfAll + (s - 1) * t->G, t->phiSelfAll + s * t->G, gb, cudaMemcpyDeviceToDevice);
+		cudaMemcpy(t->dScale + (s - 1), t->dScale + s, sizeof(double), cudaMemcpyDeviceToDevice);
+		t->plasmas[s]->index = (int)s - 1;
+	}
+	t->plasmas.erase(t->plasmas.begin() + p->index);
+	t->eNodesValid = false;
+	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt);
+	cudaFree(p->dRowOff); cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds); cudaFree(p->dLost);
+	delete p;
+	return PTP_OK;
+}
+
+int ptp_plasma_deposit(ptp_plasma* p)
+{
+	if (!p) { ptp_set_error("ptp_plasma_deposit: null plasma"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+	void* rho = t->rhoAll + (size_t)p->index * t->G;
+	PTP_CUDA(cudaMemsetAsync(rho, 0, (size_t)t->G * sizeof(double), t->stream));
+	PTP_TRY(ptp_push_launch(t, p, 0.0, false));
+	return ptp_comm_allreduce(t, rho, (size_t)t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
+}
+
+int ptp_plasma_deposit_solve(ptp_plasma* p)
+{
+	PTP_TRY(ptp_plasma_deposit(p));
+	ptp_trap* t = p->trap;
+	PTP_TRY(solve_species(t, p->index, 1));
+	t->eNodesValid = false;
+	return PTP_OK;
+}
+
+int ptp_plasma_get_rhs(ptp_plasma* p, double* rhs)
+{
+	if (!p || !rhs) { ptp_set_error("ptp_plasma_get_rhs: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	const size_t gb = (size_t)t->G * sizeof(double);
+	PTP_CUDA(cudaMemcpyAsync(rhs, t->rhoAll + (size_t)p->index * t->G, gb, cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	const double scale = -p->macroChargeDensity / 8.8541878128e-12;
+	if (t->depositMode == PTP_DEPOSIT_FIXED64) {
+		const double inv = 1.0 / (double)(1ULL << t->fixedBits);
+		for (long long i = 0; i < t->G; ++i) {
+			long long w;
+			std::memcpy(&w, &rhs[i], sizeof(w));
+			rhs[i] = ((double)w * inv) * scale;
+		}
+	}
+	else for (long long i = 0; i < t->G; ++i) rhs[i] *= scale;
+	return PTP_OK;
+}
+
+int ptp_plasma_get_self_potential(ptp_plasma* p, double* phi)
+{
+	if (!p || !phi) { ptp_set_error("ptp_plasma_get_self_potential: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaMemcpyAsync(phi, t->phiSelfAll + (size_t)p->index * t->G, (size_t)t->G * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	return PTP_OK;
+}
+
+int ptp_plasma_set_self_potential(ptp_plasma* p, const double* phi)
+{
+	if (!p || !phi) { ptp_set_error("ptp_plasma_set_self_potential: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_CUDA(cudaMemcpyAsync(t->phiSelfAll + (size_t)p->index * t->G, phi, (size_t)t->G * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	t->eNodesValid = false;
+	return PTP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,144 @@
+// Internal declarations shared by the .cu files of libptp_b200.so. Not part of the ABI (see include/ptp.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "ptp.h"
+
+#define PTP_VERSION 100
+
+// Row buckets are padded to this many ring slots so that every tile of the push kernel lies inside one
+// radial row and double2 accesses stay 16-byte aligned (8 rings/thread x 512 threads max).
+#define PTP_ROW_ALIGN 4096
+#define PTP_RINGS_PER_THREAD 8
+
+// One contiguous run of ring slots of ONE radial row, owned by one CTA of the push kernel.
+struct PtpSegment {
+	int row;
+	int pad;
+	long long begin, end; // slot range, multiples of the tile size
+};
+
+struct ptp_plasma {
+	ptp_trap* trap = nullptr;
+	int index = -1;              // position in trap->plasmas = summation order of the node field
+	double mass = 0, charge = 0, macroChargeDensity = 0;
+	int64_t nUploaded = 0;       // rings given at upload
+	int64_t nAlive = 0;          // host copy, refreshed from the device loss counter
+	long long cap = 0;           // ring slots allocated (sum of padded row buckets)
+	double* z = nullptr;         // [cap] axial position, NaN = empty slot / lost ring
+	double* v = nullptr;         // [cap] axial speed at t - dt/2
+	long long* id = nullptr;     // [cap] index of the ring at upload (moves only in sort/compaction)
+	double* zAlt = nullptr;      // sort ping-pong buffers (allocated on first sort)
+	double* vAlt = nullptr;
+	long long* idAlt = nullptr;
+	std::vector<long long> rowOff;   // [Nr+1] slot offset of each row bucket (host)
+	std::vector<long long> rowLive;  // [Nr] slots of the bucket that may hold live rings (prefix of the bucket)
+	long long* dRowOff = nullptr;
+	std::vector<PtpSegment> segs;
+	std::vector<int> ctaSegBegin;    // [nCta+1]
+	PtpSegment* dSegs = nullptr;
+	int* dCtaSegBegin = nullptr;
+	int2* dSegBounds = nullptr;      // per segment: min / max axial cell of its live rings
+	int nCta = 0;
+	unsigned long long* dLost = nullptr; // rings lost since upload (device counter)
+	bool boundsValid = false;
+};
+
+struct PtpComm; // ptp_comm.cu
+
+struct ptp_trap {
+	int device = 0;
+	int Nz = 0, Nr = 0;
+	long long G = 0;
+	double hz = 0, hr = 0, length = 0, radius = 0;
+	int smCount = 148;
+	size_t smemMax = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	std::vector<cudaEvent_t> evPool; // 4 events per step of the last ptp_trap_step call (phase timing)
+	int evSteps = 0;
+	double lastMs[4] = { 0, 0, 0, 0 };
+	int64_t lastLaunches = 0;
+
+	// operator / direct solver (ptp_solve.cu)
+	double* dctFwd = nullptr;    // [(Nz+1)^2]  FT[k][m] = (2/Nz) w_k w_m cos(pi k m / Nz)
+	double* dctInv = nullptr;    // [(Nz+1)^2]  C[m][k]  = cos(pi m k / Nz)
+	double* thInv = nullptr;     // [Nr][Nz+1]  1 / pivot of the r-tridiagonal of axial mode m
+	double* thCp = nullptr;      // [Nr][Nz+1]  upper / pivot
+	double* thLower = nullptr;   // [Nr]        sub-diagonal of T_r
+	double* stLower = nullptr;   // [Nr] stencil r-lower   (operator apply / SOR)
+	double* stUpper = nullptr;   // [Nr] stencil r-upper
+	double stDiag = 0, stHz2 = 0, wallFactor = 0;
+
+	double* phiTrap = nullptr;   // [G]
+	double* eNodes = nullptr;    // [G]
+	double* tmpA = nullptr;      // [G] scratch (host-RHS solves, wall RHS)
+	double* tmpB = nullptr;      // [G]
+	double* tmpSpec = nullptr;   // [G]
+
+	// per-species grids, contiguous over species so that one all-reduce / one batched solve covers them
+	int capS = 0;
+	double* rhoAll = nullptr;    // [capS][G] deposit accumulators (double weights, or int64 fixed point)
+	double* phiSelfAll = nullptr;// [capS][G]
+	double* specAll = nullptr;   // [capS][G] spectral workspace
+	double* dScale = nullptr;    // [capS] rho -> RHS factor per species
+	std::vector<ptp_plasma*> plasmas;
+
+	int depositMode = PTP_DEPOSIT_FP64;
+	int arithMode = PTP_ARITH_FAST;
+	int solver = PTP_SOLVER_DIRECT;
+	double sorTol = 1e-12;
+	int sorMaxIter = 20000;
+	int fixedBits = 40;
+	int threads = 256, window = 64, ctas = 0;
+	int sortInterval = 0;
+	long long stepCount = 0;
+	bool eNodesValid = false;
+
+	PtpComm* comm = nullptr;
+	int allreduceKind = 0;
+};
+
+// ---- error handling -------------------------------------------------------------------------
+void ptp_set_error(const std::string& msg);
+int ptp_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define PTP_CUDA(call)                                                                    \
+	do {                                                                                  \
+		cudaError_t e_ = (call);                                                          \
+		if (e_ != cudaSuccess) return ptp_cuda_fail(e_, #call, __FILE__, __LINE__);        \
+	} while (0)
+#define PTP_TRY(call)                   \
+	do {                                \
+		int rc_ = (call);               \
+		if (rc_ != PTP_OK) return rc_;  \
+	} while (0)
+
+// ---- ptp_solve.cu ------------------------------------------------------------------------------
+int ptp_solver_build(ptp_trap* t);
+void ptp_solver_free(ptp_trap* t);
+// phi[s] = A^-1 (scale[s] * rho[s]) for nS consecutive grids; rho is double weights or int64 fixed point.
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi);
+int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
+int ptp_node_field(ptp_trap* t);
+int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);
+int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi);
+
+// ---- ptp_push.cu ---------------------------------------------------------------------------------
+int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push);
+int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p);
+size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window);
+int ptp_push_configure(ptp_trap* t);
+
+// ---- ptp_particles.cu ----------------------------------------------------------------------------
+int ptp_build_segments(ptp_trap* t, ptp_plasma* p);
+int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p);
+
+// ---- ptp_comm.cu ---------------------------------------------------------------------------------
+int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64);
+void ptp_comm_free(ptp_trap* t);
+int ptp_comm_size(ptp_trap* t);

@@ -1,0 +1,442 @@
+// Ring storage: row-bucketed SoA, segment tables for the push kernel, download/compaction, the integer
+// keys of the step, K5 (per-row counting sort by axial cell + compaction) and the diagnostics reductions.
+#include "ptp_internal.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+__device__ __forceinline__ int exact_cell(double z, double hz, int Nz)
+{
+	int k = (int)floor(__ddiv_rn(z, hz));                 // Source/Plasma.cpp:87
+	return k > Nz - 1 ? Nz - 1 : k;
+}
+
+__global__ void k_cell_index(const double* __restrict__ z, long long cap, double hz, int Nz, int* __restrict__ k)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cap) return;
+	const double zz = z[i];
+	k[i] = (zz == zz) ? exact_cell(zz, hz, Nz) : -1;
+}
+
+__global__ void k_iota_rows(long long* __restrict__ id, const long long* __restrict__ rowOff, const long long* __restrict__ rowSrc, int Nr)
+{
+	const int r = blockIdx.y;
+	if (r >= Nr) return;
+	const long long n = rowSrc[r + 1] - rowSrc[r];
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+		id[rowOff[r] + i] = rowSrc[r] + i;
+}
+
+// Plasma::getPotentialEnergy (Source/Plasma.cpp:244-252) with getTotalPhi(int,double) (Source/PenningTrap.cpp:335-351).
+__global__ void k_potential_energy(const double* __restrict__ z, const PtpSegment* __restrict__ segs, int nSegs,
+	const double* __restrict__ phiTrap, const double* __restrict__ phiSelf, int nS, long long G, int Nz, double hz,
+	double chargeMacro, double* __restrict__ out)
+{
+	double acc = 0.0;
+	for (int s = blockIdx.x; s < nSegs; s += gridDim.x) {
+		const PtpSegment seg = segs[s];
+		const long long rowBase = (long long)seg.row * (Nz + 1);
+		const double q = seg.row == 0 ? chargeMacro : (double)(seg.row * 8) * chargeMacro;
+		for (long long i = seg.begin + threadIdx.x; i < seg.end; i += blockDim.x) {
+			const double zz = z[i];
+			if (!(zz == zz)) continue;
+			const int k = exact_cell(zz, hz, Nz);
+			const double w = __ddiv_rn(__dsub_rn(zz, __dmul_rn((double)k, hz)), hz);
+			double pl = phiTrap[rowBase + k], pr = phiTrap[rowBase + k + 1];
+			for (int sp = 0; sp < nS; ++sp) { pl += phiSelf[(size_t)sp * G + rowBase + k]; pr += phiSelf[(size_t)sp * G + rowBase + k + 1]; }
+			acc += ((1 - w) * pl + w * pr) * q;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(out, acc);
+}
+
+// Plasma::getNumMacroCentralWell (Source/Plasma.cpp:151-162).
+__global__ void k_central_well(const double* __restrict__ z, const PtpSegment* __restrict__ segs, int nSegs,
+	const int* __restrict__ left, const int* __restrict__ right, double hz, unsigned long long* __restrict__ out)
+{
+	unsigned int n = 0;
+	for (int s = blockIdx.x; s < nSegs; s += gridDim.x) {
+		const PtpSegment seg = segs[s];
+		const double lo = __dmul_rn((double)left[seg.row], hz), hi = __dmul_rn((double)right[seg.row], hz);
+		for (long long i = seg.begin + threadIdx.x; i < seg.end; i += blockDim.x) {
+			const double zz = z[i];
+			if (zz >= lo && zz <= hi) ++n;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+	if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, (unsigned long long)n);
+}
+
+// ---- K5: per-row counting sort by axial cell ---------------------------------------------------------
+// pass 1: histogram of live rings per (row, cell); shared-memory histogram per CTA chunk, then global adds.
+__global__ void __launch_bounds__(256) k_sort_count(const double* __restrict__ z, const long long* __restrict__ rowOff,
+	int Nr, int Nz, double hz, unsigned int* __restrict__ counts, int chunksPerRow)
+{
+	extern __shared__ unsigned int hist[];                 // [Nz]
+	const int r = blockIdx.x / chunksPerRow, chunk = blockIdx.x % chunksPerRow;
+	const long long b = rowOff[r], e = rowOff[r + 1];
+	if (b == e) return;
+	const long long len = (e - b + chunksPerRow - 1) / chunksPerRow;
+	const long long cb = b + chunk * len, ce = min(e, cb + len);
+	for (int i = threadIdx.x; i < Nz; i += blockDim.x) hist[i] = 0;
+	__syncthreads();
+	for (long long i = cb + threadIdx.x; i < ce; i += blockDim.x) {
+		const double zz = z[i];
+		if (zz == zz) atomicAdd(&hist[exact_cell(zz, hz, Nz)], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < Nz; i += blockDim.x)
+		if (hist[i]) atomicAdd(&counts[(size_t)r * Nz + i], hist[i]);
+}
+
+// pass 2: exclusive scan of each row's cell counts -> cursor[row][cell] (slot offsets inside the bucket), live[row].
+__global__ void __launch_bounds__(256) k_sort_scan(const unsigned int* __restrict__ counts, int Nz,
+	unsigned long long* __restrict__ cursor, unsigned long long* __restrict__ live)
+{
+	__shared__ unsigned long long part[256];
+	const int r = blockIdx.x, tid = threadIdx.x;
+	const int per = (Nz + 255) / 256;
+	const int b = tid * per, e = min(Nz, b + per);
+	unsigned long long s = 0;
+	for (int i = b; i < e; ++i) s += counts[(size_t)r * Nz + i];
+	part[tid] = s;
+	__syncthreads();
+	if (tid == 0) {
+		unsigned long long run = 0;
+		for (int i = 0; i < 256; ++i) { const unsigned long long c = part[i]; part[i] = run; run += c; }
+		live[r] = run;
+	}
+	__syncthreads();
+	unsigned long long run = part[tid];
+	for (int i = b; i < e; ++i) { cursor[(size_t)r * Nz + i] = run; run += counts[(size_t)r * Nz + i]; }
+}
+
+// pass 3: scatter. One CTA per (row, chunk); ranks inside the CTA from a shared histogram, one global
+// atomic per (CTA, non-empty cell) to reserve the destination range.
+__global__ void __launch_bounds__(256) k_sort_scatter(const double* __restrict__ z, const double* __restrict__ v,
+	const long long* __restrict__ id, double* __restrict__ zOut, double* __restrict__ vOut, long long* __restrict__ idOut,
+	const long long* __restrict__ rowOff, int Nr, int Nz, double hz, unsigned long long* __restrict__ cursor, int chunksPerRow)
+{
+	extern __shared__ unsigned int sh[];                   // hist[Nz] then base (as 2 x u32 per cell)
+	unsigned int* hist = sh;
+	unsigned long long* base = reinterpret_cast<unsigned long long*>(sh + ((Nz + 1) & ~1));
+	const int r = blockIdx.x / chunksPerRow, chunk = blockIdx.x % chunksPerRow;
+	const long long b = rowOff[r], e = rowOff[r + 1];
+	if (b == e) return;
+	const long long len = (e - b + chunksPerRow - 1) / chunksPerRow;
+	const long long cb = b + chunk * len, ce = min(e, cb + len);
+	for (int i = threadIdx.x; i < Nz; i += blockDim.x) hist[i] = 0;
+	__syncthreads();
+	for (long long i = cb + threadIdx.x; i < ce; i += blockDim.x) {
+		const double zz = z[i];
+		if (zz == zz) atomicAdd(&hist[exact_cell(zz, hz, Nz)], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < Nz; i += blockDim.x) {
+		const unsigned int c = hist[i];
+		base[i] = c ? atomicAdd(&cursor[(size_t)r * Nz + i], (unsigned long long)c) : 0ULL;
+		hist[i] = 0;
+	}
+	__syncthreads();
+	for (long long i = cb + threadIdx.x; i < ce; i += blockDim.x) {
+		const double zz = z[i];
+		if (!(zz == zz)) continue;
+		const int k = exact_cell(zz, hz, Nz);
+		const long long dst = b + (long long)base[k] + atomicAdd(&hist[k], 1u);
+		zOut[dst] = zz;
+		vOut[dst] = v[i];
+		idOut[dst] = id[i];
+	}
+}
+
+} // namespace
+
+// Split the live part of every row bucket into segments and deal them to CTAs in contiguous tile ranges.
+int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
+{
+	const long long tile = (long long)PTP_RINGS_PER_THREAD * t->threads;
+	const long long maxSegTiles = 4095 / PTP_RINGS_PER_THREAD;   // 12-bit per-thread count field of the packed bins
+	long long totalTiles = 0;
+	for (int r = 0; r < t->Nr; ++r) totalTiles += (p->rowLive[r] + tile - 1) / tile;
+	int nCta = t->ctas > 0 ? t->ctas : t->smCount;
+	if (totalTiles < nCta) nCta = (int)totalTiles;
+	p->segs.clear();
+	p->ctaSegBegin.assign(1, 0);
+	p->nCta = nCta;
+	if (nCta > 0) {
+		int cta = 0;
+		long long given = 0;                                 // tiles handed out so far
+		auto quotaEnd = [&](int c) { return (totalTiles * (long long)(c + 1)) / nCta; };
+		for (int r = 0; r < t->Nr; ++r) {
+			long long tiles = (p->rowLive[r] + tile - 1) / tile, done = 0;
+			while (done < tiles) {
+				while (given >= quotaEnd(cta)) { p->ctaSegBegin.push_back((int)p->segs.size()); ++cta; }
+				long long take = std::min(std::min(tiles - done, quotaEnd(cta) - given), maxSegTiles);
+				PtpSegment s;
+				s.row = r; s.pad = 0;
+				s.begin = p->rowOff[r] + done * tile;
+				s.end = s.begin + take * tile;
+				p->segs.push_back(s);
+				done += take; given += take;
+			}
+		}
+		while ((int)p->ctaSegBegin.size() < nCta + 1) p->ctaSegBegin.push_back((int)p->segs.size());
+	}
+	cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds);
+	p->dSegs = nullptr; p->dCtaSegBegin = nullptr; p->dSegBounds = nullptr;
+	if (!p->segs.empty()) {
+		PTP_CUDA(cudaMalloc(&p->dSegs, p->segs.size() * sizeof(PtpSegment)));
+		PTP_CUDA(cudaMalloc(&p->dCtaSegBegin, p->ctaSegBegin.size() * sizeof(int)));
+		PTP_CUDA(cudaMalloc(&p->dSegBounds, p->segs.size() * sizeof(int2)));
+		PTP_CUDA(cudaMemcpyAsync(p->dSegs, p->segs.data(), p->segs.size() * sizeof(PtpSegment), cudaMemcpyHostToDevice, t->stream));
+		PTP_CUDA(cudaMemcpyAsync(p->dCtaSegBegin, p->ctaSegBegin.data(), p->ctaSegBegin.size() * sizeof(int), cudaMemcpyHostToDevice, t->stream));
+		PTP_CUDA(cudaStreamSynchronize(t->stream));
+	}
+	p->boundsValid = false;
+	return PTP_OK;
+}
+
+// K5. Rings of each row are re-ordered by axial cell into the alternate buffers (lost rings dropped), the
+// buffers are swapped and the segment tables rebuilt on the shrunken live ranges.
+int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
+{
+	if (p->cap == 0) return PTP_OK;
+	const int Nr = t->Nr, Nz = t->Nz;
+	if (!p->zAlt) {
+		PTP_CUDA(cudaMalloc(&p->zAlt, p->cap * sizeof(double)));
+		PTP_CUDA(cudaMalloc(&p->vAlt, p->cap * sizeof(double)));
+		PTP_CUDA(cudaMalloc(&p->idAlt, p->cap * sizeof(long long)));
+	}
+	unsigned int* dCounts = nullptr;
+	unsigned long long* dCursor = nullptr;
+	PTP_CUDA(cudaMalloc(&dCounts, (size_t)Nr * Nz * sizeof(unsigned int)));
+	PTP_CUDA(cudaMalloc(&dCursor, ((size_t)Nr * Nz + Nr) * sizeof(unsigned long long)));
+	unsigned long long* dLive = dCursor + (size_t)Nr * Nz;
+	PTP_CUDA(cudaMemsetAsync(dCounts, 0, (size_t)Nr * Nz * sizeof(unsigned int), t->stream));
+	PTP_CUDA(cudaMemsetAsync(p->zAlt, 0xFF, p->cap * sizeof(double), t->stream));
+	PTP_CUDA(cudaMemsetAsync(p->vAlt, 0, p->cap * sizeof(double), t->stream));
+	PTP_CUDA(cudaMemsetAsync(p->idAlt, 0xFF, p->cap * sizeof(long long), t->stream));
+	long long maxRow = 0;
+	for (int r = 0; r < Nr; ++r) maxRow = std::max(maxRow, p->rowOff[r + 1] - p->rowOff[r]);
+	int chunksPerRow = (int)std::min<long long>(std::max<long long>(1, maxRow / 16384), 4096);
+	const size_t smCount = (size_t)Nz * sizeof(unsigned int);
+	const size_t smScatter = (size_t)((Nz + 1) & ~1) * sizeof(unsigned int) + (size_t)Nz * sizeof(unsigned long long);
+	k_sort_count<<<Nr * chunksPerRow, 256, smCount, t->stream>>>(p->z, p->dRowOff, Nr, Nz, t->hz, dCounts, chunksPerRow);
+	k_sort_scan<<<Nr, 256, 0, t->stream>>>(dCounts, Nz, dCursor, dLive);
+	k_sort_scatter<<<Nr * chunksPerRow, 256, smScatter, t->stream>>>(p->z, p->v, p->id, p->zAlt, p->vAlt, p->idAlt,
+		p->dRowOff, Nr, Nz, t->hz, dCursor, chunksPerRow);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { cudaFree(dCounts); cudaFree(dCursor); return ptp_cuda_fail(e, "sort launch", __FILE__, __LINE__); }
+	t->lastLaunches += 3;
+	std::vector<unsigned long long> live(Nr);
+	PTP_CUDA(cudaMemcpyAsync(live.data(), dLive, Nr * sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dCounts); cudaFree(dCursor);
+	std::swap(p->z, p->zAlt); std::swap(p->v, p->vAlt); std::swap(p->id, p->idAlt);
+	long long total = 0;
+	for (int r = 0; r < Nr; ++r) { p->rowLive[r] = (long long)live[r]; total += (long long)live[r]; }
+	p->nAlive = total;
+	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
+	p->nUploaded = total;                                  // loss counter restarts from the compacted population
+	PTP_TRY(ptp_build_segments(t, p));
+	return ptp_bounds_launch(t, p);
+}
+
+// ---- C ABI: particle-side entry points ---------------------------------------------------------------
+extern "C" {
+
+int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* z, const double* v, double macroChargeDensity)
+{
+	if (!p || n < 0 || (n > 0 && (!r || !z || !v))) { ptp_set_error("ptp_plasma_upload: bad arguments"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	const int Nr = t->Nr;
+	std::vector<long long> count(Nr, 0);
+	bool sorted = true;
+	for (int64_t i = 0; i < n; ++i) {
+		const int ri = r[i];
+		if (ri < 0 || ri >= Nr) { ptp_set_error("ptp_plasma_upload: radial index outside [0, Nr)"); return PTP_EINVAL; }
+		++count[ri];
+		if (i && ri < r[i - 1]) sorted = false;
+	}
+	std::vector<long long> rowSrc(Nr + 1, 0);
+	p->rowOff.assign(Nr + 1, 0);
+	p->rowLive.assign(Nr, 0);
+	for (int j = 0; j < Nr; ++j) {
+		rowSrc[j + 1] = rowSrc[j] + count[j];
+		p->rowLive[j] = count[j];
+		p->rowOff[j + 1] = p->rowOff[j] + (count[j] + PTP_ROW_ALIGN - 1) / PTP_ROW_ALIGN * PTP_ROW_ALIGN;
+	}
+	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
+	p->z = p->v = p->zAlt = p->vAlt = nullptr; p->id = p->idAlt = nullptr; p->dRowOff = nullptr;
+	p->cap = p->rowOff[Nr];
+	p->nUploaded = n;
+	p->nAlive = n;
+	p->macroChargeDensity = macroChargeDensity;
+	const double scale = -macroChargeDensity / 8.8541878128e-12;     // Source/Plasma.cpp:91-92, Source/Constants.hpp:12
+	PTP_CUDA(cudaMemcpy(t->dScale + p->index, &scale, sizeof(double), cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
+	PTP_CUDA(cudaMalloc(&p->dRowOff, (Nr + 1) * sizeof(long long)));
+	PTP_CUDA(cudaMemcpy(p->dRowOff, p->rowOff.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+	if (p->cap > 0) {
+		PTP_CUDA(cudaMalloc(&p->z, p->cap * sizeof(double)));
+		PTP_CUDA(cudaMalloc(&p->v, p->cap * sizeof(double)));
+		PTP_CUDA(cudaMalloc(&p->id, p->cap * sizeof(long long)));
+		PTP_CUDA(cudaMemsetAsync(p->z, 0xFF, p->cap * sizeof(double), t->stream));   // all-ones = NaN = empty slot
+		PTP_CUDA(cudaMemsetAsync(p->v, 0, p->cap * sizeof(double), t->stream));
+		PTP_CUDA(cudaMemsetAsync(p->id, 0xFF, p->cap * sizeof(long long), t->stream));
+		if (sorted) {
+			// loaders emit rows in ascending order (Source/Plasma.cpp:510-526): each bucket is one contiguous copy
+			for (int j = 0; j < Nr; ++j) {
+				if (!count[j]) continue;
+				PTP_CUDA(cudaMemcpyAsync(p->z + p->rowOff[j], z + rowSrc[j], count[j] * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+				PTP_CUDA(cudaMemcpyAsync(p->v + p->rowOff[j], v + rowSrc[j], count[j] * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+			}
+			long long* dRowSrc = nullptr;
+			PTP_CUDA(cudaMalloc(&dRowSrc, (Nr + 1) * sizeof(long long)));
+			PTP_CUDA(cudaMemcpyAsync(dRowSrc, rowSrc.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
+			k_iota_rows<<<dim3(64, Nr), 256, 0, t->stream>>>(p->id, p->dRowOff, dRowSrc, Nr);
+			PTP_CUDA(cudaStreamSynchronize(t->stream));
+			cudaFree(dRowSrc);
+		}
+		else {
+			// general order (e.g. after the reference's swap-with-back removals): stable counting sort on the host
+			std::vector<double> zs(p->cap), vs(p->cap);
+			std::vector<long long> ids(p->cap, -1);
+			std::vector<long long> cur(p->rowOff.begin(), p->rowOff.end() - 1);
+			const double nan = std::nan("");
+			std::fill(zs.begin(), zs.end(), nan);
+			for (int64_t i = 0; i < n; ++i) {
+				const long long d = cur[r[i]]++;
+				zs[d] = z[i]; vs[d] = v[i]; ids[d] = i;
+			}
+			PTP_CUDA(cudaMemcpyAsync(p->z, zs.data(), p->cap * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+			PTP_CUDA(cudaMemcpyAsync(p->v, vs.data(), p->cap * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+			PTP_CUDA(cudaMemcpyAsync(p->id, ids.data(), p->cap * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
+			PTP_CUDA(cudaStreamSynchronize(t->stream));
+		}
+	}
+	// fixed-point scale: node sums stay below 2^62 for the whole (multi-GPU) population
+	long long total = 0;
+	for (ptp_plasma* q : t->plasmas) total += q->nUploaded;
+	total *= ptp_comm_size(t);
+	int bits = 0;
+	while ((1LL << bits) < total + 1) ++bits;
+	t->fixedBits = std::min(40, 62 - bits);
+	PTP_TRY(ptp_build_segments(t, p));
+	return ptp_bounds_launch(t, p);
+}
+
+int ptp_plasma_count(ptp_plasma* p, int64_t* nAlive)
+{
+	if (!p || !nAlive) { ptp_set_error("ptp_plasma_count: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	unsigned long long lost = 0;
+	PTP_CUDA(cudaMemcpyAsync(&lost, p->dLost, sizeof(lost), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	p->nAlive = p->nUploaded - (int64_t)lost;
+	*nAlive = p->nAlive;
+	return PTP_OK;
+}
+
+static int download_impl(ptp_plasma* p, int32_t* r, double* z, double* v, int64_t* id, int32_t* kOut, int32_t* idxOut)
+{
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	if (p->cap == 0) return PTP_OK;
+	std::vector<double> zs(p->cap), vs;
+	std::vector<long long> ids;
+	std::vector<int> ks;
+	PTP_CUDA(cudaMemcpyAsync(zs.data(), p->z, p->cap * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	if (v) { vs.resize(p->cap); PTP_CUDA(cudaMemcpyAsync(vs.data(), p->v, p->cap * sizeof(double), cudaMemcpyDeviceToHost, t->stream)); }
+	if (id) { ids.resize(p->cap); PTP_CUDA(cudaMemcpyAsync(ids.data(), p->id, p->cap * sizeof(long long), cudaMemcpyDeviceToHost, t->stream)); }
+	if (kOut || idxOut) {
+		int* dK = nullptr;
+		PTP_CUDA(cudaMalloc(&dK, p->cap * sizeof(int)));
+		k_cell_index<<<(unsigned)((p->cap + 255) / 256), 256, 0, t->stream>>>(p->z, p->cap, t->hz, t->Nz, dK);
+		ks.resize(p->cap);
+		PTP_CUDA(cudaMemcpyAsync(ks.data(), dK, p->cap * sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+		PTP_CUDA(cudaStreamSynchronize(t->stream));
+		cudaFree(dK);
+	}
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	int64_t o = 0;
+	for (int j = 0; j < t->Nr; ++j) {
+		for (long long i = p->rowOff[j]; i < p->rowOff[j] + p->rowLive[j]; ++i) {
+			if (!(zs[i] == zs[i])) continue;
+			if (r) r[o] = j;
+			if (z) z[o] = zs[i];
+			if (v) v[o] = vs[i];
+			if (id) id[o] = ids[i];
+			if (kOut) kOut[o] = ks[i];
+			if (idxOut) idxOut[o] = (t->Nz + 1) * j + ks[i];
+			++o;
+		}
+	}
+	p->nAlive = o;
+	return PTP_OK;
+}
+
+int ptp_plasma_download(ptp_plasma* p, int32_t* r, double* z, double* v, int64_t* id)
+{
+	if (!p) { ptp_set_error("ptp_plasma_download: null plasma"); return PTP_EINVAL; }
+	return download_impl(p, r, z, v, id, nullptr, nullptr);
+}
+
+int ptp_plasma_cell_index(ptp_plasma* p, int32_t* k, int32_t* idx)
+{
+	if (!p) { ptp_set_error("ptp_plasma_cell_index: null plasma"); return PTP_EINVAL; }
+	return download_impl(p, nullptr, nullptr, nullptr, nullptr, k, idx);
+}
+
+int ptp_plasma_potential_energy(ptp_plasma* p, double chargeMacro, double* pe)
+{
+	if (!p || !pe) { ptp_set_error("ptp_plasma_potential_energy: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	*pe = 0.0;
+	if (p->segs.empty()) return PTP_OK;
+	double* dOut = nullptr;
+	PTP_CUDA(cudaMalloc(&dOut, sizeof(double)));
+	PTP_CUDA(cudaMemsetAsync(dOut, 0, sizeof(double), t->stream));
+	int grid = std::min<int>((int)p->segs.size(), t->smCount * 4);
+	k_potential_energy<<<grid, 256, 0, t->stream>>>(p->z, p->dSegs, (int)p->segs.size(), t->phiTrap, t->phiSelfAll,
+		(int)t->plasmas.size(), t->G, t->Nz, t->hz, chargeMacro, dOut);
+	double h = 0;
+	PTP_CUDA(cudaMemcpyAsync(&h, dOut, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dOut);
+	*pe = h / 2;                                            // Source/Plasma.cpp:251
+	return PTP_OK;
+}
+
+int ptp_plasma_count_central_well(ptp_plasma* p, const int32_t* limitLeft, const int32_t* limitRight, int64_t* n)
+{
+	if (!p || !limitLeft || !limitRight || !n) { ptp_set_error("ptp_plasma_count_central_well: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	*n = 0;
+	if (p->segs.empty()) return PTP_OK;
+	int* dLim = nullptr;
+	unsigned long long* dOut = nullptr;
+	PTP_CUDA(cudaMalloc(&dLim, 2 * t->Nr * sizeof(int)));
+	PTP_CUDA(cudaMalloc(&dOut, sizeof(unsigned long long)));
+	PTP_CUDA(cudaMemcpyAsync(dLim, limitLeft, t->Nr * sizeof(int), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaMemcpyAsync(dLim + t->Nr, limitRight, t->Nr * sizeof(int), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaMemsetAsync(dOut, 0, sizeof(unsigned long long), t->stream));
+	int grid = std::min<int>((int)p->segs.size(), t->smCount * 4);
+	k_central_well<<<grid, 256, 0, t->stream>>>(p->z, p->dSegs, (int)p->segs.size(), dLim, dLim + t->Nr, t->hz, dOut);
+	unsigned long long h = 0;
+	PTP_CUDA(cudaMemcpyAsync(&h, dOut, sizeof(h), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dLim); cudaFree(dOut);
+	*n = (int64_t)h;
+	return PTP_OK;
+}
+
+} // extern "C"

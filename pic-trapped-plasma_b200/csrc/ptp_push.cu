@@ -1,0 +1,436 @@
+// K1 / K2: fused gather + push + loss + deposit (and deposit alone) for one species.
+//
+// Replaces, per ring, Plasma::moveRings (reference Source/Plasma.cpp:100-120) with
+// PenningTrap::getEField(int,double) (Source/PenningTrap.cpp:326-334) inlined, followed by the ring's
+// contribution to Plasma::updateRHS (Source/Plasma.cpp:77-94) at its NEW position - so a ring is read
+// once and written once per step (32 B of HBM traffic).
+//
+// Layout: rings are SoA (z[], v[]), bucketed by radial row (posR never changes, Source/Plasma.hpp:22-24),
+// each bucket padded with NaN slots to PTP_ROW_ALIGN. A CTA owns "segments" = runs of tiles of one row.
+// Deposition: every thread owns a private column of W axial-cell bins in shared memory
+// (bins[cell - k0][thread]) and accumulates (count, sum of weights) there with plain read-modify-write -
+// no atomics, no bank conflicts (column index = thread index), independent of how many rings share a
+// cell (the default plasma puts ~5e5 rings of a 100 M load into each of ~400 cells). At the end of a
+// segment the columns are tree-reduced and flushed with one global atomic per touched node. Rings whose
+// cell falls outside the window [k0, k0+W) use global atomics directly (rare; the window is re-centred on
+// the segment's measured cell range every step). 64-bit shared atomics are CAS loops on sm_100a
+// (ATOMS.CAST.SPIN.64), which is why the accumulation is privatised instead.
+//
+// Node weights: with c_k = #rings in cell k and s_k = sum of their w, node k receives (c_k - s_k) + s_{k-1}
+// in units of one ring; the -macroChargeDensity/epsilon0 factor (Source/Plasma.cpp:91-92) is applied when
+// the Poisson solver reads the grid. Fixed-point mode packs (count:12 | sum:52) into one 64-bit word per
+// bin with w quantised to 2^-F: all sums are exact integers, so the result is independent of summation
+// order, CTA count and GPU count.
+#include "ptp_internal.h"
+
+#include <limits.h>
+
+namespace {
+
+constexpr double kMagic = 6755399441055744.0;            // 2^52 + 2^51: floor via add.rm, integer in the low word
+constexpr unsigned long long kPackBias = 0x4320000000000000ULL; // bits(2^52 + x) - bias = (1 << 52) | x
+constexpr unsigned long long kSumMask = (1ULL << 52) - 1;
+
+struct PushArgs {
+	int Nz, W, fixedBits, pad0;
+	double hz, invHz, eps, length;
+	double dt, charge, mass, invMass;
+	double fixedScale;          // 2^fixedBits
+	const double* eNodes;       // [G] node field of the pre-step potentials
+	double* z;
+	double* v;
+	const PtpSegment* segs;
+	const int* ctaSegBegin;
+	int2* segBounds;
+	void* rho;                  // [G] double weights or int64 fixed point
+	unsigned long long* lost;
+};
+
+// Axial cell of a position: bit-exact (int)floor(z / hz) (Source/Plasma.cpp:87, Source/PenningTrap.cpp:328).
+// Fast path: q = z * (1/hz), floor through a round-down add of 2^52+2^51. |q - z/hz| < eps/2, so whenever
+// frac(q) is at least eps away from 0 and 1 both floors agree; otherwise (probability ~2*eps per ring, and
+// always in EXACT mode) the true IEEE division decides. Also returns the reference's weightFactor
+// w = (z - k*hz) / hz (:89-90 / :331-332); the reciprocal multiply is the only non-reference operation.
+template <bool EXACT>
+__device__ __forceinline__ int cell_of(double z, const PushArgs& a, double& w)
+{
+	int k;
+	double kd;
+	if (EXACT) {
+		kd = floor(__ddiv_rn(z, a.hz));
+		k = (int)kd;
+	}
+	else {
+		double q = __dmul_rn(z, a.invHz);
+		double m = __dadd_rd(q, kMagic);
+		k = __double2loint(m);
+		kd = __dsub_rn(m, kMagic);
+		double f = __dsub_rn(q, kd);
+		if (!(f >= a.eps && f <= 1.0 - a.eps)) {
+			kd = floor(__ddiv_rn(z, a.hz));
+			k = (int)kd;
+		}
+	}
+	// z < length always holds for a live ring, but z/hz may still round up to Nz; the reference would read
+	// node Nz+1 there (its own warning at Source/PenningTrap.cpp:326). Deliberate divergence: stay in the last cell.
+	if (k > a.Nz - 1) { k = a.Nz - 1; kd = (double)k; }
+	double dz = __dsub_rn(z, __dmul_rn(kd, a.hz));
+	w = EXACT ? __ddiv_rn(dz, a.hz) : __dmul_rn(dz, a.invHz);
+	return k;
+}
+
+template <typename T> __device__ __forceinline__ T warp_sum(T x)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+	return x;
+}
+
+template <int T, bool PUSH, bool FIXED, bool EXACT>
+__global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int W = a.W;
+	double2* eTile = reinterpret_cast<double2*>(smem);                       // [W] (E[k], E[k+1]) of cell k0+i
+	unsigned long long* redC = reinterpret_cast<unsigned long long*>(eTile + W); // [W]
+	unsigned long long* redS = redC + W;                                     // [W] u64 (fixed) or double bits
+	unsigned long long* bins = redS + W;                                     // [W][T] packed words / double sums
+	unsigned int* cnts = reinterpret_cast<unsigned int*>(bins + (size_t)W * T); // [W][T] fp64 mode only
+	__shared__ int sKmin, sKmax;
+	__shared__ unsigned int sLost;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int n1 = a.Nz + 1;
+
+	for (int s = a.ctaSegBegin[blockIdx.x]; s < a.ctaSegBegin[blockIdx.x + 1]; ++s) {
+		const PtpSegment seg = a.segs[s];
+		const int2 bounds = a.segBounds[s];
+		if (bounds.x > bounds.y) continue;           // no live ring in this segment (uniform per CTA)
+		const long long rowBase = (long long)seg.row * n1;
+		int k0 = bounds.x - max(0, (W - (bounds.y - bounds.x + 1)) >> 1);
+		k0 = max(0, min(k0, a.Nz - W));
+		for (int i = 0; i < W; ++i) {
+			bins[(size_t)i * T + tid] = 0ULL;
+			if (!FIXED) cnts[(size_t)i * T + tid] = 0u;
+		}
+		if (PUSH) {
+			for (int i = tid; i < W; i += T) {
+				int node = k0 + i;
+				double eL = node <= a.Nz ? a.eNodes[rowBase + node] : 0.0;
+				double eR = node + 1 <= a.Nz ? a.eNodes[rowBase + node + 1] : 0.0;
+				eTile[i] = make_double2(eL, eR);
+			}
+		}
+		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLost = 0u; }
+		__syncthreads();
+
+		int kMin = INT_MAX, kMax = INT_MIN;
+		unsigned int lost = 0;
+
+		// deposit of one live ring at position zN
+		auto deposit = [&](double zN) {
+			double w;
+			const int k = cell_of<EXACT>(zN, a, w);
+			kMin = min(kMin, k);
+			kMax = max(kMax, k);
+			const unsigned int i = (unsigned int)(k - k0);
+			if (i < (unsigned int)W) {
+				if (FIXED) {
+					// round(w * 2^F) lands in the mantissa of (2^52 + x); subtracting the bias leaves (1 << 52) | x
+					double t = __fma_rn(w, a.fixedScale, 4503599627370496.0);
+					bins[(size_t)i * T + tid] += (unsigned long long)__double_as_longlong(t) - kPackBias;
+				}
+				else {
+					double* b = reinterpret_cast<double*>(bins) + (size_t)i * T + tid;
+					*b = __dadd_rn(*b, w);
+					cnts[(size_t)i * T + tid] += 1u;
+				}
+			}
+			else {
+				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
+				if (FIXED) {
+					double t = __fma_rn(w, a.fixedScale, 4503599627370496.0);
+					unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
+					unsigned long long* g = reinterpret_cast<unsigned long long*>(a.rho) + rowBase + k;
+					atomicAdd(g, (1ULL << a.fixedBits) - wq);
+					atomicAdd(g + 1, wq);
+				}
+				else {
+					double* g = reinterpret_cast<double*>(a.rho) + rowBase + k;
+					atomicAdd(g, __dsub_rn(1.0, w));
+					atomicAdd(g + 1, w);
+				}
+			}
+		};
+
+		// Plasma::moveRings body for one ring (Source/Plasma.cpp:105-118)
+		auto push = [&](double& z, double& v) {
+			if (!(z == z)) return;                       // empty slot / ring lost earlier
+			double w;
+			const int k = cell_of<EXACT>(z, a, w);
+			const unsigned int i = (unsigned int)(k - k0);
+			double eL, eR;
+			if (i < (unsigned int)W) { const double2 e = eTile[i]; eL = e.x; eR = e.y; }
+			else { eL = a.eNodes[rowBase + k]; eR = a.eNodes[rowBase + k + 1]; }
+			// (1 - w) * fieldLeft + w * fieldRight            Source/PenningTrap.cpp:333
+			const double e = __dadd_rn(__dmul_rn(__dsub_rn(1.0, w), eL), __dmul_rn(w, eR));
+			// deltaT * E * charge / mass + speed              Source/Plasma.cpp:105
+			double kick = __dmul_rn(__dmul_rn(a.dt, e), a.charge);
+			kick = EXACT ? __ddiv_rn(kick, a.mass) : __dmul_rn(kick, a.invMass);
+			const double vN = __dadd_rn(kick, v);
+			// deltaT * vNew + z                               Source/Plasma.cpp:106
+			const double zN = __dadd_rn(__dmul_rn(a.dt, vN), z);
+			if (zN < a.length && zN > 0.0) {             // Source/Plasma.cpp:108 (NaN -> removed, like the reference)
+				z = zN;
+				v = vN;
+				deposit(zN);
+			}
+			else {
+				z = __longlong_as_double(0x7ff8000000000000LL); // tombstone instead of swap-with-back + pop (:116-117)
+				++lost;
+			}
+		};
+
+		const double2* z2 = reinterpret_cast<const double2*>(a.z);
+		const double2* v2 = reinterpret_cast<const double2*>(a.v);
+		double2* z2w = reinterpret_cast<double2*>(a.z);
+		double2* v2w = reinterpret_cast<double2*>(a.v);
+		constexpr int NV = PTP_RINGS_PER_THREAD / 2;
+		for (long long t0 = seg.begin; t0 < seg.end; t0 += (long long)PTP_RINGS_PER_THREAD * T) {
+			const long long p0 = (t0 >> 1) + tid;
+			double2 zz[NV], vv[NV];
+#pragma unroll
+			for (int j = 0; j < NV; ++j) zz[j] = z2[p0 + (long long)j * T];
+			if (PUSH) {
+#pragma unroll
+				for (int j = 0; j < NV; ++j) vv[j] = v2[p0 + (long long)j * T];
+#pragma unroll
+				for (int j = 0; j < NV; ++j) {
+					const bool live = (zz[j].x == zz[j].x) || (zz[j].y == zz[j].y);
+					push(zz[j].x, vv[j].x);
+					push(zz[j].y, vv[j].y);
+					if (live) {
+						z2w[p0 + (long long)j * T] = zz[j];
+						v2w[p0 + (long long)j * T] = vv[j];
+					}
+				}
+			}
+			else {
+#pragma unroll
+				for (int j = 0; j < NV; ++j) {
+					if (zz[j].x == zz[j].x) deposit(zz[j].x);
+					if (zz[j].y == zz[j].y) deposit(zz[j].y);
+				}
+			}
+		}
+
+		// segment epilogue: cell range, column reduction, flush
+		for (int o = 16; o > 0; o >>= 1) {
+			kMin = min(kMin, __shfl_xor_sync(0xffffffffu, kMin, o));
+			kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
+		}
+		lost = warp_sum(lost);
+		if (lane == 0) {
+			if (kMin <= kMax) { atomicMin(&sKmin, kMin); atomicMax(&sKmax, kMax); }
+			if (lost) atomicAdd(&sLost, lost);
+		}
+		__syncthreads();
+		const int gMin = sKmin, gMax = sKmax;
+		if (gMin <= gMax) {
+			const int lo = max(gMin, k0) - k0, hi = min(gMax, k0 + W - 1) - k0;
+			for (int b = lo + warp; b <= hi; b += T / 32) {
+				if (FIXED) {
+					unsigned long long c = 0, sm = 0;
+					for (int t = lane; t < T; t += 32) {
+						const unsigned long long word = bins[(size_t)b * T + t];
+						c += word >> 52;
+						sm += word & kSumMask;
+					}
+					c = warp_sum(c);
+					sm = warp_sum(sm);
+					if (lane == 0) { redC[b] = c; redS[b] = sm; }
+				}
+				else {
+					unsigned int c = 0;
+					double sm = 0.0;
+					for (int t = lane; t < T; t += 32) {
+						c += cnts[(size_t)b * T + t];
+						sm += reinterpret_cast<const double*>(bins)[(size_t)b * T + t];
+					}
+					c = warp_sum(c);
+					sm = warp_sum(sm);
+					if (lane == 0) { redC[b] = c; redS[b] = (unsigned long long)__double_as_longlong(sm); }
+				}
+			}
+			__syncthreads();
+			for (int i = lo + tid; i <= hi + 1; i += T) {
+				if (FIXED) {
+					unsigned long long val = 0;
+					if (i <= hi) val += (redC[i] << a.fixedBits) - redS[i];
+					if (i > lo) val += redS[i - 1];
+					if (val) atomicAdd(reinterpret_cast<unsigned long long*>(a.rho) + rowBase + k0 + i, val);
+				}
+				else {
+					double val = 0.0;
+					if (i <= hi) val = (double)redC[i] - __longlong_as_double((long long)redS[i]);
+					if (i > lo) val += __longlong_as_double((long long)redS[i - 1]);
+					if (val != 0.0) atomicAdd(reinterpret_cast<double*>(a.rho) + rowBase + k0 + i, val);
+				}
+			}
+		}
+		if (PUSH && tid == 0) {
+			a.segBounds[s] = make_int2(gMin, gMax);      // next step's window (this CTA owns the segment)
+			if (sLost) atomicAdd(a.lost, (unsigned long long)sLost);
+		}
+		__syncthreads();
+	}
+}
+
+// Per-segment axial cell range of the live rings (window for the first deposit / after a sort) and validation.
+__global__ void __launch_bounds__(256) k_bounds(const PushArgs a, int nSegs, unsigned long long* nLive, int* invalid)
+{
+	__shared__ int sKmin, sKmax;
+	__shared__ unsigned int sLive;
+	const int tid = threadIdx.x;
+	for (int s = blockIdx.x; s < nSegs; s += gridDim.x) {
+		const PtpSegment seg = a.segs[s];
+		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLive = 0; }
+		__syncthreads();
+		int kMin = INT_MAX, kMax = INT_MIN;
+		unsigned int live = 0;
+		for (long long i = seg.begin + tid; i < seg.end; i += blockDim.x) {
+			const double z = a.z[i];
+			if (!(z == z)) continue;
+			if (!(z > 0.0 && z < a.length)) { *invalid = 1; continue; }
+			double w;
+			const int k = cell_of<true>(z, a, w);
+			kMin = min(kMin, k);
+			kMax = max(kMax, k);
+			++live;
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			kMin = min(kMin, __shfl_xor_sync(0xffffffffu, kMin, o));
+			kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
+		}
+		live = warp_sum(live);
+		if ((tid & 31) == 0) {
+			if (kMin <= kMax) { atomicMin(&sKmin, kMin); atomicMax(&sKmax, kMax); }
+			atomicAdd(&sLive, live);
+		}
+		__syncthreads();
+		if (tid == 0) {
+			a.segBounds[s] = make_int2(sKmin, sKmax);
+			if (sLive) atomicAdd(nLive, (unsigned long long)sLive);
+		}
+		__syncthreads();
+	}
+}
+
+template <int T, bool PUSH> struct Launcher {
+	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st)
+	{
+		auto kern = k_push_deposit<T, PUSH, FIXED, EXACT>;
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		kern<<<grid, T, smem, st>>>(a);
+		return cudaGetLastError();
+	}
+	static cudaError_t dispatch(bool fixed, bool exact, const PushArgs& a, int grid, size_t smem, cudaStream_t st)
+	{
+		if (fixed) return exact ? go<true, true>(a, grid, smem, st) : go<true, false>(a, grid, smem, st);
+		return exact ? go<false, true>(a, grid, smem, st) : go<false, false>(a, grid, smem, st);
+	}
+};
+
+PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
+{
+	PushArgs a{};
+	a.Nz = t->Nz;
+	a.W = t->window < t->Nz ? t->window : t->Nz;
+	a.fixedBits = t->fixedBits;
+	a.hz = t->hz;
+	a.invHz = 1.0 / t->hz;
+	a.eps = (t->Nz + 2) * 1e-15;
+	a.length = t->length;
+	a.dt = dt;
+	a.charge = p->charge;
+	a.mass = p->mass;
+	a.invMass = 1.0 / p->mass;
+	a.fixedScale = (double)(1ULL << t->fixedBits);
+	a.eNodes = t->eNodes;
+	a.z = p->z;
+	a.v = p->v;
+	a.segs = p->dSegs;
+	a.ctaSegBegin = p->dCtaSegBegin;
+	a.segBounds = p->dSegBounds;
+	a.rho = t->rhoAll + (size_t)p->index * t->G;
+	a.lost = p->dLost;
+	return a;
+}
+
+} // namespace
+
+size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window)
+{
+	size_t w = (size_t)(window < t->Nz ? window : t->Nz);
+	size_t perBin = t->depositMode == PTP_DEPOSIT_FIXED64 ? 8 : 12;
+	return w * 16 + w * 16 + w * (size_t)threads * perBin;
+}
+
+int ptp_push_configure(ptp_trap* t)
+{
+	if (t->threads != 256 && t->threads != 512) { ptp_set_error("threads per CTA must be 256 or 512"); return PTP_EINVAL; }
+	if (t->window < 4) { ptp_set_error("window must be at least 4 cells"); return PTP_EINVAL; }
+	if (ptp_push_smem_bytes(t, t->threads, t->window) > t->smemMax) {
+		ptp_set_error("threads x window does not fit in shared memory");
+		return PTP_EINVAL;
+	}
+	return PTP_OK;
+}
+
+// Launch K1 (push = true) or K2 (push = false) for one species on the trap's stream.
+int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
+{
+	if (p->cap == 0 || p->nCta == 0) return PTP_OK;
+	const PushArgs a = make_args(t, p, dt);
+	const size_t smem = ptp_push_smem_bytes(t, t->threads, t->window);
+	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64, exact = t->arithMode == PTP_ARITH_EXACT;
+	cudaError_t e;
+	if (t->threads == 512)
+		e = push ? Launcher<512, true>::dispatch(fixed, exact, a, p->nCta, smem, t->stream)
+		         : Launcher<512, false>::dispatch(fixed, exact, a, p->nCta, smem, t->stream);
+	else
+		e = push ? Launcher<256, true>::dispatch(fixed, exact, a, p->nCta, smem, t->stream)
+		         : Launcher<256, false>::dispatch(fixed, exact, a, p->nCta, smem, t->stream);
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_push_deposit launch", __FILE__, __LINE__);
+	t->lastLaunches++;
+	return PTP_OK;
+}
+
+// Recompute the per-segment cell windows from the ring positions; validates 0 < z < length.
+int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p)
+{
+	if (p->cap == 0 || p->segs.empty()) { p->boundsValid = true; return PTP_OK; }
+	const PushArgs a = make_args(t, p, 0.0);
+	unsigned long long* dLive = nullptr;
+	int* dInvalid = nullptr;
+	PTP_CUDA(cudaMalloc(&dLive, sizeof(unsigned long long) + sizeof(int) * 2));
+	dInvalid = reinterpret_cast<int*>(dLive + 1);
+	PTP_CUDA(cudaMemsetAsync(dLive, 0, sizeof(unsigned long long) + sizeof(int) * 2, t->stream));
+	int grid = (int)p->segs.size();
+	if (grid > t->smCount * 8) grid = t->smCount * 8;
+	k_bounds<<<grid, 256, 0, t->stream>>>(a, (int)p->segs.size(), dLive, dInvalid);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { cudaFree(dLive); return ptp_cuda_fail(e, "k_bounds launch", __FILE__, __LINE__); }
+	t->lastLaunches++;
+	unsigned long long live = 0;
+	int invalid = 0;
+	PTP_CUDA(cudaMemcpyAsync(&live, dLive, sizeof(live), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaMemcpyAsync(&invalid, dInvalid, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dLive);
+	if (invalid) { ptp_set_error("ring position outside (0, trap length)"); return PTP_EINVAL; }
+	p->nAlive = (int64_t)live;
+	p->boundsValid = true;
+	return PTP_OK;
+}

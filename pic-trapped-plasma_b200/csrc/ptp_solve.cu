@@ -1,0 +1,362 @@
+// K3 / K4: the electrostatic solve and the node field.
+//
+// The reference assembles the 5-point cylindrical finite-difference matrix in
+// PenningTrap::generateSparse (Source/PenningTrap.cpp:94-162), LU-factorises it once with Eigen::SparseLU
+// (:56-57) and calls solver.solve(b) for the trap potential (:202) and for every species' self potential
+// (Source/Plasma.cpp:98). The operator is separable, A = T_r (x) I_z + I_r (x) T_z:
+//   T_z: -2/hz^2 on the diagonal, 1/hz^2 off it, 2/hz^2 to the single neighbour at k = 0 and k = Nz
+//        (Neumann mirror, :102,113,126,130,147,159)  ->  diagonalised exactly by the DCT-I of length Nz+1,
+//        eigenvalues -2/hz^2 + 2/hz^2 cos(pi m / Nz);
+//   T_r: tridiagonal in the radial index with the coefficients of :103,121-122,139,142-144.
+// So A^-1 b = DCT-I^-1 . [Thomas solve in r per axial mode m] . DCT-I b, a direct solve of the same
+// matrix (agreement with sparse LU ~1e-12 rel-L2, the rounding level of the LU itself).
+//
+// Kernels: k_dct_gemm (dense DCT-I as an fp64 GEMM against a precomputed cosine matrix - works for any
+// Nz; the grid sizes of this code are not powers of two), k_thomas (one thread per axial mode, factors
+// precomputed in extended precision on the host), k_node_field = PenningTrap::getEField(int,int)
+// (Source/PenningTrap.cpp:208-236) for all nodes, k_apply (A x), k_wall_rhs (Source/PenningTrap.cpp:163-198).
+#include "ptp_internal.h"
+
+#include <cmath>
+
+namespace {
+
+constexpr int BM = 32, BN = 64, BK = 16, TM = 4, TN = 4; // CTA tile 32x64, 128 threads, 4x4 per thread
+
+// C[M][N] = (rowScale . A)[M][K] * B[K][N], row-major fp64. A may be int64 fixed point (converted on load).
+// rowScale[row / rowsPerScale] multiplies every element of A's row (species factor -rho_macro/eps0).
+template <bool A_FIXED>
+__global__ void __launch_bounds__(128) k_dct_gemm(const double* __restrict__ A, const double* __restrict__ B,
+	double* __restrict__ C, int M, int N, int K, const double* __restrict__ rowScale, int rowsPerScale, double fixedInv)
+{
+	__shared__ double As[BK][BM + 1];
+	__shared__ double Bs[BK][BN];
+	const int tid = threadIdx.x;
+	const int tx = tid % (BN / TN), ty = tid / (BN / TN); // 16 x 8
+	const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+	double acc[TM][TN];
+#pragma unroll
+	for (int i = 0; i < TM; ++i)
+#pragma unroll
+		for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
+
+	for (int k0 = 0; k0 < K; k0 += BK) {
+		// A tile: BM x BK, 512 elements, 4 per thread, coalesced along k
+		for (int e = tid; e < BM * BK; e += 128) {
+			const int r = e / BK, c = e % BK;
+			const int gm = m0 + r, gk = k0 + c;
+			double val = 0.0;
+			if (gm < M && gk < K) {
+				if (A_FIXED) val = (double)reinterpret_cast<const long long*>(A)[(size_t)gm * K + gk] * fixedInv;
+				else val = A[(size_t)gm * K + gk];
+				if (rowScale) val *= rowScale[gm / rowsPerScale];
+			}
+			As[c][r] = val;
+		}
+		for (int e = tid; e < BK * BN; e += 128) {
+			const int r = e / BN, c = e % BN;
+			const int gk = k0 + r, gn = n0 + c;
+			Bs[r][c] = (gk < K && gn < N) ? B[(size_t)gk * N + gn] : 0.0;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int kk = 0; kk < BK; ++kk) {
+			double av[TM], bv[TN];
+#pragma unroll
+			for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+			for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+			for (int i = 0; i < TM; ++i)
+#pragma unroll
+				for (int j = 0; j < TN; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int i = 0; i < TM; ++i) {
+		const int gm = m0 + ty * TM + i;
+		if (gm >= M) continue;
+#pragma unroll
+		for (int j = 0; j < TN; ++j) {
+			const int gn = n0 + tx * TN + j;
+			if (gn < N) C[(size_t)gm * N + gn] = acc[i][j];
+		}
+	}
+}
+
+// Thomas solve of (T_r + lambda_m I) alpha = beta for every axial mode m (thread) and species (blockIdx.y),
+// in place on spec[s][j][m]. Factors: inv = 1/pivot, cp = upper/pivot; forward y_j = (beta_j - l_j y_{j-1}) inv_j.
+__global__ void __launch_bounds__(64) k_thomas(double* __restrict__ spec, const double* __restrict__ thInv,
+	const double* __restrict__ thCp, const double* __restrict__ thLower, int Nr, int n1)
+{
+	const int m = blockIdx.x * blockDim.x + threadIdx.x;
+	if (m >= n1) return;
+	double* x = spec + (size_t)blockIdx.y * Nr * n1 + m;
+	double y = x[0] * thInv[m];
+	x[0] = y;
+	for (int j = 1; j < Nr; ++j) {
+		const double inv = thInv[(size_t)j * n1 + m];
+		const double g = x[(size_t)j * n1] * inv;
+		y = fma(-(thLower[j] * inv), y, g);
+		x[(size_t)j * n1] = y;
+	}
+	for (int j = Nr - 2; j >= 0; --j) {
+		y = fma(-thCp[(size_t)j * n1 + m], y, x[(size_t)j * n1]);
+		x[(size_t)j * n1] = y;
+	}
+}
+
+// PenningTrap::getEField(int,int), Source/PenningTrap.cpp:208-236: E = (sumPhi[idx-1] - sumPhi[idx+1]) / (2 hz),
+// zero at both axial ends, species added in registration order.
+__global__ void k_node_field(const double* __restrict__ phiTrap, const double* __restrict__ phiSelf, int nS,
+	long long G, int n1, double hz, double* __restrict__ eNodes)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= G) return;
+	const int k = (int)(idx % n1);
+	if (k == 0 || k == n1 - 1) { eNodes[idx] = 0.0; return; }
+	double left = phiTrap[idx - 1], right = phiTrap[idx + 1];
+	for (int s = 0; s < nS; ++s) {
+		left = __dadd_rn(left, phiSelf[(size_t)s * G + idx - 1]);
+		right = __dadd_rn(right, phiSelf[(size_t)s * G + idx + 1]);
+	}
+	eNodes[idx] = __ddiv_rn(__dsub_rn(left, right), __dmul_rn(2.0, hz));
+}
+
+// y = A x with the stencil of generateSparse (Source/PenningTrap.cpp:94-162).
+__global__ void k_apply(const double* __restrict__ x, double* __restrict__ y, int Nr, int n1, double diag, double hz2,
+	const double* __restrict__ lower, const double* __restrict__ upper)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= (long long)Nr * n1) return;
+	const int j = (int)(idx / n1), k = (int)(idx % n1);
+	double s = diag * x[idx];
+	if (k > 0) s += (k == n1 - 1 ? 2.0 * hz2 : hz2) * x[idx - 1];
+	if (k < n1 - 1) s += (k == 0 ? 2.0 * hz2 : hz2) * x[idx + 1];
+	if (j > 0) s += lower[j] * x[idx - n1];
+	if (j < Nr - 1) s += upper[j] * x[idx + n1];
+	y[idx] = s;
+}
+
+// PenningTrap::updateRHS, Source/PenningTrap.cpp:177,185,195: RHS(last row) = -1 * matrixFactor * boundary.
+__global__ void k_wall_rhs(const double* __restrict__ wall, double* __restrict__ rhs, long long G, int n1, double factor)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= G) return;
+	const long long first = G - n1;
+	rhs[idx] = idx >= first ? __dmul_rn(__dmul_rn(-1.0, factor), wall[idx - first]) : 0.0;
+}
+
+// Red-black SOR sweep (cross-check solver): one colour of  A phi = b.
+template <bool A_FIXED>
+__global__ void k_sor_sweep(double* __restrict__ phi, const double* __restrict__ rho, const double* __restrict__ scale,
+	int species, double fixedInv, int Nr, int n1, double diag, double hz2, const double* __restrict__ lower,
+	const double* __restrict__ upper, double omega, int colour, double* __restrict__ resid2)
+{
+	const long long half = ((long long)Nr * n1 + 1) / 2;
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	double r2 = 0.0;
+	if (t < half) {
+		// enumerate nodes of this colour: (j + k) % 2 == colour
+		const int perRow = n1;
+		long long idx = 2 * t;
+		int j = (int)(idx / perRow), k = (int)(idx % perRow);
+		if (((j + k) & 1) != colour) { ++idx; j = (int)(idx / perRow); k = (int)(idx % perRow); }
+		if (idx < (long long)Nr * n1 && ((j + k) & 1) == colour) {
+			double b;
+			if (A_FIXED) b = (double)reinterpret_cast<const long long*>(rho)[idx] * fixedInv;
+			else b = rho[idx];
+			if (scale) b *= scale[species];
+			double s = 0.0;
+			if (k > 0) s += (k == n1 - 1 ? 2.0 * hz2 : hz2) * phi[idx - 1];
+			if (k < n1 - 1) s += (k == 0 ? 2.0 * hz2 : hz2) * phi[idx + 1];
+			if (j > 0) s += lower[j] * phi[idx - n1];
+			if (j < Nr - 1) s += upper[j] * phi[idx + n1];
+			const double res = b - s - diag * phi[idx];
+			phi[idx] += omega * res / diag;
+			r2 = res * res;
+		}
+	}
+	if (resid2) {
+		for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+		if ((threadIdx.x & 31) == 0 && r2 != 0.0) atomicAdd(resid2, r2);
+	}
+}
+
+__global__ void k_norm2(const double* __restrict__ rho, const double* __restrict__ scale, int species, bool fixed,
+	double fixedInv, long long G, double* __restrict__ out)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	double v = 0.0;
+	if (idx < G) {
+		v = fixed ? (double)reinterpret_cast<const long long*>(rho)[idx] * fixedInv : rho[idx];
+		if (scale) v *= scale[species];
+		v *= v;
+	}
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
+
+} // namespace
+
+// Host precompute of the operator: stencil coefficients exactly as the reference evaluates them, DCT matrices and
+// Thomas factors in extended precision.
+int ptp_solver_build(ptp_trap* t)
+{
+	const int Nz = t->Nz, Nr = t->Nr, n1 = Nz + 1;
+	const double hz = t->hz, hr = t->hr;
+	const double hz2 = std::pow(hz, -2);                                   // Source/PenningTrap.cpp:97
+	const double hr2 = std::pow(hr, -2);                                   // :98
+	const double diag = -2 * (hr2 + hz2);                                  // :101
+	std::vector<double> lower(Nr, 0.0), upper(Nr, 0.0);
+	upper[0] = 2 * hr2;                                                    // :103
+	for (int j = 1; j < Nr - 1; ++j) {
+		const double radius = std::floor((double)j) * hr;                  // :121
+		lower[j] = hr2 - std::pow(2 * radius * hr, -1);                    // :122
+		upper[j] = hr2 + std::pow(2 * radius * hr, -1);                    // :139
+	}
+	if (Nr > 1) {
+		const double radius = t->radius - hr;                              // :142
+		lower[Nr - 1] = hr2 - std::pow(2 * radius * hr, -1);               // :144
+		upper[Nr - 1] = 0.0;                                               // Dirichlet: wall term lives in the RHS
+	}
+	t->stDiag = diag;
+	t->stHz2 = hz2;
+	t->wallFactor = hr2 + std::pow(2 * (t->radius - hr) * hr, -1);         // :165-167
+
+	const long double pi = 3.141592653589793238462643383279502884L;
+	std::vector<double> fwd((size_t)n1 * n1), inv((size_t)n1 * n1);
+	for (int k = 0; k < n1; ++k) {
+		const long double wk = (k == 0 || k == Nz) ? 0.5L : 1.0L;
+		for (int m = 0; m < n1; ++m) {
+			const long double wm = (m == 0 || m == Nz) ? 0.5L : 1.0L;
+			const long long red = ((long long)k * m) % (2LL * Nz);         // exact argument reduction
+			const long double c = cosl(pi * (long double)red / (long double)Nz);
+			fwd[(size_t)k * n1 + m] = (double)((2.0L / Nz) * wk * wm * c);
+			inv[(size_t)m * n1 + k] = (double)c;
+		}
+	}
+	std::vector<double> thInv((size_t)Nr * n1), thCp((size_t)Nr * n1);
+	for (int m = 0; m < n1; ++m) {
+		const long double dm = (long double)diag + 2.0L * (long double)hz2 * cosl(pi * (long double)m / (long double)Nz);
+		long double cpPrev = 0.0L;
+		for (int j = 0; j < Nr; ++j) {
+			const long double pivot = dm - (long double)lower[j] * cpPrev;
+			const long double pinv = 1.0L / pivot;
+			cpPrev = (long double)upper[j] * pinv;
+			thInv[(size_t)j * n1 + m] = (double)pinv;
+			thCp[(size_t)j * n1 + m] = (double)cpPrev;
+		}
+	}
+	const size_t nn = (size_t)n1 * n1 * sizeof(double), gg = (size_t)Nr * n1 * sizeof(double);
+	PTP_CUDA(cudaMalloc(&t->dctFwd, nn));
+	PTP_CUDA(cudaMalloc(&t->dctInv, nn));
+	PTP_CUDA(cudaMalloc(&t->thInv, gg));
+	PTP_CUDA(cudaMalloc(&t->thCp, gg));
+	PTP_CUDA(cudaMalloc(&t->thLower, Nr * sizeof(double)));
+	PTP_CUDA(cudaMalloc(&t->stLower, Nr * sizeof(double)));
+	PTP_CUDA(cudaMalloc(&t->stUpper, Nr * sizeof(double)));
+	PTP_CUDA(cudaMemcpy(t->dctFwd, fwd.data(), nn, cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->dctInv, inv.data(), nn, cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->thInv, thInv.data(), gg, cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->thCp, thCp.data(), gg, cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->thLower, lower.data(), Nr * sizeof(double), cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->stLower, lower.data(), Nr * sizeof(double), cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->stUpper, upper.data(), Nr * sizeof(double), cudaMemcpyHostToDevice));
+	return PTP_OK;
+}
+
+void ptp_solver_free(ptp_trap* t)
+{
+	cudaFree(t->dctFwd); cudaFree(t->dctInv); cudaFree(t->thInv); cudaFree(t->thCp);
+	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
+}
+
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi)
+{
+	if (nS <= 0) return PTP_OK;
+	const int n1 = t->Nz + 1, M = nS * t->Nr;
+	const dim3 grid((n1 + BN - 1) / BN, (M + BM - 1) / BM);
+	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
+	if (rhoIsFixed) k_dct_gemm<true><<<grid, 128, 0, t->stream>>>(rho, t->dctFwd, spec, M, n1, n1, dScale, t->Nr, fixedInv);
+	else k_dct_gemm<false><<<grid, 128, 0, t->stream>>>(rho, t->dctFwd, spec, M, n1, n1, dScale, t->Nr, 1.0);
+	k_thomas<<<dim3((n1 + 63) / 64, nS), 64, 0, t->stream>>>(spec, t->thInv, t->thCp, t->thLower, t->Nr, n1);
+	k_dct_gemm<false><<<grid, 128, 0, t->stream>>>(spec, t->dctInv, phi, M, n1, n1, nullptr, 1, 1.0);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "solver launch", __FILE__, __LINE__);
+	t->lastLaunches += 3;
+	return PTP_OK;
+}
+
+int ptp_solver_apply(ptp_trap* t, const double* x, double* y)
+{
+	const int n1 = t->Nz + 1;
+	k_apply<<<(unsigned)((t->G + 255) / 256), 256, 0, t->stream>>>(x, y, t->Nr, n1, t->stDiag, t->stHz2, t->stLower, t->stUpper);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_apply launch", __FILE__, __LINE__);
+	return PTP_OK;
+}
+
+int ptp_node_field(ptp_trap* t)
+{
+	const int n1 = t->Nz + 1;
+	k_node_field<<<(unsigned)((t->G + 255) / 256), 256, 0, t->stream>>>(t->phiTrap, t->phiSelfAll, (int)t->plasmas.size(), t->G, n1, t->hz, t->eNodes);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_node_field launch", __FILE__, __LINE__);
+	t->lastLaunches++;
+	t->eNodesValid = true;
+	return PTP_OK;
+}
+
+int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs)
+{
+	k_wall_rhs<<<(unsigned)((t->G + 255) / 256), 256, 0, t->stream>>>(dWall, dRhs, t->G, t->Nz + 1, t->wallFactor);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_wall_rhs launch", __FILE__, __LINE__);
+	return PTP_OK;
+}
+
+// Red-black SOR on the same operator (north_star names it; here a cross-check of the direct solver: it needs
+// ~1e-12 residual for 1e-10 parity, i.e. thousands of sweeps, so it is not the default).
+int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi)
+{
+	const int n1 = t->Nz + 1;
+	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
+	// optimal-ish omega for a (Nr x Nz) Laplacian
+	const double pi = 3.14159265358979323846;
+	const double rhoJ = 0.5 * (std::cos(pi / (t->Nr + 1)) + std::cos(pi / (t->Nz + 1)));
+	const double omega = 2.0 / (1.0 + std::sqrt(1.0 - rhoJ * rhoJ));
+	const long long half = (t->G + 1) / 2;
+	const unsigned blocks = (unsigned)((half + 255) / 256);
+	double* dRes = nullptr;
+	PTP_CUDA(cudaMalloc(&dRes, 2 * sizeof(double)));
+	for (int s = 0; s < nS; ++s) {
+		const double* b = rho + (size_t)s * t->G;
+		double* x = phi + (size_t)s * t->G;
+		PTP_CUDA(cudaMemsetAsync(dRes, 0, 2 * sizeof(double), t->stream));
+		k_norm2<<<(unsigned)((t->G + 255) / 256), 256, 0, t->stream>>>(b, dScale, s, rhoIsFixed, fixedInv, t->G, dRes + 1);
+		double h[2];
+		PTP_CUDA(cudaMemcpyAsync(h, dRes, 2 * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+		PTP_CUDA(cudaStreamSynchronize(t->stream));
+		const double bnorm2 = h[1] > 0 ? h[1] : 1.0;
+		for (int it = 0; it < t->sorMaxIter; ++it) {
+			const bool check = (it % 50) == 49;
+			if (check) PTP_CUDA(cudaMemsetAsync(dRes, 0, sizeof(double), t->stream));
+			for (int colour = 0; colour < 2; ++colour) {
+				if (rhoIsFixed)
+					k_sor_sweep<true><<<blocks, 256, 0, t->stream>>>(x, b, dScale, s, fixedInv, t->Nr, n1, t->stDiag, t->stHz2, t->stLower, t->stUpper, omega, colour, check ? dRes : nullptr);
+				else
+					k_sor_sweep<false><<<blocks, 256, 0, t->stream>>>(x, b, dScale, s, 1.0, t->Nr, n1, t->stDiag, t->stHz2, t->stLower, t->stUpper, omega, colour, check ? dRes : nullptr);
+				t->lastLaunches++;
+			}
+			if (check) {
+				PTP_CUDA(cudaMemcpyAsync(h, dRes, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+				PTP_CUDA(cudaStreamSynchronize(t->stream));
+				if (std::sqrt(h[0] / bnorm2) < t->sorTol) break;
+			}
+		}
+	}
+	cudaFree(dRes);
+	return PTP_OK;
+}

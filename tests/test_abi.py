@@ -1,0 +1,64 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/ptp.h
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import importlib
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+ptp = importlib.import_module("pic-trapped-plasma_b200")
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "ptp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    names = _declared()
+    assert len(names) >= 35
+    L = C.CDLL(ptp.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_binding_covers_header():
+    assert sorted(ptp.SIGNATURES) == _declared()
+
+
+def test_every_declaration_cites_the_reference():
+    text = open(os.path.join(ROOT, "include", "ptp.h")).read()
+    assert text.count("Source/") >= 25
+
+
+def test_version_and_error_string():
+    L = ptp.lib()
+    assert L.ptp_version() >= 100
+    assert isinstance(L.ptp_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_gpu():
+    L = ptp.lib()
+    if L.ptp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = L.ptp_trap_create(C.byref(h), 585, 128, 1e-4, 1e-4, 0.0681, 0.01488, 0)
+    assert rc == 2 and not h.value            # PTP_ECUDA
+    assert b"no CPU fallback" in L.ptp_last_error()
+    with pytest.raises(ptp.PtpError):
+        ptp.default_trap()
+
+
+def test_product_does_not_touch_the_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "pic-trapped-plasma_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".hpp", ".cpp", "Makefile")):
+                src = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle" not in src.replace("no oracle", ""), os.path.join(base, f)
+                assert "libptp_ref" not in src and "ptp_oracle" not in src

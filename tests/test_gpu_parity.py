@@ -1,0 +1,375 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle -- runs on the B200 box (-m gpu).
+
+Tier 1 = lock-step: each GPU phase is fed the oracle's state at the start of that step.
+  integer keys (cell index, flat index, loss flags, alive counts) ............ bit-exact
+  per-ring z, v after one step, FAST arithmetic ............................... rel <= 1e-14
+  per-ring z, v after one step, EXACT arithmetic ............................... bit-exact
+  node field from identical potentials ......................................... bit-exact
+  RHS (= -rho/eps0), fp64 accumulation ......................................... rel-L2 <= 1e-12
+  RHS, fixed-point accumulation (2^-F quantisation of the weights) ............. rel-L2 <= 1e-11, bitwise reproducible
+  phi_self / phi_trap (direct solver vs LU oracle) ............................. rel-L2 <= 1e-10
+Tier 2 = free-running C1 for 175 steps (5 plasma periods): counts equal, z rel-L2 <= 1e-7 (e-) / 1e-9 (pbar),
+  RHS rel-L2 <= 1e-5 (solver-level differences are amplified ~1e5x over that horizon, SURVEY A-8).
+"""
+import importlib
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_l2
+from oracle import port, ref
+
+ptp = importlib.import_module("pic-trapped-plasma_b200")
+pytestmark = pytest.mark.gpu
+
+KAT = json.load(open(os.path.join(GOLDEN, "trap_kat.json")))
+
+
+@pytest.fixture(scope="module")
+def trap():
+    t = ptp.default_trap()
+    yield t
+    t.close()
+
+
+def _fresh_c1(kat, deposit_mode=ptp.PTP_DEPOSIT_FP64, arith=ptp.PTP_ARITH_FAST):
+    t = ptp.default_trap()
+    t.set_deposit_mode(deposit_mode)
+    t.set_arith_mode(arith)
+    el = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+    ap = ptp.Plasma(t, "Antiprotons", ptp.massP, -ptp.ePos)
+    for tag, p in (("e", el), ("p", ap)):
+        p.upload(kat[f"{tag}_r0"], kat[f"{tag}_z0"], kat[f"{tag}_v0"], float(kat[f"{tag}_chargeMacro"]))
+        assert p.macroChargeDensity == float(kat[f"{tag}_mcd"])
+    return t, el, ap
+
+
+def _by_id(p):
+    r, z, v, ids = p.download()
+    o = np.argsort(ids)
+    return r[o], z[o], v[o], ids[o]
+
+
+# ------------------------------------------------------------------------------------------ solver (a6, a7, a8)
+def test_trap_potential_matches_reference(trap, c1_kat):
+    phi = trap.phi()
+    assert rel_l2(phi, c1_kat["phi_trap"]) < 1e-10
+    assert phi[293] == pytest.approx(KAT["phi_r0_k293"], rel=1e-10)
+    # extractTrapLaplacian convention: A phi - RHS ~ 0
+    pt = port.default_trap()
+    rhs = pt.wall_rhs()
+    assert np.linalg.norm(trap.apply(phi) - rhs) / np.linalg.norm(rhs) < 1e-13
+    assert np.array_equal(trap.wallPotential(), pt.wall_potential())
+    x = np.random.default_rng(0).standard_normal(trap.G)
+    assert rel_l2(trap.apply(x), pt.apply(x)) < 1e-15
+    assert rel_l2(trap.solve(x), pt.solve(x)) < 1e-10
+    pt.close()
+
+
+def test_set_potential_every_step_protocol(trap, c1_kat):
+    pt = port.default_trap()
+    for v in (-51.0, -63.5, -70.0):
+        trap.setPotential(1, v)
+        pt.set_potential(1, v)
+        assert rel_l2(trap.phi(), pt.phi) < 1e-10
+    assert rel_l2(trap.phi(), c1_kat["phi_trap"]) < 1e-10
+    pt.close()
+
+
+def test_self_potential_of_reference_rhs(trap, c1_kat):
+    for tag in ("e", "p"):
+        assert rel_l2(trap.solve(c1_kat[f"{tag}_rhs0"]), c1_kat[f"{tag}_phi0"]) < 1e-10
+
+
+def test_sor_cross_check_small_grid():
+    el = [ptp.Electrode(0.01, 5.0), ptp.Electrode(0.02, -40.0), ptp.Electrode(0.015, 3.0)]
+    t = ptp.PenningTrap(0.02, el, [0.002, 0.001], 57, 9)
+    direct = t.phi()
+    t.set_solver(ptp.PTP_SOLVER_SOR, 1e-13, 40000)
+    t.set_phi(np.zeros(t.G))
+    t.solveLaplace()
+    assert rel_l2(t.phi(), direct) < 1e-9
+    t.close()
+
+
+# ------------------------------------------------------------------------------------------ deposit (a5)
+@pytest.mark.parametrize("mode,tol", [(ptp.PTP_DEPOSIT_FP64, 1e-12), (ptp.PTP_DEPOSIT_FIXED64, 1e-11)])
+def test_deposit_lockstep(c1_kat, mode, tol):
+    t, el, ap = _fresh_c1(c1_kat, mode)
+    pt = port.default_trap()
+    for tag, p in (("e", el), ("p", ap)):
+        p.updateRHS()
+        assert rel_l2(p.rhs(), c1_kat[f"{tag}_rhs0"]) < tol
+        # integer keys: bit-exact
+        op = pt.plasma(tag, p.mass, p.charge)
+        op.set_rings(c1_kat[f"{tag}_r0"], c1_kat[f"{tag}_z0"], c1_kat[f"{tag}_v0"], float(c1_kat[f"{tag}_chargeMacro"]))
+        k_o, idx_o = op.cell_index()
+        _, _, _, ids = p.download()
+        k_g, idx_g = p.cell_index()
+        assert np.array_equal(k_g, k_o[ids]) and np.array_equal(idx_g, idx_o[ids])
+        assert p.getNumMacro() == len(ids) == 4001
+    pt.close()
+    t.close()
+
+
+def test_deposit_reproduces_reference_data_file():
+    """Diagnostics/Charge_Density-0.txt through the CUDA deposit (the reference's only golden data)."""
+    d = np.load(os.path.join(GOLDEN, "fixture_rings_r0.npz"))
+    fixture = np.loadtxt(os.path.join(GOLDEN, "charge_density_0.txt"))
+    t = ptp.default_trap()
+    for mode, tol in ((ptp.PTP_DEPOSIT_FP64, 1e-12), (ptp.PTP_DEPOSIT_FIXED64, 1e-11)):
+        t.set_deposit_mode(mode)
+        p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+        z = d["z"]
+        p.upload(np.zeros(len(z), np.int32), z, np.zeros(len(z)), float(d["chargeMacro"]))
+        p.updateRHS()
+        assert rel_l2(p.rhs()[275:311] * ptp.epsilon / ptp.ePos, fixture[:, 1]) < tol
+    t.close()
+
+
+# ------------------------------------------------------------------------------------------ node field (a4)
+def test_node_field_bit_exact(c1_kat):
+    t, el, ap = _fresh_c1(c1_kat)
+    t.set_phi(c1_kat["phi_trap"])
+    el.set_self_potential(c1_kat["e_phi0"])
+    ap.set_self_potential(c1_kat["p_phi0"])
+    assert np.array_equal(t.enodes(), c1_kat["enodes0"])
+    t.close()
+
+
+# ------------------------------------------------------------------------------------------ push (a2, a3) + step (a1)
+@pytest.mark.parametrize("arith", [ptp.PTP_ARITH_FAST, ptp.PTP_ARITH_EXACT])
+@pytest.mark.parametrize("mode", [ptp.PTP_DEPOSIT_FP64, ptp.PTP_DEPOSIT_FIXED64])
+def test_step_lockstep(c1_kat, arith, mode):
+    t, el, ap = _fresh_c1(c1_kat, mode, arith)
+    t.set_phi(c1_kat["phi_trap"])
+    el.set_self_potential(c1_kat["e_phi0"])
+    ap.set_self_potential(c1_kat["p_phi0"])
+    dt = float(c1_kat["dt"])
+    t.push_deposit(dt)
+    for tag, p in (("e", el), ("p", ap)):
+        r, z, v, ids = _by_id(p)
+        assert np.array_equal(ids, np.arange(4001)) and np.array_equal(r, c1_kat[f"{tag}_r0"])
+        z1, v1 = c1_kat[f"{tag}_z1"], c1_kat[f"{tag}_v1"]
+        if arith == ptp.PTP_ARITH_EXACT:
+            assert np.array_equal(z, z1) and np.array_equal(v, v1)
+        else:
+            assert np.max(np.abs(z - z1) / np.abs(z1)) <= 1e-14
+            assert np.max(np.abs(v - v1)) <= 1e-14 * np.max(np.abs(v1)) and rel_l2(v, v1) <= 1e-14
+        assert rel_l2(p.rhs(), c1_kat[f"{tag}_rhs1"]) < (1e-12 if mode == ptp.PTP_DEPOSIT_FP64 else 1e-11)
+    t.solve_fields()
+    for tag, p in (("e", el), ("p", ap)):
+        assert rel_l2(p.selfPotential(), c1_kat[f"{tag}_phi1"]) < 1e-10
+    assert rel_l2(t.enodes(), c1_kat["enodes1"]) < 1e-9
+    t.close()
+
+
+def test_free_running_175_steps(c1_kat):
+    t, el, ap = _fresh_c1(c1_kat)
+    el.solvePoisson()
+    ap.solvePoisson()
+    assert rel_l2(el.selfPotential(), c1_kat["e_phi0"]) < 1e-10
+    t.movePlasmas(float(c1_kat["dt"]), 175)
+    assert el.getNumMacro() == KAT["c1_count_e_175"] and ap.getNumMacro() == KAT["c1_count_p_175"]
+    _, ze, _, _ = _by_id(el)
+    _, zp, _, _ = _by_id(ap)
+    assert rel_l2(ze, c1_kat["e_z175"]) < 1e-7 and rel_l2(zp, c1_kat["p_z175"]) < 1e-9
+    assert rel_l2(el.rhs(), c1_kat["e_rhs175"]) < 1e-5
+    # potential energy against the oracle's getPotentialEnergy on the same state (Source/Plasma.cpp:244-252)
+    pe = el.getPotentialEnergy() + ap.getPotentialEnergy()
+    assert pe == pytest.approx(KAT["c1_PE_175"], rel=1e-8)
+    t.close()
+
+
+def test_driver_d_loss_counts(c1_kat):
+    """Diagnostics/D) Useless Boundary Test.txt:118-136: per-step setPotential + e-kick losses, integer KAT."""
+    gold = json.load(open(os.path.join(GOLDEN, "driver_d_counts.json")))
+    dt = gold["dt"]
+
+    def changed_voltage(Vi, Vf, duration, compression, tt):
+        return (Vf - Vi) * (1 + math.exp(-(tt - duration / 2) * compression * 2 / duration)) ** -1 + Vi
+
+    t, el, ap = _fresh_c1(c1_kat)
+    el.solvePoisson()
+    ap.solvePoisson()
+    counts = [[el.getNumMacro(), ap.getNumMacro()]]
+
+    def step():
+        t.movePlasmas(dt)
+        counts.append([el.getNumMacro(), ap.getNumMacro()])
+
+    i = 1
+    while i * dt <= 10e-9:
+        t.setPotential(1, changed_voltage(-70, -51, 10e-9, 4.5, i * dt))
+        step()
+        i += 1
+    t.setPotential(1, -51)
+    i = 1
+    while i * dt <= 80e-9:
+        step()
+        i += 1
+    i = 1
+    while i * dt <= 10e-9:
+        t.setPotential(1, changed_voltage(-51, -70, 10e-9, 4.5, i * dt))
+        step()
+        i += 1
+    assert counts == gold["counts"]
+    pt = port.default_trap()
+    left, right = pt.limits()
+    assert el.getNumMacroCentralWell(left, right) == gold["central_well_e"]
+    assert ap.getNumMacroCentralWell(left, right) == gold["central_well_p"]
+    pt.close()
+    # the survivors are the same rings (ids) as in the oracle run
+    t.sort()
+    assert el.getNumMacro() == 3965
+    t.close()
+
+
+def test_losses_match_oracle_ring_by_ring():
+    """Small odd grid, hot rings: loss flags and survivors bit-exact against the restated swap-pop loop."""
+    args = (0.02, [0.01, 0.02, 0.015], [5.0, -40.0, 3.0], [0.002, 0.001], 57, 9)
+    pt = port.PortTrap(*args)
+    t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], args[4], args[5])
+    t.set_arith_mode(ptp.PTP_ARITH_EXACT)
+    assert rel_l2(t.phi(), pt.phi) < 1e-11
+    rng = np.random.default_rng(3)
+    n = 30000
+    r = rng.integers(0, 9, n).astype(np.int32)
+    z = rng.uniform(0.001, pt.length - 0.001, n)
+    v = rng.normal(0, 4e5, n)
+    op = pt.plasma("Electrons", ptp.massE, -ptp.ePos)
+    op.set_rings(r, z, v, -1e-16)
+    gp = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+    gp.upload(r, z, v, -1e-16)
+    op.solve_poisson()
+    gp.solvePoisson()
+    ids_alive = np.arange(n)
+    for step in range(6):
+        # lock-step: oracle potentials in
+        t.set_phi(pt.phi)
+        gp.set_self_potential(op.self_potential)
+        en = pt.enodes()
+        assert np.array_equal(t.enodes(), en)
+        # oracle step on (z, v) tagged with ids: run the restated loop on a copy carrying ids through r's swaps
+        z_before, v_before, r_before = op.z.copy(), op.v.copy(), op.r.copy()
+        pt.move_plasmas(2e-9)
+        t.push_deposit(2e-9)
+        t.solve_fields()
+        rg, zg, vg, idg = _by_id(gp)
+        # survivors of the oracle, matched by (r, z_new, v_new) multiset since swap-pop permutes them
+        ko = np.lexsort((op.v, op.z, op.r))
+        kg = np.lexsort((vg, zg, rg))
+        assert len(zg) == op.count()
+        assert np.array_equal(rg[kg], op.r[ko]) and np.array_equal(zg[kg], op.z[ko]) and np.array_equal(vg[kg], op.v[ko])
+        assert rel_l2(gp.rhs(), op.rhs) < 1e-12
+        assert rel_l2(gp.selfPotential(), op.self_potential) < 1e-10
+    assert op.count() < n
+    t.close()
+    pt.close()
+
+
+# ------------------------------------------------------------------------------------------ determinism / sort / large N
+def _synthetic(n, trap, seed=1):
+    """Synthetic load of the default plasma's shape: ~12 rows, ~37 cells around the trap centre."""
+    rng = np.random.default_rng(seed)
+    occ = np.array([1.94, 1.94, 1.88, 1.68, 1.30, 0.80, 0.35, 0.10, 0.017, 0.0015])
+    r = np.sort(rng.choice(len(occ), size=n, p=occ / occ.sum())).astype(np.int32)
+    z = 0.03405 + 0.0021 * np.clip(rng.standard_normal(n) * 0.45, -1, 1)
+    v = rng.normal(0, 4.768e4, n)
+    return r, z, v
+
+
+def test_fixed_point_is_bitwise_reproducible(c1_kat):
+    outs = []
+    for ctas in (0, 7, 40):
+        t = ptp.default_trap()
+        t.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64)
+        t.set_tuning(ctas=ctas)
+        p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+        r, z, v = _synthetic(300000, t)
+        p.upload(r, z, v, -1e-18)
+        p.solvePoisson()
+        t.movePlasmas(float(c1_kat["dt"]), 3)
+        outs.append((p.rhs(), p.selfPotential()))
+        t.close()
+    for rhs, phi in outs[1:]:
+        assert np.array_equal(rhs, outs[0][0]) and np.array_equal(phi, outs[0][1])
+
+
+@pytest.mark.parametrize("mode", [ptp.PTP_DEPOSIT_FP64, ptp.PTP_DEPOSIT_FIXED64])
+def test_large_load_properties(c1_kat, mode):
+    """10 M rings (BASELINE config 3 size): size-independent properties.
+    total deposited weight == live ring count; sort keeps the multiset and makes cells non-decreasing;
+    sorting does not change the deposit; deposit after push == stand-alone deposit of the pushed rings."""
+    n = 10_000_000
+    t = ptp.default_trap()
+    t.set_deposit_mode(mode)
+    p = ptp.Plasma(t, "Antiprotons", ptp.massP, -ptp.ePos)
+    r, z, v = _synthetic(n, t, seed=5)
+    p.upload(r, z, v, -1e-19)
+    scale = -p.macroChargeDensity / ptp.epsilon
+    p.solvePoisson()
+    w0 = p.rhs() / scale
+    assert abs(w0.sum() - n) < (1e-6 if mode == ptp.PTP_DEPOSIT_FP64 else 1e-3)
+    dt = float(c1_kat["dt"])
+    t.movePlasmas(dt, 2)
+    rhs_fused = p.rhs()
+    assert p.getNumMacro() == n
+    p.updateRHS()                                   # K2 on the pushed rings
+    rhs_alone = p.rhs()
+    if mode == ptp.PTP_DEPOSIT_FIXED64:
+        assert np.array_equal(rhs_fused, rhs_alone)
+    else:
+        assert rel_l2(rhs_fused, rhs_alone) < 1e-13
+    r1, z1, v1, id1 = p.download()
+    t.sort()
+    r2, z2, v2, id2 = p.download()
+    assert len(id2) == n
+    o1, o2 = np.argsort(id1), np.argsort(id2)
+    assert np.array_equal(z1[o1], z2[o2]) and np.array_equal(v1[o1], v2[o2]) and np.array_equal(r1[o1], r2[o2])
+    k2, _ = p.cell_index()
+    key = r2.astype(np.int64) * 100000 + k2
+    assert np.all(np.diff(key) >= 0)                # sortedness by (row, cell)
+    p.updateRHS()
+    if mode == ptp.PTP_DEPOSIT_FIXED64:
+        assert np.array_equal(p.rhs(), rhs_alone)
+    else:
+        assert rel_l2(p.rhs(), rhs_alone) < 1e-13
+    t.sort()                                        # idempotence
+    _, z3, _, id3 = p.download()
+    assert np.array_equal(np.sort(id3), np.sort(id2)) and np.array_equal(np.sort(z3), np.sort(z2))
+    t.close()
+
+
+def test_edge_cases():
+    t = ptp.default_trap()
+    p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+    # empty plasma: a step is a no-op
+    p.upload(np.zeros(0, np.int32), np.zeros(0), np.zeros(0), -1e-18)
+    t.movePlasmas(1e-10, 2)
+    assert p.getNumMacro() == 0 and not p.rhs().any()
+    # ragged: one ring in the last row, one in the first, unsorted input, positions next to both ends
+    r = np.array([127, 0, 5], np.int32)
+    z = np.array([t.hz * 0.25, t.lengthTrap - t.hz * 0.25, t.hz * 300.5])
+    v = np.array([-1e9, 1e9, 0.0])                   # the two end rings leave on the first step
+    p.upload(r, z, v, -1e-18)
+    p.solvePoisson()
+    rr, zz, vv, ids = p.download()
+    assert sorted(ids.tolist()) == [0, 1, 2] and np.array_equal(rr[np.argsort(ids)], r)
+    t.movePlasmas(1e-10, 1)
+    assert p.getNumMacro() == 1
+    rr, zz, vv, ids = p.download()
+    assert ids.tolist() == [2] and rr.tolist() == [5]
+    w = p.rhs() / (-p.macroChargeDensity / ptp.epsilon)
+    assert w.sum() == pytest.approx(1.0, abs=1e-12)
+    # bad input is rejected
+    with pytest.raises(ptp.PtpError):
+        p.upload(np.array([128], np.int32), np.array([0.01]), np.array([0.0]), -1e-18)
+    with pytest.raises(ptp.PtpError):
+        p.upload(np.array([1], np.int32), np.array([1.0]), np.array([0.0]), -1e-18)
+    with pytest.raises(ValueError):
+        ptp.PenningTrap(0.01, [ptp.Electrode(0.01, 0)], [0.001], 16, 4)
+    t.close()
