@@ -74,6 +74,8 @@ struct ptp_trap {
 	double* stLower = nullptr;   // [Nr] stencil r-lower   (operator apply / SOR)
 	double* stUpper = nullptr;   // [Nr] stencil r-upper
 	double stDiag = 0, stHz2 = 0, wallFactor = 0;
+	int2* rowBounds = nullptr;   // [species x Nr] non-zero axial range of each deposit row (forward transform)
+	int rowBoundsCap = 0;
 
 	double* phiTrap = nullptr;   // [G]
 	double* eNodes = nullptr;    // [G]

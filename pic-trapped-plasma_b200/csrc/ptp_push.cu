@@ -21,19 +21,26 @@
 // the Poisson solver reads the grid. Fixed-point mode packs (count:12 | sum:52) into one 64-bit word per
 // bin with w quantised to 2^-F: all sums are exact integers, so the result is independent of summation
 // order, CTA count and GPU count.
+//
+// Latency: the per-ring arithmetic is a ~40-deep dependent fp64 chain and only 8-16 warps fit next to the
+// bins, so a thread handles 8 rings per tile in lock-step stages (branch-free fast path, rare cases
+// deferred to fix-up loops) to give the scheduler 8 independent chains, and the loads of the next tile are
+// issued before the current one is processed.
 #include "ptp_internal.h"
 
 #include <limits.h>
 
 namespace {
 
+constexpr int R = PTP_RINGS_PER_THREAD;
+constexpr int NV = R / 2;
 constexpr double kMagic = 6755399441055744.0;            // 2^52 + 2^51: floor via add.rm, integer in the low word
 constexpr unsigned long long kPackBias = 0x4320000000000000ULL; // bits(2^52 + x) - bias = (1 << 52) | x
 constexpr unsigned long long kSumMask = (1ULL << 52) - 1;
 
 struct PushArgs {
 	int Nz, W, fixedBits, pad0;
-	double hz, invHz, eps, length;
+	double hz, invHz, eps, epsHi, length;
 	double dt, charge, mass, invMass;
 	double fixedScale;          // 2^fixedBits
 	const double* eNodes;       // [G] node field of the pre-step potentials
@@ -48,35 +55,56 @@ struct PushArgs {
 
 // Axial cell of a position: bit-exact (int)floor(z / hz) (Source/Plasma.cpp:87, Source/PenningTrap.cpp:328).
 // Fast path: q = z * (1/hz), floor through a round-down add of 2^52+2^51. |q - z/hz| < eps/2, so whenever
-// frac(q) is at least eps away from 0 and 1 both floors agree; otherwise (probability ~2*eps per ring, and
-// always in EXACT mode) the true IEEE division decides. Also returns the reference's weightFactor
-// w = (z - k*hz) / hz (:89-90 / :331-332); the reciprocal multiply is the only non-reference operation.
-template <bool EXACT>
-__device__ __forceinline__ int cell_of(double z, const PushArgs& a, double& w)
+// frac(q) is at least eps away from 0 and 1 both floors agree (ok = true); otherwise (probability ~2*eps per
+// ring) the caller falls back to cell_exact.
+__device__ __forceinline__ void cell_fast(double z, const PushArgs& a, int& k, double& kd, bool& ok)
 {
-	int k;
-	double kd;
-	if (EXACT) {
-		kd = floor(__ddiv_rn(z, a.hz));
-		k = (int)kd;
-	}
-	else {
-		double q = __dmul_rn(z, a.invHz);
-		double m = __dadd_rd(q, kMagic);
-		k = __double2loint(m);
-		kd = __dsub_rn(m, kMagic);
-		double f = __dsub_rn(q, kd);
-		if (!(f >= a.eps && f <= 1.0 - a.eps)) {
-			kd = floor(__ddiv_rn(z, a.hz));
-			k = (int)kd;
+	const double q = __dmul_rn(z, a.invHz);
+	const double m = __dadd_rd(q, kMagic);
+	k = __double2loint(m);
+	kd = __dsub_rn(m, kMagic);
+	const double f = __dsub_rn(q, kd);
+	ok = (f >= a.eps) && (f <= a.epsHi);
+}
+
+__device__ __forceinline__ void cell_exact(double z, const PushArgs& a, int& k, double& kd)
+{
+	kd = floor(__ddiv_rn(z, a.hz));
+	k = (int)kd;
+}
+
+// Cells and weights of R positions. w = (z - k*hz) / hz is the reference's weightFactor (Source/Plasma.cpp:89-90,
+// Source/PenningTrap.cpp:331-332); in FAST arithmetic the division is a reciprocal multiply.
+template <bool EXACT>
+__device__ __forceinline__ void cells_of(const double (&z)[R], const bool (&live)[R], const PushArgs& a, int (&k)[R], double (&w)[R])
+{
+	double kd[R];
+	bool ok[R];
+	bool bad = false;
+	if (!EXACT) {
+#pragma unroll
+		for (int i = 0; i < R; ++i) {
+			cell_fast(z[i], a, k[i], kd[i], ok[i]);
+			bad |= live[i] && !ok[i];
 		}
 	}
-	// z < length always holds for a live ring, but z/hz may still round up to Nz; the reference would read
-	// node Nz+1 there (its own warning at Source/PenningTrap.cpp:326). Deliberate divergence: stay in the last cell.
-	if (k > a.Nz - 1) { k = a.Nz - 1; kd = (double)k; }
-	double dz = __dsub_rn(z, __dmul_rn(kd, a.hz));
-	w = EXACT ? __ddiv_rn(dz, a.hz) : __dmul_rn(dz, a.invHz);
-	return k;
+	else {
+#pragma unroll
+		for (int i = 0; i < R; ++i) { k[i] = 0; kd[i] = 0.0; ok[i] = false; }
+	}
+	if (EXACT || bad) {
+#pragma unroll
+		for (int i = 0; i < R; ++i)
+			if (live[i] && (EXACT || !ok[i])) cell_exact(z[i], a, k[i], kd[i]);
+	}
+#pragma unroll
+	for (int i = 0; i < R; ++i) {
+		// z < length always holds for a live ring, but z/hz may still round up to Nz; the reference would read
+		// node Nz+1 there (its own warning at Source/PenningTrap.cpp:326). Deliberate divergence: stay in the last cell.
+		if (k[i] > a.Nz - 1) { k[i] = a.Nz - 1; kd[i] = (double)k[i]; }
+		const double dz = __dsub_rn(z[i], __dmul_rn(kd[i], a.hz));
+		w[i] = EXACT ? __ddiv_rn(dz, a.hz) : __dmul_rn(dz, a.invHz);
+	}
 }
 
 template <typename T> __device__ __forceinline__ T warp_sum(T x)
@@ -101,6 +129,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n1 = a.Nz + 1;
+	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
 
 	for (int s = a.ctaSegBegin[blockIdx.x]; s < a.ctaSegBegin[blockIdx.x + 1]; ++s) {
 		const PtpSegment seg = a.segs[s];
@@ -115,9 +144,9 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		}
 		if (PUSH) {
 			for (int i = tid; i < W; i += T) {
-				int node = k0 + i;
-				double eL = node <= a.Nz ? a.eNodes[rowBase + node] : 0.0;
-				double eR = node + 1 <= a.Nz ? a.eNodes[rowBase + node + 1] : 0.0;
+				const int node = k0 + i;
+				const double eL = node <= a.Nz ? a.eNodes[rowBase + node] : 0.0;
+				const double eR = node + 1 <= a.Nz ? a.eNodes[rowBase + node + 1] : 0.0;
 				eTile[i] = make_double2(eL, eR);
 			}
 		}
@@ -127,100 +156,138 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		int kMin = INT_MAX, kMax = INT_MIN;
 		unsigned int lost = 0;
 
-		// deposit of one live ring at position zN
-		auto deposit = [&](double zN) {
-			double w;
-			const int k = cell_of<EXACT>(zN, a, w);
-			kMin = min(kMin, k);
-			kMax = max(kMax, k);
-			const unsigned int i = (unsigned int)(k - k0);
-			if (i < (unsigned int)W) {
-				if (FIXED) {
-					// round(w * 2^F) lands in the mantissa of (2^52 + x); subtracting the bias leaves (1 << 52) | x
-					double t = __fma_rn(w, a.fixedScale, 4503599627370496.0);
-					bins[(size_t)i * T + tid] += (unsigned long long)__double_as_longlong(t) - kPackBias;
-				}
-				else {
-					double* b = reinterpret_cast<double*>(bins) + (size_t)i * T + tid;
-					*b = __dadd_rn(*b, w);
-					cnts[(size_t)i * T + tid] += 1u;
-				}
-			}
-			else {
-				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
-				if (FIXED) {
-					double t = __fma_rn(w, a.fixedScale, 4503599627370496.0);
-					unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
-					unsigned long long* g = reinterpret_cast<unsigned long long*>(a.rho) + rowBase + k;
-					atomicAdd(g, (1ULL << a.fixedBits) - wq);
-					atomicAdd(g + 1, wq);
-				}
-				else {
-					double* g = reinterpret_cast<double*>(a.rho) + rowBase + k;
-					atomicAdd(g, __dsub_rn(1.0, w));
-					atomicAdd(g + 1, w);
-				}
-			}
-		};
-
-		// Plasma::moveRings body for one ring (Source/Plasma.cpp:105-118)
-		auto push = [&](double& z, double& v) {
-			if (!(z == z)) return;                       // empty slot / ring lost earlier
-			double w;
-			const int k = cell_of<EXACT>(z, a, w);
-			const unsigned int i = (unsigned int)(k - k0);
-			double eL, eR;
-			if (i < (unsigned int)W) { const double2 e = eTile[i]; eL = e.x; eR = e.y; }
-			else { eL = a.eNodes[rowBase + k]; eR = a.eNodes[rowBase + k + 1]; }
-			// (1 - w) * fieldLeft + w * fieldRight            Source/PenningTrap.cpp:333
-			const double e = __dadd_rn(__dmul_rn(__dsub_rn(1.0, w), eL), __dmul_rn(w, eR));
-			// deltaT * E * charge / mass + speed              Source/Plasma.cpp:105
-			double kick = __dmul_rn(__dmul_rn(a.dt, e), a.charge);
-			kick = EXACT ? __ddiv_rn(kick, a.mass) : __dmul_rn(kick, a.invMass);
-			const double vN = __dadd_rn(kick, v);
-			// deltaT * vNew + z                               Source/Plasma.cpp:106
-			const double zN = __dadd_rn(__dmul_rn(a.dt, vN), z);
-			if (zN < a.length && zN > 0.0) {             // Source/Plasma.cpp:108 (NaN -> removed, like the reference)
-				z = zN;
-				v = vN;
-				deposit(zN);
-			}
-			else {
-				z = __longlong_as_double(0x7ff8000000000000LL); // tombstone instead of swap-with-back + pop (:116-117)
-				++lost;
-			}
-		};
-
 		const double2* z2 = reinterpret_cast<const double2*>(a.z);
 		const double2* v2 = reinterpret_cast<const double2*>(a.v);
 		double2* z2w = reinterpret_cast<double2*>(a.z);
 		double2* v2w = reinterpret_cast<double2*>(a.v);
-		constexpr int NV = PTP_RINGS_PER_THREAD / 2;
-		for (long long t0 = seg.begin; t0 < seg.end; t0 += (long long)PTP_RINGS_PER_THREAD * T) {
-			const long long p0 = (t0 >> 1) + tid;
-			double2 zz[NV], vv[NV];
+		const long long tile = (long long)R * T;
+
+		double2 zzN[NV], vvN[NV];
+		{
+			const long long p0 = (seg.begin >> 1) + tid;
 #pragma unroll
-			for (int j = 0; j < NV; ++j) zz[j] = z2[p0 + (long long)j * T];
+			for (int j = 0; j < NV; ++j) zzN[j] = z2[p0 + (long long)j * T];
 			if (PUSH) {
 #pragma unroll
-				for (int j = 0; j < NV; ++j) vv[j] = v2[p0 + (long long)j * T];
+				for (int j = 0; j < NV; ++j) vvN[j] = v2[p0 + (long long)j * T];
+			}
+		}
+		for (long long t0 = seg.begin; t0 < seg.end; t0 += tile) {
+			const long long p0 = (t0 >> 1) + tid;
+			double z[R], v[R];
 #pragma unroll
-				for (int j = 0; j < NV; ++j) {
-					const bool live = (zz[j].x == zz[j].x) || (zz[j].y == zz[j].y);
-					push(zz[j].x, vv[j].x);
-					push(zz[j].y, vv[j].y);
-					if (live) {
-						z2w[p0 + (long long)j * T] = zz[j];
-						v2w[p0 + (long long)j * T] = vv[j];
+			for (int j = 0; j < NV; ++j) {
+				z[2 * j] = zzN[j].x; z[2 * j + 1] = zzN[j].y;
+				if (PUSH) { v[2 * j] = vvN[j].x; v[2 * j + 1] = vvN[j].y; }
+			}
+			if (t0 + tile < seg.end) {               // next tile's loads are in flight while this one is processed
+				const long long pn = p0 + (tile >> 1);
+#pragma unroll
+				for (int j = 0; j < NV; ++j) zzN[j] = z2[pn + (long long)j * T];
+				if (PUSH) {
+#pragma unroll
+					for (int j = 0; j < NV; ++j) vvN[j] = v2[pn + (long long)j * T];
+				}
+			}
+
+			bool live[R];
+			bool liveIn[NV];
+#pragma unroll
+			for (int i = 0; i < R; ++i) live[i] = (z[i] == z[i]);   // NaN = empty slot / ring lost earlier
+#pragma unroll
+			for (int j = 0; j < NV; ++j) liveIn[j] = live[2 * j] || live[2 * j + 1];
+
+			int k[R];
+			double w[R];
+			if (PUSH) {
+				// ---- gather + kick + drift: Plasma::moveRings body (Source/Plasma.cpp:105-118) -------------
+				cells_of<EXACT>(z, live, a, k, w);
+				double eL[R], eR[R];
+				bool far = false;
+#pragma unroll
+				for (int i = 0; i < R; ++i) {
+					const unsigned int io = (unsigned int)(k[i] - k0);
+					const bool in = io < (unsigned int)W;
+					far |= live[i] && !in;
+					const double2 e = eTile[in ? io : 0u];
+					eL[i] = e.x; eR[i] = e.y;
+				}
+				if (far) {
+#pragma unroll
+					for (int i = 0; i < R; ++i)
+						if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)W) {
+							eL[i] = a.eNodes[rowBase + k[i]];
+							eR[i] = a.eNodes[rowBase + k[i] + 1];
+						}
+				}
+#pragma unroll
+				for (int i = 0; i < R; ++i) {
+					// (1 - w) * fieldLeft + w * fieldRight            Source/PenningTrap.cpp:333
+					const double e = __dadd_rn(__dmul_rn(__dsub_rn(1.0, w[i]), eL[i]), __dmul_rn(w[i], eR[i]));
+					// deltaT * E * charge / mass + speed              Source/Plasma.cpp:105
+					double kick = __dmul_rn(__dmul_rn(a.dt, e), a.charge);
+					kick = EXACT ? __ddiv_rn(kick, a.mass) : __dmul_rn(kick, a.invMass);
+					const double vN = __dadd_rn(kick, v[i]);
+					// deltaT * vNew + z                               Source/Plasma.cpp:106
+					const double zN = __dadd_rn(__dmul_rn(a.dt, vN), z[i]);
+					// zNew < length && zNew > 0 keeps the ring (Source/Plasma.cpp:108; NaN -> removed, as in the reference);
+					// a removed ring becomes a NaN tombstone instead of swap-with-back + pop (:116-117)
+					const bool keep = live[i] && (zN < a.length) && (zN > 0.0);
+					lost += (live[i] && !keep) ? 1u : 0u;
+					z[i] = keep ? zN : qNaN;
+					v[i] = keep ? vN : v[i];
+					live[i] = keep;
+				}
+			}
+
+			// ---- deposit at the (new) position: Plasma::updateRHS body (Source/Plasma.cpp:86-92) -----------
+			cells_of<EXACT>(z, live, a, k, w);
+			bool farD = false;
+#pragma unroll
+			for (int i = 0; i < R; ++i) {
+				const unsigned int io = (unsigned int)(k[i] - k0);
+				const bool in = live[i] && io < (unsigned int)W;
+				farD |= live[i] && io >= (unsigned int)W;
+				if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); }
+				if (in) {
+					if (FIXED) {
+						// round(w * 2^F) lands in the mantissa of (2^52 + x); subtracting the bias leaves (1 << 52) | x
+						const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
+						bins[(size_t)io * T + tid] += (unsigned long long)__double_as_longlong(t) - kPackBias;
+					}
+					else {
+						double* b = reinterpret_cast<double*>(bins) + (size_t)io * T + tid;
+						*b = __dadd_rn(*b, w[i]);
+						cnts[(size_t)io * T + tid] += 1u;
 					}
 				}
 			}
-			else {
+			if (farD) {
+				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
 #pragma unroll
-				for (int j = 0; j < NV; ++j) {
-					if (zz[j].x == zz[j].x) deposit(zz[j].x);
-					if (zz[j].y == zz[j].y) deposit(zz[j].y);
-				}
+				for (int i = 0; i < R; ++i)
+					if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)W) {
+						if (FIXED) {
+							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
+							const unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
+							unsigned long long* g = reinterpret_cast<unsigned long long*>(a.rho) + rowBase + k[i];
+							atomicAdd(g, (1ULL << a.fixedBits) - wq);
+							atomicAdd(g + 1, wq);
+						}
+						else {
+							double* g = reinterpret_cast<double*>(a.rho) + rowBase + k[i];
+							atomicAdd(g, __dsub_rn(1.0, w[i]));
+							atomicAdd(g + 1, w[i]);
+						}
+					}
+			}
+			if (PUSH) {
+#pragma unroll
+				for (int j = 0; j < NV; ++j)
+					if (liveIn[j]) {
+						z2w[p0 + (long long)j * T] = make_double2(z[2 * j], z[2 * j + 1]);
+						v2w[p0 + (long long)j * T] = make_double2(v[2 * j], v[2 * j + 1]);
+					}
 			}
 		}
 
@@ -286,43 +353,44 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 	}
 }
 
-// Per-segment axial cell range of the live rings (window for the first deposit / after a sort) and validation.
-__global__ void __launch_bounds__(256) k_bounds(const PushArgs a, int nSegs, unsigned long long* nLive, int* invalid)
+__global__ void k_bounds_init(int2* bounds, int n)
 {
-	__shared__ int sKmin, sKmax;
-	__shared__ unsigned int sLive;
-	const int tid = threadIdx.x;
-	for (int s = blockIdx.x; s < nSegs; s += gridDim.x) {
-		const PtpSegment seg = a.segs[s];
-		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLive = 0; }
-		__syncthreads();
-		int kMin = INT_MAX, kMax = INT_MIN;
-		unsigned int live = 0;
-		for (long long i = seg.begin + tid; i < seg.end; i += blockDim.x) {
-			const double z = a.z[i];
-			if (!(z == z)) continue;
-			if (!(z > 0.0 && z < a.length)) { *invalid = 1; continue; }
-			double w;
-			const int k = cell_of<true>(z, a, w);
-			kMin = min(kMin, k);
-			kMax = max(kMax, k);
-			++live;
-		}
-		for (int o = 16; o > 0; o >>= 1) {
-			kMin = min(kMin, __shfl_xor_sync(0xffffffffu, kMin, o));
-			kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
-		}
-		live = warp_sum(live);
-		if ((tid & 31) == 0) {
-			if (kMin <= kMax) { atomicMin(&sKmin, kMin); atomicMax(&sKmax, kMax); }
-			atomicAdd(&sLive, live);
-		}
-		__syncthreads();
-		if (tid == 0) {
-			a.segBounds[s] = make_int2(sKmin, sKmax);
-			if (sLive) atomicAdd(nLive, (unsigned long long)sLive);
-		}
-		__syncthreads();
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) bounds[i] = make_int2(INT_MAX, INT_MIN);
+}
+
+// Per-segment axial cell range of the live rings (window for the first deposit / after a sort) and validation.
+// blockIdx.y = segment, blockIdx.x = chunk of it.
+__global__ void __launch_bounds__(256) k_bounds(const PushArgs a, unsigned long long* nLive, int* invalid)
+{
+	const PtpSegment seg = a.segs[blockIdx.y];
+	const long long len = ((seg.end - seg.begin + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+	const long long b = seg.begin + (long long)blockIdx.x * len, e = min(seg.end, b + len);
+	int kMin = INT_MAX, kMax = INT_MIN;
+	unsigned int live = 0;
+	for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+		const double z = a.z[i];
+		if (!(z == z)) continue;
+		if (!(z > 0.0 && z < a.length)) { *invalid = 1; continue; }
+		int k;
+		double kd;
+		bool ok;
+		cell_fast(z, a, k, kd, ok);
+		if (!ok) cell_exact(z, a, k, kd);
+		k = min(k, a.Nz - 1);
+		kMin = min(kMin, k);
+		kMax = max(kMax, k);
+		++live;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		kMin = min(kMin, __shfl_xor_sync(0xffffffffu, kMin, o));
+		kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
+	}
+	live = warp_sum(live);
+	if ((threadIdx.x & 31) == 0 && live) {
+		atomicMin(&a.segBounds[blockIdx.y].x, kMin);
+		atomicMax(&a.segBounds[blockIdx.y].y, kMax);
+		atomicAdd(nLive, (unsigned long long)live);
 	}
 }
 
@@ -351,6 +419,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.hz = t->hz;
 	a.invHz = 1.0 / t->hz;
 	a.eps = (t->Nz + 2) * 1e-15;
+	a.epsHi = 1.0 - a.eps;
 	a.length = t->length;
 	a.dt = dt;
 	a.charge = p->charge;
@@ -413,16 +482,17 @@ int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p)
 	if (p->cap == 0 || p->segs.empty()) { p->boundsValid = true; return PTP_OK; }
 	const PushArgs a = make_args(t, p, 0.0);
 	unsigned long long* dLive = nullptr;
-	int* dInvalid = nullptr;
 	PTP_CUDA(cudaMalloc(&dLive, sizeof(unsigned long long) + sizeof(int) * 2));
-	dInvalid = reinterpret_cast<int*>(dLive + 1);
+	int* dInvalid = reinterpret_cast<int*>(dLive + 1);
 	PTP_CUDA(cudaMemsetAsync(dLive, 0, sizeof(unsigned long long) + sizeof(int) * 2, t->stream));
-	int grid = (int)p->segs.size();
-	if (grid > t->smCount * 8) grid = t->smCount * 8;
-	k_bounds<<<grid, 256, 0, t->stream>>>(a, (int)p->segs.size(), dLive, dInvalid);
+	const int nSegs = (int)p->segs.size();
+	k_bounds_init<<<(nSegs + 255) / 256, 256, 0, t->stream>>>(p->dSegBounds, nSegs);
+	int chunks = (t->smCount * 16 + nSegs - 1) / nSegs;
+	if (chunks > 64) chunks = 64;
+	k_bounds<<<dim3(chunks, nSegs), 256, 0, t->stream>>>(a, dLive, dInvalid);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) { cudaFree(dLive); return ptp_cuda_fail(e, "k_bounds launch", __FILE__, __LINE__); }
-	t->lastLaunches++;
+	t->lastLaunches += 2;
 	unsigned long long live = 0;
 	int invalid = 0;
 	PTP_CUDA(cudaMemcpyAsync(&live, dLive, sizeof(live), cudaMemcpyDeviceToHost, t->stream));

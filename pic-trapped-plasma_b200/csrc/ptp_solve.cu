@@ -11,99 +11,154 @@
 // So A^-1 b = DCT-I^-1 . [Thomas solve in r per axial mode m] . DCT-I b, a direct solve of the same
 // matrix (agreement with sparse LU ~1e-12 rel-L2, the rounding level of the LU itself).
 //
-// Kernels: k_dct_gemm (dense DCT-I as an fp64 GEMM against a precomputed cosine matrix - works for any
-// Nz; the grid sizes of this code are not powers of two), k_thomas (one thread per axial mode, factors
-// precomputed in extended precision on the host), k_node_field = PenningTrap::getEField(int,int)
+// Kernels: k_row_bounds + k_fwd_thomas (forward DCT-I restricted to each row's non-zero deposit range, fused
+// with the Thomas solve per axial mode, factors precomputed in extended precision on the host), k_inv_gemm
+// (dense inverse DCT-I as an fp64 GEMM against a precomputed cosine matrix - works for any Nz; the grid
+// sizes of this code are not powers of two), k_node_field = PenningTrap::getEField(int,int)
 // (Source/PenningTrap.cpp:208-236) for all nodes, k_apply (A x), k_wall_rhs (Source/PenningTrap.cpp:163-198).
 #include "ptp_internal.h"
+
+#include <limits.h>
 
 #include <cmath>
 
 namespace {
 
-constexpr int BM = 32, BN = 64, BK = 16, TM = 4, TN = 4; // CTA tile 32x64, 128 threads, 4x4 per thread
+constexpr int FWD_MB = 16;      // axial modes per CTA of the forward kernel
+constexpr int INV_TM = 16;      // output rows (radial nodes) per CTA of the inverse kernel
+constexpr int INV_TN = 40;      // output columns (axial nodes) per CTA
+constexpr int INV_KC = 1024;    // modes staged in shared memory per chunk
 
-// C[M][N] = (rowScale . A)[M][K] * B[K][N], row-major fp64. A may be int64 fixed point (converted on load).
-// rowScale[row / rowsPerScale] multiplies every element of A's row (species factor -rho_macro/eps0).
-template <bool A_FIXED>
-__global__ void __launch_bounds__(128) k_dct_gemm(const double* __restrict__ A, const double* __restrict__ B,
-	double* __restrict__ C, int M, int N, int K, const double* __restrict__ rowScale, int rowsPerScale, double fixedInv)
+// Per radial row: first / last axial node with a non-zero deposit (lo > hi: empty row). Deposits are exact
+// zeros outside the plasma, so skipping them in the forward transform changes nothing bitwise.
+__global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ rho, int rows, int n1, int2* __restrict__ bounds)
 {
-	__shared__ double As[BK][BM + 1];
-	__shared__ double Bs[BK][BN];
-	const int tid = threadIdx.x;
-	const int tx = tid % (BN / TN), ty = tid / (BN / TN); // 16 x 8
-	const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-	double acc[TM][TN];
-#pragma unroll
-	for (int i = 0; i < TM; ++i)
-#pragma unroll
-		for (int j = 0; j < TN; ++j) acc[i][j] = 0.0;
-
-	for (int k0 = 0; k0 < K; k0 += BK) {
-		// A tile: BM x BK, 512 elements, 4 per thread, coalesced along k
-		for (int e = tid; e < BM * BK; e += 128) {
-			const int r = e / BK, c = e % BK;
-			const int gm = m0 + r, gk = k0 + c;
-			double val = 0.0;
-			if (gm < M && gk < K) {
-				if (A_FIXED) val = (double)reinterpret_cast<const long long*>(A)[(size_t)gm * K + gk] * fixedInv;
-				else val = A[(size_t)gm * K + gk];
-				if (rowScale) val *= rowScale[gm / rowsPerScale];
-			}
-			As[c][r] = val;
-		}
-		for (int e = tid; e < BK * BN; e += 128) {
-			const int r = e / BN, c = e % BN;
-			const int gk = k0 + r, gn = n0 + c;
-			Bs[r][c] = (gk < K && gn < N) ? B[(size_t)gk * N + gn] : 0.0;
-		}
-		__syncthreads();
-#pragma unroll
-		for (int kk = 0; kk < BK; ++kk) {
-			double av[TM], bv[TN];
-#pragma unroll
-			for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
-#pragma unroll
-			for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
-#pragma unroll
-			for (int i = 0; i < TM; ++i)
-#pragma unroll
-				for (int j = 0; j < TN; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-		}
-		__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (row >= rows) return;
+	const unsigned long long* w = reinterpret_cast<const unsigned long long*>(rho) + (size_t)row * n1;
+	int lo = INT_MAX, hi = INT_MIN;
+	for (int k = lane; k < n1; k += 32)
+		if (w[k] << 1) { lo = min(lo, k); hi = max(hi, k); }     // any bit but the sign: non-zero as double and as int64
+	for (int o = 16; o > 0; o >>= 1) {
+		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+		hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
 	}
-#pragma unroll
-	for (int i = 0; i < TM; ++i) {
-		const int gm = m0 + ty * TM + i;
-		if (gm >= M) continue;
-#pragma unroll
-		for (int j = 0; j < TN; ++j) {
-			const int gn = n0 + tx * TN + j;
-			if (gn < N) C[(size_t)gm * N + gn] = acc[i][j];
-		}
-	}
+	if (lane == 0) bounds[row] = make_int2(lo, hi);
 }
 
-// Thomas solve of (T_r + lambda_m I) alpha = beta for every axial mode m (thread) and species (blockIdx.y),
-// in place on spec[s][j][m]. Factors: inv = 1/pivot, cp = upper/pivot; forward y_j = (beta_j - l_j y_{j-1}) inv_j.
-__global__ void __launch_bounds__(64) k_thomas(double* __restrict__ spec, const double* __restrict__ thInv,
-	const double* __restrict__ thCp, const double* __restrict__ thLower, int Nr, int n1)
+// Forward half of the solve for FWD_MB axial modes per CTA and one species per blockIdx.y:
+//   beta[j][m] = sum_k (scale * rho[j][k]) * FT[k][m]      (DCT-I with its weights, only over each row's non-zero range)
+//   alpha[.][m] = (T_r + lambda_m I)^-1 beta[.][m]          (Thomas in r, factors precomputed)
+// alpha is written to spec[s][j][m].
+template <bool A_FIXED>
+__global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ rho, const int2* __restrict__ bounds,
+	const double* __restrict__ FT, const double* __restrict__ rowScale, double fixedInv,
+	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thLower,
+	double* __restrict__ spec, int Nr, int n1)
 {
-	const int m = blockIdx.x * blockDim.x + threadIdx.x;
-	if (m >= n1) return;
-	double* x = spec + (size_t)blockIdx.y * Nr * n1 + m;
-	double y = x[0] * thInv[m];
-	x[0] = y;
-	for (int j = 1; j < Nr; ++j) {
-		const double inv = thInv[(size_t)j * n1 + m];
-		const double g = x[(size_t)j * n1] * inv;
-		y = fma(-(thLower[j] * inv), y, g);
-		x[(size_t)j * n1] = y;
+	extern __shared__ double sB[];                              // [Nr][FWD_MB]
+	const int tid = threadIdx.x, mi = tid % FWD_MB, slot = tid / FWD_MB;
+	const int m = blockIdx.x * FWD_MB + mi;
+	const int s = blockIdx.y;
+	const bool mOk = m < n1;
+	const double scale = (rowScale ? rowScale[s] : 1.0) * (A_FIXED ? fixedInv : 1.0);
+	const double* b = rho + (size_t)s * Nr * n1;
+	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
+		const int2 bd = bounds[s * Nr + j];
+		double acc = 0.0;
+		if (mOk && bd.x <= bd.y) {
+			const double* row = b + (size_t)j * n1;
+			const double* f = FT + (size_t)bd.x * n1 + m;
+			for (int k = bd.x; k <= bd.y; ++k, f += n1) {
+				const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(row)[k] : row[k];
+				acc = fma(val, __ldg(f), acc);
+			}
+			acc *= scale;
+		}
+		sB[j * FWD_MB + mi] = acc;
 	}
-	for (int j = Nr - 2; j >= 0; --j) {
-		y = fma(-thCp[(size_t)j * n1 + m], y, x[(size_t)j * n1]);
-		x[(size_t)j * n1] = y;
+	__syncthreads();
+	if (tid < FWD_MB && mOk) {
+		double y = sB[mi] * thInv[m];
+		sB[mi] = y;
+#pragma unroll 8
+		for (int j = 1; j < Nr; ++j) {
+			const double inv = thInv[(size_t)j * n1 + m];
+			const double g = sB[j * FWD_MB + mi] * inv;
+			y = fma(-(thLower[j] * inv), y, g);
+			sB[j * FWD_MB + mi] = y;
+		}
+#pragma unroll 8
+		for (int j = Nr - 2; j >= 0; --j) {
+			y = fma(-thCp[(size_t)j * n1 + m], y, sB[j * FWD_MB + mi]);
+			sB[j * FWD_MB + mi] = y;
+		}
+	}
+	__syncthreads();
+	double* out = spec + (size_t)s * Nr * n1;
+	for (int j = slot; j < Nr; j += 256 / FWD_MB)
+		if (mOk) out[(size_t)j * n1 + m] = sB[j * FWD_MB + mi];
+}
+
+// Inverse DCT-I as a dense fp64 GEMM: C[M][N] = A[M][K] * B[K][N] (A = alpha, B = cosine matrix).
+// The output is small (M*N ~ 75 k values) and K long, so a CTA owns a 16 x 40 output tile and its 8 warps
+// split K between them: every lane keeps a 4 x 5 register tile (9 operand loads per 20 FMAs), A rows are
+// staged once in shared memory, B is streamed through the read-only path, and the 8 partial tiles are
+// summed through shared memory at the end.
+__global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, const double* __restrict__ B,
+	double* __restrict__ C, int M, int N, int K)
+{
+	extern __shared__ double sm[];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int la = lane >> 3, lb = lane & 7;                    // 4 row groups x 8 column groups
+	const int m0 = blockIdx.y * INV_TM, n0 = blockIdx.x * INV_TN;
+	const int kc = K < INV_KC ? K : INV_KC;
+	const int lda = kc | 1;                                     // odd leading dimension: the 4 row groups hit distinct banks
+	double acc[4][5];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < 5; ++j) acc[i][j] = 0.0;
+	bool colOk[5];
+#pragma unroll
+	for (int j = 0; j < 5; ++j) colOk[j] = n0 + 5 * lb + j < N;
+
+	for (int k0 = 0; k0 < K; k0 += kc) {
+		const int kn = min(kc, K - k0);
+		__syncthreads();
+		for (int e = tid; e < INV_TM * kn; e += 256) {
+			const int r = e / kn, c = e - r * kn;
+			sm[r * lda + c] = (m0 + r < M) ? A[(size_t)(m0 + r) * K + k0 + c] : 0.0;
+		}
+		__syncthreads();
+		const double* a = sm + (4 * la) * lda;
+		for (int k = warp; k < kn; k += 8) {
+			const double* brow = B + (size_t)(k0 + k) * N + n0 + 5 * lb;
+			double bv[5], av[4];
+#pragma unroll
+			for (int j = 0; j < 5; ++j) bv[j] = colOk[j] ? __ldg(brow + j) : 0.0;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) av[i] = a[i * lda + k];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+#pragma unroll
+				for (int j = 0; j < 5; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+		}
+	}
+	__syncthreads();
+	double* red = sm;                                           // [8][16][40]
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+#pragma unroll
+		for (int j = 0; j < 5; ++j) red[(warp * INV_TM + 4 * la + i) * INV_TN + 5 * lb + j] = acc[i][j];
+	__syncthreads();
+	for (int o = tid; o < INV_TM * INV_TN; o += 256) {
+		double v = 0.0;
+#pragma unroll
+		for (int w = 0; w < 8; ++w) v += red[w * INV_TM * INV_TN + o];
+		const int r = o / INV_TN, c = o - r * INV_TN;
+		if (m0 + r < M && n0 + c < N) C[(size_t)(m0 + r) * N + n0 + c] = v;
 	}
 }
 
@@ -269,20 +324,38 @@ int ptp_solver_build(ptp_trap* t)
 
 void ptp_solver_free(ptp_trap* t)
 {
-	cudaFree(t->dctFwd); cudaFree(t->dctInv); cudaFree(t->thInv); cudaFree(t->thCp);
+	cudaFree(t->dctFwd); cudaFree(t->dctInv); cudaFree(t->thInv); cudaFree(t->thCp); cudaFree(t->rowBounds);
 	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
 }
 
 int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi)
 {
 	if (nS <= 0) return PTP_OK;
-	const int n1 = t->Nz + 1, M = nS * t->Nr;
-	const dim3 grid((n1 + BN - 1) / BN, (M + BM - 1) / BM);
+	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
-	if (rhoIsFixed) k_dct_gemm<true><<<grid, 128, 0, t->stream>>>(rho, t->dctFwd, spec, M, n1, n1, dScale, t->Nr, fixedInv);
-	else k_dct_gemm<false><<<grid, 128, 0, t->stream>>>(rho, t->dctFwd, spec, M, n1, n1, dScale, t->Nr, 1.0);
-	k_thomas<<<dim3((n1 + 63) / 64, nS), 64, 0, t->stream>>>(spec, t->thInv, t->thCp, t->thLower, t->Nr, n1);
-	k_dct_gemm<false><<<grid, 128, 0, t->stream>>>(spec, t->dctInv, phi, M, n1, n1, nullptr, 1, 1.0);
+	if ((int)t->rowBoundsCap < M) {
+		cudaFree(t->rowBounds);
+		t->rowBounds = nullptr;
+		PTP_CUDA(cudaMalloc(&t->rowBounds, (size_t)M * sizeof(int2)));
+		t->rowBoundsCap = M;
+	}
+	k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds);
+	const size_t smFwd = (size_t)Nr * FWD_MB * sizeof(double);
+	const dim3 gridFwd((n1 + FWD_MB - 1) / FWD_MB, nS);
+	if (rhoIsFixed) {
+		if (smFwd > 48 * 1024) PTP_CUDA(cudaFuncSetAttribute(k_fwd_thomas<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd));
+		k_fwd_thomas<true><<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, fixedInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
+	}
+	else {
+		if (smFwd > 48 * 1024) PTP_CUDA(cudaFuncSetAttribute(k_fwd_thomas<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd));
+		k_fwd_thomas<false><<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, 1.0, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
+	}
+	const int kc = n1 < INV_KC ? n1 : INV_KC;
+	size_t smInv = (size_t)INV_TM * (kc | 1) * sizeof(double);
+	if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);
+	PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
+	const dim3 gridInv((n1 + INV_TN - 1) / INV_TN, (M + INV_TM - 1) / INV_TM);
+	k_inv_gemm<<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "solver launch", __FILE__, __LINE__);
 	t->lastLaunches += 3;

@@ -2,9 +2,26 @@
 # One gpurun call: GPU parity tests, smoke, bench lines. Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt; free -g | head -2 >> gpurun_out/gpu.txt
 timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
-timeout 600 python bench.py --workload c2 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2.log 2>&1; echo "bench c2 rc=$?"
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_c4.log 2>&1; echo "bench c4 rc=$?"
-tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; tail -1 gpurun_out/bench_c2.log; tail -1 gpurun_out/bench_c4.log
+tail -2 gpurun_out/smoke.log
+run() { # name, args...
+  n=$1; shift
+  timeout 900 python bench.py "$@" > gpurun_out/bench_$n.log 2>&1; echo "bench $n rc=$?"
+  tail -1 gpurun_out/bench_$n.log | python -c "
+import sys,json
+try:
+    d=json.loads(sys.stdin.read())
+    print('  value %.3e  ms/step %.4f  k1 %.4f ms  frac %.3f  solve %.4f ms  e2e %s' % (d['value'], d['ms_per_step'], d['roofline']['k1_ms_per_launch'], d['roofline']['frac'], d['phases_ms_per_step']['solve_node_field'], d['e2e'] and '%.3e' % d['e2e']['value']))
+except Exception as e: print('  parse fail', e)
+"
+}
+run c2 --workload c2 --steps 100 --warmup 5 --no-cpu-baseline
+run c4_t256_w64_fp64 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e
+run c4_t256_w64_fixed --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed
+run c4_t256_w96_fixed --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 96
+run c4_t512_w32_fp64 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --threads 512 --window 32
+run c4_t512_w48_fixed --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --threads 512 --window 48 --deposit fixed
+run c4_t256_w48_fp64 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --window 48
+run c3 --workload c3 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e
