@@ -141,7 +141,7 @@ def cpu_reference_run(workload, steps, warmup, sample_rings):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=-1)
+    ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -213,8 +214,8 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         trap.comm_init(uid[0], world, rank)
     trap.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64 if args.deposit == "fixed" else ptp.PTP_DEPOSIT_FP64)
-    if args.threads or args.window or args.ctas >= 0:
-        trap.set_tuning(args.threads, args.window, args.ctas)
+    if args.threads or args.window or args.ctas >= 0 or args.rings:
+        trap.set_tuning(args.threads, args.window, args.ctas, args.rings)
     trap.set_sort_interval(args.sort_interval)
 
     load = build_load(ptp, loaders, args.workload, rank, world, trap.hz, trap.hr)
@@ -307,7 +308,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "phases_ms_per_step": {"push_deposit": ms_push / args.steps, "allreduce": float(times[2]) / args.steps,
                                        "solve_node_field": float(times[3]) / args.steps},
-                "tuning": {"threads": args.threads or 256, "window": args.window or 64, "ctas": args.ctas}}
+                "tuning": {"threads": args.threads or 512, "window": args.window or 44, "ctas": args.ctas, "rings_per_thread": args.rings or 8}}
         print(json.dumps(line))
     trap.close()
     if world > 1:

@@ -102,8 +102,9 @@ int ptp_trap_set_sort_interval(ptp_trap* t, int interval);
 int ptp_trap_set_deposit_mode(ptp_trap* t, int mode);
 int ptp_trap_set_arith_mode(ptp_trap* t, int mode);
 int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMaxIterations);
-/* Tuning: threads per CTA (256/512), bins per thread-private tile window, CTAs (0 = one per SM). */
-int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas);
+/* Tuning of the push kernel: threads per CTA (256/512), cells of the thread-private deposit window, CTAs
+ * (0 = one per SM), rings per thread and tile (4/8). 0 (ctas: -1) keeps the current value. */
+int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ringsPerThread);
 
 /* ---- multi-GPU (one process per GPU; rings sharded, rho all-reduced, solve replicated) --- */
 

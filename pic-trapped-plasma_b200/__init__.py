@@ -63,7 +63,7 @@ SIGNATURES = {
     "ptp_trap_set_deposit_mode": (_i, [_vp, _i]),
     "ptp_trap_set_arith_mode": (_i, [_vp, _i]),
     "ptp_trap_set_solver": (_i, [_vp, _i, _d, _i]),
-    "ptp_trap_set_tuning": (_i, [_vp, _i, _i, _i]),
+    "ptp_trap_set_tuning": (_i, [_vp, _i, _i, _i, _i]),
     "ptp_comm_unique_id": (_i, [_vp]),
     "ptp_trap_comm_init": (_i, [_vp, _vp, _i, _i]),
     "ptp_trap_set_allreduce": (_i, [_vp, _i]),
@@ -253,8 +253,8 @@ class PenningTrap:
     def set_solver(self, solver, tol=0.0, max_iter=0):
         _check(lib().ptp_trap_set_solver(self.h, solver, tol, max_iter))
 
-    def set_tuning(self, threads=0, window=0, ctas=-1):
-        _check(lib().ptp_trap_set_tuning(self.h, threads, window, ctas))
+    def set_tuning(self, threads=0, window=0, ctas=-1, rings_per_thread=0):
+        _check(lib().ptp_trap_set_tuning(self.h, threads, window, ctas, rings_per_thread))
 
     def set_sort_interval(self, interval):
         _check(lib().ptp_trap_set_sort_interval(self.h, interval))

@@ -342,15 +342,16 @@ int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMax
 	return PTP_OK;
 }
 
-int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas)
+int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ringsPerThread)
 {
 	if (!t) { ptp_set_error("ptp_trap_set_tuning: null trap"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
-	const int oT = t->threads, oW = t->window, oC = t->ctas;
+	const int oT = t->threads, oW = t->window, oC = t->ctas, oR = t->ringsPerThread;
 	if (threads > 0) t->threads = threads;
 	if (window > 0) t->window = window;
 	if (ctas >= 0) t->ctas = ctas;
-	if (ptp_push_configure(t) != PTP_OK) { t->threads = oT; t->window = oW; t->ctas = oC; return PTP_EINVAL; }
+	if (ringsPerThread > 0) t->ringsPerThread = ringsPerThread;
+	if (ptp_push_configure(t) != PTP_OK) { t->threads = oT; t->window = oW; t->ctas = oC; t->ringsPerThread = oR; return PTP_EINVAL; }
 	for (ptp_plasma* p : t->plasmas)
 		if (p->cap) { PTP_TRY(ptp_build_segments(t, p)); PTP_TRY(ptp_bounds_launch(t, p)); }
 	return PTP_OK;

@@ -14,7 +14,6 @@
 // Row buckets are padded to this many ring slots so that every tile of the push kernel lies inside one
 // radial row and double2 accesses stay 16-byte aligned (8 rings/thread x 512 threads max).
 #define PTP_ROW_ALIGN 4096
-#define PTP_RINGS_PER_THREAD 8
 
 // One contiguous run of ring slots of ONE radial row, owned by one CTA of the push kernel.
 struct PtpSegment {
@@ -97,7 +96,7 @@ struct ptp_trap {
 	double sorTol = 1e-12;
 	int sorMaxIter = 20000;
 	int fixedBits = 40;
-	int threads = 256, window = 64, ctas = 0;
+	int threads = 512, window = 44, ctas = 0, ringsPerThread = 8;
 	int sortInterval = 0;
 	long long stepCount = 0;
 	bool eNodesValid = false;

@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const double* __restrict__
 // Split the live part of every row bucket into segments and deal them to CTAs in contiguous tile ranges.
 int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 {
-	const long long tile = (long long)PTP_RINGS_PER_THREAD * t->threads;
-	const long long maxSegTiles = 4095 / PTP_RINGS_PER_THREAD;   // 12-bit per-thread count field of the packed bins
+	const long long tile = (long long)t->ringsPerThread * t->threads;
+	const long long maxSegTiles = 4095 / t->ringsPerThread;   // 12-bit per-thread count field of the packed bins
 	long long totalTiles = 0;
 	for (int r = 0; r < t->Nr; ++r) totalTiles += (p->rowLive[r] + tile - 1) / tile;
 	int nCta = t->ctas > 0 ? t->ctas : t->smCount;

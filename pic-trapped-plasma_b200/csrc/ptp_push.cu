@@ -32,8 +32,6 @@
 
 namespace {
 
-constexpr int R = PTP_RINGS_PER_THREAD;
-constexpr int NV = R / 2;
 constexpr double kMagic = 6755399441055744.0;            // 2^52 + 2^51: floor via add.rm, integer in the low word
 constexpr unsigned long long kPackBias = 0x4320000000000000ULL; // bits(2^52 + x) - bias = (1 << 52) | x
 constexpr unsigned long long kSumMask = (1ULL << 52) - 1;
@@ -75,7 +73,7 @@ __device__ __forceinline__ void cell_exact(double z, const PushArgs& a, int& k, 
 
 // Cells and weights of R positions. w = (z - k*hz) / hz is the reference's weightFactor (Source/Plasma.cpp:89-90,
 // Source/PenningTrap.cpp:331-332); in FAST arithmetic the division is a reciprocal multiply.
-template <bool EXACT>
+template <int R, bool EXACT>
 __device__ __forceinline__ void cells_of(const double (&z)[R], const bool (&live)[R], const PushArgs& a, int (&k)[R], double (&w)[R])
 {
 	double kd[R];
@@ -114,16 +112,17 @@ template <typename T> __device__ __forceinline__ T warp_sum(T x)
 	return x;
 }
 
-template <int T, bool PUSH, bool FIXED, bool EXACT>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT>
 __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
+	constexpr int NV = R / 2;
 	extern __shared__ __align__(16) unsigned char smem[];
 	const int W = a.W;
 	double2* eTile = reinterpret_cast<double2*>(smem);                       // [W] (E[k], E[k+1]) of cell k0+i
 	unsigned long long* redC = reinterpret_cast<unsigned long long*>(eTile + W); // [W]
 	unsigned long long* redS = redC + W;                                     // [W] u64 (fixed) or double bits
 	unsigned long long* bins = redS + W;                                     // [W][T] packed words / double sums
-	unsigned int* cnts = reinterpret_cast<unsigned int*>(bins + (size_t)W * T); // [W][T] fp64 mode only
+	unsigned short* cnts = reinterpret_cast<unsigned short*>(bins + (size_t)W * T); // [W][T] fp64 mode only (a thread sees < 4096 rings per segment)
 	__shared__ int sKmin, sKmax;
 	__shared__ unsigned int sLost;
 
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		k0 = max(0, min(k0, a.Nz - W));
 		for (int i = 0; i < W; ++i) {
 			bins[(size_t)i * T + tid] = 0ULL;
-			if (!FIXED) cnts[(size_t)i * T + tid] = 0u;
+			if (!FIXED) cnts[(size_t)i * T + tid] = 0;
 		}
 		if (PUSH) {
 			for (int i = tid; i < W; i += T) {
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			double w[R];
 			if (PUSH) {
 				// ---- gather + kick + drift: Plasma::moveRings body (Source/Plasma.cpp:105-118) -------------
-				cells_of<EXACT>(z, live, a, k, w);
+				cells_of<R, EXACT>(z, live, a, k, w);
 				double eL[R], eR[R];
 				bool far = false;
 #pragma unroll
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			}
 
 			// ---- deposit at the (new) position: Plasma::updateRHS body (Source/Plasma.cpp:86-92) -----------
-			cells_of<EXACT>(z, live, a, k, w);
+			cells_of<R, EXACT>(z, live, a, k, w);
 			bool farD = false;
 #pragma unroll
 			for (int i = 0; i < R; ++i) {
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 					else {
 						double* b = reinterpret_cast<double*>(bins) + (size_t)io * T + tid;
 						*b = __dadd_rn(*b, w[i]);
-						cnts[(size_t)io * T + tid] += 1u;
+						cnts[(size_t)io * T + tid] += 1;
 					}
 				}
 			}
@@ -394,10 +393,10 @@ __global__ void __launch_bounds__(256) k_bounds(const PushArgs a, unsigned long 
 	}
 }
 
-template <int T, bool PUSH> struct Launcher {
+template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st)
 	{
-		auto kern = k_push_deposit<T, PUSH, FIXED, EXACT>;
+		auto kern = k_push_deposit<T, R, PUSH, FIXED, EXACT>;
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
 		kern<<<grid, T, smem, st>>>(a);
@@ -409,6 +408,12 @@ template <int T, bool PUSH> struct Launcher {
 		return exact ? go<false, true>(a, grid, smem, st) : go<false, false>(a, grid, smem, st);
 	}
 };
+
+template <int T, int R> cudaError_t launch_tr(bool push, bool fixed, bool exact, const PushArgs& a, int grid, size_t smem, cudaStream_t st)
+{
+	return push ? Launcher<T, R, true>::dispatch(fixed, exact, a, grid, smem, st)
+	            : Launcher<T, R, false>::dispatch(fixed, exact, a, grid, smem, st);
+}
 
 PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 {
@@ -442,13 +447,14 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window)
 {
 	size_t w = (size_t)(window < t->Nz ? window : t->Nz);
-	size_t perBin = t->depositMode == PTP_DEPOSIT_FIXED64 ? 8 : 12;
+	size_t perBin = t->depositMode == PTP_DEPOSIT_FIXED64 ? 8 : 10;
 	return w * 16 + w * 16 + w * (size_t)threads * perBin;
 }
 
 int ptp_push_configure(ptp_trap* t)
 {
 	if (t->threads != 256 && t->threads != 512) { ptp_set_error("threads per CTA must be 256 or 512"); return PTP_EINVAL; }
+	if (t->ringsPerThread != 4 && t->ringsPerThread != 8) { ptp_set_error("rings per thread must be 4 or 8"); return PTP_EINVAL; }
 	if (t->window < 4) { ptp_set_error("window must be at least 4 cells"); return PTP_EINVAL; }
 	if (ptp_push_smem_bytes(t, t->threads, t->window) > t->smemMax) {
 		ptp_set_error("threads x window does not fit in shared memory");
@@ -466,11 +472,11 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64, exact = t->arithMode == PTP_ARITH_EXACT;
 	cudaError_t e;
 	if (t->threads == 512)
-		e = push ? Launcher<512, true>::dispatch(fixed, exact, a, p->nCta, smem, t->stream)
-		         : Launcher<512, false>::dispatch(fixed, exact, a, p->nCta, smem, t->stream);
+		e = t->ringsPerThread == 8 ? launch_tr<512, 8>(push, fixed, exact, a, p->nCta, smem, t->stream)
+		                           : launch_tr<512, 4>(push, fixed, exact, a, p->nCta, smem, t->stream);
 	else
-		e = push ? Launcher<256, true>::dispatch(fixed, exact, a, p->nCta, smem, t->stream)
-		         : Launcher<256, false>::dispatch(fixed, exact, a, p->nCta, smem, t->stream);
+		e = t->ringsPerThread == 8 ? launch_tr<256, 8>(push, fixed, exact, a, p->nCta, smem, t->stream)
+		                           : launch_tr<256, 4>(push, fixed, exact, a, p->nCta, smem, t->stream);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_push_deposit launch", __FILE__, __LINE__);
 	t->lastLaunches++;
 	return PTP_OK;

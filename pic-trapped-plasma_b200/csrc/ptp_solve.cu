@@ -57,13 +57,21 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thLower,
 	double* __restrict__ spec, int Nr, int n1)
 {
-	extern __shared__ double sB[];                              // [Nr][FWD_MB]
+	extern __shared__ double sB[];                              // [Nr][FWD_MB] beta -> alpha, then the two factor tiles
+	double* sInv = sB + (size_t)Nr * FWD_MB;                    // [Nr][FWD_MB]
+	double* sCp = sInv + (size_t)Nr * FWD_MB;                   // [Nr][FWD_MB]
 	const int tid = threadIdx.x, mi = tid % FWD_MB, slot = tid / FWD_MB;
 	const int m = blockIdx.x * FWD_MB + mi;
 	const int s = blockIdx.y;
 	const bool mOk = m < n1;
 	const double scale = (rowScale ? rowScale[s] : 1.0) * (A_FIXED ? fixedInv : 1.0);
 	const double* b = rho + (size_t)s * Nr * n1;
+	// Thomas factors of this CTA's modes: staged once (coalesced, all loads independent) so that the serial
+	// sweeps below only touch shared memory
+	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
+		sInv[j * FWD_MB + mi] = mOk ? thInv[(size_t)j * n1 + m] : 1.0;
+		sCp[j * FWD_MB + mi] = mOk ? thCp[(size_t)j * n1 + m] : 0.0;
+	}
 	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
 		const int2 bd = bounds[s * Nr + j];
 		double acc = 0.0;
@@ -80,18 +88,18 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	}
 	__syncthreads();
 	if (tid < FWD_MB && mOk) {
-		double y = sB[mi] * thInv[m];
+		double y = sB[mi] * sInv[mi];
 		sB[mi] = y;
 #pragma unroll 8
 		for (int j = 1; j < Nr; ++j) {
-			const double inv = thInv[(size_t)j * n1 + m];
+			const double inv = sInv[j * FWD_MB + mi];
 			const double g = sB[j * FWD_MB + mi] * inv;
 			y = fma(-(thLower[j] * inv), y, g);
 			sB[j * FWD_MB + mi] = y;
 		}
 #pragma unroll 8
 		for (int j = Nr - 2; j >= 0; --j) {
-			y = fma(-thCp[(size_t)j * n1 + m], y, sB[j * FWD_MB + mi]);
+			y = fma(-sCp[j * FWD_MB + mi], y, sB[j * FWD_MB + mi]);
 			sB[j * FWD_MB + mi] = y;
 		}
 	}
@@ -133,17 +141,26 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 		}
 		__syncthreads();
 		const double* a = sm + (4 * la) * lda;
-		for (int k = warp; k < kn; k += 8) {
-			const double* brow = B + (size_t)(k0 + k) * N + n0 + 5 * lb;
-			double bv[5], av[4];
+		// 4 k-steps per iteration: their 20 B loads are issued together so that one L2 round trip feeds 80 FMAs
+		constexpr int U = 4;
+		for (int kb = warp; kb < kn; kb += 8 * U) {
+			double bv[U][5], av[U][4];
 #pragma unroll
-			for (int j = 0; j < 5; ++j) bv[j] = colOk[j] ? __ldg(brow + j) : 0.0;
+			for (int u = 0; u < U; ++u) {
+				const int k = kb + 8 * u;
+				const bool kOk = k < kn;
+				const double* brow = B + (size_t)(k0 + (kOk ? k : 0)) * N + n0 + 5 * lb;
 #pragma unroll
-			for (int i = 0; i < 4; ++i) av[i] = a[i * lda + k];
+				for (int j = 0; j < 5; ++j) bv[u][j] = (kOk && colOk[j]) ? __ldg(brow + j) : 0.0;
 #pragma unroll
-			for (int i = 0; i < 4; ++i)
+				for (int i = 0; i < 4; ++i) av[u][i] = kOk ? a[i * lda + k] : 0.0;
+			}
 #pragma unroll
-				for (int j = 0; j < 5; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+			for (int u = 0; u < U; ++u)
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+#pragma unroll
+					for (int j = 0; j < 5; ++j) acc[i][j] = fma(av[u][i], bv[u][j], acc[i][j]);
 		}
 	}
 	__syncthreads();
@@ -340,7 +357,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		t->rowBoundsCap = M;
 	}
 	k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds);
-	const size_t smFwd = (size_t)Nr * FWD_MB * sizeof(double);
+	const size_t smFwd = (size_t)3 * Nr * FWD_MB * sizeof(double);
 	const dim3 gridFwd((n1 + FWD_MB - 1) / FWD_MB, nS);
 	if (rhoIsFixed) {
 		if (smFwd > 48 * 1024) PTP_CUDA(cudaFuncSetAttribute(k_fwd_thomas<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd));

@@ -62,3 +62,15 @@ def test_product_does_not_touch_the_oracle():
                 src = open(os.path.join(base, f), errors="ignore").read()
                 assert "oracle" not in src.replace("no oracle", ""), os.path.join(base, f)
                 assert "libptp_ref" not in src and "ptp_oracle" not in src
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Diagnostics"), reason="reference only present in the dev container")
+def test_reference_drivers_compile_unchanged_against_host_classes():
+    """Diagnostics/A..D) *.txt are complete C++ programs; they must build against our headers without edits."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import build_drivers
+    if not os.path.exists(os.path.join(ROOT, "pic-trapped-plasma_b200", "libptp_host.so")):
+        pytest.skip("libptp_host.so not built")
+    built = build_drivers.build()
+    assert [os.path.basename(b) for b in built] == ["driver_A", "driver_B", "driver_C", "driver_D"]

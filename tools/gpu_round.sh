@@ -17,11 +17,12 @@ try:
 except Exception as e: print('  parse fail', e)
 "
 }
-run c2 --workload c2 --steps 100 --warmup 5 --no-cpu-baseline
-run c4_t256_w64_fp64 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e
-run c4_t256_w64_fixed --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed
-run c4_t256_w96_fixed --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 96
-run c4_t512_w32_fp64 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --threads 512 --window 32
-run c4_t512_w48_fixed --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --threads 512 --window 48 --deposit fixed
-run c4_t256_w48_fp64 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --window 48
-run c3 --workload c3 --steps 50 --warmup 3 --no-cpu-baseline --no-e2e
+run c2 --workload c2 --steps 200 --warmup 5 --no-cpu-baseline
+run c4_default --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
+run c4_t512_w44_r4 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --rings 4
+run c4_t256_w64_r8 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --threads 256 --window 64
+run c4_t256_w64_r4 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --threads 256 --window 64 --rings 4
+run c4_fixed_t512_w56_r8 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 56
+run c4_fixed_t512_w56_r4 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 56 --rings 4
+run c4_t512_w32_r8 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --window 32
+run c3 --workload c3 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
