@@ -96,7 +96,7 @@ struct ptp_trap {
 	double sorTol = 1e-12;
 	int sorMaxIter = 20000;
 	int fixedBits = 40;
-	int threads = 512, window = 44, ctas = 0, ringsPerThread = 8;
+	int threads = 512, window = 44, ctas = 0, ringsPerThread = 4;
 	int sortInterval = 0;
 	long long stepCount = 0;
 	bool eNodesValid = false;

@@ -38,8 +38,14 @@ __global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ r
 	if (row >= rows) return;
 	const unsigned long long* w = reinterpret_cast<const unsigned long long*>(rho) + (size_t)row * n1;
 	int lo = INT_MAX, hi = INT_MIN;
-	for (int k = lane; k < n1; k += 32)
-		if (w[k] << 1) { lo = min(lo, k); hi = max(hi, k); }     // any bit but the sign: non-zero as double and as int64
+	for (int k0 = lane; k0 < n1; k0 += 32 * 8) {                // 8 independent loads in flight per lane
+		unsigned long long word[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) word[u] = (k0 + 32 * u < n1) ? w[k0 + 32 * u] : 0ULL;
+#pragma unroll
+		for (int u = 0; u < 8; ++u)
+			if (word[u] << 1) { lo = min(lo, k0 + 32 * u); hi = max(hi, k0 + 32 * u); } // any bit but the sign: non-zero as double and as int64
+	}
 	for (int o = 16; o > 0; o >>= 1) {
 		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
 		hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
@@ -58,8 +64,8 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	double* __restrict__ spec, int Nr, int n1)
 {
 	extern __shared__ double sB[];                              // [Nr][FWD_MB] beta -> alpha, then the two factor tiles
-	double* sInv = sB + (size_t)Nr * FWD_MB;                    // [Nr][FWD_MB]
-	double* sCp = sInv + (size_t)Nr * FWD_MB;                   // [Nr][FWD_MB]
+	double* sInv = sB + (size_t)Nr * FWD_MB;                    // [Nr][FWD_MB] 1/pivot
+	double* sCp = sInv + (size_t)Nr * FWD_MB;                   // [Nr][FWD_MB] upper/pivot
 	const int tid = threadIdx.x, mi = tid % FWD_MB, slot = tid / FWD_MB;
 	const int m = blockIdx.x * FWD_MB + mi;
 	const int s = blockIdx.y;
@@ -78,7 +84,18 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 		if (mOk && bd.x <= bd.y) {
 			const double* row = b + (size_t)j * n1;
 			const double* f = FT + (size_t)bd.x * n1 + m;
-			for (int k = bd.x; k <= bd.y; ++k, f += n1) {
+			int k = bd.x;
+			for (; k + 3 <= bd.y; k += 4, f += 4 * (size_t)n1) {   // 8 independent loads per trip
+				double val[4], fv[4];
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					val[u] = A_FIXED ? (double)reinterpret_cast<const long long*>(row)[k + u] : row[k + u];
+					fv[u] = __ldg(f + u * (size_t)n1);
+				}
+#pragma unroll
+				for (int u = 0; u < 4; ++u) acc = fma(val[u], fv[u], acc);
+			}
+			for (; k <= bd.y; ++k, f += n1) {
 				const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(row)[k] : row[k];
 				acc = fma(val, __ldg(f), acc);
 			}
@@ -88,19 +105,41 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	}
 	__syncthreads();
 	if (tid < FWD_MB && mOk) {
+		// forward sweep y_j = g_j - (l_j inv_j) y_{j-1}; the coefficients of 8 rows are prepared off the chain, so the
+		// serial part is one dependent FMA per row
 		double y = sB[mi] * sInv[mi];
 		sB[mi] = y;
-#pragma unroll 8
-		for (int j = 1; j < Nr; ++j) {
-			const double inv = sInv[j * FWD_MB + mi];
-			const double g = sB[j * FWD_MB + mi] * inv;
-			y = fma(-(thLower[j] * inv), y, g);
-			sB[j * FWD_MB + mi] = y;
+		for (int j0 = 1; j0 < Nr; j0 += 8) {
+			double c[8], g[8];
+#pragma unroll
+			for (int u = 0; u < 8; ++u) {
+				const int j = min(j0 + u, Nr - 1);
+				const double inv = sInv[j * FWD_MB + mi];
+				g[u] = sB[j * FWD_MB + mi] * inv;
+				c[u] = -(thLower[j] * inv);
+			}
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				if (j0 + u < Nr) { y = fma(c[u], y, g[u]); g[u] = y; }
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				if (j0 + u < Nr) sB[(j0 + u) * FWD_MB + mi] = g[u];
 		}
-#pragma unroll 8
-		for (int j = Nr - 2; j >= 0; --j) {
-			y = fma(-sCp[j * FWD_MB + mi], y, sB[j * FWD_MB + mi]);
-			sB[j * FWD_MB + mi] = y;
+		// backward sweep x_j = y_j - cp_j x_{j+1}
+		for (int j0 = Nr - 2; j0 >= 0; j0 -= 8) {
+			double c[8], g[8];
+#pragma unroll
+			for (int u = 0; u < 8; ++u) {
+				const int j = max(j0 - u, 0);
+				c[u] = -sCp[j * FWD_MB + mi];
+				g[u] = sB[j * FWD_MB + mi];
+			}
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				if (j0 - u >= 0) { y = fma(c[u], y, g[u]); g[u] = y; }
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				if (j0 - u >= 0) sB[(j0 - u) * FWD_MB + mi] = g[u];
 		}
 	}
 	__syncthreads();
@@ -109,11 +148,22 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 		if (mOk) out[(size_t)j * n1 + m] = sB[j * FWD_MB + mi];
 }
 
+__device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc, bool valid)
+{
+	const unsigned int d = (unsigned int)__cvta_generic_to_shared(smemDst);
+	const int bytes = valid ? 8 : 0;                            // src-size 0 -> the 8 bytes are zero-filled
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmemSrc), "r"(bytes));
+}
+
 // Inverse DCT-I as a dense fp64 GEMM: C[M][N] = A[M][K] * B[K][N] (A = alpha, B = cosine matrix).
 // The output is small (M*N ~ 75 k values) and K long, so a CTA owns a 16 x 40 output tile and its 8 warps
-// split K between them: every lane keeps a 4 x 5 register tile (9 operand loads per 20 FMAs), A rows are
-// staged once in shared memory, B is streamed through the read-only path, and the 8 partial tiles are
+// split K between them (warp w takes k = w, w+8, ...): every lane keeps a 4 x 5 register tile (9 operand
+// loads per 20 FMAs), the A rows are staged once in shared memory, and each warp streams its rows of B
+// through a private 4-stage cp.async ring (8 rows = 2.5 KB per stage), so ~60 KB per SM are in flight and
+// the kernel is bound by L2 bandwidth / fp64 issue rather than by load latency. The 8 partial tiles are
 // summed through shared memory at the end.
+constexpr int INV_KS = 8;       // B rows per pipeline stage and warp
+constexpr int INV_ST = 4;       // stages
 __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, const double* __restrict__ B,
 	double* __restrict__ C, int M, int N, int K)
 {
@@ -123,45 +173,62 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 	const int m0 = blockIdx.y * INV_TM, n0 = blockIdx.x * INV_TN;
 	const int kc = K < INV_KC ? K : INV_KC;
 	const int lda = kc | 1;                                     // odd leading dimension: the 4 row groups hit distinct banks
+	double* sA = sm;                                            // [16][lda]
+	double* ring = sm + (size_t)INV_TM * lda + (size_t)warp * INV_ST * INV_KS * INV_TN; // [ST][KS][TN] of this warp
 	double acc[4][5];
 #pragma unroll
 	for (int i = 0; i < 4; ++i)
 #pragma unroll
 		for (int j = 0; j < 5; ++j) acc[i][j] = 0.0;
-	bool colOk[5];
-#pragma unroll
-	for (int j = 0; j < 5; ++j) colOk[j] = n0 + 5 * lb + j < N;
 
 	for (int k0 = 0; k0 < K; k0 += kc) {
 		const int kn = min(kc, K - k0);
+		const int rowsMine = kn > warp ? (kn - warp + 7) / 8 : 0;    // k = warp + 8 i, i < rowsMine
+		const int nStages = (rowsMine + INV_KS - 1) / INV_KS;
+		auto issue = [&](int st) {
+			if (st < nStages) {
+				double* dst = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN;
+#pragma unroll
+				for (int c = 0; c < INV_KS * INV_TN / 32; ++c) {
+					const int e = lane + 32 * c, rr = e / INV_TN, cc = e - rr * INV_TN;
+					const int i = st * INV_KS + rr;
+					const bool valid = i < rowsMine && n0 + cc < N;
+					const double* src = B + (size_t)(k0 + warp + 8 * (valid ? i : 0)) * N + (valid ? n0 + cc : 0);
+					cp_async8(dst + rr * INV_TN + cc, src, valid);
+				}
+			}
+			asm volatile("cp.async.commit_group;\n" ::);
+		};
+#pragma unroll
+		for (int st = 0; st < INV_ST - 1; ++st) issue(st);          // B is in flight while A is staged
 		__syncthreads();
 		for (int e = tid; e < INV_TM * kn; e += 256) {
 			const int r = e / kn, c = e - r * kn;
-			sm[r * lda + c] = (m0 + r < M) ? A[(size_t)(m0 + r) * K + k0 + c] : 0.0;
+			sA[r * lda + c] = (m0 + r < M) ? A[(size_t)(m0 + r) * K + k0 + c] : 0.0;
 		}
 		__syncthreads();
-		const double* a = sm + (4 * la) * lda;
-		// 4 k-steps per iteration: their 20 B loads are issued together so that one L2 round trip feeds 80 FMAs
-		constexpr int U = 4;
-		for (int kb = warp; kb < kn; kb += 8 * U) {
-			double bv[U][5], av[U][4];
+		const double* a = sA + (4 * la) * lda;
+		for (int st = 0; st < nStages; ++st) {
+			issue(st + INV_ST - 1);
+			asm volatile("cp.async.wait_group %0;\n" ::"n"(INV_ST - 1));
+			__syncwarp();
+			const double* bs = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN + 5 * lb;
 #pragma unroll
-			for (int u = 0; u < U; ++u) {
-				const int k = kb + 8 * u;
-				const bool kOk = k < kn;
-				const double* brow = B + (size_t)(k0 + (kOk ? k : 0)) * N + n0 + 5 * lb;
+			for (int rr = 0; rr < INV_KS; ++rr) {
+				const int k = min(warp + 8 * (st * INV_KS + rr), kn - 1);   // rows past the end were zero-filled
+				double bv[5], av[4];
 #pragma unroll
-				for (int j = 0; j < 5; ++j) bv[u][j] = (kOk && colOk[j]) ? __ldg(brow + j) : 0.0;
+				for (int j = 0; j < 5; ++j) bv[j] = bs[rr * INV_TN + j];
 #pragma unroll
-				for (int i = 0; i < 4; ++i) av[u][i] = kOk ? a[i * lda + k] : 0.0;
-			}
-#pragma unroll
-			for (int u = 0; u < U; ++u)
+				for (int i = 0; i < 4; ++i) av[i] = a[i * lda + k];
 #pragma unroll
 				for (int i = 0; i < 4; ++i)
 #pragma unroll
-					for (int j = 0; j < 5; ++j) acc[i][j] = fma(av[u][i], bv[u][j], acc[i][j]);
+					for (int j = 0; j < 5; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+			}
+			__syncwarp();
 		}
+		asm volatile("cp.async.wait_group 0;\n" ::);
 	}
 	__syncthreads();
 	double* red = sm;                                           // [8][16][40]
@@ -368,7 +435,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		k_fwd_thomas<false><<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, 1.0, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
 	}
 	const int kc = n1 < INV_KC ? n1 : INV_KC;
-	size_t smInv = (size_t)INV_TM * (kc | 1) * sizeof(double);
+	size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
 	if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);
 	PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
 	const dim3 gridInv((n1 + INV_TN - 1) / INV_TN, (M + INV_TM - 1) / INV_TM);
