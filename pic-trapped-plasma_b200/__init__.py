@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptp_b200.so")
+LIB_PATH = os.environ.get("PTP_LIB") or os.path.join(_HERE, "libptp_b200.so")  # PTP_LIB: A/B builds of the same ABI
 
 # Source/Constants.hpp:11-16 (values)
 ePos = 1.602176634e-19

@@ -65,6 +65,7 @@ struct ptp_trap {
 	int64_t lastLaunches = 0;
 
 	// operator / direct solver (ptp_solve.cu)
+	double* solverConst = nullptr; // one allocation: dctInv | dctFwd | thInv | thCp (L2-persisting window)
 	double* dctFwd = nullptr;    // [(Nz+1)^2]  FT[k][m] = (2/Nz) w_k w_m cos(pi k m / Nz)
 	double* dctInv = nullptr;    // [(Nz+1)^2]  C[m][k]  = cos(pi m k / Nz)
 	double* thInv = nullptr;     // [Nr][Nz+1]  1 / pivot of the r-tridiagonal of axial mode m

@@ -2,8 +2,11 @@
 // keys of the step, K5 (per-row counting sort by axial cell + compaction) and the diagnostics reductions.
 #include "ptp_internal.h"
 
+#include <limits.h>
+
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 namespace {
 
@@ -255,14 +258,37 @@ int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* 
 	ptp_trap* t = p->trap;
 	PTP_CUDA(cudaSetDevice(t->device));
 	const int Nr = t->Nr;
+	// row histogram + "already bucketed?" test, split over host threads (one pass over r is the only O(n) host work
+	// of a sorted upload; the loaders emit rows in ascending order)
 	std::vector<long long> count(Nr, 0);
-	bool sorted = true;
-	for (int64_t i = 0; i < n; ++i) {
-		const int ri = r[i];
-		if (ri < 0 || ri >= Nr) { ptp_set_error("ptp_plasma_upload: radial index outside [0, Nr)"); return PTP_EINVAL; }
-		++count[ri];
-		if (i && ri < r[i - 1]) sorted = false;
+	bool sorted = true, bad = false;
+	{
+		const int nThreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())), n / 1000000));
+		std::vector<std::vector<long long>> part(nThreads, std::vector<long long>(Nr, 0));
+		std::vector<char> partSorted(nThreads, 1), partBad(nThreads, 0);
+		auto scan = [&](int th) {
+			const int64_t b = n * th / nThreads, e = n * (th + 1) / nThreads;
+			std::vector<long long>& c = part[th];
+			int prev = b > 0 ? r[b - 1] : INT_MIN;
+			for (int64_t i = b; i < e; ++i) {
+				const int ri = r[i];
+				if (ri < 0 || ri >= Nr) { partBad[th] = 1; return; }
+				++c[ri];
+				if (ri < prev) partSorted[th] = 0;
+				prev = ri;
+			}
+		};
+		std::vector<std::thread> pool;
+		for (int th = 1; th < nThreads; ++th) pool.emplace_back(scan, th);
+		scan(0);
+		for (std::thread& th : pool) th.join();
+		for (int th = 0; th < nThreads; ++th) {
+			bad |= partBad[th] != 0;
+			sorted &= partSorted[th] != 0;
+			for (int j = 0; j < Nr; ++j) count[j] += part[th][j];
+		}
 	}
+	if (bad) { ptp_set_error("ptp_plasma_upload: radial index outside [0, Nr)"); return PTP_EINVAL; }
 	std::vector<long long> rowSrc(Nr + 1, 0);
 	p->rowOff.assign(Nr + 1, 0);
 	p->rowLive.assign(Nr, 0);
@@ -271,24 +297,37 @@ int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* 
 		p->rowLive[j] = count[j];
 		p->rowOff[j + 1] = p->rowOff[j] + (count[j] + PTP_ROW_ALIGN - 1) / PTP_ROW_ALIGN * PTP_ROW_ALIGN;
 	}
-	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
-	p->z = p->v = p->zAlt = p->vAlt = nullptr; p->id = p->idAlt = nullptr; p->dRowOff = nullptr;
-	p->cap = p->rowOff[Nr];
+	const long long newCap = p->rowOff[Nr];
+	if (newCap != p->cap) {                                    // same-size reloads keep their buffers
+		cudaFree(p->z); cudaFree(p->v); cudaFree(p->id);
+		p->z = p->v = nullptr; p->id = nullptr;
+	}
+	cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
+	p->zAlt = p->vAlt = nullptr; p->idAlt = nullptr; p->dRowOff = nullptr;
+	p->cap = newCap;
 	p->nUploaded = n;
 	p->nAlive = n;
 	p->macroChargeDensity = macroChargeDensity;
 	const double scale = -macroChargeDensity / 8.8541878128e-12;     // Source/Plasma.cpp:91-92, Source/Constants.hpp:12
-	PTP_CUDA(cudaMemcpy(t->dScale + p->index, &scale, sizeof(double), cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpyAsync(t->dScale + p->index, &scale, sizeof(double), cudaMemcpyHostToDevice, t->stream));
 	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
 	PTP_CUDA(cudaMalloc(&p->dRowOff, (Nr + 1) * sizeof(long long)));
-	PTP_CUDA(cudaMemcpy(p->dRowOff, p->rowOff.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpyAsync(p->dRowOff, p->rowOff.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));                  // `scale` is a stack variable
 	if (p->cap > 0) {
-		PTP_CUDA(cudaMalloc(&p->z, p->cap * sizeof(double)));
-		PTP_CUDA(cudaMalloc(&p->v, p->cap * sizeof(double)));
-		PTP_CUDA(cudaMalloc(&p->id, p->cap * sizeof(long long)));
-		PTP_CUDA(cudaMemsetAsync(p->z, 0xFF, p->cap * sizeof(double), t->stream));   // all-ones = NaN = empty slot
-		PTP_CUDA(cudaMemsetAsync(p->v, 0, p->cap * sizeof(double), t->stream));
-		PTP_CUDA(cudaMemsetAsync(p->id, 0xFF, p->cap * sizeof(long long), t->stream));
+		if (!p->z) {
+			PTP_CUDA(cudaMalloc(&p->z, p->cap * sizeof(double)));
+			PTP_CUDA(cudaMalloc(&p->v, p->cap * sizeof(double)));
+			PTP_CUDA(cudaMalloc(&p->id, p->cap * sizeof(long long)));
+		}
+		// only the padding at the end of every bucket needs the empty-slot pattern (all-ones = NaN / id -1)
+		for (int j = 0; j < Nr; ++j) {
+			const long long padBegin = p->rowOff[j] + count[j], padLen = p->rowOff[j + 1] - padBegin;
+			if (padLen <= 0) continue;
+			PTP_CUDA(cudaMemsetAsync(p->z + padBegin, 0xFF, padLen * sizeof(double), t->stream));
+			PTP_CUDA(cudaMemsetAsync(p->v + padBegin, 0, padLen * sizeof(double), t->stream));
+			PTP_CUDA(cudaMemsetAsync(p->id + padBegin, 0xFF, padLen * sizeof(long long), t->stream));
+		}
 		if (sorted) {
 			// loaders emit rows in ascending order (Source/Plasma.cpp:510-526): each bucket is one contiguous copy
 			for (int j = 0; j < Nr; ++j) {

@@ -105,6 +105,16 @@ __device__ __forceinline__ void cells_of(const double (&z)[R], const bool (&live
 	}
 }
 
+// Ring data is touched exactly once per step: evict-first loads / stores keep it from displacing the grids and
+// solver constants that the next solve needs from L2.
+#ifndef PTP_NO_STREAM
+__device__ __forceinline__ double2 ld_ring(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_ring(double2* p, double2 v) { __stcs(p, v); }
+#else
+__device__ __forceinline__ double2 ld_ring(const double2* p) { return *p; }
+__device__ __forceinline__ void st_ring(double2* p, double2 v) { *p = v; }
+#endif
+
 template <typename T> __device__ __forceinline__ T warp_sum(T x)
 {
 #pragma unroll
@@ -165,10 +175,10 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		{
 			const long long p0 = (seg.begin >> 1) + tid;
 #pragma unroll
-			for (int j = 0; j < NV; ++j) zzN[j] = z2[p0 + (long long)j * T];
+			for (int j = 0; j < NV; ++j) zzN[j] = ld_ring(z2 + p0 + (long long)j * T);
 			if (PUSH) {
 #pragma unroll
-				for (int j = 0; j < NV; ++j) vvN[j] = v2[p0 + (long long)j * T];
+				for (int j = 0; j < NV; ++j) vvN[j] = ld_ring(v2 + p0 + (long long)j * T);
 			}
 		}
 		for (long long t0 = seg.begin; t0 < seg.end; t0 += tile) {
@@ -182,10 +192,10 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			if (t0 + tile < seg.end) {               // next tile's loads are in flight while this one is processed
 				const long long pn = p0 + (tile >> 1);
 #pragma unroll
-				for (int j = 0; j < NV; ++j) zzN[j] = z2[pn + (long long)j * T];
+				for (int j = 0; j < NV; ++j) zzN[j] = ld_ring(z2 + pn + (long long)j * T);
 				if (PUSH) {
 #pragma unroll
-					for (int j = 0; j < NV; ++j) vvN[j] = v2[pn + (long long)j * T];
+					for (int j = 0; j < NV; ++j) vvN[j] = ld_ring(v2 + pn + (long long)j * T);
 				}
 			}
 
@@ -284,8 +294,8 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 #pragma unroll
 				for (int j = 0; j < NV; ++j)
 					if (liveIn[j]) {
-						z2w[p0 + (long long)j * T] = make_double2(z[2 * j], z[2 * j + 1]);
-						v2w[p0 + (long long)j * T] = make_double2(v[2 * j], v[2 * j + 1]);
+						st_ring(z2w + p0 + (long long)j * T, make_double2(z[2 * j], z[2 * j + 1]));
+						st_ring(v2w + p0 + (long long)j * T, make_double2(v[2 * j], v[2 * j + 1]));
 					}
 			}
 		}

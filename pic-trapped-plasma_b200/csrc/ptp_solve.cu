@@ -20,11 +20,11 @@
 
 #include <limits.h>
 
+#include <algorithm>
 #include <cmath>
 
 namespace {
 
-constexpr int FWD_MB = 16;      // axial modes per CTA of the forward kernel
 constexpr int INV_TM = 16;      // output rows (radial nodes) per CTA of the inverse kernel
 constexpr int INV_TN = 40;      // output columns (axial nodes) per CTA
 constexpr int INV_KC = 1024;    // modes staged in shared memory per chunk
@@ -38,13 +38,17 @@ __global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ r
 	if (row >= rows) return;
 	const unsigned long long* w = reinterpret_cast<const unsigned long long*>(rho) + (size_t)row * n1;
 	int lo = INT_MAX, hi = INT_MIN;
-	for (int k0 = lane; k0 < n1; k0 += 32 * 8) {                // 8 independent loads in flight per lane
+	for (int k0 = lane; k0 < n1; k0 += 32 * 8) {                // 8 independent, unconditional loads in flight per lane
 		unsigned long long word[8];
 #pragma unroll
-		for (int u = 0; u < 8; ++u) word[u] = (k0 + 32 * u < n1) ? w[k0 + 32 * u] : 0ULL;
+		for (int u = 0; u < 8; ++u) word[u] = w[min(k0 + 32 * u, n1 - 1)];
 #pragma unroll
-		for (int u = 0; u < 8; ++u)
-			if (word[u] << 1) { lo = min(lo, k0 + 32 * u); hi = max(hi, k0 + 32 * u); } // any bit but the sign: non-zero as double and as int64
+		for (int u = 0; u < 8; ++u) {
+			const int k = k0 + 32 * u;
+			const bool nz = (k < n1) && ((word[u] << 1) != 0ULL);   // any bit but the sign: non-zero as double and as int64
+			lo = nz ? min(lo, k) : lo;
+			hi = nz ? max(hi, k) : hi;
+		}
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -53,56 +57,99 @@ __global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ r
 	if (lane == 0) bounds[row] = make_int2(lo, hi);
 }
 
+__device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc, bool valid)
+{
+	const unsigned int d = (unsigned int)__cvta_generic_to_shared(smemDst);
+	const int bytes = valid ? 8 : 0;                            // src-size 0 -> the 8 bytes are zero-filled
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmemSrc), "r"(bytes));
+}
+
 // Forward half of the solve for FWD_MB axial modes per CTA and one species per blockIdx.y:
 //   beta[j][m] = sum_k (scale * rho[j][k]) * FT[k][m]      (DCT-I with its weights, only over each row's non-zero range)
 //   alpha[.][m] = (T_r + lambda_m I)^-1 beta[.][m]          (Thomas in r, factors precomputed)
 // alpha is written to spec[s][j][m].
-template <bool A_FIXED>
+constexpr int FWD_KB = 64;      // axial nodes of the deposit staged per chunk
+constexpr int FWD_RP = 128;     // deposit rows handled per pass
+template <bool A_FIXED, int FWD_MB>
 __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ rho, const int2* __restrict__ bounds,
 	const double* __restrict__ FT, const double* __restrict__ rowScale, double fixedInv,
 	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thLower,
 	double* __restrict__ spec, int Nr, int n1)
 {
-	extern __shared__ double sB[];                              // [Nr][FWD_MB] beta -> alpha, then the two factor tiles
+	// Everything global is brought in with cp.async in a few large waves (the solve runs right after the push kernel
+	// has streamed gigabytes through L2, so every serial round trip costs a DRAM latency).
+	extern __shared__ double sB[];                              // [Nr][FWD_MB] beta -> alpha
 	double* sInv = sB + (size_t)Nr * FWD_MB;                    // [Nr][FWD_MB] 1/pivot
 	double* sCp = sInv + (size_t)Nr * FWD_MB;                   // [Nr][FWD_MB] upper/pivot
+	double* sFT = sCp + (size_t)Nr * FWD_MB;                    // [FWD_KB][FWD_MB] chunk of the forward matrix
+	double* sRho = sFT + FWD_KB * FWD_MB;                       // [FWD_RP][FWD_KB] chunk of the deposit rows of this pass
+	int2* sBd = reinterpret_cast<int2*>(sRho + (size_t)FWD_RP * FWD_KB); // [Nr] non-zero range per row
+	__shared__ int sLo, sHi;
 	const int tid = threadIdx.x, mi = tid % FWD_MB, slot = tid / FWD_MB;
-	const int m = blockIdx.x * FWD_MB + mi;
+	const int mBase = blockIdx.x * FWD_MB;
+	const int m = mBase + mi;
 	const int s = blockIdx.y;
 	const bool mOk = m < n1;
 	const double scale = (rowScale ? rowScale[s] : 1.0) * (A_FIXED ? fixedInv : 1.0);
 	const double* b = rho + (size_t)s * Nr * n1;
-	// Thomas factors of this CTA's modes: staged once (coalesced, all loads independent) so that the serial
-	// sweeps below only touch shared memory
+	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; }
 	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
-		sInv[j * FWD_MB + mi] = mOk ? thInv[(size_t)j * n1 + m] : 1.0;
-		sCp[j * FWD_MB + mi] = mOk ? thCp[(size_t)j * n1 + m] : 0.0;
+		cp_async8(&sInv[j * FWD_MB + mi], thInv + (size_t)j * n1 + (mOk ? m : 0), mOk);
+		cp_async8(&sCp[j * FWD_MB + mi], thCp + (size_t)j * n1 + (mOk ? m : 0), mOk);
+		sB[j * FWD_MB + mi] = 0.0;
 	}
-	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
+	asm volatile("cp.async.commit_group;\n" ::);
+	__syncthreads();
+	for (int j = tid; j < Nr; j += 256) {
 		const int2 bd = bounds[s * Nr + j];
-		double acc = 0.0;
-		if (mOk && bd.x <= bd.y) {
-			const double* row = b + (size_t)j * n1;
-			const double* f = FT + (size_t)bd.x * n1 + m;
-			int k = bd.x;
-			for (; k + 3 <= bd.y; k += 4, f += 4 * (size_t)n1) {   // 8 independent loads per trip
-				double val[4], fv[4];
-#pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					val[u] = A_FIXED ? (double)reinterpret_cast<const long long*>(row)[k + u] : row[k + u];
-					fv[u] = __ldg(f + u * (size_t)n1);
-				}
-#pragma unroll
-				for (int u = 0; u < 4; ++u) acc = fma(val[u], fv[u], acc);
-			}
-			for (; k <= bd.y; ++k, f += n1) {
-				const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(row)[k] : row[k];
-				acc = fma(val, __ldg(f), acc);
-			}
-			acc *= scale;
-		}
-		sB[j * FWD_MB + mi] = acc;
+		sBd[j] = bd;
+		if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); }
 	}
+	__syncthreads();
+	const int kLo = sLo, kHi = sHi;
+	constexpr int SLOTS = 256 / FWD_MB, U = FWD_RP / SLOTS;     // this thread's rows of a pass: jp + slot + u * SLOTS
+	double acc[U];
+	for (int jp = 0; jp < Nr; jp += FWD_RP) {
+#pragma unroll
+		for (int u = 0; u < U; ++u) acc[u] = 0.0;
+		for (int k0 = kLo; k0 <= kHi; k0 += FWD_KB) {
+			const int kn = min(FWD_KB, kHi - k0 + 1);
+			__syncthreads();
+			for (int e = tid; e < kn * FWD_MB; e += 256) {
+				const int kk = e / FWD_MB, mm = e % FWD_MB;
+				const bool ok = mBase + mm < n1;
+				cp_async8(&sFT[e], FT + (size_t)(k0 + kk) * n1 + (ok ? mBase + mm : 0), ok);
+			}
+			for (int jj = 0; jj < FWD_RP && jp + jj < Nr; ++jj) {
+				const int j = jp + jj;
+				const int2 bd = sBd[j];
+				if (bd.x > bd.y || bd.y < k0 || bd.x >= k0 + kn) continue;      // uniform per CTA
+				for (int kk = tid; kk < kn; kk += 256) cp_async8(&sRho[(size_t)jj * FWD_KB + kk], b + (size_t)j * n1 + k0 + kk, true);
+			}
+			asm volatile("cp.async.commit_group;\n" ::);
+			asm volatile("cp.async.wait_group 0;\n" ::);
+			__syncthreads();
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int jj = slot + u * SLOTS, j = jp + jj;
+				if (j >= Nr) continue;
+				const int2 bd = sBd[j];
+				const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
+				double t = acc[u];
+				for (int kk = a0; kk <= a1; ++kk) {
+					const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(sRho)[(size_t)jj * FWD_KB + kk] : sRho[(size_t)jj * FWD_KB + kk];
+					t = fma(val, sFT[kk * FWD_MB + mi], t);
+				}
+				acc[u] = t;
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const int j = jp + slot + u * SLOTS;
+			if (j < Nr) sB[j * FWD_MB + mi] = acc[u] * scale;
+		}
+	}
+	asm volatile("cp.async.wait_group 0;\n" ::);
 	__syncthreads();
 	if (tid < FWD_MB && mOk) {
 		// forward sweep y_j = g_j - (l_j inv_j) y_{j-1}; the coefficients of 8 rows are prepared off the chain, so the
@@ -146,13 +193,6 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	double* out = spec + (size_t)s * Nr * n1;
 	for (int j = slot; j < Nr; j += 256 / FWD_MB)
 		if (mOk) out[(size_t)j * n1 + m] = sB[j * FWD_MB + mi];
-}
-
-__device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc, bool valid)
-{
-	const unsigned int d = (unsigned int)__cvta_generic_to_shared(smemDst);
-	const int bytes = valid ? 8 : 0;                            // src-size 0 -> the 8 bytes are zero-filled
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmemSrc), "r"(bytes));
 }
 
 // Inverse DCT-I as a dense fp64 GEMM: C[M][N] = A[M][K] * B[K][N] (A = alpha, B = cosine matrix).
@@ -202,10 +242,13 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 #pragma unroll
 		for (int st = 0; st < INV_ST - 1; ++st) issue(st);          // B is in flight while A is staged
 		__syncthreads();
-		for (int e = tid; e < INV_TM * kn; e += 256) {
+		for (int e = tid; e < INV_TM * kn; e += 256) {              // A tile: all copies in flight at once
 			const int r = e / kn, c = e - r * kn;
-			sA[r * lda + c] = (m0 + r < M) ? A[(size_t)(m0 + r) * K + k0 + c] : 0.0;
+			const bool ok = m0 + r < M;
+			cp_async8(&sA[r * lda + c], A + (size_t)(ok ? m0 + r : 0) * K + k0 + c, ok);
 		}
+		asm volatile("cp.async.commit_group;\n" ::);
+		asm volatile("cp.async.wait_group 0;\n" ::);
 		__syncthreads();
 		const double* a = sA + (4 * la) * lda;
 		for (int st = 0; st < nStages; ++st) {
@@ -389,10 +432,31 @@ int ptp_solver_build(ptp_trap* t)
 		}
 	}
 	const size_t nn = (size_t)n1 * n1 * sizeof(double), gg = (size_t)Nr * n1 * sizeof(double);
-	PTP_CUDA(cudaMalloc(&t->dctFwd, nn));
-	PTP_CUDA(cudaMalloc(&t->dctInv, nn));
-	PTP_CUDA(cudaMalloc(&t->thInv, gg));
-	PTP_CUDA(cudaMalloc(&t->thCp, gg));
+	// one allocation for all solver constants, so that a single L2 access-policy window can keep them resident
+	// while the push kernel streams the ring arrays through L2 between two solves
+	const size_t constBytes = 2 * nn + 2 * gg;
+	PTP_CUDA(cudaMalloc(&t->solverConst, constBytes));
+	t->dctInv = t->solverConst;
+	t->dctFwd = t->dctInv + (size_t)n1 * n1;
+	t->thInv = t->dctFwd + (size_t)n1 * n1;
+	t->thCp = t->thInv + (size_t)Nr * n1;
+	{
+		cudaDeviceProp prop;
+		PTP_CUDA(cudaGetDeviceProperties(&prop, t->device));
+		if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+			const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, constBytes);
+			size_t current = 0;
+			cudaDeviceGetLimit(&current, cudaLimitPersistingL2CacheSize);
+			if (current < carve) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+			cudaStreamAttrValue attr{};
+			attr.accessPolicyWindow.base_ptr = t->solverConst;
+			attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)prop.accessPolicyMaxWindowSize, constBytes);
+			attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+			attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			if (cudaStreamSetAttribute(t->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+		}
+	}
 	PTP_CUDA(cudaMalloc(&t->thLower, Nr * sizeof(double)));
 	PTP_CUDA(cudaMalloc(&t->stLower, Nr * sizeof(double)));
 	PTP_CUDA(cudaMalloc(&t->stUpper, Nr * sizeof(double)));
@@ -408,7 +472,7 @@ int ptp_solver_build(ptp_trap* t)
 
 void ptp_solver_free(ptp_trap* t)
 {
-	cudaFree(t->dctFwd); cudaFree(t->dctInv); cudaFree(t->thInv); cudaFree(t->thCp); cudaFree(t->rowBounds);
+	cudaFree(t->solverConst); cudaFree(t->rowBounds);
 	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
 }
 
@@ -424,16 +488,23 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		t->rowBoundsCap = M;
 	}
 	k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds);
-	const size_t smFwd = (size_t)3 * Nr * FWD_MB * sizeof(double);
-	const dim3 gridFwd((n1 + FWD_MB - 1) / FWD_MB, nS);
-	if (rhoIsFixed) {
-		if (smFwd > 48 * 1024) PTP_CUDA(cudaFuncSetAttribute(k_fwd_thomas<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd));
-		k_fwd_thomas<true><<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, fixedInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
-	}
-	else {
-		if (smFwd > 48 * 1024) PTP_CUDA(cudaFuncSetAttribute(k_fwd_thomas<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd));
-		k_fwd_thomas<false><<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, 1.0, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
-	}
+	auto smFwdBytes = [&](int mb) {
+		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB) * sizeof(double) + (size_t)Nr * sizeof(int2);
+	};
+	const int mb = smFwdBytes(16) <= t->smemMax ? 16 : 4;       // fewer modes per CTA when the radial tiles get large
+	const size_t smFwd = smFwdBytes(mb);
+	if (smFwd > t->smemMax) { ptp_set_error("direct solver: Nr too large for the shared-memory tiles of this build"); return PTP_EINVAL; }
+	const dim3 gridFwd((n1 + mb - 1) / mb, nS);
+	auto launchFwd = [&](auto kern, double fInv) -> cudaError_t {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd);
+		if (e != cudaSuccess) return e;
+		kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
+		return cudaGetLastError();
+	};
+	cudaError_t ef;
+	if (rhoIsFixed) ef = mb == 16 ? launchFwd(k_fwd_thomas<true, 16>, fixedInv) : launchFwd(k_fwd_thomas<true, 4>, fixedInv);
+	else ef = mb == 16 ? launchFwd(k_fwd_thomas<false, 16>, 1.0) : launchFwd(k_fwd_thomas<false, 4>, 1.0);
+	if (ef != cudaSuccess) return ptp_cuda_fail(ef, "k_fwd_thomas launch", __FILE__, __LINE__);
 	const int kc = n1 < INV_KC ? n1 : INV_KC;
 	size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
 	if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);

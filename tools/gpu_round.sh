@@ -18,11 +18,7 @@ except Exception as e: print('  parse fail', e)
 "
 }
 run c2 --workload c2 --steps 200 --warmup 5 --no-cpu-baseline
-run c4_default --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
-run c4_t512_w44_r4 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --rings 4
-run c4_t256_w64_r8 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --threads 256 --window 64
-run c4_t256_w64_r4 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --threads 256 --window 64 --rings 4
-run c4_fixed_t512_w56_r8 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 56
-run c4_fixed_t512_w56_r4 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 56 --rings 4
-run c4_t512_w32_r8 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --window 32
+run c4_default --steps 100 --warmup 3 --no-cpu-baseline
+PTP_LIB=$PWD/build/ab/libptp_nostream.so run c4_nostream --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
+run c4_fixed_w56 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 56
 run c3 --workload c3 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
