@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=0)
+    ap.add_argument("--allreduce", default="peer", choices=["nccl", "peer"], help="exchange step for N > 1")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -163,6 +164,7 @@ def main():
     species, total, desc = WORKLOADS[args.workload]
     config = {"workload": "%s: %s" % (args.workload, desc), "grid": "Nz=585 Nr=128", "dt_s": DT, "species": len(species),
               "rings_total": total, "deposit": args.deposit,
+              "exchange": ("peer-memory push fused into the deposit flush + flag barrier" if args.allreduce == "peer" else "NCCL all-reduce") if world > 1 else "none (1 GPU)",
               "l2": "ring arrays %d MB per GPU vs 126 MB L2 (no flush needed)" % (total // world * 16 // 2**20) if total // world * 16 > 200e6
               else "ring arrays %d MB per GPU: L2-resident, NOT an HBM-bound measurement" % (total // world * 16 // 2**20)}
 
@@ -213,6 +215,7 @@ def main():
         uid = [ptp.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         trap.comm_init(uid[0], world, rank)
+        trap.set_allreduce(1 if args.allreduce == "peer" else 0)
     trap.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64 if args.deposit == "fixed" else ptp.PTP_DEPOSIT_FP64)
     if args.threads or args.window or args.ctas >= 0 or args.rings:
         trap.set_tuning(args.threads, args.window, args.ctas, args.rings)

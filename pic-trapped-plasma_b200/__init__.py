@@ -259,6 +259,10 @@ class PenningTrap:
     def set_sort_interval(self, interval):
         _check(lib().ptp_trap_set_sort_interval(self.h, interval))
 
+    def set_allreduce(self, kind):
+        """0: NCCL all-reduce of the deposit grids; 1: peer-memory mode (the push kernel adds into every rank's grid)."""
+        _check(lib().ptp_trap_set_allreduce(self.h, kind))
+
     def comm_init(self, unique_id, n_ranks, rank):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         _check(lib().ptp_trap_comm_init(self.h, C.cast(buf, C.c_void_p), n_ranks, rank))

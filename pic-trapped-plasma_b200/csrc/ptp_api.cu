@@ -27,11 +27,11 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	while (cap < need) cap *= 2;
 	const size_t bytes = (size_t)cap * t->G * sizeof(double), old = (size_t)t->capS * t->G * sizeof(double);
 	double *rho = nullptr, *phi = nullptr, *spec = nullptr, *scale = nullptr;
-	PTP_CUDA(cudaMalloc(&rho, bytes));
+	PTP_CUDA(cudaMalloc(&rho, 2 * bytes + 64 * sizeof(unsigned long long)));
 	PTP_CUDA(cudaMalloc(&phi, bytes));
 	PTP_CUDA(cudaMalloc(&spec, bytes));
 	PTP_CUDA(cudaMalloc(&scale, cap * sizeof(double)));
-	PTP_CUDA(cudaMemset(rho, 0, bytes));
+	PTP_CUDA(cudaMemset(rho, 0, 2 * bytes + 64 * sizeof(unsigned long long)));
 	PTP_CUDA(cudaMemset(phi, 0, bytes));
 	PTP_CUDA(cudaMemset(scale, 0, cap * sizeof(double)));
 	if (t->capS) {
@@ -39,8 +39,9 @@ int ensure_species_capacity(ptp_trap* t, int need)
 		PTP_CUDA(cudaMemcpy(phi, t->phiSelfAll, old, cudaMemcpyDeviceToDevice));
 		PTP_CUDA(cudaMemcpy(scale, t->dScale, t->capS * sizeof(double), cudaMemcpyDeviceToDevice));
 	}
-	cudaFree(t->rhoAll); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
-	t->rhoAll = rho; t->phiSelfAll = phi; t->specAll = spec; t->dScale = scale;
+	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
+	t->rhoStore = rho; t->rhoParity = 0; t->rhoAll = rho; t->peerStale = true;
+	t->phiSelfAll = phi; t->specAll = spec; t->dScale = scale;
 	t->capS = cap;
 	return PTP_OK;
 }
@@ -58,8 +59,16 @@ int solve_species(ptp_trap* t, int first, int count)
 int push_deposit_all(ptp_trap* t, double dt)
 {
 	const int nS = (int)t->plasmas.size();
+	const size_t span = (size_t)t->capS * t->G;
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
-	PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, (size_t)nS * t->G * sizeof(double), t->stream));
+	if (ptp_peer_mode(t)) {
+		// this step's target parity was zeroed one step ago (or at the start of the call); the other one - last step's
+		// sums, already consumed by its solve - is zeroed now, ahead of the step that will push into it
+		t->rhoParity ^= 1;
+		t->rhoAll = t->rhoStore + (size_t)t->rhoParity * span;
+		PTP_CUDA(cudaMemsetAsync(t->rhoStore + (size_t)(t->rhoParity ^ 1) * span, 0, span * sizeof(double), t->stream));
+	}
+	else PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, (size_t)nS * t->G * sizeof(double), t->stream));
 	for (ptp_plasma* p : t->plasmas) {
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 		PTP_TRY(ptp_push_launch(t, p, dt, true));
@@ -67,10 +76,23 @@ int push_deposit_all(ptp_trap* t, double dt)
 	return PTP_OK;
 }
 
+// The exchange step: either an NCCL all-reduce of the rank-local grids, or - in peer-memory mode, where the push kernel has
+// already added every rank's deposits into every rank's grid - just the barrier that says all of them have landed.
 int reduce_rho(ptp_trap* t)
 {
 	const int nS = (int)t->plasmas.size();
+	if (ptp_peer_mode(t)) return ptp_peer_barrier(t);
 	return ptp_comm_allreduce(t, t->rhoAll, (size_t)nS * t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
+}
+
+// Peer-memory mode, once per ptp_trap_step / ptp_trap_push_deposit call: map the peers, start from two clean parities.
+int begin_exchange(ptp_trap* t)
+{
+	if (!ptp_peer_mode(t)) return PTP_OK;
+	PTP_TRY(ptp_peer_prepare(t));
+	const size_t span = (size_t)t->capS * t->G;
+	PTP_CUDA(cudaMemsetAsync(t->rhoStore, 0, 2 * span * sizeof(double), t->stream));
+	return ptp_peer_barrier(t);
 }
 
 int solve_all(ptp_trap* t)
@@ -145,7 +167,7 @@ int ptp_trap_destroy(ptp_trap* t)
 	ptp_comm_free(t);
 	ptp_solver_free(t);
 	cudaFree(t->phiTrap); cudaFree(t->eNodes); cudaFree(t->tmpA); cudaFree(t->tmpB); cudaFree(t->tmpSpec);
-	cudaFree(t->rhoAll); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
+	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
 	for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : t->evPool) cudaEventDestroy(ev);
 	if (t->stream) cudaStreamDestroy(t->stream);
@@ -229,6 +251,7 @@ int ptp_trap_push_deposit(ptp_trap* t, double dt)
 	if (!t) { ptp_set_error("ptp_trap_push_deposit: null trap"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
+	PTP_TRY(begin_exchange(t));
 	PTP_TRY(push_deposit_all(t, dt));
 	PTP_TRY(reduce_rho(t));
 	return PTP_OK;
@@ -255,6 +278,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 		t->evPool.push_back(e);
 	}
 	t->evSteps = timed;
+	PTP_TRY(begin_exchange(t));
 	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
 	for (int s = 0; s < nSteps; ++s) {
 		cudaEvent_t* e = s < timed ? &t->evPool[4 * s] : nullptr;

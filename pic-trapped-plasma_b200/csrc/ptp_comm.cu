@@ -13,6 +13,11 @@
 struct PtpComm {
 	ncclComm_t comm = nullptr;
 	int nRanks = 1, rank = 0;
+	// peer-memory mode: every rank's rhoStore mapped into this process (own entry = own pointer)
+	double* peerBase[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool mapped = false;
+	size_t spanDoubles = 0;          // capS * G at mapping time
+	unsigned long long epoch = 0;    // barrier generation; all ranks advance it in lock-step
 };
 
 namespace {
@@ -22,6 +27,7 @@ struct NcclApi {
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	const char* (*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
 } g_nccl;
@@ -39,8 +45,9 @@ bool load_nccl()
 	g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.handle, "ncclCommInitRank");
 	g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
 	g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.handle, "ncclAllReduce");
+	g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.handle, "ncclAllGather");
 	g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
-	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.GetErrorString;
+	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.AllGather && g_nccl.GetErrorString;
 	if (!g_nccl.ok) ptp_set_error("NCCL library lacks required symbols");
 	return g_nccl.ok;
 }
@@ -50,9 +57,106 @@ int nccl_fail(ncclResult_t r, const char* what)
 	ptp_set_error(std::string(what) + ": " + g_nccl.GetErrorString(r));
 	return PTP_ECOMM;
 }
+
+// Flag barrier over peer memory: rank r stores the epoch into slot r of every rank's flag array (release, system scope),
+// then spins on its own array until every slot has reached the epoch (acquire). Launched after the push kernel in stream
+// order, so this rank's remote adds are complete before its flag can be seen.
+struct PeerFlags { unsigned long long* f[8]; };
+__global__ void k_peer_barrier(PeerFlags flags, int rank, int nRanks, unsigned long long epoch)
+{
+	const int p = threadIdx.x;
+	if (p < nRanks) {
+		__threadfence_system();
+		unsigned long long* remote = flags.f[p] + rank;
+		asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(remote), "l"(epoch) : "memory");
+		const unsigned long long* mine = flags.f[rank] + p;
+		unsigned long long seen;
+		do {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(seen) : "l"(mine) : "memory");
+		} while (seen < epoch);
+	}
+	__syncthreads();
+	__threadfence_system();
+}
+
+void unmap_peers(ptp_trap* t)
+{
+	PtpComm* c = t->comm;
+	if (!c || !c->mapped) return;
+	for (int r = 0; r < c->nRanks; ++r)
+		if (r != c->rank && c->peerBase[r]) cudaIpcCloseMemHandle(c->peerBase[r]);
+	for (auto& b : c->peerBase) b = nullptr;
+	c->mapped = false;
+}
 } // namespace
 
 int ptp_comm_size(ptp_trap* t) { return t->comm ? t->comm->nRanks : 1; }
+int ptp_comm_rank(ptp_trap* t) { return t->comm ? t->comm->rank : 0; }
+
+bool ptp_peer_mode(ptp_trap* t) { return t->comm && t->comm->nRanks > 1 && t->allreduceKind == 1; }
+
+// Collective over all ranks: exchange the CUDA IPC handles of the rhoStore allocations (through an NCCL all-gather)
+// and map every peer's allocation. Needed once, and again whenever a rank had to reallocate (more species).
+int ptp_peer_prepare(ptp_trap* t)
+{
+	PtpComm* c = t->comm;
+	// the decision to remap must be collective too: any rank stale -> everybody remaps
+	int* dFlag = nullptr;
+	PTP_CUDA(cudaMalloc(&dFlag, sizeof(int)));
+	int stale = (t->peerStale || !c->mapped) ? 1 : 0;
+	PTP_CUDA(cudaMemcpyAsync(dFlag, &stale, sizeof(int), cudaMemcpyHostToDevice, t->stream));
+	ncclResult_t r = g_nccl.AllReduce(dFlag, dFlag, 1, ncclInt32, ncclMax, c->comm, t->stream);
+	if (r != ncclSuccess) { cudaFree(dFlag); return nccl_fail(r, "ncclAllReduce(stale)"); }
+	PTP_CUDA(cudaMemcpyAsync(&stale, dFlag, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dFlag);
+	if (!stale) return PTP_OK;
+	if (c->nRanks > 8) { ptp_set_error("peer-memory mode supports at most 8 ranks"); return PTP_EINVAL; }
+	unmap_peers(t);
+	cudaIpcMemHandle_t mine;
+	PTP_CUDA(cudaIpcGetMemHandle(&mine, t->rhoStore));
+	unsigned char* dH = nullptr;
+	const size_t hs = sizeof(cudaIpcMemHandle_t);
+	PTP_CUDA(cudaMalloc(&dH, hs * c->nRanks));
+	PTP_CUDA(cudaMemcpyAsync(dH + hs * c->rank, &mine, hs, cudaMemcpyHostToDevice, t->stream));
+	r = g_nccl.AllGather(dH + hs * c->rank, dH, hs, ncclChar, c->comm, t->stream);
+	if (r != ncclSuccess) { cudaFree(dH); return nccl_fail(r, "ncclAllGather(ipc handles)"); }
+	std::vector<cudaIpcMemHandle_t> all(c->nRanks);
+	PTP_CUDA(cudaMemcpyAsync(all.data(), dH, hs * c->nRanks, cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dH);
+	for (int p = 0; p < c->nRanks; ++p) {
+		if (p == c->rank) { c->peerBase[p] = t->rhoStore; continue; }
+		void* ptr = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) return ptp_cuda_fail(e, "cudaIpcOpenMemHandle (peer-memory mode needs P2P-capable GPUs)", __FILE__, __LINE__);
+		c->peerBase[p] = static_cast<double*>(ptr);
+	}
+	c->mapped = true;
+	c->spanDoubles = (size_t)t->capS * t->G;
+	t->peerStale = false;
+	return PTP_OK;
+}
+
+void ptp_peer_targets(ptp_trap* t, int parity, size_t offsetDoubles, void** out, int* n)
+{
+	PtpComm* c = t->comm;
+	*n = c->nRanks;
+	for (int p = 0; p < c->nRanks; ++p) out[p] = c->peerBase[p] + (size_t)parity * c->spanDoubles + offsetDoubles;
+}
+
+int ptp_peer_barrier(ptp_trap* t)
+{
+	PtpComm* c = t->comm;
+	PeerFlags f{};
+	for (int p = 0; p < c->nRanks; ++p) f.f[p] = reinterpret_cast<unsigned long long*>(c->peerBase[p] + 2 * c->spanDoubles);
+	++c->epoch;
+	k_peer_barrier<<<1, 32, 0, t->stream>>>(f, c->rank, c->nRanks, c->epoch);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_peer_barrier launch", __FILE__, __LINE__);
+	t->lastLaunches++;
+	return PTP_OK;
+}
 
 int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64)
 {
@@ -65,6 +169,7 @@ int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64)
 void ptp_comm_free(ptp_trap* t)
 {
 	if (t->comm) {
+		unmap_peers(t);
 		if (t->comm->comm && g_nccl.ok) g_nccl.CommDestroy(t->comm->comm);
 		delete t->comm;
 		t->comm = nullptr;
@@ -103,7 +208,7 @@ int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank)
 int ptp_trap_set_allreduce(ptp_trap* t, int kind)
 {
 	if (!t || kind < 0 || kind > 1) { ptp_set_error("ptp_trap_set_allreduce: bad arguments"); return PTP_EINVAL; }
-	if (kind == 1) { ptp_set_error("peer-memory all-reduce not available in this build"); return PTP_EINVAL; }
+	if (kind == 1 && !t->comm) { ptp_set_error("ptp_trap_set_allreduce: peer-memory mode needs ptp_trap_comm_init first"); return PTP_ESTATE; }
 	t->allreduceKind = kind;
 	return PTP_OK;
 }

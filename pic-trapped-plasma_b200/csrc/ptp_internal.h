@@ -85,7 +85,11 @@ struct ptp_trap {
 
 	// per-species grids, contiguous over species so that one all-reduce / one batched solve covers them
 	int capS = 0;
-	double* rhoAll = nullptr;    // [capS][G] deposit accumulators (double weights, or int64 fixed point)
+	double* rhoStore = nullptr;  // one allocation: [2][capS][G] deposit accumulators (two parities) + 64 barrier flags;
+	                             // IPC-shared with the other ranks in peer-memory mode
+	int rhoParity = 0;
+	bool peerStale = true;       // rhoStore was (re)allocated: the peers' mappings must be exchanged again
+	double* rhoAll = nullptr;    // = rhoStore + rhoParity*capS*G: [capS][G] current accumulators (double weights / int64 fixed point)
 	double* phiSelfAll = nullptr;// [capS][G]
 	double* specAll = nullptr;   // [capS][G] spectral workspace
 	double* dScale = nullptr;    // [capS] rho -> RHS factor per species
@@ -144,3 +148,9 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p);
 int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64);
 void ptp_comm_free(ptp_trap* t);
 int ptp_comm_size(ptp_trap* t);
+int ptp_comm_rank(ptp_trap* t);
+// peer-memory mode (ptp_trap_set_allreduce(t, 1)): the push kernel's flush adds into every rank's grid over NVLink
+bool ptp_peer_mode(ptp_trap* t);
+int ptp_peer_prepare(ptp_trap* t);                               // collective: (re)map the peers' rhoStore
+void ptp_peer_targets(ptp_trap* t, int parity, size_t offsetDoubles, void** out, int* n); // grid pointers of all ranks
+int ptp_peer_barrier(ptp_trap* t);                                // all ranks' pushes of this epoch have landed

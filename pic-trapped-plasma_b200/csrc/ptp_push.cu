@@ -47,7 +47,8 @@ struct PushArgs {
 	const PtpSegment* segs;
 	const int* ctaSegBegin;
 	int2* segBounds;
-	void* rho;                  // [G] double weights or int64 fixed point
+	void* rho[8];               // [G] double weights or int64 fixed point: this rank's grid, or every rank's (peer-memory mode)
+	int nRho, pad1;
 	unsigned long long* lost;
 };
 
@@ -279,14 +280,18 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 						if (FIXED) {
 							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 							const unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
-							unsigned long long* g = reinterpret_cast<unsigned long long*>(a.rho) + rowBase + k[i];
-							atomicAdd(g, (1ULL << a.fixedBits) - wq);
-							atomicAdd(g + 1, wq);
+							for (int pr = 0; pr < a.nRho; ++pr) {
+								unsigned long long* g = reinterpret_cast<unsigned long long*>(a.rho[pr]) + rowBase + k[i];
+								atomicAdd(g, (1ULL << a.fixedBits) - wq);
+								atomicAdd(g + 1, wq);
+							}
 						}
 						else {
-							double* g = reinterpret_cast<double*>(a.rho) + rowBase + k[i];
-							atomicAdd(g, __dsub_rn(1.0, w[i]));
-							atomicAdd(g + 1, w[i]);
+							for (int pr = 0; pr < a.nRho; ++pr) {
+								double* g = reinterpret_cast<double*>(a.rho[pr]) + rowBase + k[i];
+								atomicAdd(g, __dsub_rn(1.0, w[i]));
+								atomicAdd(g + 1, w[i]);
+							}
 						}
 					}
 			}
@@ -344,16 +349,19 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 					unsigned long long val = 0;
 					if (i <= hi) val += (redC[i] << a.fixedBits) - redS[i];
 					if (i > lo) val += redS[i - 1];
-					if (val) atomicAdd(reinterpret_cast<unsigned long long*>(a.rho) + rowBase + k0 + i, val);
+					if (val)
+						for (int pr = 0; pr < a.nRho; ++pr) atomicAdd(reinterpret_cast<unsigned long long*>(a.rho[pr]) + rowBase + k0 + i, val);
 				}
 				else {
 					double val = 0.0;
 					if (i <= hi) val = (double)redC[i] - __longlong_as_double((long long)redS[i]);
 					if (i > lo) val += __longlong_as_double((long long)redS[i - 1]);
-					if (val != 0.0) atomicAdd(reinterpret_cast<double*>(a.rho) + rowBase + k0 + i, val);
+					if (val != 0.0)
+						for (int pr = 0; pr < a.nRho; ++pr) atomicAdd(reinterpret_cast<double*>(a.rho[pr]) + rowBase + k0 + i, val);
 				}
 			}
 		}
+		if (a.nRho > 1) __threadfence_system();          // remote adds performed before the grid can be declared complete
 		if (PUSH && tid == 0) {
 			a.segBounds[s] = make_int2(gMin, gMax);      // next step's window (this CTA owns the segment)
 			if (sLost) atomicAdd(a.lost, (unsigned long long)sLost);
@@ -447,7 +455,8 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.segs = p->dSegs;
 	a.ctaSegBegin = p->dCtaSegBegin;
 	a.segBounds = p->dSegBounds;
-	a.rho = t->rhoAll + (size_t)p->index * t->G;
+	a.nRho = 1;
+	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
 	a.lost = p->dLost;
 	return a;
 }
@@ -477,7 +486,8 @@ int ptp_push_configure(ptp_trap* t)
 int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 {
 	if (p->cap == 0 || p->nCta == 0) return PTP_OK;
-	const PushArgs a = make_args(t, p, dt);
+	PushArgs a = make_args(t, p, dt);
+	if (push && ptp_peer_mode(t)) ptp_peer_targets(t, t->rhoParity, (size_t)p->index * t->G, a.rho, &a.nRho);
 	const size_t smem = ptp_push_smem_bytes(t, t->threads, t->window);
 	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64, exact = t->arithMode == PTP_ARITH_EXACT;
 	cudaError_t e;

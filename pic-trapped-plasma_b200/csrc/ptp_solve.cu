@@ -38,12 +38,13 @@ __global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ r
 	if (row >= rows) return;
 	const unsigned long long* w = reinterpret_cast<const unsigned long long*>(rho) + (size_t)row * n1;
 	int lo = INT_MAX, hi = INT_MIN;
-	for (int k0 = lane; k0 < n1; k0 += 32 * 8) {                // 8 independent, unconditional loads in flight per lane
-		unsigned long long word[8];
+	constexpr int UB = 20;                                      // one wave of loads covers a row of up to 640 nodes
+	for (int k0 = lane; k0 < n1; k0 += 32 * UB) {
+		unsigned long long word[UB];
 #pragma unroll
-		for (int u = 0; u < 8; ++u) word[u] = w[min(k0 + 32 * u, n1 - 1)];
+		for (int u = 0; u < UB; ++u) word[u] = w[min(k0 + 32 * u, n1 - 1)];
 #pragma unroll
-		for (int u = 0; u < 8; ++u) {
+		for (int u = 0; u < UB; ++u) {
 			const int k = k0 + 32 * u;
 			const bool nz = (k < n1) && ((word[u] << 1) != 0ULL);   // any bit but the sign: non-zero as double and as int64
 			lo = nz ? min(lo, k) : lo;
@@ -92,12 +93,15 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	const bool mOk = m < n1;
 	const double scale = (rowScale ? rowScale[s] : 1.0) * (A_FIXED ? fixedInv : 1.0);
 	const double* b = rho + (size_t)s * Nr * n1;
+	double* sLower = reinterpret_cast<double*>(sBd + Nr);       // [Nr] sub-diagonal of T_r
+	const int lane = tid & 31, warp = tid >> 5;
 	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; }
 	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
 		cp_async8(&sInv[j * FWD_MB + mi], thInv + (size_t)j * n1 + (mOk ? m : 0), mOk);
 		cp_async8(&sCp[j * FWD_MB + mi], thCp + (size_t)j * n1 + (mOk ? m : 0), mOk);
 		sB[j * FWD_MB + mi] = 0.0;
 	}
+	for (int j = tid; j < Nr; j += 256) cp_async8(&sLower[j], thLower + j, true);
 	asm volatile("cp.async.commit_group;\n" ::);
 	__syncthreads();
 	for (int j = tid; j < Nr; j += 256) {
@@ -120,11 +124,12 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 				const bool ok = mBase + mm < n1;
 				cp_async8(&sFT[e], FT + (size_t)(k0 + kk) * n1 + (ok ? mBase + mm : 0), ok);
 			}
-			for (int jj = 0; jj < FWD_RP && jp + jj < Nr; ++jj) {
+			// deposit rows of this pass: one warp per row, only rows that have data in this chunk
+			for (int jj = warp; jj < FWD_RP && jp + jj < Nr; jj += 8) {
 				const int j = jp + jj;
 				const int2 bd = sBd[j];
-				if (bd.x > bd.y || bd.y < k0 || bd.x >= k0 + kn) continue;      // uniform per CTA
-				for (int kk = tid; kk < kn; kk += 256) cp_async8(&sRho[(size_t)jj * FWD_KB + kk], b + (size_t)j * n1 + k0 + kk, true);
+				if (bd.x > bd.y || bd.y < k0 || bd.x >= k0 + kn) continue;      // uniform per warp
+				for (int kk = lane; kk < kn; kk += 32) cp_async8(&sRho[(size_t)jj * FWD_KB + kk], b + (size_t)j * n1 + k0 + kk, true);
 			}
 			asm volatile("cp.async.commit_group;\n" ::);
 			asm volatile("cp.async.wait_group 0;\n" ::);
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 				const int j = min(j0 + u, Nr - 1);
 				const double inv = sInv[j * FWD_MB + mi];
 				g[u] = sB[j * FWD_MB + mi] * inv;
-				c[u] = -(thLower[j] * inv);
+				c[u] = -(sLower[j] * inv);
 			}
 #pragma unroll
 			for (int u = 0; u < 8; ++u)
@@ -204,6 +209,16 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 // summed through shared memory at the end.
 constexpr int INV_KS = 8;       // B rows per pipeline stage and warp
 constexpr int INV_ST = 4;       // stages
+
+__device__ __forceinline__ void cp_async16(void* smemDst, const void* gmemSrc, bool valid)
+{
+	const unsigned int d = (unsigned int)__cvta_generic_to_shared(smemDst);
+	const int bytes = valid ? 16 : 0;
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmemSrc), "r"(bytes));
+}
+
+// VEC: N is even, so every B row starts 16-byte aligned and the ring is filled with 16-byte copies.
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, const double* __restrict__ B,
 	double* __restrict__ C, int M, int N, int K)
 {
@@ -221,20 +236,33 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 #pragma unroll
 		for (int j = 0; j < 5; ++j) acc[i][j] = 0.0;
 
+	// per-lane copy slots of one stage (KS rows x TN columns), fixed for the whole kernel
+	constexpr int EPL = VEC ? INV_KS * INV_TN / 2 / 32 : INV_KS * INV_TN / 32;   // copies per lane and stage
+	int cpRow[EPL], cpCol[EPL];
+	bool cpOk[EPL];
+#pragma unroll
+	for (int c = 0; c < EPL; ++c) {
+		const int e = lane + 32 * c;
+		cpRow[c] = VEC ? e / (INV_TN / 2) : e / INV_TN;
+		cpCol[c] = VEC ? 2 * (e % (INV_TN / 2)) : e % INV_TN;
+		cpOk[c] = n0 + cpCol[c] < N;
+	}
+
 	for (int k0 = 0; k0 < K; k0 += kc) {
 		const int kn = min(kc, K - k0);
 		const int rowsMine = kn > warp ? (kn - warp + 7) / 8 : 0;    // k = warp + 8 i, i < rowsMine
 		const int nStages = (rowsMine + INV_KS - 1) / INV_KS;
+		const double* bBase = B + (size_t)(k0 + warp) * N + n0;
 		auto issue = [&](int st) {
 			if (st < nStages) {
 				double* dst = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN;
 #pragma unroll
-				for (int c = 0; c < INV_KS * INV_TN / 32; ++c) {
-					const int e = lane + 32 * c, rr = e / INV_TN, cc = e - rr * INV_TN;
-					const int i = st * INV_KS + rr;
-					const bool valid = i < rowsMine && n0 + cc < N;
-					const double* src = B + (size_t)(k0 + warp + 8 * (valid ? i : 0)) * N + (valid ? n0 + cc : 0);
-					cp_async8(dst + rr * INV_TN + cc, src, valid);
+				for (int c = 0; c < EPL; ++c) {
+					const int i = st * INV_KS + cpRow[c];
+					const bool valid = cpOk[c] && i < rowsMine;
+					const double* src = bBase + (valid ? (size_t)8 * i * N + cpCol[c] : 0);
+					if (VEC) cp_async16(dst + cpRow[c] * INV_TN + cpCol[c], src, valid);
+					else cp_async8(dst + cpRow[c] * INV_TN + cpCol[c], src, valid);
 				}
 			}
 			asm volatile("cp.async.commit_group;\n" ::);
@@ -242,10 +270,10 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 #pragma unroll
 		for (int st = 0; st < INV_ST - 1; ++st) issue(st);          // B is in flight while A is staged
 		__syncthreads();
-		for (int e = tid; e < INV_TM * kn; e += 256) {              // A tile: all copies in flight at once
-			const int r = e / kn, c = e - r * kn;
+		for (int r = 0; r < INV_TM; ++r) {                          // A tile: all copies in flight at once
 			const bool ok = m0 + r < M;
-			cp_async8(&sA[r * lda + c], A + (size_t)(ok ? m0 + r : 0) * K + k0 + c, ok);
+			const double* src = A + (size_t)(ok ? m0 + r : 0) * K + k0;
+			for (int c = tid; c < kn; c += 256) cp_async8(&sA[r * lda + c], src + c, ok);
 		}
 		asm volatile("cp.async.commit_group;\n" ::);
 		asm volatile("cp.async.wait_group 0;\n" ::);
@@ -256,9 +284,10 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 			asm volatile("cp.async.wait_group %0;\n" ::"n"(INV_ST - 1));
 			__syncwarp();
 			const double* bs = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN + 5 * lb;
+			const int kFirst = warp + 8 * st * INV_KS;
 #pragma unroll
 			for (int rr = 0; rr < INV_KS; ++rr) {
-				const int k = min(warp + 8 * (st * INV_KS + rr), kn - 1);   // rows past the end were zero-filled
+				const int k = min(kFirst + 8 * rr, kn - 1);             // rows past the end were zero-filled
 				double bv[5], av[4];
 #pragma unroll
 				for (int j = 0; j < 5; ++j) bv[j] = bs[rr * INV_TN + j];
@@ -489,7 +518,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	}
 	k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds);
 	auto smFwdBytes = [&](int mb) {
-		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB) * sizeof(double) + (size_t)Nr * sizeof(int2);
+		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB + (size_t)Nr) * sizeof(double) + (size_t)Nr * sizeof(int2);
 	};
 	const int mb = smFwdBytes(16) <= t->smemMax ? 16 : 4;       // fewer modes per CTA when the radial tiles get large
 	const size_t smFwd = smFwdBytes(mb);
@@ -508,9 +537,15 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	const int kc = n1 < INV_KC ? n1 : INV_KC;
 	size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
 	if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);
-	PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
 	const dim3 gridInv((n1 + INV_TN - 1) / INV_TN, (M + INV_TM - 1) / INV_TM);
-	k_inv_gemm<<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+	if (n1 % 2 == 0) {
+		PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
+		k_inv_gemm<true><<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+	}
+	else {
+		PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
+		k_inv_gemm<false><<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "solver launch", __FILE__, __LINE__);
 	t->lastLaunches += 3;

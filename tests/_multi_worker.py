@@ -25,6 +25,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = ptp.PTP_DEPOSIT_FIXED64 if sys.argv[1] == "fixed" else ptp.PTP_DEPOSIT_FP64
     n_total, steps, dt = int(sys.argv[2]), int(sys.argv[3]), 2e-8 / 35
+    exchange = sys.argv[4] if len(sys.argv) > 4 else "nccl"
     dens = expected_density()
 
     def run(trap, r, z, v, cm):
@@ -40,6 +41,7 @@ def main():
     uid = [ptp.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     trap.comm_init(uid[0], world, rank)
+    trap.set_allreduce(1 if exchange == "peer" else 0)
     r, z, cm, _ = loaders.place_rings(dens, 585, 128, trap.hz, trap.hr, n_total, rank, world)
     # speeds must not depend on the sharding: draw the full row-ordered sequence and take this rank's rings
     r_all, z_all, _, num_at_r = loaders.place_rings(dens, 585, 128, trap.hz, trap.hr, n_total)

@@ -29,23 +29,27 @@ def _free_port():
     return port
 
 
-def _launch(world, mode, n_total, steps):
+def _launch(world, mode, n_total, steps, exchange="nccl"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_multi_worker.py"), mode, str(n_total), str(steps)]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_multi_worker.py"), mode, str(n_total), str(steps), exchange]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-3000:])
     line = [x for x in p.stdout.splitlines() if x.startswith("RESULT ")][-1]
     return json.loads(line[len("RESULT "):])
 
 
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_step_matches_single_gpu(world):
+def test_sharded_step_matches_single_gpu(world, exchange):
+    """exchange = "nccl": all-reduce of rank-local grids; "peer": the push kernel's flush adds into every rank's grid over
+    NVLink (CUDA IPC mappings) and a flag barrier replaces the collective."""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
-    res = _launch(world, "fp64", 2_000_000, 5)
+    res = _launch(world, "fp64", 2_000_000, 5, exchange)
     assert res["count_sharded"] == res["count_single"]
-    assert res["replicas_identical"]
     assert res["rhs_rel"] < 1e-12 and res["phi_rel"] < 1e-10
-    res = _launch(world, "fixed", 2_000_000, 5)
+    if exchange == "nccl":
+        assert res["replicas_identical"]             # fp64 atomics from several ranks land in arbitrary order in peer mode
+    res = _launch(world, "fixed", 2_000_000, 5, exchange)
     assert res["count_sharded"] == res["count_single"]
     assert res["replicas_identical"] and res["rhs_bitwise"] and res["phi_bitwise"]

@@ -15,6 +15,6 @@ timeout 900 python bench.py --gpus 1 --steps 100 --warmup 3 --no-cpu-baseline > 
 for n in 2 4 8; do
   if [ $n -le $N ]; then
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 100 --warmup 3 > gpurun_out/scale_$n.log 2>&1; echo "bench $n rc=$?"; summ gpurun_out/scale_$n.log
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 100 --warmup 3 --deposit fixed --window 56 --no-e2e > gpurun_out/scale_${n}_fixed.log 2>&1; echo "bench $n fixed rc=$?"; summ gpurun_out/scale_${n}_fixed.log
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 100 --warmup 3 --allreduce nccl --no-e2e > gpurun_out/scale_${n}_nccl.log 2>&1; echo "bench $n nccl rc=$?"; summ gpurun_out/scale_${n}_nccl.log
   fi
 done

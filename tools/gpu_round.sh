@@ -18,7 +18,7 @@ except Exception as e: print('  parse fail', e)
 "
 }
 run c2 --workload c2 --steps 200 --warmup 5 --no-cpu-baseline
-run c4_default --steps 100 --warmup 3 --no-cpu-baseline
-PTP_LIB=$PWD/build/ab/libptp_nostream.so run c4_nostream --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
-run c4_fixed_w56 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --deposit fixed --window 56
+run c4_default --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
 run c3 --workload c3 --steps 100 --warmup 3 --no-cpu-baseline --no-e2e
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_c4.csv \
+    python bench.py --steps 8 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_bench_c4.log 2>&1
