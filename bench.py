@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=0)
-    ap.add_argument("--allreduce", default="peer", choices=["nccl", "peer"], help="exchange step for N > 1")
+    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "peer"], help="exchange step for N > 1")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -254,6 +254,12 @@ def main():
     clocks = sampler.stop()
     ms_total = max_over_ranks(float(times[0]))
     ms_push = max_over_ranks(float(times[1]))
+    per_rank = None
+    if world > 1:
+        tt = torch.tensor([float(x) for x in times], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(gathered, tt)
+        per_rank = [[round(float(x) / args.steps, 5) for x in g.tolist()] for g in gathered]
     alive_after = sum_over_ranks(sum(p.getNumMacro() for p in plasmas))
     ring_steps = 0.5 * (alive_before + alive_after) * args.steps
     value = ring_steps / (ms_total * 1e-3)
@@ -311,6 +317,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "phases_ms_per_step": {"push_deposit": ms_push / args.steps, "allreduce": float(times[2]) / args.steps,
                                        "solve_node_field": float(times[3]) / args.steps},
+                "phases_ms_per_step_per_rank[whole,push,exchange,solve]": per_rank,
                 "tuning": {"threads": args.threads or 512, "window": args.window or 44, "ctas": args.ctas, "rings_per_thread": args.rings or 4}}
         print(json.dumps(line))
     trap.close()

@@ -30,6 +30,8 @@
 
 #include <limits.h>
 
+#include <cstdlib>
+
 namespace {
 
 constexpr double kMagic = 6755399441055744.0;            // 2^52 + 2^51: floor via add.rm, integer in the low word
@@ -361,7 +363,10 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				}
 			}
 		}
-		if (a.nRho > 1) __threadfence_system();          // remote adds performed before the grid can be declared complete
+		if (a.nRho > 1 && a.pad1) {                      // remote adds performed before the grid can be declared complete:
+			__syncthreads();                             // one system fence per CTA (cumulative over the CTA's flush)
+			if (tid == 0) __threadfence_system();
+		}
 		if (PUSH && tid == 0) {
 			a.segBounds[s] = make_int2(gMin, gMax);      // next step's window (this CTA owns the segment)
 			if (sLost) atomicAdd(a.lost, (unsigned long long)sLost);
@@ -456,6 +461,10 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.ctaSegBegin = p->dCtaSegBegin;
 	a.segBounds = p->dSegBounds;
 	a.nRho = 1;
+	{
+		static const int fence = std::getenv("PTP_PEER_NOFENCE") ? 0 : 1;   // A/B switch for the per-CTA system fence
+		a.pad1 = fence;
+	}
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
 	a.lost = p->dLost;
 	return a;
