@@ -118,6 +118,16 @@ __device__ __forceinline__ double2 ld_ring(const double2* p) { return *p; }
 __device__ __forceinline__ void st_ring(double2* p, double2 v) { *p = v; }
 #endif
 
+// Tiles further ahead than the register prefetch are pulled into L2, so that the register loads of the next tile
+// see L2 latency instead of DRAM latency (the kernel is latency-bound: ~32 KB of loads in flight per SM).
+#ifndef PTP_L2_PREFETCH_TILES
+#define PTP_L2_PREFETCH_TILES 2
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+	asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
 template <typename T> __device__ __forceinline__ T warp_sum(T x)
 {
 #pragma unroll
@@ -191,6 +201,14 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			for (int j = 0; j < NV; ++j) {
 				z[2 * j] = zzN[j].x; z[2 * j + 1] = zzN[j].y;
 				if (PUSH) { v[2 * j] = vvN[j].x; v[2 * j + 1] = vvN[j].y; }
+			}
+			if (PTP_L2_PREFETCH_TILES > 0 && t0 + PTP_L2_PREFETCH_TILES * tile < seg.end) {
+				const long long pf = p0 + PTP_L2_PREFETCH_TILES * (tile >> 1);
+#pragma unroll
+				for (int j = 0; j < NV; ++j) {
+					prefetch_l2(z2 + pf + (long long)j * T);
+					if (PUSH) prefetch_l2(v2 + pf + (long long)j * T);
+				}
 			}
 			if (t0 + tile < seg.end) {               // next tile's loads are in flight while this one is processed
 				const long long pn = p0 + (tile >> 1);
