@@ -46,13 +46,16 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	return PTP_OK;
 }
 
-int solve_species(ptp_trap* t, int first, int count)
+int solve_species(ptp_trap* t, int first, int count, bool withField = false)
 {
 	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64;
 	const double* rho = t->rhoAll + (size_t)first * t->G;
 	double* phi = t->phiSelfAll + (size_t)first * t->G;
-	if (t->solver == PTP_SOLVER_SOR) return ptp_sor_run(t, rho, fixed, t->dScale + first, count, phi);
-	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi);
+	if (t->solver == PTP_SOLVER_SOR) {
+		PTP_TRY(ptp_sor_run(t, rho, fixed, t->dScale + first, count, phi));
+		return withField ? ptp_node_field(t) : PTP_OK;
+	}
+	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField);
 }
 
 // Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
@@ -97,8 +100,8 @@ int begin_exchange(ptp_trap* t)
 
 int solve_all(ptp_trap* t)
 {
-	PTP_TRY(solve_species(t, 0, (int)t->plasmas.size()));
-	return ptp_node_field(t);
+	if (t->plasmas.empty()) return ptp_node_field(t);
+	return solve_species(t, 0, (int)t->plasmas.size(), true);
 }
 
 } // namespace

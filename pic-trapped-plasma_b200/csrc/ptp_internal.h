@@ -128,7 +128,8 @@ int ptp_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int ptp_solver_build(ptp_trap* t);
 void ptp_solver_free(ptp_trap* t);
 // phi[s] = A^-1 (scale[s] * rho[s]) for nS consecutive grids; rho is double weights or int64 fixed point.
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi);
+// withField: nS covers ALL species (phi = phiSelfAll) and the node field is produced too (fused when possible).
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false);
 int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
 int ptp_node_field(ptp_trap* t);
 int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);

@@ -318,6 +318,149 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 	}
 }
 
+// Inverse DCT-I for all species of a 16-row strip + (optionally) the node field, in one kernel.
+//   * cos(pi (Nz-m) k / Nz) = (-1)^k cos(pi m k / Nz): modes are paired, phi[k] = sum_{m < K2} (alpha_m +- alpha_{Nz-m}) C[m][k],
+//     '+' for even k, '-' for odd k. The A tile is transformed in place (alpha_m + alpha_{Nz-m} at [m], the difference at
+//     [Nz-m]) and every lane reads the variant that matches the parity of its columns: half the FMAs and half the B rows.
+//   * FIELD: column tiles overlap by one node on each side (stride 38, width 40); the species' potentials of the tile are
+//     summed onto phi_trap in registration order and E = (Phi[k-1] - Phi[k+1]) / (2 hz) is written for the 38 inner nodes -
+//     the same arithmetic as k_node_field (Source/PenningTrap.cpp:226-233), so the result is bit-identical.
+template <bool VEC, bool FIELD>
+__global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ alpha, const double* __restrict__ B,
+	double* __restrict__ phiSelf, const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int n1, double hz)
+{
+	extern __shared__ double sm[];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int la = lane >> 3, lb = lane & 7;                    // 4 row groups x 8 column groups
+	const int Nz = n1 - 1, K2 = (n1 + 1) / 2;
+	const int j0 = blockIdx.y * INV_TM;
+	const int c0 = FIELD ? (int)blockIdx.x * (INV_TN - 2) - 2 : (int)blockIdx.x * INV_TN;   // first column of the tile (even; may be -2)
+	const int lda = n1 | 1;
+	double* sA = sm;                                            // [16][lda]
+	double* ringAll = sm + (size_t)INV_TM * lda;               // 8 warps x [ST][KS][TN]; reused for the cross-warp reduction
+	double* ring = ringAll + (size_t)warp * INV_ST * INV_KS * INV_TN;
+	double* sTot = ringAll + (size_t)8 * INV_ST * INV_KS * INV_TN; // [16][40] total potential of the tile (FIELD)
+
+	// per-lane copy slots of one stage (KS rows x TN columns). VEC needs 16-byte aligned sources: even n1 and even c0.
+	constexpr int EPL = VEC ? INV_KS * INV_TN / 2 / 32 : INV_KS * INV_TN / 32;
+	int cpRow[EPL], cpCol[EPL];
+	bool cpOk[EPL];
+#pragma unroll
+	for (int c = 0; c < EPL; ++c) {
+		const int e = lane + 32 * c;
+		cpRow[c] = VEC ? e / (INV_TN / 2) : e / INV_TN;
+		cpCol[c] = VEC ? 2 * (e % (INV_TN / 2)) : e % INV_TN;
+		cpOk[c] = c0 + cpCol[c] >= 0 && c0 + cpCol[c] + (VEC ? 1 : 0) < n1;
+	}
+	// parity of this lane's first column decides which variant (sum / difference) its even-j columns use
+	const bool firstEven = ((c0 + 5 * lb) & 1) == 0;
+	const int offE = firstEven ? 0 : Nz, sgnE = firstEven ? 1 : -1;  // index of the value for columns j = 0, 2, 4: offE + sgnE * m
+	const int offO = firstEven ? Nz : 0, sgnO = -sgnE;               // ... and for j = 1, 3
+	const int rowsMine = K2 > warp ? (K2 - warp + 7) / 8 : 0;        // this warp's modes: m = warp + 8 i
+	const int nStages = (rowsMine + INV_KS - 1) / INV_KS;
+	const double* bBase = B + (size_t)warp * n1 + c0;
+
+	if (FIELD) {
+		for (int o = tid; o < INV_TM * INV_TN; o += 256) {
+			const int r = o / INV_TN, c = o - r * INV_TN, col = c0 + c;
+			sTot[o] = (j0 + r < Nr && col >= 0 && col < n1) ? phiTrap[(size_t)(j0 + r) * n1 + col] : 0.0;
+		}
+	}
+	for (int sp = 0; sp < nS; ++sp) {
+		double acc[4][5];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+#pragma unroll
+			for (int j = 0; j < 5; ++j) acc[i][j] = 0.0;
+		auto issue = [&](int st) {
+			if (st < nStages) {
+				double* dst = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN;
+#pragma unroll
+				for (int c = 0; c < EPL; ++c) {
+					const int i = st * INV_KS + cpRow[c];
+					const bool valid = cpOk[c] && i < rowsMine;
+					const double* src = valid ? bBase + (size_t)8 * i * n1 + cpCol[c] : B;
+					if (VEC) cp_async16(dst + cpRow[c] * INV_TN + cpCol[c], src, valid);
+					else cp_async8(dst + cpRow[c] * INV_TN + cpCol[c], src, valid);
+				}
+			}
+			asm volatile("cp.async.commit_group;\n" ::);
+		};
+		__syncthreads();                                            // previous species' reduction buffers are free again
+#pragma unroll
+		for (int st = 0; st < INV_ST - 1; ++st) issue(st);          // B is in flight while A is staged
+		const double* aSrc = alpha + ((size_t)sp * Nr + j0) * n1;
+		for (int r = 0; r < INV_TM; ++r) {
+			const bool ok = j0 + r < Nr;
+			for (int c = tid; c < n1; c += 256) cp_async8(&sA[r * lda + c], aSrc + (ok ? (size_t)r * n1 + c : 0), ok);
+		}
+		asm volatile("cp.async.commit_group;\n" ::);
+		asm volatile("cp.async.wait_group 0;\n" ::);
+		__syncthreads();
+		for (int e = tid; e < INV_TM * K2; e += 256) {              // pair the modes: [m] <- a_m + a_{Nz-m}, [Nz-m] <- a_m - a_{Nz-m}
+			const int r = e / K2, m = e - r * K2;
+			if (m != Nz - m) {
+				const double p = sA[r * lda + m], q = sA[r * lda + Nz - m];
+				sA[r * lda + m] = p + q;
+				sA[r * lda + Nz - m] = p - q;
+			}
+		}
+		__syncthreads();
+		const double* a = sA + (4 * la) * lda;
+		for (int st = 0; st < nStages; ++st) {
+			issue(st + INV_ST - 1);
+			asm volatile("cp.async.wait_group %0;\n" ::"n"(INV_ST - 1));
+			__syncwarp();
+			const double* bs = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN + 5 * lb;
+			const int mFirst = warp + 8 * st * INV_KS;
+#pragma unroll
+			for (int rr = 0; rr < INV_KS; ++rr) {
+				const int m = min(mFirst + 8 * rr, K2 - 1);             // rows past the end were zero-filled
+				const int iE = offE + sgnE * m, iO = offO + sgnO * m;
+				double bv[5], ae[4], ao[4];
+#pragma unroll
+				for (int j = 0; j < 5; ++j) bv[j] = bs[rr * INV_TN + j];
+#pragma unroll
+				for (int i = 0; i < 4; ++i) { ae[i] = a[i * lda + iE]; ao[i] = a[i * lda + iO]; }
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+#pragma unroll
+					for (int j = 0; j < 5; ++j) acc[i][j] = fma((j & 1) ? ao[i] : ae[i], bv[j], acc[i][j]);
+			}
+			__syncwarp();
+		}
+		asm volatile("cp.async.wait_group 0;\n" ::);
+		__syncthreads();                                            // every warp is done with its ring: reuse as [8][16][40]
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+#pragma unroll
+			for (int j = 0; j < 5; ++j) ringAll[(warp * INV_TM + 4 * la + i) * INV_TN + 5 * lb + j] = acc[i][j];
+		__syncthreads();
+		double* out = phiSelf + (size_t)sp * Nr * n1;
+		for (int o = tid; o < INV_TM * INV_TN; o += 256) {
+			double v = 0.0;
+#pragma unroll
+			for (int w = 0; w < 8; ++w) v += ringAll[w * INV_TM * INV_TN + o];
+			const int r = o / INV_TN, c = o - r * INV_TN, col = c0 + c;
+			if (j0 + r < Nr && col >= 0 && col < n1) {
+				out[(size_t)(j0 + r) * n1 + col] = v;             // overlapping columns get the identical value from both tiles
+				if (FIELD) sTot[o] = __dadd_rn(sTot[o], v);
+			}
+		}
+	}
+	if (FIELD) {
+		__syncthreads();
+		for (int o = tid; o < INV_TM * (INV_TN - 2); o += 256) {
+			const int r = o / (INV_TN - 2), c = 1 + o % (INV_TN - 2), col = c0 + c;
+			if (j0 + r >= Nr || col >= n1) continue;
+			double e = 0.0;
+			if (col > 0 && col < n1 - 1)
+				e = __ddiv_rn(__dsub_rn(sTot[r * INV_TN + c - 1], sTot[r * INV_TN + c + 1]), __dmul_rn(2.0, hz));
+			eNodes[(size_t)(j0 + r) * n1 + col] = e;
+		}
+	}
+}
+
 // PenningTrap::getEField(int,int), Source/PenningTrap.cpp:208-236: E = (sumPhi[idx-1] - sumPhi[idx+1]) / (2 hz),
 // zero at both axial ends, species added in registration order.
 __global__ void k_node_field(const double* __restrict__ phiTrap, const double* __restrict__ phiSelf, int nS,
@@ -505,7 +648,7 @@ void ptp_solver_free(ptp_trap* t)
 	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
 }
 
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi)
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField)
 {
 	if (nS <= 0) return PTP_OK;
 	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
@@ -534,21 +677,45 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	if (rhoIsFixed) ef = mb == 16 ? launchFwd(k_fwd_thomas<true, 16>, fixedInv) : launchFwd(k_fwd_thomas<true, 4>, fixedInv);
 	else ef = mb == 16 ? launchFwd(k_fwd_thomas<false, 16>, 1.0) : launchFwd(k_fwd_thomas<false, 4>, 1.0);
 	if (ef != cudaSuccess) return ptp_cuda_fail(ef, "k_fwd_thomas launch", __FILE__, __LINE__);
-	const int kc = n1 < INV_KC ? n1 : INV_KC;
-	size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
-	if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);
-	const dim3 gridInv((n1 + INV_TN - 1) / INV_TN, (M + INV_TM - 1) / INV_TM);
-	if (n1 % 2 == 0) {
-		PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
-		k_inv_gemm<true><<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+	// inverse transform (+ node field): paired-mode kernel when its tiles fit in shared memory, chunked GEMM otherwise
+	const size_t smField = ((size_t)INV_TM * (n1 | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
+	bool fieldDone = false;
+	if (smField <= t->smemMax) {
+		auto launchInv = [&](auto kern, bool field) -> cudaError_t {
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smField);
+			if (e != cudaSuccess) return e;
+			const dim3 grid(field ? (n1 + 1 + INV_TN - 3) / (INV_TN - 2) : (n1 + INV_TN - 1) / INV_TN, (Nr + INV_TM - 1) / INV_TM);
+			kern<<<grid, 256, smField, t->stream>>>(spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz);
+			return cudaGetLastError();
+		};
+		const bool vec = n1 % 2 == 0;
+		cudaError_t ei;
+		if (withField) ei = vec ? launchInv(k_inv_field<true, true>, true) : launchInv(k_inv_field<false, true>, true);
+		else ei = vec ? launchInv(k_inv_field<true, false>, false) : launchInv(k_inv_field<false, false>, false);
+		if (ei != cudaSuccess) return ptp_cuda_fail(ei, "k_inv_field launch", __FILE__, __LINE__);
+		fieldDone = withField;
 	}
 	else {
-		PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
-		k_inv_gemm<false><<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+		const int kc = n1 < INV_KC ? n1 : INV_KC;
+		size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
+		if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);
+		const dim3 gridInv((n1 + INV_TN - 1) / INV_TN, (M + INV_TM - 1) / INV_TM);
+		if (n1 % 2 == 0) {
+			PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
+			k_inv_gemm<true><<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+		}
+		else {
+			PTP_CUDA(cudaFuncSetAttribute(k_inv_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smInv));
+			k_inv_gemm<false><<<gridInv, 256, smInv, t->stream>>>(spec, t->dctInv, phi, M, n1, n1);
+		}
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "solver launch", __FILE__, __LINE__);
 	t->lastLaunches += 3;
+	if (withField) {
+		if (fieldDone) t->eNodesValid = true;
+		else return ptp_node_field(t);
+	}
 	return PTP_OK;
 }
 
