@@ -27,11 +27,12 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	while (cap < need) cap *= 2;
 	const size_t bytes = (size_t)cap * t->G * sizeof(double), old = (size_t)t->capS * t->G * sizeof(double);
 	double *rho = nullptr, *phi = nullptr, *spec = nullptr, *scale = nullptr;
-	PTP_CUDA(cudaMalloc(&rho, 2 * bytes + 64 * sizeof(unsigned long long)));
+	const size_t span = (size_t)cap * t->G + (size_t)cap * t->Nr;       // doubles per parity: grids + row bounds
+	PTP_CUDA(cudaMalloc(&rho, 2 * span * sizeof(double) + 64 * sizeof(unsigned long long)));
 	PTP_CUDA(cudaMalloc(&phi, bytes));
 	PTP_CUDA(cudaMalloc(&spec, bytes));
 	PTP_CUDA(cudaMalloc(&scale, cap * sizeof(double)));
-	PTP_CUDA(cudaMemset(rho, 0, 2 * bytes + 64 * sizeof(unsigned long long)));
+	PTP_CUDA(cudaMemset(rho, 0, 2 * span * sizeof(double) + 64 * sizeof(unsigned long long)));
 	PTP_CUDA(cudaMemset(phi, 0, bytes));
 	PTP_CUDA(cudaMemset(scale, 0, cap * sizeof(double)));
 	if (t->capS) {
@@ -40,7 +41,7 @@ int ensure_species_capacity(ptp_trap* t, int need)
 		PTP_CUDA(cudaMemcpy(scale, t->dScale, t->capS * sizeof(double), cudaMemcpyDeviceToDevice));
 	}
 	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
-	t->rhoStore = rho; t->rhoParity = 0; t->rhoAll = rho; t->peerStale = true;
+	t->rhoStore = rho; t->rhoParity = 0; t->rhoAll = rho; t->peerStale = true; t->spanDoubles = span;
 	t->phiSelfAll = phi; t->specAll = spec; t->dScale = scale;
 	t->capS = cap;
 	return PTP_OK;
@@ -55,14 +56,18 @@ int solve_species(ptp_trap* t, int first, int count, bool withField = false)
 		PTP_TRY(ptp_sor_run(t, rho, fixed, t->dScale + first, count, phi));
 		return withField ? ptp_node_field(t) : PTP_OK;
 	}
-	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField);
+	// the touched node range per row comes from the push kernel's flush when it has seen every deposit of the grid:
+	// one GPU, or peer-memory mode inside a step; an NCCL-reduced grid is scanned instead
+	const bool trust = ptp_comm_size(t) == 1 || (withField && ptp_peer_mode(t));
+	const uint2* enc = trust ? reinterpret_cast<const uint2*>(t->rhoAll + (size_t)t->capS * t->G) + (size_t)first * t->Nr : nullptr;
+	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField, enc);
 }
 
 // Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
 int push_deposit_all(ptp_trap* t, double dt)
 {
 	const int nS = (int)t->plasmas.size();
-	const size_t span = (size_t)t->capS * t->G;
+	const size_t span = t->spanDoubles;
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	if (ptp_peer_mode(t)) {
 		// this step's target parity was zeroed one step ago (or at the start of the call); the other one - last step's
@@ -71,7 +76,7 @@ int push_deposit_all(ptp_trap* t, double dt)
 		t->rhoAll = t->rhoStore + (size_t)t->rhoParity * span;
 		PTP_CUDA(cudaMemsetAsync(t->rhoStore + (size_t)(t->rhoParity ^ 1) * span, 0, span * sizeof(double), t->stream));
 	}
-	else PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, (size_t)nS * t->G * sizeof(double), t->stream));
+	else PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, span * sizeof(double), t->stream));   // grids and row bounds of all species
 	for (ptp_plasma* p : t->plasmas) {
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 		PTP_TRY(ptp_push_launch(t, p, dt, true));
@@ -93,7 +98,7 @@ int begin_exchange(ptp_trap* t)
 {
 	if (!ptp_peer_mode(t)) return PTP_OK;
 	PTP_TRY(ptp_peer_prepare(t));
-	const size_t span = (size_t)t->capS * t->G;
+	const size_t span = t->spanDoubles;
 	PTP_CUDA(cudaMemsetAsync(t->rhoStore, 0, 2 * span * sizeof(double), t->stream));
 	return ptp_peer_barrier(t);
 }
@@ -439,6 +444,7 @@ int ptp_plasma_deposit(ptp_plasma* p)
 	if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 	void* rho = t->rhoAll + (size_t)p->index * t->G;
 	PTP_CUDA(cudaMemsetAsync(rho, 0, (size_t)t->G * sizeof(double), t->stream));
+	PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)t->capS * t->G + (size_t)p->index * t->Nr, 0, (size_t)t->Nr * sizeof(double), t->stream));
 	PTP_TRY(ptp_push_launch(t, p, 0.0, false));
 	return ptp_comm_allreduce(t, rho, (size_t)t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
 }

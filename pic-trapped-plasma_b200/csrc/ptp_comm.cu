@@ -133,7 +133,7 @@ int ptp_peer_prepare(ptp_trap* t)
 		c->peerBase[p] = static_cast<double*>(ptr);
 	}
 	c->mapped = true;
-	c->spanDoubles = (size_t)t->capS * t->G;
+	c->spanDoubles = t->spanDoubles;
 	t->peerStale = false;
 	return PTP_OK;
 }

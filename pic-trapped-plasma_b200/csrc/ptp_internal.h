@@ -85,7 +85,9 @@ struct ptp_trap {
 
 	// per-species grids, contiguous over species so that one all-reduce / one batched solve covers them
 	int capS = 0;
-	double* rhoStore = nullptr;  // one allocation: [2][capS][G] deposit accumulators (two parities) + 64 barrier flags;
+	size_t spanDoubles = 0;      // one parity of rhoStore: capS*G accumulators + capS*Nr row bounds (8 bytes each)
+	double* rhoStore = nullptr;  // one allocation: 2 parities x { [capS][G] deposit accumulators, [capS][Nr] touched node range
+	                             // per row (two u32, maintained by the push kernel's flush) } + 64 barrier flags;
 	                             // IPC-shared with the other ranks in peer-memory mode
 	int rhoParity = 0;
 	bool peerStale = true;       // rhoStore was (re)allocated: the peers' mappings must be exchanged again
@@ -129,7 +131,8 @@ int ptp_solver_build(ptp_trap* t);
 void ptp_solver_free(ptp_trap* t);
 // phi[s] = A^-1 (scale[s] * rho[s]) for nS consecutive grids; rho is double weights or int64 fixed point.
 // withField: nS covers ALL species (phi = phiSelfAll) and the node field is produced too (fused when possible).
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false);
+// encBounds: per (species,row) touched node range as written by the push kernel (nullptr: scan rho for non-zeros).
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false, const uint2* encBounds = nullptr);
 int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
 int ptp_node_field(ptp_trap* t);
 int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);

@@ -51,6 +51,7 @@ struct PushArgs {
 	int2* segBounds;
 	void* rho[8];               // [G] double weights or int64 fixed point: this rank's grid, or every rank's (peer-memory mode)
 	int nRho, pad1;
+	long long bndOffset;        // (uint2*)((double*)rho[r] + bndOffset) = this species' touched-node range per row (encoded maxima)
 	unsigned long long* lost;
 };
 
@@ -297,6 +298,11 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 #pragma unroll
 				for (int i = 0; i < R; ++i)
 					if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)W) {
+						for (int pr = 0; pr < a.nRho; ++pr) {
+							unsigned int* bd = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(a.rho[pr]) + a.bndOffset) + 2 * seg.row;
+							atomicMax(bd, (unsigned int)(a.Nz + 2 - k[i]));
+							atomicMax(bd + 1, (unsigned int)(k[i] + 2));
+						}
 						if (FIXED) {
 							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 							const unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
@@ -380,6 +386,14 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 						for (int pr = 0; pr < a.nRho; ++pr) atomicAdd(reinterpret_cast<double*>(a.rho[pr]) + rowBase + k0 + i, val);
 				}
 			}
+			// nodes k0+lo .. k0+hi+1 of this row were touched: keep the row's range for the solver's forward transform
+			// (both ends stored as maxima so that a memset(0) resets them: Nz+2-kmin and kmax+1)
+			if (tid == 0)
+				for (int pr = 0; pr < a.nRho; ++pr) {
+					unsigned int* bd = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(a.rho[pr]) + a.bndOffset) + 2 * seg.row;
+					atomicMax(bd, (unsigned int)(a.Nz + 2 - (k0 + lo)));
+					atomicMax(bd + 1, (unsigned int)(k0 + hi + 2));
+				}
 		}
 		if (a.nRho > 1 && a.pad1) {                      // remote adds performed before the grid can be declared complete:
 			__syncthreads();                             // one system fence per CTA (cumulative over the CTA's flush)
@@ -484,6 +498,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 		a.pad1 = fence;
 	}
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
+	a.bndOffset = (long long)((size_t)t->capS * t->G - (size_t)p->index * t->G + (size_t)p->index * t->Nr);
 	a.lost = p->dLost;
 	return a;
 }

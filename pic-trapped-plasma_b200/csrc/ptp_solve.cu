@@ -72,7 +72,7 @@ __device__ __forceinline__ void cp_async8(void* smemDst, const void* gmemSrc, bo
 constexpr int FWD_KB = 64;      // axial nodes of the deposit staged per chunk
 constexpr int FWD_RP = 128;     // deposit rows handled per pass
 template <bool A_FIXED, int FWD_MB>
-__global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ rho, const int2* __restrict__ bounds,
+__global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ rho, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
 	const double* __restrict__ FT, const double* __restrict__ rowScale, double fixedInv,
 	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thLower,
 	double* __restrict__ spec, int Nr, int n1)
@@ -105,7 +105,12 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	asm volatile("cp.async.commit_group;\n" ::);
 	__syncthreads();
 	for (int j = tid; j < Nr; j += 256) {
-		const int2 bd = bounds[s * Nr + j];
+		int2 bd;
+		if (encBounds) {                                        // maxima written by the push kernel's flush: (Nz+2-kmin, kmax+1), 0 = untouched
+			const uint2 e = encBounds[s * Nr + j];
+			bd = e.y ? make_int2(n1 + 1 - (int)e.x, (int)e.y - 1) : make_int2(INT_MAX, INT_MIN);
+		}
+		else bd = bounds[s * Nr + j];
 		sBd[j] = bd;
 		if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); }
 	}
@@ -327,8 +332,11 @@ __global__ void __launch_bounds__(256) k_inv_gemm(const double* __restrict__ A, 
 //     the same arithmetic as k_node_field (Source/PenningTrap.cpp:226-233), so the result is bit-identical.
 template <bool VEC, bool FIELD>
 __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ alpha, const double* __restrict__ B,
-	double* __restrict__ phiSelf, const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int n1, double hz)
+	double* __restrict__ phiSelf, const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int n1, double hz, int ST)
 {
+	// ST = stages of the per-warp B ring. When the whole K-slice of a warp fits (ST >= its stage count; the default grid
+	// needs 5 x 2.5 KB) everything is requested up front together with the A tile and the main loop never waits;
+	// otherwise the ring is refilled one stage per iteration with INV_ST - 1 stages in flight.
 	extern __shared__ double sm[];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int la = lane >> 3, lb = lane & 7;                    // 4 row groups x 8 column groups
@@ -338,8 +346,8 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 	const int lda = n1 | 1;
 	double* sA = sm;                                            // [16][lda]
 	double* ringAll = sm + (size_t)INV_TM * lda;               // 8 warps x [ST][KS][TN]; reused for the cross-warp reduction
-	double* ring = ringAll + (size_t)warp * INV_ST * INV_KS * INV_TN;
-	double* sTot = ringAll + (size_t)8 * INV_ST * INV_KS * INV_TN; // [16][40] total potential of the tile (FIELD)
+	double* ring = ringAll + (size_t)warp * ST * INV_KS * INV_TN;
+	double* sTot = ringAll + (size_t)8 * ST * INV_KS * INV_TN; // [16][40] total potential of the tile (FIELD)
 
 	// per-lane copy slots of one stage (KS rows x TN columns). VEC needs 16-byte aligned sources: even n1 and even c0.
 	constexpr int EPL = VEC ? INV_KS * INV_TN / 2 / 32 : INV_KS * INV_TN / 32;
@@ -358,6 +366,7 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 	const int offO = firstEven ? Nz : 0, sgnO = -sgnE;               // ... and for j = 1, 3
 	const int rowsMine = K2 > warp ? (K2 - warp + 7) / 8 : 0;        // this warp's modes: m = warp + 8 i
 	const int nStages = (rowsMine + INV_KS - 1) / INV_KS;
+	const bool upFront = ST >= (K2 + 8 * INV_KS - 1) / (8 * INV_KS);   // uniform over the CTA (warp 0 has the most rows)
 	const double* bBase = B + (size_t)warp * n1 + c0;
 
 	if (FIELD) {
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 			for (int j = 0; j < 5; ++j) acc[i][j] = 0.0;
 		auto issue = [&](int st) {
 			if (st < nStages) {
-				double* dst = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN;
+				double* dst = ring + (size_t)(st % ST) * INV_KS * INV_TN;
 #pragma unroll
 				for (int c = 0; c < EPL; ++c) {
 					const int i = st * INV_KS + cpRow[c];
@@ -387,8 +396,11 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 			asm volatile("cp.async.commit_group;\n" ::);
 		};
 		__syncthreads();                                            // previous species' reduction buffers are free again
+		if (upFront) for (int st = 0; st < nStages; ++st) issue(st);
+		else {
 #pragma unroll
-		for (int st = 0; st < INV_ST - 1; ++st) issue(st);          // B is in flight while A is staged
+			for (int st = 0; st < INV_ST - 1; ++st) issue(st);      // B is in flight while A is staged
+		}
 		const double* aSrc = alpha + ((size_t)sp * Nr + j0) * n1;
 		for (int r = 0; r < INV_TM; ++r) {
 			const bool ok = j0 + r < Nr;
@@ -408,10 +420,12 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 		__syncthreads();
 		const double* a = sA + (4 * la) * lda;
 		for (int st = 0; st < nStages; ++st) {
-			issue(st + INV_ST - 1);
-			asm volatile("cp.async.wait_group %0;\n" ::"n"(INV_ST - 1));
-			__syncwarp();
-			const double* bs = ring + (size_t)(st % INV_ST) * INV_KS * INV_TN + 5 * lb;
+			if (!upFront) {
+				issue(st + INV_ST - 1);
+				asm volatile("cp.async.wait_group %0;\n" ::"n"(INV_ST - 1));
+				__syncwarp();
+			}
+			const double* bs = ring + (size_t)(st % ST) * INV_KS * INV_TN + 5 * lb;
 			const int mFirst = warp + 8 * st * INV_KS;
 #pragma unroll
 			for (int rr = 0; rr < INV_KS; ++rr) {
@@ -427,7 +441,7 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 #pragma unroll
 					for (int j = 0; j < 5; ++j) acc[i][j] = fma((j & 1) ? ao[i] : ae[i], bv[j], acc[i][j]);
 			}
-			__syncwarp();
+			if (!upFront) __syncwarp();
 		}
 		asm volatile("cp.async.wait_group 0;\n" ::);
 		__syncthreads();                                            // every warp is done with its ring: reuse as [8][16][40]
@@ -648,7 +662,7 @@ void ptp_solver_free(ptp_trap* t)
 	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
 }
 
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField)
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds)
 {
 	if (nS <= 0) return PTP_OK;
 	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
@@ -659,7 +673,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		PTP_CUDA(cudaMalloc(&t->rowBounds, (size_t)M * sizeof(int2)));
 		t->rowBoundsCap = M;
 	}
-	k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds);
+	if (!encBounds) { k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds); t->lastLaunches++; }
 	auto smFwdBytes = [&](int mb) {
 		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB + (size_t)Nr) * sizeof(double) + (size_t)Nr * sizeof(int2);
 	};
@@ -670,7 +684,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	auto launchFwd = [&](auto kern, double fInv) -> cudaError_t {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd);
 		if (e != cudaSuccess) return e;
-		kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
+		kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
 		return cudaGetLastError();
 	};
 	cudaError_t ef;
@@ -678,14 +692,17 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	else ef = mb == 16 ? launchFwd(k_fwd_thomas<false, 16>, 1.0) : launchFwd(k_fwd_thomas<false, 4>, 1.0);
 	if (ef != cudaSuccess) return ptp_cuda_fail(ef, "k_fwd_thomas launch", __FILE__, __LINE__);
 	// inverse transform (+ node field): paired-mode kernel when its tiles fit in shared memory, chunked GEMM otherwise
-	const size_t smField = ((size_t)INV_TM * (n1 | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
+	const int stagesAll = ((n1 + 1) / 2 + 8 * INV_KS - 1) / (8 * INV_KS);    // stages that hold a warp's whole K-slice
+	auto smFieldBytes = [&](int st) { return ((size_t)INV_TM * (n1 | 1) + (size_t)8 * st * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double); };
+	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= t->smemMax ? std::max(stagesAll, 2) : INV_ST;
+	const size_t smField = smFieldBytes(ringStages);
 	bool fieldDone = false;
 	if (smField <= t->smemMax) {
 		auto launchInv = [&](auto kern, bool field) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smField);
 			if (e != cudaSuccess) return e;
 			const dim3 grid(field ? (n1 + 1 + INV_TN - 3) / (INV_TN - 2) : (n1 + INV_TN - 1) / INV_TN, (Nr + INV_TM - 1) / INV_TM);
-			kern<<<grid, 256, smField, t->stream>>>(spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz);
+			kern<<<grid, 256, smField, t->stream>>>(spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz, ringStages);
 			return cudaGetLastError();
 		};
 		const bool vec = n1 % 2 == 0;
@@ -711,7 +728,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "solver launch", __FILE__, __LINE__);
-	t->lastLaunches += 3;
+	t->lastLaunches += 2;
 	if (withField) {
 		if (fieldDone) t->eNodesValid = true;
 		else return ptp_node_field(t);
