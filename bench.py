@@ -48,22 +48,57 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). NVML through pynvml
+    (a query takes ~1 ms, so even a 100 ms region gets tens of samples); nvidia-smi polling as a fallback."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag, self.th, self.how = index, [], [], set(), False, None, "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a list of ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv, self.how = None, "nvidia-smi"
 
     def _run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.splitlines()[0].split(",")])
+                if self.nv:
+                    nv = self.nv
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    for bit, name in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                    time.sleep(0.002)
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        r = [x.strip() for x in out.splitlines()[0].split(",")]
+                        self.sm.append(float(r[0]))
+                        self.mx.append(float(r[1]))
+                        for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                            if val.lower().startswith("active"):
+                                self.reasons.add(name)
+                    time.sleep(0.02)
             except Exception:
-                pass
-            time.sleep(0.05)
+                time.sleep(0.01)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -73,15 +108,8 @@ class ClockSampler:
         self.stop_flag = True
         if self.th:
             self.th.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
 def build_load(ptp, loaders, workload, rank, n_ranks, hz, hr):
@@ -105,6 +133,8 @@ def cpu_reference_run(workload, steps, warmup, sample_rings):
     from oracle import port, ref
     kind = "reference" if ref.available() else "port"
     species, total, _ = WORKLOADS[workload]
+    # bounded sample: keep the whole arm within a couple of minutes of CPU time (~2e7 ring-steps/s on one core)
+    sample_rings = int(max(100_000, min(sample_rings, 1.2e9 / max(steps + warmup, 1))))
     stride = max(1, total // sample_rings)
     trap = ref.default_trap() if kind == "reference" else port.default_trap()
     load = build_load(ptp, loaders, workload, 0, stride, trap.hz, trap.hr)   # ring i % stride == 0 of every row
