@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=0)
-    ap.add_argument("--allreduce", default="nccl", choices=["nccl", "peer"], help="exchange step for N > 1")
+    ap.add_argument("--allreduce", default="peer", choices=["nccl", "peer"], help="exchange step for N > 1")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -494,7 +494,10 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.segBounds = p->dSegBounds;
 	a.nRho = 1;
 	{
-		static const int fence = std::getenv("PTP_PEER_NOFENCE") ? 0 : 1;   // A/B switch for the per-CTA system fence
+		// Peer-memory mode: the remote adds of this kernel are complete at kernel end (stream order is a system-scope
+		// release), and the flag barrier is a separate kernel behind it, so no in-kernel fence is needed. PTP_PEER_FENCE=1
+		// adds one system fence per CTA after the flush anyway (measured cost: ~12 us per step at 4 GPUs).
+		static const int fence = std::getenv("PTP_PEER_FENCE") ? 1 : 0;
 		a.pad1 = fence;
 	}
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
