@@ -102,6 +102,10 @@ int ptp_trap_set_sort_interval(ptp_trap* t, int interval);
 int ptp_trap_set_deposit_mode(ptp_trap* t, int mode);
 int ptp_trap_set_arith_mode(ptp_trap* t, int mode);
 int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMaxIterations);
+/* Replay each step (or pair of steps in peer-memory mode) as a CUDA graph inside ptp_trap_step: removes the per-kernel
+ * launch cost that dominates small configurations (the reference's default 8 k-ring case). Per-phase times are not
+ * recorded in this mode ([1..3] of ptp_trap_last_times read 0). */
+int ptp_trap_set_graph(ptp_trap* t, int on);
 /* Tuning of the push kernel: threads per CTA (256/512), cells of the thread-private deposit window, CTAs
  * (0 = one per SM), rings per thread and tile (4/8). 0 (ctas: -1) keeps the current value. */
 int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ringsPerThread);

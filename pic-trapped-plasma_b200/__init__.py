@@ -64,6 +64,7 @@ SIGNATURES = {
     "ptp_trap_set_arith_mode": (_i, [_vp, _i]),
     "ptp_trap_set_solver": (_i, [_vp, _i, _d, _i]),
     "ptp_trap_set_tuning": (_i, [_vp, _i, _i, _i, _i]),
+    "ptp_trap_set_graph": (_i, [_vp, _i]),
     "ptp_comm_unique_id": (_i, [_vp]),
     "ptp_trap_comm_init": (_i, [_vp, _vp, _i, _i]),
     "ptp_trap_set_allreduce": (_i, [_vp, _i]),
@@ -255,6 +256,9 @@ class PenningTrap:
 
     def set_tuning(self, threads=0, window=0, ctas=-1, rings_per_thread=0):
         _check(lib().ptp_trap_set_tuning(self.h, threads, window, ctas, rings_per_thread))
+
+    def set_graph(self, on=True):
+        _check(lib().ptp_trap_set_graph(self.h, 1 if on else 0))
 
     def set_sort_interval(self, interval):
         _check(lib().ptp_trap_set_sort_interval(self.h, interval))

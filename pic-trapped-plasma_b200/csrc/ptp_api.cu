@@ -42,6 +42,7 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	}
 	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
 	t->rhoStore = rho; t->rhoParity = 0; t->rhoAll = rho; t->peerStale = true; t->spanDoubles = span;
+	++t->cfgEpoch;
 	t->phiSelfAll = phi; t->specAll = spec; t->dScale = scale;
 	t->capS = cap;
 	return PTP_OK;
@@ -178,6 +179,7 @@ int ptp_trap_destroy(ptp_trap* t)
 	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
 	for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : t->evPool) cudaEventDestroy(ev);
+	if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return PTP_OK;
@@ -273,13 +275,77 @@ int ptp_trap_solve_fields(ptp_trap* t)
 	return solve_all(t);
 }
 
+namespace {
+
+int one_step(ptp_trap* t, double dt, cudaEvent_t* e)
+{
+	if (e) PTP_CUDA(cudaEventRecord(e[0], t->stream));
+	PTP_TRY(push_deposit_all(t, dt));
+	if (e) PTP_CUDA(cudaEventRecord(e[1], t->stream));
+	PTP_TRY(reduce_rho(t));
+	if (e) PTP_CUDA(cudaEventRecord(e[2], t->stream));
+	PTP_TRY(solve_all(t));
+	if (e) PTP_CUDA(cudaEventRecord(e[3], t->stream));
+	++t->stepCount;
+	return PTP_OK;
+}
+
+void drop_graph(ptp_trap* t)
+{
+	if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
+	t->graphExec = nullptr;
+	t->graphCfg = -1;
+}
+
+// Capture one step (two in peer-memory mode, where consecutive steps use alternating grid parities) into a graph.
+// Everything a step would allocate or synchronise on lazily is settled before the capture starts.
+int capture_step_graph(ptp_trap* t, double dt)
+{
+	drop_graph(t);
+	for (ptp_plasma* p : t->plasmas)
+		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
+	PTP_TRY(ptp_solver_reserve(t, (int)t->plasmas.size()));
+	const int unit = ptp_peer_mode(t) ? 2 : 1;
+	const int parity0 = t->rhoParity;
+	const long long steps0 = t->stepCount;
+	const int64_t launches0 = t->lastLaunches;
+	PTP_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+	int rc = PTP_OK;
+	for (int u = 0; u < unit && rc == PTP_OK; ++u) rc = one_step(t, dt, nullptr);
+	cudaGraph_t graph = nullptr;
+	cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
+	t->stepCount = steps0;                                        // nothing has run yet
+	t->graphLaunches = t->lastLaunches - launches0;
+	t->lastLaunches = launches0;
+	if (rc != PTP_OK || e != cudaSuccess || !graph) {
+		if (graph) cudaGraphDestroy(graph);
+		cudaGetLastError();
+		t->rhoParity = parity0;
+		t->rhoAll = t->rhoStore + (size_t)parity0 * t->spanDoubles;
+		if (rc == PTP_OK) return ptp_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+		return rc;
+	}
+	e = cudaGraphInstantiate(&t->graphExec, graph, 0);
+	cudaGraphDestroy(graph);
+	if (e != cudaSuccess) { t->graphExec = nullptr; return ptp_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+	t->graphCfg = t->cfgEpoch;
+	t->graphDt = dt;
+	t->graphParity = parity0;
+	t->graphUnit = unit;
+	return PTP_OK;
+}
+
+} // namespace
+
 int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 {
 	if (!t || nSteps < 0) { ptp_set_error("ptp_trap_step: bad arguments"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
+	const bool graph = t->useGraph && t->sortInterval == 0 && t->solver == PTP_SOLVER_DIRECT && !t->plasmas.empty();
 	// phase events for every step (up to a bound), so that callers can report the mean kernel time
-	const int timed = nSteps <= 4096 ? nSteps : 0;
+	const int timed = (!graph && nSteps <= 4096) ? nSteps : 0;
 	while ((int)t->evPool.size() < 4 * timed) {
 		cudaEvent_t e;
 		PTP_CUDA(cudaEventCreate(&e));
@@ -287,21 +353,33 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	}
 	t->evSteps = timed;
 	PTP_TRY(begin_exchange(t));
-	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
-	for (int s = 0; s < nSteps; ++s) {
-		cudaEvent_t* e = s < timed ? &t->evPool[4 * s] : nullptr;
-		if (e) PTP_CUDA(cudaEventRecord(e[0], t->stream));
-		PTP_TRY(push_deposit_all(t, dt));
-		if (e) PTP_CUDA(cudaEventRecord(e[1], t->stream));
-		PTP_TRY(reduce_rho(t));
-		if (e) PTP_CUDA(cudaEventRecord(e[2], t->stream));
-		PTP_TRY(solve_all(t));
-		if (e) PTP_CUDA(cudaEventRecord(e[3], t->stream));
-		++t->stepCount;
+	int done = 0;
+	if (graph && nSteps > 0) {
+		if (!t->graphExec || t->graphCfg != t->cfgEpoch || t->graphDt != dt || t->graphParity != t->rhoParity)
+			PTP_TRY(capture_step_graph(t, dt));
+		PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
+		for (; done + t->graphUnit <= nSteps; done += t->graphUnit) {
+			PTP_CUDA(cudaGraphLaunch(t->graphExec, t->stream));
+			t->lastLaunches += t->graphLaunches;
+			t->stepCount += t->graphUnit;
+		}
+		t->eNodesValid = true;
+	}
+	else PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
+	for (int s = done; s < nSteps; ++s) {
+		PTP_TRY(one_step(t, dt, s < timed ? &t->evPool[4 * s] : nullptr));
 		if (t->sortInterval > 0 && t->stepCount % t->sortInterval == 0)
 			for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
 	}
 	PTP_CUDA(cudaEventRecord(t->ev[4], t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_set_graph(ptp_trap* t, int on)
+{
+	if (!t) { ptp_set_error("ptp_trap_set_graph: null trap"); return PTP_EINVAL; }
+	t->useGraph = on != 0;
+	if (!on) drop_graph(t);
 	return PTP_OK;
 }
 
@@ -335,6 +413,7 @@ int64_t ptp_trap_last_launches(ptp_trap* t) { return t ? t->lastLaunches : 0; }
 
 int ptp_trap_sort(ptp_trap* t)
 {
+	if (t) ++t->cfgEpoch;
 	if (!t) { ptp_set_error("ptp_trap_sort: null trap"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
@@ -351,6 +430,7 @@ int ptp_trap_set_sort_interval(ptp_trap* t, int interval)
 
 int ptp_trap_set_deposit_mode(ptp_trap* t, int mode)
 {
+	if (t) ++t->cfgEpoch;
 	if (!t || (mode != PTP_DEPOSIT_FP64 && mode != PTP_DEPOSIT_FIXED64)) { ptp_set_error("ptp_trap_set_deposit_mode: bad mode"); return PTP_EINVAL; }
 	const int old = t->depositMode;
 	t->depositMode = mode;
@@ -360,6 +440,7 @@ int ptp_trap_set_deposit_mode(ptp_trap* t, int mode)
 
 int ptp_trap_set_arith_mode(ptp_trap* t, int mode)
 {
+	if (t) ++t->cfgEpoch;
 	if (!t || (mode != PTP_ARITH_FAST && mode != PTP_ARITH_EXACT)) { ptp_set_error("ptp_trap_set_arith_mode: bad mode"); return PTP_EINVAL; }
 	t->arithMode = mode;
 	return PTP_OK;
@@ -367,6 +448,7 @@ int ptp_trap_set_arith_mode(ptp_trap* t, int mode)
 
 int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMaxIterations)
 {
+	if (t) ++t->cfgEpoch;
 	if (!t || (solver != PTP_SOLVER_DIRECT && solver != PTP_SOLVER_SOR)) { ptp_set_error("ptp_trap_set_solver: bad solver"); return PTP_EINVAL; }
 	t->solver = solver;
 	if (sorTolerance > 0) t->sorTol = sorTolerance;
@@ -376,6 +458,7 @@ int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMax
 
 int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ringsPerThread)
 {
+	if (t) ++t->cfgEpoch;
 	if (!t) { ptp_set_error("ptp_trap_set_tuning: null trap"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	const int oT = t->threads, oW = t->window, oC = t->ctas, oR = t->ringsPerThread;
@@ -391,6 +474,7 @@ int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ring
 
 int ptp_plasma_create(ptp_trap* t, ptp_plasma** out, double mass, double charge)
 {
+	if (t) ++t->cfgEpoch;
 	if (!t || !out || !(mass > 0) || charge == 0) { ptp_set_error("ptp_plasma_create: bad arguments"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
@@ -417,6 +501,7 @@ int ptp_plasma_destroy(ptp_plasma* p)
 {
 	if (!p) return PTP_OK;
 	ptp_trap* t = p->trap;
+	++t->cfgEpoch;
 	cudaSetDevice(t->device);
 	cudaStreamSynchronize(t->stream);
 	// later species move down one slice so that slices stay contiguous and in registration order

@@ -17,7 +17,8 @@ struct PtpComm {
 	double* peerBase[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	bool mapped = false;
 	size_t spanDoubles = 0;          // capS * G at mapping time
-	unsigned long long epoch = 0;    // barrier generation; all ranks advance it in lock-step
+	unsigned long long* dEpoch = nullptr; // barrier generation, kept on the device so that barrier launches can be replayed from a CUDA graph;
+	                                      // all ranks advance it in lock-step
 };
 
 namespace {
@@ -62,8 +63,12 @@ int nccl_fail(ncclResult_t r, const char* what)
 // then spins on its own array until every slot has reached the epoch (acquire). Launched after the push kernel in stream
 // order, so this rank's remote adds are complete before its flag can be seen.
 struct PeerFlags { unsigned long long* f[8]; };
-__global__ void k_peer_barrier(PeerFlags flags, int rank, int nRanks, unsigned long long epoch)
+__global__ void k_peer_barrier(PeerFlags flags, int rank, int nRanks, unsigned long long* dEpoch)
 {
+	__shared__ unsigned long long sEpoch;
+	if (threadIdx.x == 0) { sEpoch = *dEpoch + 1; *dEpoch = sEpoch; }
+	__syncthreads();
+	const unsigned long long epoch = sEpoch;
 	const int p = threadIdx.x;
 	if (p < nRanks) {
 		__threadfence_system();
@@ -135,6 +140,16 @@ int ptp_peer_prepare(ptp_trap* t)
 	c->mapped = true;
 	c->spanDoubles = t->spanDoubles;
 	t->peerStale = false;
+	// every rank restarts its barrier generation and flags at zero; nobody may signal before everybody has done so
+	if (!c->dEpoch) PTP_CUDA(cudaMalloc(&c->dEpoch, sizeof(unsigned long long)));
+	PTP_CUDA(cudaMemsetAsync(c->dEpoch, 0, sizeof(unsigned long long), t->stream));
+	PTP_CUDA(cudaMemsetAsync(t->rhoStore + 2 * t->spanDoubles, 0, 64 * sizeof(unsigned long long), t->stream));
+	PTP_CUDA(cudaMalloc(&dFlag, sizeof(int)));
+	PTP_CUDA(cudaMemsetAsync(dFlag, 0, sizeof(int), t->stream));
+	r = g_nccl.AllReduce(dFlag, dFlag, 1, ncclInt32, ncclMax, c->comm, t->stream);
+	if (r != ncclSuccess) { cudaFree(dFlag); return nccl_fail(r, "ncclAllReduce(barrier reset)"); }
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dFlag);
 	return PTP_OK;
 }
 
@@ -150,8 +165,7 @@ int ptp_peer_barrier(ptp_trap* t)
 	PtpComm* c = t->comm;
 	PeerFlags f{};
 	for (int p = 0; p < c->nRanks; ++p) f.f[p] = reinterpret_cast<unsigned long long*>(c->peerBase[p] + 2 * c->spanDoubles);
-	++c->epoch;
-	k_peer_barrier<<<1, 32, 0, t->stream>>>(f, c->rank, c->nRanks, c->epoch);
+	k_peer_barrier<<<1, 32, 0, t->stream>>>(f, c->rank, c->nRanks, c->dEpoch);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_peer_barrier launch", __FILE__, __LINE__);
 	t->lastLaunches++;
@@ -170,6 +184,7 @@ void ptp_comm_free(ptp_trap* t)
 {
 	if (t->comm) {
 		unmap_peers(t);
+		cudaFree(t->comm->dEpoch);
 		if (t->comm->comm && g_nccl.ok) g_nccl.CommDestroy(t->comm->comm);
 		delete t->comm;
 		t->comm = nullptr;
@@ -194,6 +209,7 @@ int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank)
 	if (!t || !id128 || nRanks < 1 || rank < 0 || rank >= nRanks) { ptp_set_error("ptp_trap_comm_init: bad arguments"); return PTP_EINVAL; }
 	if (!load_nccl()) return PTP_ECOMM;
 	PTP_CUDA(cudaSetDevice(t->device));
+	++t->cfgEpoch;
 	ptp_comm_free(t);
 	t->comm = new PtpComm;
 	t->comm->nRanks = nRanks;
@@ -210,6 +226,7 @@ int ptp_trap_set_allreduce(ptp_trap* t, int kind)
 	if (!t || kind < 0 || kind > 1) { ptp_set_error("ptp_trap_set_allreduce: bad arguments"); return PTP_EINVAL; }
 	if (kind == 1 && !t->comm) { ptp_set_error("ptp_trap_set_allreduce: peer-memory mode needs ptp_trap_comm_init first"); return PTP_ESTATE; }
 	t->allreduceKind = kind;
+	++t->cfgEpoch;
 	return PTP_OK;
 }
 

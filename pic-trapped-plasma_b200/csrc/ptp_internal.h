@@ -110,6 +110,15 @@ struct ptp_trap {
 
 	PtpComm* comm = nullptr;
 	int allreduceKind = 0;
+
+	// CUDA-graph replay of the step (ptp_trap_set_graph)
+	bool useGraph = false;
+	long long cfgEpoch = 0;          // bumped by everything that changes what a step launches (uploads, modes, tuning, ...)
+	cudaGraphExec_t graphExec = nullptr;
+	long long graphCfg = -1;
+	double graphDt = 0;
+	int graphParity = 0, graphUnit = 1;
+	int64_t graphLaunches = 0;
 };
 
 // ---- error handling -------------------------------------------------------------------------
@@ -158,3 +167,4 @@ bool ptp_peer_mode(ptp_trap* t);
 int ptp_peer_prepare(ptp_trap* t);                               // collective: (re)map the peers' rhoStore
 void ptp_peer_targets(ptp_trap* t, int parity, size_t offsetDoubles, void** out, int* n); // grid pointers of all ranks
 int ptp_peer_barrier(ptp_trap* t);                                // all ranks' pushes of this epoch have landed
+int ptp_solver_reserve(ptp_trap* t, int nS);                       // allocate what ptp_solver_run would allocate lazily

@@ -208,6 +208,7 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 {
 	if (p->cap == 0) return PTP_OK;
+	++t->cfgEpoch;
 	const int Nr = t->Nr, Nz = t->Nz;
 	if (!p->zAlt) {
 		PTP_CUDA(cudaMalloc(&p->zAlt, p->cap * sizeof(double)));
@@ -257,6 +258,7 @@ int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* 
 	if (!p || n < 0 || (n > 0 && (!r || !z || !v))) { ptp_set_error("ptp_plasma_upload: bad arguments"); return PTP_EINVAL; }
 	ptp_trap* t = p->trap;
 	PTP_CUDA(cudaSetDevice(t->device));
+	++t->cfgEpoch;                                               // ring buffers / segment tables change: cached step graph is stale
 	const int Nr = t->Nr;
 	// row histogram + "already bucketed?" test, split over host threads (one pass over r is the only O(n) host work
 	// of a sorted upload; the loaders emit rows in ascending order)

@@ -662,17 +662,24 @@ void ptp_solver_free(ptp_trap* t)
 	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
 }
 
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds)
+int ptp_solver_reserve(ptp_trap* t, int nS)
 {
-	if (nS <= 0) return PTP_OK;
-	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
-	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
+	const int M = nS * t->Nr;
 	if ((int)t->rowBoundsCap < M) {
 		cudaFree(t->rowBounds);
 		t->rowBounds = nullptr;
 		PTP_CUDA(cudaMalloc(&t->rowBounds, (size_t)M * sizeof(int2)));
 		t->rowBoundsCap = M;
 	}
+	return PTP_OK;
+}
+
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds)
+{
+	if (nS <= 0) return PTP_OK;
+	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
+	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
+	PTP_TRY(ptp_solver_reserve(t, nS));
 	if (!encBounds) { k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds); t->lastLaunches++; }
 	auto smFwdBytes = [&](int mb) {
 		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB + (size_t)Nr) * sizeof(double) + (size_t)Nr * sizeof(int2);

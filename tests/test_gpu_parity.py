@@ -373,3 +373,79 @@ def test_edge_cases():
     with pytest.raises(ValueError):
         ptp.PenningTrap(0.01, [ptp.Electrode(0.01, 0)], [0.001], 16, 4)
     t.close()
+
+
+# ------------------------------------------------------------------------------------------ other grid shapes
+@pytest.mark.parametrize("Nz,Nr", [(1024, 96), (2048, 16), (301, 130), (48, 420)])
+def test_solver_and_step_on_other_grids(Nz, Nr):
+    """Grid shapes that take the other code paths of the solver (odd Nz+1 -> 8-byte copies, pipelined B ring, chunked
+    inverse GEMM + separate node field for long rows, 4 modes per CTA for many radial nodes) against the CPU oracle."""
+    args = (0.012, [0.02, 0.03, 0.02], [0.0, -50.0, 0.0], [0.001, 0.001], Nz, Nr)
+    pt = port.PortTrap(*args)
+    t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], Nz, Nr)
+    assert rel_l2(t.phi(), pt.phi) < 1e-10
+    rng = np.random.default_rng(Nz + Nr)
+    x = rng.standard_normal(t.G)
+    assert rel_l2(t.solve(x), pt.solve(x)) < 1e-9
+    n = 50000
+    rows = min(Nr, 40)
+    r = np.sort(rng.integers(0, rows, n)).astype(np.int32)
+    z = pt.length * (0.5 + 0.1 * np.clip(rng.standard_normal(n) * 0.4, -1, 1))
+    v = rng.normal(0, 3e4, n)
+    op = pt.plasma("Electrons", ptp.massE, -ptp.ePos)
+    op.set_rings(r, z, v, -2e-18)
+    gp = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+    gp.upload(r, z, v, -2e-18)
+    op.solve_poisson()
+    gp.solvePoisson()
+    assert rel_l2(gp.rhs(), op.rhs) < 1e-12
+    assert rel_l2(gp.selfPotential(), op.self_potential) < 1e-9
+    dt = 0.2 * pt.hz / 3e4
+    for _ in range(3):
+        t.set_phi(pt.phi)
+        gp.set_self_potential(op.self_potential)
+        pt.move_plasmas(dt)
+        t.movePlasmas(dt)
+        rr, zz, vv, ids = gp.download()
+        o = np.argsort(ids)
+        assert np.max(np.abs(zz[o] - op.z) / op.z) < 1e-14
+        k_g, _ = gp.cell_index()
+        k_o, _ = op.cell_index()
+        assert np.array_equal(k_g[o], k_o)
+        assert rel_l2(gp.rhs(), op.rhs) < 1e-12
+        assert rel_l2(gp.selfPotential(), op.self_potential) < 1e-9
+        assert rel_l2(t.enodes(), pt.enodes()) < 1e-7
+    t.close()
+    pt.close()
+
+
+def test_graph_replay_is_bitwise_identical(c1_kat):
+    """ptp_trap_set_graph: the step replayed as a CUDA graph gives exactly the stream-launched result (fixed-point deposit,
+    so that the comparison is bitwise), is faster for the launch-bound default configuration, and survives a change of
+    dt, an electrode change and a re-upload."""
+    import time
+    res = []
+    for graph in (False, True):
+        t, el, ap = _fresh_c1(c1_kat, ptp.PTP_DEPOSIT_FIXED64)
+        t.set_graph(graph)
+        el.solvePoisson()
+        ap.solvePoisson()
+        dt = float(c1_kat["dt"])
+        t.movePlasmas(dt, 20)
+        t.sync()
+        t0 = time.perf_counter()
+        t.movePlasmas(dt, 300)
+        t.sync()
+        sec = time.perf_counter() - t0
+        t.movePlasmas(dt * 0.5, 7)                 # new dt -> new graph
+        t.setPotential(1, -60.0)                  # same graph, new trap potential
+        t.movePlasmas(dt * 0.5, 5)
+        _, z, v, ids = el.download()
+        o = np.argsort(ids)
+        res.append((z[o], v[o], el.rhs(), ap.selfPotential(), t.enodes(), sec, t.last_launches()))
+        t.close()
+    a, b = res
+    for x, y in zip(a[:5], b[:5]):
+        assert np.array_equal(x, y)
+    assert b[6] == a[6]                            # same kernels launched, through the graph
+    print("300 steps of C1: stream %.1f us/step, graph %.1f us/step" % (a[5] / 300 * 1e6, b[5] / 300 * 1e6))
