@@ -44,8 +44,9 @@ enum { PTP_DEPOSIT_FP64 = 0, PTP_DEPOSIT_FIXED64 = 1 };
  * PTP_ARITH_EXACT: IEEE divisions in the reference's expression order -> per-ring
  * z, v bit-identical to the reference for identical node fields. */
 enum { PTP_ARITH_FAST = 0, PTP_ARITH_EXACT = 1 };
-/* Poisson solver: direct separable (DCT-I in z + Thomas in r), or red-black SOR (cross-check). */
-enum { PTP_SOLVER_DIRECT = 0, PTP_SOLVER_SOR = 1 };
+/* Poisson solver: direct separable (DCT-I in z + Thomas in r), red-black SOR (cross-check), or the direct solver with
+ * the inverse DCT forced through the FFT kernel (needs a power-of-two Nz; chosen automatically for long rows). */
+enum { PTP_SOLVER_DIRECT = 0, PTP_SOLVER_SOR = 1, PTP_SOLVER_DIRECT_FFT = 2 };
 
 const char* ptp_last_error(void);
 int ptp_version(void);

@@ -27,7 +27,7 @@ KB = 1.380649e-23
 
 PTP_DEPOSIT_FP64, PTP_DEPOSIT_FIXED64 = 0, 1
 PTP_ARITH_FAST, PTP_ARITH_EXACT = 0, 1
-PTP_SOLVER_DIRECT, PTP_SOLVER_SOR = 0, 1
+PTP_SOLVER_DIRECT, PTP_SOLVER_SOR, PTP_SOLVER_DIRECT_FFT = 0, 1, 2
 
 
 class PtpError(RuntimeError):

@@ -343,7 +343,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	if (!t || nSteps < 0) { ptp_set_error("ptp_trap_step: bad arguments"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
-	const bool graph = t->useGraph && t->sortInterval == 0 && t->solver == PTP_SOLVER_DIRECT && !t->plasmas.empty();
+	const bool graph = t->useGraph && t->sortInterval == 0 && t->solver != PTP_SOLVER_SOR && !t->plasmas.empty();
 	// phase events for every step (up to a bound), so that callers can report the mean kernel time
 	const int timed = (!graph && nSteps <= 4096) ? nSteps : 0;
 	while ((int)t->evPool.size() < 4 * timed) {
@@ -449,7 +449,8 @@ int ptp_trap_set_arith_mode(ptp_trap* t, int mode)
 int ptp_trap_set_solver(ptp_trap* t, int solver, double sorTolerance, int sorMaxIterations)
 {
 	if (t) ++t->cfgEpoch;
-	if (!t || (solver != PTP_SOLVER_DIRECT && solver != PTP_SOLVER_SOR)) { ptp_set_error("ptp_trap_set_solver: bad solver"); return PTP_EINVAL; }
+	if (!t || (solver != PTP_SOLVER_DIRECT && solver != PTP_SOLVER_SOR && solver != PTP_SOLVER_DIRECT_FFT)) { ptp_set_error("ptp_trap_set_solver: bad solver"); return PTP_EINVAL; }
+	if (solver == PTP_SOLVER_DIRECT_FFT && !t->fftTw) { ptp_set_error("ptp_trap_set_solver: the FFT inverse needs a power-of-two Nz"); return PTP_EINVAL; }
 	t->solver = solver;
 	if (sorTolerance > 0) t->sorTol = sorTolerance;
 	if (sorMaxIterations > 0) t->sorMaxIter = sorMaxIterations;

@@ -74,6 +74,7 @@ struct ptp_trap {
 	double* stLower = nullptr;   // [Nr] stencil r-lower   (operator apply / SOR)
 	double* stUpper = nullptr;   // [Nr] stencil r-upper
 	double stDiag = 0, stHz2 = 0, wallFactor = 0;
+	double2* fftTw = nullptr;    // [Nz] exp(-i pi j / Nz), only when Nz is a power of two (FFT inverse transform)
 	int2* rowBounds = nullptr;   // [species x Nr] non-zero axial range of each deposit row (forward transform)
 	int rowBoundsCap = 0;
 

@@ -475,6 +475,41 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 	}
 }
 
+// Inverse DCT-I of one grid row through an FFT, for long rows with a power-of-two number of cells (config 5: Nz = 4096,
+// where the dense transform would cost 17 GFMA per solve). The even extension of the row (length 2 Nz, real, symmetric)
+// has the real spectrum  X_k = a_0 + (-1)^k a_N + 2 sum_{m=1}^{N-1} a_m cos(pi m k / N), hence
+//   phi_k = sum_{m=0}^{N} a_m cos(pi m k / N) = X_k / 2 + (a_0 + (-1)^k a_N) / 2.
+// One CTA per row: the extension lives in shared memory as 2N complex values (128 KB at N = 4096), in-place radix-2
+// decimation-in-frequency passes with twiddles from a table computed in extended precision on the host; the result of
+// index k is read from the bit-reversed position.
+__global__ void __launch_bounds__(512) k_idct_fft(const double* __restrict__ alpha, double* __restrict__ phi,
+	const double2* __restrict__ tw, int N, int bits /* log2(2N) */)
+{
+	extern __shared__ double2 fb[];                             // [2N]
+	const int tid = threadIdx.x, T = blockDim.x, n1 = N + 1;
+	const double* a = alpha + (size_t)blockIdx.x * n1;
+	for (int k = tid; k < 2 * N; k += T) fb[k] = make_double2(a[k <= N ? k : 2 * N - k], 0.0);
+	const double a0 = a[0], aN = a[N];
+	__syncthreads();
+	for (int half = N; half >= 1; half >>= 1) {
+		const int stride = N / half;                            // twiddle exponent step: W_{2 half}^j = W_{2N}^{j stride}
+		for (int i = tid; i < N; i += T) {
+			const int j = i & (half - 1);
+			const int p = ((i - j) << 1) + j, q = p + half;
+			const double2 u = fb[p], v = fb[q], w = __ldg(&tw[j * stride]);
+			fb[p] = make_double2(u.x + v.x, u.y + v.y);
+			const double dx = u.x - v.x, dy = u.y - v.y;
+			fb[q] = make_double2(dx * w.x - dy * w.y, dx * w.y + dy * w.x);
+		}
+		__syncthreads();
+	}
+	double* out = phi + (size_t)blockIdx.x * n1;
+	for (int k = tid; k <= N; k += T) {
+		const unsigned int r = __brev((unsigned int)k) >> (32 - bits);
+		out[k] = 0.5 * fb[r].x + 0.5 * (a0 + ((k & 1) ? -aN : aN));
+	}
+}
+
 // PenningTrap::getEField(int,int), Source/PenningTrap.cpp:208-236: E = (sumPhi[idx-1] - sumPhi[idx+1]) / (2 hz),
 // zero at both axial ends, species added in registration order.
 __global__ void k_node_field(const double* __restrict__ phiTrap, const double* __restrict__ phiSelf, int nS,
@@ -617,6 +652,15 @@ int ptp_solver_build(ptp_trap* t)
 			thCp[(size_t)j * n1 + m] = (double)cpPrev;
 		}
 	}
+	if (Nz >= 8 && (Nz & (Nz - 1)) == 0) {                      // power-of-two cell count: FFT path for the inverse transform
+		std::vector<double2> tw((size_t)Nz);
+		for (int j = 0; j < Nz; ++j) {
+			const long double ang = -pi * (long double)j / (long double)Nz;     // exp(-2 pi i j / (2 Nz))
+			tw[j] = make_double2((double)cosl(ang), (double)sinl(ang));
+		}
+		PTP_CUDA(cudaMalloc(&t->fftTw, (size_t)Nz * sizeof(double2)));
+		PTP_CUDA(cudaMemcpy(t->fftTw, tw.data(), (size_t)Nz * sizeof(double2), cudaMemcpyHostToDevice));
+	}
 	const size_t nn = (size_t)n1 * n1 * sizeof(double), gg = (size_t)Nr * n1 * sizeof(double);
 	// one allocation for all solver constants, so that a single L2 access-policy window can keep them resident
 	// while the push kernel streams the ring arrays through L2 between two solves
@@ -658,7 +702,7 @@ int ptp_solver_build(ptp_trap* t)
 
 void ptp_solver_free(ptp_trap* t)
 {
-	cudaFree(t->solverConst); cudaFree(t->rowBounds);
+	cudaFree(t->solverConst); cudaFree(t->rowBounds); cudaFree(t->fftTw);
 	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
 }
 
@@ -704,7 +748,17 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= t->smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const size_t smField = smFieldBytes(ringStages);
 	bool fieldDone = false;
-	if (smField <= t->smemMax) {
+	const size_t smFft = (size_t)2 * t->Nz * sizeof(double2);
+	const bool useFft = t->fftTw && smFft <= t->smemMax && (t->solver == PTP_SOLVER_DIRECT_FFT || smField > t->smemMax);
+	if (useFft) {
+		int bits = 0;
+		while ((1 << bits) < 2 * t->Nz) ++bits;
+		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFft));
+		k_idct_fft<<<M, 512, smFft, t->stream>>>(spec, phi, t->fftTw, t->Nz, bits);
+		cudaError_t ei = cudaGetLastError();
+		if (ei != cudaSuccess) return ptp_cuda_fail(ei, "k_idct_fft launch", __FILE__, __LINE__);
+	}
+	else if (smField <= t->smemMax) {
 		auto launchInv = [&](auto kern, bool field) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smField);
 			if (e != cudaSuccess) return e;

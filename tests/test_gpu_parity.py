@@ -376,13 +376,17 @@ def test_edge_cases():
 
 
 # ------------------------------------------------------------------------------------------ other grid shapes
-@pytest.mark.parametrize("Nz,Nr", [(1024, 96), (2048, 16), (301, 130), (48, 420)])
-def test_solver_and_step_on_other_grids(Nz, Nr):
-    """Grid shapes that take the other code paths of the solver (odd Nz+1 -> 8-byte copies, pipelined B ring, chunked
-    inverse GEMM + separate node field for long rows, 4 modes per CTA for many radial nodes) against the CPU oracle."""
+@pytest.mark.parametrize("Nz,Nr,solver", [(1024, 96, 0), (2048, 16, 0), (1500, 12, 0), (301, 130, 0), (48, 420, 0), (256, 24, 2)])
+def test_solver_and_step_on_other_grids(Nz, Nr, solver):
+    """Grid shapes that take the other code paths of the solver against the CPU oracle: odd Nz+1 (8-byte copies), pipelined
+    cosine ring (1024), FFT inverse for long power-of-two rows (2048; forced at 256), chunked inverse GEMM + separate node
+    field for long rows that are not a power of two (1500), 4 modes per CTA for many radial nodes (420)."""
     args = (0.012, [0.02, 0.03, 0.02], [0.0, -50.0, 0.0], [0.001, 0.001], Nz, Nr)
     pt = port.PortTrap(*args)
     t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], Nz, Nr)
+    if solver:
+        t.set_solver(solver)
+        t.solveLaplace()
     assert rel_l2(t.phi(), pt.phi) < 1e-10
     rng = np.random.default_rng(Nz + Nr)
     x = rng.standard_normal(t.G)
