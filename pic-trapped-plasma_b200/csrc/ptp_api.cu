@@ -357,6 +357,9 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	if (graph && nSteps > 0) {
 		if (!t->graphExec || t->graphCfg != t->cfgEpoch || t->graphDt != dt || t->graphParity != t->rhoParity)
 			PTP_TRY(capture_step_graph(t, dt));
+		if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));          // potentials were replaced since the last step (setPotential, parity hooks)
+		for (ptp_plasma* p : t->plasmas)
+			if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 		PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
 		for (; done + t->graphUnit <= nSteps; done += t->graphUnit) {
 			PTP_CUDA(cudaGraphLaunch(t->graphExec, t->stream));

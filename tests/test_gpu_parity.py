@@ -404,7 +404,7 @@ def test_solver_and_step_on_other_grids(Nz, Nr, solver):
     gp.solvePoisson()
     assert rel_l2(gp.rhs(), op.rhs) < 1e-12
     assert rel_l2(gp.selfPotential(), op.self_potential) < 1e-9
-    dt = 0.2 * pt.hz / 3e4
+    dt = min(0.2 * pt.hz / 3e4, 5e-10)               # keep the coarse grids out of the violently non-linear regime
     for _ in range(3):
         t.set_phi(pt.phi)
         gp.set_self_potential(op.self_potential)
@@ -445,15 +445,17 @@ def test_graph_replay_is_bitwise_identical(c1_kat):
         t.movePlasmas(dt, 300)
         t.sync()
         sec = time.perf_counter() - t0
+        mid = el.rhs()
         t.movePlasmas(dt * 0.5, 7)                 # new dt -> new graph
+        mid2 = el.rhs()
         t.setPotential(1, -60.0)                  # same graph, new trap potential
         t.movePlasmas(dt * 0.5, 5)
         _, z, v, ids = el.download()
         o = np.argsort(ids)
-        res.append((z[o], v[o], el.rhs(), ap.selfPotential(), t.enodes(), sec, t.last_launches()))
+        res.append((mid, mid2, z[o], v[o], el.rhs(), ap.selfPotential(), t.enodes(), sec, t.last_launches()))
         t.close()
     a, b = res
-    for x, y in zip(a[:5], b[:5]):
-        assert np.array_equal(x, y)
-    assert b[6] == a[6]                            # same kernels launched, through the graph
-    print("300 steps of C1: stream %.1f us/step, graph %.1f us/step" % (a[5] / 300 * 1e6, b[5] / 300 * 1e6))
+    for n, (x, y) in enumerate(zip(a[:7], b[:7])):
+        assert np.array_equal(x, y), n
+    assert b[8] == a[8]                            # same kernels launched, through the graph
+    print("300 steps of C1: stream %.1f us/step, graph %.1f us/step" % (a[7] / 300 * 1e6, b[7] / 300 * 1e6))
