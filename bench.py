@@ -28,7 +28,9 @@ WORKLOADS = {
     "c4": ([("Antiprotons", "massP", 1.0)], 100_000_000, "single-species 100M macro-rings, default trap 585x128 (BASELINE configs[3])"),
     "c2": ([("Antiprotons", "massP", 1.0)], 1_000_000, "antiproton plasma, 1M macro-rings, default trap (BASELINE configs[1]; L2-resident)"),
     "c3": ([("Electrons", "massE", 0.5), ("Antiprotons", "massP", 0.5)], 10_000_000, "e- + pbar co-trapped, 10M macro-rings (BASELINE configs[2])"),
+    "c5": ([("Antiprotons", "massP", 1.0)], 50_000_000, "fine-grid stress: 4096x1024 trap grid, 50M macro-rings (BASELINE configs[4])"),
 }
+GRIDS = {"c5": (4096, 1024)}          # (Nz, Nr); everything else runs on the reference's default 585 x 128
 DT = 2e-8 / 35            # Diagnostics/C) Visualise Evolution.txt:34-36
 TEMPERATURE = 150.0
 
@@ -112,13 +114,43 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
+def grid_of(workload):
+    return GRIDS.get(workload, (585, 128))
+
+
+def density_on(Nz, Nr):
+    """The committed equilibrium density (585 x 128 grid); for other grids interpolated bilinearly in (r, z) over the
+    same trap, which keeps the plasma's physical extent (the reference recomputes the equilibrium on the new grid)."""
+    dens = expected_density()
+    if (Nz, Nr) == (585, 128):
+        return dens
+    d = dens.reshape(128, 586)
+    zi = np.linspace(0, 585, Nz + 1)
+    ri = np.minimum(np.arange(Nr) * (128.0 / Nr), 127.0)
+    z0 = np.minimum(zi.astype(int), 584)
+    r0 = np.minimum(ri.astype(int), 126)
+    fz, fr = zi - z0, ri - r0
+    top = d[r0][:, z0] * (1 - fz) + d[r0][:, z0 + 1] * fz
+    bot = d[r0 + 1][:, z0] * (1 - fz) + d[r0 + 1][:, z0 + 1] * fz
+    return (top * (1 - fr)[:, None] + bot * fr[:, None]).reshape(-1)
+
+
+def make_trap(mod, workload, **kw):
+    Nz, Nr = grid_of(workload)
+    if hasattr(mod, "PenningTrap"):
+        el = [mod.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
+        return mod.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr, **kw)
+    return mod.default_trap(Nz, Nr)
+
+
 def build_load(ptp, loaders, workload, rank, n_ranks, hz, hr):
     species, total, _ = WORKLOADS[workload]
-    dens = expected_density()
+    Nz, Nr = grid_of(workload)
+    dens = density_on(Nz, Nr)
     out = []
     for si, (name, mkey, share) in enumerate(species):
         mass = getattr(ptp, mkey)
-        r, z, charge_macro, _ = loaders.place_rings(dens * share, 585, 128, hz, hr, int(total * share), rank, n_ranks)
+        r, z, charge_macro, _ = loaders.place_rings(dens * share, Nz, Nr, hz, hr, int(total * share), rank, n_ranks)
         v = loaders.maxwellian_speeds(len(r), TEMPERATURE, mass, seed=1000 * si + rank)
         out.append((name, mass, r, z, v, charge_macro))
     return out
@@ -136,7 +168,7 @@ def cpu_reference_run(workload, steps, warmup, sample_rings):
     # bounded sample: keep the whole arm within a couple of minutes of CPU time (~2e7 ring-steps/s on one core)
     sample_rings = int(max(100_000, min(sample_rings, 1.2e9 / max(steps + warmup, 1))))
     stride = max(1, total // sample_rings)
-    trap = ref.default_trap() if kind == "reference" else port.default_trap()
+    trap = make_trap(ref if kind == "reference" else port, workload)
     load = build_load(ptp, loaders, workload, 0, stride, trap.hz, trap.hr)   # ring i % stride == 0 of every row
     n = 0
     plasmas = []
@@ -193,7 +225,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     species, total, desc = WORKLOADS[args.workload]
-    config = {"workload": "%s: %s" % (args.workload, desc), "grid": "Nz=585 Nr=128", "dt_s": DT, "species": len(species),
+    config = {"workload": "%s: %s" % (args.workload, desc), "grid": "Nz=%d Nr=%d" % grid_of(args.workload), "dt_s": DT, "species": len(species),
               "rings_total": total, "deposit": args.deposit,
               "exchange": ("peer-memory push fused into the deposit flush + flag barrier" if args.allreduce == "peer" else "NCCL all-reduce") if world > 1 else "none (1 GPU)",
               "l2": "ring arrays %d MB per GPU vs 126 MB L2 (no flush needed)" % (total // world * 16 // 2**20) if total // world * 16 > 200e6
@@ -241,7 +273,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    trap = ptp.default_trap(device=local_rank)
+    trap = make_trap(ptp, args.workload, device=local_rank)
     if world > 1:
         uid = [ptp.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -341,6 +373,8 @@ def main():
                            "rings stay resident between steps as in the reference's API (movePlasmas(dt) takes no ring data)" % (20, e2e_steps)}
 
     cpu = None
+    if args.workload == "c5":
+        args.no_cpu_baseline = True       # the stand-in LU cannot factorise the 4.2 M-node grid in reasonable time
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_reference_run(args.workload, 3, 1, min(args.cpu_sample, total))
 

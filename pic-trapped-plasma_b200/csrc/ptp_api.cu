@@ -472,7 +472,7 @@ int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ring
 	if (ringsPerThread > 0) t->ringsPerThread = ringsPerThread;
 	if (ptp_push_configure(t) != PTP_OK) { t->threads = oT; t->window = oW; t->ctas = oC; t->ringsPerThread = oR; return PTP_EINVAL; }
 	for (ptp_plasma* p : t->plasmas)
-		if (p->cap) { PTP_TRY(ptp_build_segments(t, p)); PTP_TRY(ptp_bounds_launch(t, p)); }
+		if (p->cap) PTP_TRY(ptp_build_segments(t, p));
 	return PTP_OK;
 }
 

@@ -151,6 +151,7 @@ int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* d
 // ---- ptp_push.cu ---------------------------------------------------------------------------------
 int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push);
 int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p);
+int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& tiles, std::vector<int2>& tileBounds, int64_t* nLive);
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window);
 int ptp_push_configure(ptp_trap* t);
 

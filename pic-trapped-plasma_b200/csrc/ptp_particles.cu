@@ -158,36 +158,65 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const double* __restrict__
 
 } // namespace
 
-// Split the live part of every row bucket into segments and deal them to CTAs in contiguous tile ranges.
+// Plan the push kernel's work: the live part of every row bucket is cut into tiles, tiles are dealt to CTAs in
+// contiguous ranges of equal length, and inside a CTA's range consecutive tiles of one row are merged into a segment
+// as long as their combined axial cell range still fits the thread-private deposit window (with some slack for the drift
+// until the next re-plan) - so a z-ordered load of a long plasma (config 5: ~240 cells) gets many narrow segments while
+// the default plasma (37 cells) keeps one segment per CTA and row. Also yields the live ring count and validates z.
 int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 {
 	const long long tile = (long long)t->ringsPerThread * t->threads;
-	const long long maxSegTiles = 4095 / t->ringsPerThread;   // 12-bit per-thread count field of the packed bins
-	long long totalTiles = 0;
-	for (int r = 0; r < t->Nr; ++r) totalTiles += (p->rowLive[r] + tile - 1) / tile;
+	const long long maxSegTiles = 4095 / t->ringsPerThread;     // 12-bit per-thread count field of the packed bins
+	std::vector<PtpSegment> tiles;
+	for (int r = 0; r < t->Nr; ++r)
+		for (long long b = 0; b < p->rowLive[r]; b += tile) {
+			PtpSegment s;
+			s.row = r; s.pad = 0;
+			s.begin = p->rowOff[r] + b;
+			s.end = s.begin + tile;
+			tiles.push_back(s);
+		}
+	std::vector<int2> tb;
+	int64_t live = 0;
+	PTP_TRY(ptp_tile_bounds(t, p, tiles, tb, &live));
+	p->nAlive = live;
+	const long long totalTiles = (long long)tiles.size();
 	int nCta = t->ctas > 0 ? t->ctas : t->smCount;
 	if (totalTiles < nCta) nCta = (int)totalTiles;
+	const int W = t->window < t->Nz ? t->window : t->Nz;
+	const int limit = std::max(1, W - std::max(2, W / 8));      // cells a planned segment may span
 	p->segs.clear();
 	p->ctaSegBegin.assign(1, 0);
 	p->nCta = nCta;
-	if (nCta > 0) {
-		int cta = 0;
-		long long given = 0;                                 // tiles handed out so far
-		auto quotaEnd = [&](int c) { return (totalTiles * (long long)(c + 1)) / nCta; };
-		for (int r = 0; r < t->Nr; ++r) {
-			long long tiles = (p->rowLive[r] + tile - 1) / tile, done = 0;
-			while (done < tiles) {
-				while (given >= quotaEnd(cta)) { p->ctaSegBegin.push_back((int)p->segs.size()); ++cta; }
-				long long take = std::min(std::min(tiles - done, quotaEnd(cta) - given), maxSegTiles);
-				PtpSegment s;
-				s.row = r; s.pad = 0;
-				s.begin = p->rowOff[r] + done * tile;
-				s.end = s.begin + take * tile;
-				p->segs.push_back(s);
-				done += take; given += take;
+	std::vector<int2> segBounds;
+	for (int c = 0; c < nCta; ++c) {
+		const long long qa = totalTiles * c / nCta, qb = totalTiles * (c + 1) / nCta;
+		long long i = qa;
+		while (i < qb) {
+			// (lo, hi): range used for the split decision - tiles that are wider than the window on their own (rings not
+			// ordered in z at tile granularity; a sort fixes that) cannot be helped by splitting and are left out of it;
+			// (flo, fhi): the true range of the segment
+			PtpSegment s = tiles[i];
+			auto ordered = [&](const int2& b) { return b.x > b.y || b.y - b.x + 1 <= limit; };
+			int lo = INT_MAX, hi = INT_MIN, flo = tb[i].x, fhi = tb[i].y;
+			if (ordered(tb[i])) { lo = tb[i].x; hi = tb[i].y; }
+			long long n = 1;
+			while (i + n < qb && n < maxSegTiles && tiles[i + n].row == s.row) {
+				const int2 nb = tb[i + n];
+				if (ordered(nb)) {
+					const int nlo = std::min(lo, nb.x), nhi = std::max(hi, nb.y);
+					if (nlo <= nhi && nhi - nlo + 1 > limit) break;
+					lo = nlo; hi = nhi;
+				}
+				flo = std::min(flo, nb.x); fhi = std::max(fhi, nb.y);
+				++n;
 			}
+			s.end = tiles[i + n - 1].end;
+			p->segs.push_back(s);
+			segBounds.push_back(make_int2(flo, fhi));
+			i += n;
 		}
-		while ((int)p->ctaSegBegin.size() < nCta + 1) p->ctaSegBegin.push_back((int)p->segs.size());
+		p->ctaSegBegin.push_back((int)p->segs.size());
 	}
 	cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds);
 	p->dSegs = nullptr; p->dCtaSegBegin = nullptr; p->dSegBounds = nullptr;
@@ -197,9 +226,11 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 		PTP_CUDA(cudaMalloc(&p->dSegBounds, p->segs.size() * sizeof(int2)));
 		PTP_CUDA(cudaMemcpyAsync(p->dSegs, p->segs.data(), p->segs.size() * sizeof(PtpSegment), cudaMemcpyHostToDevice, t->stream));
 		PTP_CUDA(cudaMemcpyAsync(p->dCtaSegBegin, p->ctaSegBegin.data(), p->ctaSegBegin.size() * sizeof(int), cudaMemcpyHostToDevice, t->stream));
+		PTP_CUDA(cudaMemcpyAsync(p->dSegBounds, segBounds.data(), segBounds.size() * sizeof(int2), cudaMemcpyHostToDevice, t->stream));
 		PTP_CUDA(cudaStreamSynchronize(t->stream));
 	}
-	p->boundsValid = false;
+	++t->cfgEpoch;
+	p->boundsValid = true;
 	return PTP_OK;
 }
 
@@ -246,8 +277,7 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 	p->nAlive = total;
 	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
 	p->nUploaded = total;                                  // loss counter restarts from the compacted population
-	PTP_TRY(ptp_build_segments(t, p));
-	return ptp_bounds_launch(t, p);
+	return ptp_build_segments(t, p);
 }
 
 // ---- C ABI: particle-side entry points ---------------------------------------------------------------
@@ -368,8 +398,7 @@ int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* 
 	int bits = 0;
 	while ((1LL << bits) < total + 1) ++bits;
 	t->fixedBits = std::min(40, 62 - bits);
-	PTP_TRY(ptp_build_segments(t, p));
-	return ptp_bounds_launch(t, p);
+	return ptp_build_segments(t, p);
 }
 
 int ptp_plasma_count(ptp_plasma* p, int64_t* nAlive)

@@ -407,44 +407,45 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 	}
 }
 
-__global__ void k_bounds_init(int2* bounds, int n)
+// Axial cell range and live count of every tile (window planning at upload / after a sort) and validation of the
+// positions. One CTA per tile; tiles[] lists them as one-tile segments.
+__global__ void __launch_bounds__(256) k_tile_bounds(const PushArgs a, const PtpSegment* __restrict__ tiles, int nTiles,
+	int2* __restrict__ tileBounds, unsigned long long* nLive, int* invalid)
 {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) bounds[i] = make_int2(INT_MAX, INT_MIN);
-}
-
-// Per-segment axial cell range of the live rings (window for the first deposit / after a sort) and validation.
-// blockIdx.y = segment, blockIdx.x = chunk of it.
-__global__ void __launch_bounds__(256) k_bounds(const PushArgs a, unsigned long long* nLive, int* invalid)
-{
-	const PtpSegment seg = a.segs[blockIdx.y];
-	const long long len = ((seg.end - seg.begin + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
-	const long long b = seg.begin + (long long)blockIdx.x * len, e = min(seg.end, b + len);
-	int kMin = INT_MAX, kMax = INT_MIN;
-	unsigned int live = 0;
-	for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
-		const double z = a.z[i];
-		if (!(z == z)) continue;
-		if (!(z > 0.0 && z < a.length)) { *invalid = 1; continue; }
-		int k;
-		double kd;
-		bool ok;
-		cell_fast(z, a, k, kd, ok);
-		if (!ok) cell_exact(z, a, k, kd);
-		k = min(k, a.Nz - 1);
-		kMin = min(kMin, k);
-		kMax = max(kMax, k);
-		++live;
-	}
-	for (int o = 16; o > 0; o >>= 1) {
-		kMin = min(kMin, __shfl_xor_sync(0xffffffffu, kMin, o));
-		kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
-	}
-	live = warp_sum(live);
-	if ((threadIdx.x & 31) == 0 && live) {
-		atomicMin(&a.segBounds[blockIdx.y].x, kMin);
-		atomicMax(&a.segBounds[blockIdx.y].y, kMax);
-		atomicAdd(nLive, (unsigned long long)live);
+	__shared__ int sKmin, sKmax;
+	for (int tIdx = blockIdx.x; tIdx < nTiles; tIdx += gridDim.x) {
+		const PtpSegment seg = tiles[tIdx];
+		if (threadIdx.x == 0) { sKmin = INT_MAX; sKmax = INT_MIN; }
+		__syncthreads();
+		int kMin = INT_MAX, kMax = INT_MIN;
+		unsigned int live = 0;
+		for (long long i = seg.begin + threadIdx.x; i < seg.end; i += blockDim.x) {
+			const double z = a.z[i];
+			if (!(z == z)) continue;
+			if (!(z > 0.0 && z < a.length)) { *invalid = 1; continue; }
+			int k;
+			double kd;
+			bool ok;
+			cell_fast(z, a, k, kd, ok);
+			if (!ok) cell_exact(z, a, k, kd);
+			k = min(k, a.Nz - 1);
+			kMin = min(kMin, k);
+			kMax = max(kMax, k);
+			++live;
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			kMin = min(kMin, __shfl_xor_sync(0xffffffffu, kMin, o));
+			kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
+		}
+		live = warp_sum(live);
+		if ((threadIdx.x & 31) == 0 && live) {
+			atomicMin(&sKmin, kMin);
+			atomicMax(&sKmax, kMax);
+			atomicAdd(nLive, (unsigned long long)live);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) tileBounds[tIdx] = make_int2(sKmin, sKmax);
+		__syncthreads();
 	}
 }
 
@@ -547,31 +548,39 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 	return PTP_OK;
 }
 
-// Recompute the per-segment cell windows from the ring positions; validates 0 < z < length.
-int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p)
+// Cell range of every tile in `tiles` (host list) -> tileBounds (host), live ring count; validates 0 < z < length.
+int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& tiles, std::vector<int2>& tileBounds, int64_t* nLive)
 {
-	if (p->cap == 0 || p->segs.empty()) { p->boundsValid = true; return PTP_OK; }
+	tileBounds.assign(tiles.size(), make_int2(INT_MAX, INT_MIN));
+	*nLive = 0;
+	if (tiles.empty()) return PTP_OK;
 	const PushArgs a = make_args(t, p, 0.0);
+	const int n = (int)tiles.size();
+	PtpSegment* dTiles = nullptr;
+	int2* dB = nullptr;
 	unsigned long long* dLive = nullptr;
-	PTP_CUDA(cudaMalloc(&dLive, sizeof(unsigned long long) + sizeof(int) * 2));
+	PTP_CUDA(cudaMalloc(&dTiles, (size_t)n * sizeof(PtpSegment)));
+	PTP_CUDA(cudaMalloc(&dB, (size_t)n * sizeof(int2)));
+	PTP_CUDA(cudaMalloc(&dLive, sizeof(unsigned long long) + 2 * sizeof(int)));
 	int* dInvalid = reinterpret_cast<int*>(dLive + 1);
-	PTP_CUDA(cudaMemsetAsync(dLive, 0, sizeof(unsigned long long) + sizeof(int) * 2, t->stream));
-	const int nSegs = (int)p->segs.size();
-	k_bounds_init<<<(nSegs + 255) / 256, 256, 0, t->stream>>>(p->dSegBounds, nSegs);
-	int chunks = (t->smCount * 16 + nSegs - 1) / nSegs;
-	if (chunks > 64) chunks = 64;
-	k_bounds<<<dim3(chunks, nSegs), 256, 0, t->stream>>>(a, dLive, dInvalid);
+	PTP_CUDA(cudaMemcpyAsync(dTiles, tiles.data(), (size_t)n * sizeof(PtpSegment), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaMemsetAsync(dLive, 0, sizeof(unsigned long long) + 2 * sizeof(int), t->stream));
+	const int grid = n < t->smCount * 32 ? n : t->smCount * 32;
+	k_tile_bounds<<<grid, 256, 0, t->stream>>>(a, dTiles, n, dB, dLive, dInvalid);
 	cudaError_t e = cudaGetLastError();
-	if (e != cudaSuccess) { cudaFree(dLive); return ptp_cuda_fail(e, "k_bounds launch", __FILE__, __LINE__); }
-	t->lastLaunches += 2;
 	unsigned long long live = 0;
 	int invalid = 0;
-	PTP_CUDA(cudaMemcpyAsync(&live, dLive, sizeof(live), cudaMemcpyDeviceToHost, t->stream));
-	PTP_CUDA(cudaMemcpyAsync(&invalid, dInvalid, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-	PTP_CUDA(cudaStreamSynchronize(t->stream));
-	cudaFree(dLive);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(tileBounds.data(), dB, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&live, dLive, sizeof(live), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&invalid, dInvalid, sizeof(int), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+	cudaFree(dTiles); cudaFree(dB); cudaFree(dLive);
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_tile_bounds", __FILE__, __LINE__);
+	t->lastLaunches++;
 	if (invalid) { ptp_set_error("ring position outside (0, trap length)"); return PTP_EINVAL; }
-	p->nAlive = (int64_t)live;
-	p->boundsValid = true;
+	*nLive = (int64_t)live;
 	return PTP_OK;
 }
+
+// Segment tables and windows are planned together (ptp_particles.cu).
+int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p) { return ptp_build_segments(t, p); }
