@@ -42,7 +42,7 @@ struct ptp_plasma {
 	std::vector<int> ctaSegBegin;    // [nCta+1]
 	PtpSegment* dSegs = nullptr;
 	int* dCtaSegBegin = nullptr;
-	int2* dSegBounds = nullptr;      // per segment: min / max axial cell of its live rings
+	int4* dSegBounds = nullptr;      // per segment: min / max / mean axial cell of its live rings (x, y, z)
 	int nCta = 0;
 	unsigned long long* dLost = nullptr; // rings lost since upload (device counter)
 	bool boundsValid = false;

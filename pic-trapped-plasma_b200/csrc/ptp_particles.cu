@@ -188,32 +188,32 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 	p->segs.clear();
 	p->ctaSegBegin.assign(1, 0);
 	p->nCta = nCta;
-	std::vector<int2> segBounds;
+	std::vector<int4> segBounds;
 	for (int c = 0; c < nCta; ++c) {
 		const long long qa = totalTiles * c / nCta, qb = totalTiles * (c + 1) / nCta;
+		long long wide = 0;
+		for (long long q = qa; q < qb; ++q) wide += (tb[q].x <= tb[q].y && tb[q].y - tb[q].x + 1 > limit) ? 1 : 0;
+		const bool mostlyWide = 2 * wide > qb - qa;
 		long long i = qa;
 		while (i < qb) {
-			// (lo, hi): range used for the split decision - tiles that are wider than the window on their own (rings not
-			// ordered in z at tile granularity; a sort fixes that) cannot be helped by splitting and are left out of it;
-			// (flo, fhi): the true range of the segment
+			// A tile that is wider than the window on its own (the sparse tails of a z-ordered load, or rings that are not
+			// ordered at tile granularity at all) cannot be helped by splitting. In an ordered load such tiles are rare and
+			// become segments of their own, so that they do not widen their neighbours' windows; when most tiles of the
+			// CTA's range are wide (unordered rings: a sort fixes that) everything of a row is merged instead.
 			PtpSegment s = tiles[i];
-			auto ordered = [&](const int2& b) { return b.x > b.y || b.y - b.x + 1 <= limit; };
-			int lo = INT_MAX, hi = INT_MIN, flo = tb[i].x, fhi = tb[i].y;
-			if (ordered(tb[i])) { lo = tb[i].x; hi = tb[i].y; }
+			int lo = tb[i].x, hi = tb[i].y;
 			long long n = 1;
-			while (i + n < qb && n < maxSegTiles && tiles[i + n].row == s.row) {
+			const bool wideFirst = !mostlyWide && lo <= hi && hi - lo + 1 > limit;
+			while (!wideFirst && i + n < qb && n < maxSegTiles && tiles[i + n].row == s.row) {
 				const int2 nb = tb[i + n];
-				if (ordered(nb)) {
-					const int nlo = std::min(lo, nb.x), nhi = std::max(hi, nb.y);
-					if (nlo <= nhi && nhi - nlo + 1 > limit) break;
-					lo = nlo; hi = nhi;
-				}
-				flo = std::min(flo, nb.x); fhi = std::max(fhi, nb.y);
+				const int nlo = std::min(lo, nb.x), nhi = std::max(hi, nb.y);
+				if (!mostlyWide && nlo <= nhi && nhi - nlo + 1 > limit) break;
+				lo = nlo; hi = nhi;
 				++n;
 			}
 			s.end = tiles[i + n - 1].end;
 			p->segs.push_back(s);
-			segBounds.push_back(make_int2(flo, fhi));
+			segBounds.push_back(make_int4(lo, hi, lo <= hi ? (lo + hi) / 2 : 0, 0));
 			i += n;
 		}
 		p->ctaSegBegin.push_back((int)p->segs.size());
@@ -223,10 +223,10 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 	if (!p->segs.empty()) {
 		PTP_CUDA(cudaMalloc(&p->dSegs, p->segs.size() * sizeof(PtpSegment)));
 		PTP_CUDA(cudaMalloc(&p->dCtaSegBegin, p->ctaSegBegin.size() * sizeof(int)));
-		PTP_CUDA(cudaMalloc(&p->dSegBounds, p->segs.size() * sizeof(int2)));
+		PTP_CUDA(cudaMalloc(&p->dSegBounds, p->segs.size() * sizeof(int4)));
 		PTP_CUDA(cudaMemcpyAsync(p->dSegs, p->segs.data(), p->segs.size() * sizeof(PtpSegment), cudaMemcpyHostToDevice, t->stream));
 		PTP_CUDA(cudaMemcpyAsync(p->dCtaSegBegin, p->ctaSegBegin.data(), p->ctaSegBegin.size() * sizeof(int), cudaMemcpyHostToDevice, t->stream));
-		PTP_CUDA(cudaMemcpyAsync(p->dSegBounds, segBounds.data(), segBounds.size() * sizeof(int2), cudaMemcpyHostToDevice, t->stream));
+		PTP_CUDA(cudaMemcpyAsync(p->dSegBounds, segBounds.data(), segBounds.size() * sizeof(int4), cudaMemcpyHostToDevice, t->stream));
 		PTP_CUDA(cudaStreamSynchronize(t->stream));
 	}
 	++t->cfgEpoch;

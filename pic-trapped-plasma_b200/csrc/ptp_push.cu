@@ -48,7 +48,7 @@ struct PushArgs {
 	double* v;
 	const PtpSegment* segs;
 	const int* ctaSegBegin;
-	int2* segBounds;
+	int4* segBounds;            // per segment: (min cell, max cell, mean cell, -) of its live rings, updated every step
 	void* rho[8];               // [G] double weights or int64 fixed point: this rank's grid, or every rank's (peer-memory mode)
 	int nRho, pad1;
 	long long bndOffset;        // (uint2*)((double*)rho[r] + bndOffset) = this species' touched-node range per row (encoded maxima)
@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 	unsigned short* cnts = reinterpret_cast<unsigned short*>(bins + (size_t)W * T); // [W][T] fp64 mode only (a thread sees < 4096 rings per segment)
 	__shared__ int sKmin, sKmax;
 	__shared__ unsigned int sLost;
+	__shared__ long long sKsum[T / 32];
+	__shared__ unsigned int sNdep[T / 32];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n1 = a.Nz + 1;
@@ -156,10 +158,13 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 
 	for (int s = a.ctaSegBegin[blockIdx.x]; s < a.ctaSegBegin[blockIdx.x + 1]; ++s) {
 		const PtpSegment seg = a.segs[s];
-		const int2 bounds = a.segBounds[s];
+		const int4 bounds = a.segBounds[s];
 		if (bounds.x > bounds.y) continue;           // no live ring in this segment (uniform per CTA)
 		const long long rowBase = (long long)seg.row * n1;
-		int k0 = bounds.x - max(0, (W - (bounds.y - bounds.x + 1)) >> 1);
+		// window: centred on the cell range when it fits; otherwise on the mean cell, so that a few far-away rings (the
+		// sparse tails of a distribution, a stray fast ring) cannot drag the window off the bulk - they take the slow path
+		const int span = bounds.y - bounds.x + 1;
+		int k0 = span <= W ? bounds.x - ((W - span) >> 1) : bounds.z - (W >> 1);
 		k0 = max(0, min(k0, a.Nz - W));
 		for (int i = 0; i < W; ++i) {
 			bins[(size_t)i * T + tid] = 0ULL;
@@ -177,7 +182,8 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		__syncthreads();
 
 		int kMin = INT_MAX, kMax = INT_MIN;
-		unsigned int lost = 0;
+		unsigned int lost = 0, nDep = 0;
+		long long kSum = 0;
 
 		const double2* z2 = reinterpret_cast<const double2*>(a.z);
 		const double2* v2 = reinterpret_cast<const double2*>(a.v);
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				const unsigned int io = (unsigned int)(k[i] - k0);
 				const bool in = live[i] && io < (unsigned int)W;
 				farD |= live[i] && io >= (unsigned int)W;
-				if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); }
+				if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
 				if (in) {
 					if (FIXED) {
 						// round(w * 2^F) lands in the mantissa of (2^52 + x); subtracting the bias leaves (1 << 52) | x
@@ -337,9 +343,13 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
 		}
 		lost = warp_sum(lost);
+		kSum = warp_sum(kSum);
+		nDep = warp_sum(nDep);
 		if (lane == 0) {
 			if (kMin <= kMax) { atomicMin(&sKmin, kMin); atomicMax(&sKmax, kMax); }
 			if (lost) atomicAdd(&sLost, lost);
+			sKsum[warp] = kSum;
+			sNdep[warp] = nDep;
 		}
 		__syncthreads();
 		const int gMin = sKmin, gMax = sKmax;
@@ -400,7 +410,10 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			if (tid == 0) __threadfence_system();
 		}
 		if (PUSH && tid == 0) {
-			a.segBounds[s] = make_int2(gMin, gMax);      // next step's window (this CTA owns the segment)
+			long long ks = 0;
+			unsigned int nd = 0;
+			for (int w = 0; w < T / 32; ++w) { ks += sKsum[w]; nd += sNdep[w]; }
+			a.segBounds[s] = make_int4(gMin, gMax, nd ? (int)(ks / nd) : 0, 0);   // next step's window (this CTA owns the segment)
 			if (sLost) atomicAdd(a.lost, (unsigned long long)sLost);
 		}
 		__syncthreads();
