@@ -189,34 +189,60 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 	p->ctaSegBegin.assign(1, 0);
 	p->nCta = nCta;
 	std::vector<int4> segBounds;
-	for (int c = 0; c < nCta; ++c) {
-		const long long qa = totalTiles * c / nCta, qb = totalTiles * (c + 1) / nCta;
+	if (nCta > 0) {
+		// pass 1: runs of tiles of one row whose combined cell range fits the window. A tile that is wider than the window
+		// on its own (the sparse tails of a z-ordered load, or rings not ordered at tile granularity at all) cannot be helped
+		// by splitting: in an ordered load such tiles are rare and become runs of their own so that they do not widen their
+		// neighbours' windows; when most tiles are wide (unordered rings - a sort fixes that) rows are not split at all.
+		auto isWide = [&](long long q) { return tb[q].x <= tb[q].y && tb[q].y - tb[q].x + 1 > limit; };
 		long long wide = 0;
-		for (long long q = qa; q < qb; ++q) wide += (tb[q].x <= tb[q].y && tb[q].y - tb[q].x + 1 > limit) ? 1 : 0;
-		const bool mostlyWide = 2 * wide > qb - qa;
-		long long i = qa;
-		while (i < qb) {
-			// A tile that is wider than the window on its own (the sparse tails of a z-ordered load, or rings that are not
-			// ordered at tile granularity at all) cannot be helped by splitting. In an ordered load such tiles are rare and
-			// become segments of their own, so that they do not widen their neighbours' windows; when most tiles of the
-			// CTA's range are wide (unordered rings: a sort fixes that) everything of a row is merged instead.
-			PtpSegment s = tiles[i];
+		for (long long q = 0; q < totalTiles; ++q) wide += isWide(q) ? 1 : 0;
+		const bool mostlyWide = 2 * wide > totalTiles;
+		std::vector<std::pair<long long, long long>> runs;      // [first tile, end tile)
+		for (long long i = 0; i < totalTiles;) {
 			int lo = tb[i].x, hi = tb[i].y;
 			long long n = 1;
-			const bool wideFirst = !mostlyWide && lo <= hi && hi - lo + 1 > limit;
-			while (!wideFirst && i + n < qb && n < maxSegTiles && tiles[i + n].row == s.row) {
-				const int2 nb = tb[i + n];
-				const int nlo = std::min(lo, nb.x), nhi = std::max(hi, nb.y);
+			const bool alone = !mostlyWide && isWide(i);
+			while (!alone && i + n < totalTiles && tiles[i + n].row == tiles[i].row) {
+				const int nlo = std::min(lo, tb[i + n].x), nhi = std::max(hi, tb[i + n].y);
 				if (!mostlyWide && nlo <= nhi && nhi - nlo + 1 > limit) break;
 				lo = nlo; hi = nhi;
 				++n;
 			}
-			s.end = tiles[i + n - 1].end;
-			p->segs.push_back(s);
-			segBounds.push_back(make_int4(lo, hi, lo <= hi ? (lo + hi) / 2 : 0, 0));
+			runs.emplace_back(i, i + n);
 			i += n;
 		}
-		p->ctaSegBegin.push_back((int)p->segs.size());
+		// pass 2: deal the runs to CTAs in order, balancing cost = tiles + a fixed charge per segment (zeroing and reducing
+		// the bins, the flush, the pipeline restart); runs are cut at tile granularity where a CTA's budget ends
+		const double segCharge = 4.0;
+		double totalCost = 0;
+		for (auto& r : runs) totalCost += (double)(r.second - r.first) + segCharge * (double)((r.second - r.first + maxSegTiles - 1) / maxSegTiles);
+		const double budget = totalCost / nCta;
+		double used = 0;
+		int cta = 0;
+		auto emit = [&](long long a0, long long b0) {
+			PtpSegment sg = tiles[a0];
+			sg.end = tiles[b0 - 1].end;
+			int lo = INT_MAX, hi = INT_MIN;
+			for (long long q = a0; q < b0; ++q) { lo = std::min(lo, tb[q].x); hi = std::max(hi, tb[q].y); }
+			while ((int)p->ctaSegBegin.size() < cta + 1) p->ctaSegBegin.push_back((int)p->segs.size());
+			p->segs.push_back(sg);
+			segBounds.push_back(make_int4(lo, hi, lo <= hi ? (lo + hi) / 2 : 0, 0));
+			used += (double)(b0 - a0) + segCharge;
+		};
+		for (auto& r : runs) {
+			long long a0 = r.first;
+			while (a0 < r.second) {
+				while (cta < nCta - 1 && used >= budget * (cta + 1) - 0.5) ++cta;
+				const double room = cta == nCta - 1 ? 1e300 : budget * (cta + 1) - used;
+				long long take = std::min<long long>(r.second - a0, maxSegTiles);
+				if ((double)take + segCharge > room + segCharge) take = std::max<long long>(1, (long long)(room - segCharge + 0.5));
+				take = std::min<long long>(take, r.second - a0);
+				emit(a0, a0 + take);
+				a0 += take;
+			}
+		}
+		while ((int)p->ctaSegBegin.size() < nCta + 1) p->ctaSegBegin.push_back((int)p->segs.size());
 	}
 	cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds);
 	p->dSegs = nullptr; p->dCtaSegBegin = nullptr; p->dSegBounds = nullptr;
