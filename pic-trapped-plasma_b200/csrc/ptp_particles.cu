@@ -215,11 +215,11 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 		// pass 2: deal the runs to CTAs in order, balancing cost = tiles + a fixed charge per segment (zeroing and reducing
 		// the bins, the flush, the pipeline restart); runs are cut at tile granularity where a CTA's budget ends
 		const double segCharge = 4.0;
-		double totalCost = 0;
-		for (auto& r : runs) totalCost += (double)(r.second - r.first) + segCharge * (double)((r.second - r.first + maxSegTiles - 1) / maxSegTiles);
-		const double budget = totalCost / nCta;
-		double used = 0;
+		long long remTiles = totalTiles;
 		int cta = 0;
+		double mine = 0;                                        // cost dealt to the current CTA
+		auto target = [&](size_t runsLeft) { return ((double)remTiles + segCharge * (double)runsLeft) / (double)(nCta - cta); };
+		double tgt = target(runs.size());
 		auto emit = [&](long long a0, long long b0) {
 			PtpSegment sg = tiles[a0];
 			sg.end = tiles[b0 - 1].end;
@@ -228,16 +228,21 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 			while ((int)p->ctaSegBegin.size() < cta + 1) p->ctaSegBegin.push_back((int)p->segs.size());
 			p->segs.push_back(sg);
 			segBounds.push_back(make_int4(lo, hi, lo <= hi ? (lo + hi) / 2 : 0, 0));
-			used += (double)(b0 - a0) + segCharge;
+			mine += (double)(b0 - a0) + segCharge;
+			remTiles -= b0 - a0;
 		};
-		for (auto& r : runs) {
-			long long a0 = r.first;
-			while (a0 < r.second) {
-				while (cta < nCta - 1 && used >= budget * (cta + 1) - 0.5) ++cta;
-				const double room = cta == nCta - 1 ? 1e300 : budget * (cta + 1) - used;
-				long long take = std::min<long long>(r.second - a0, maxSegTiles);
-				if ((double)take + segCharge > room + segCharge) take = std::max<long long>(1, (long long)(room - segCharge + 0.5));
-				take = std::min<long long>(take, r.second - a0);
+		for (size_t ri = 0; ri < runs.size(); ++ri) {
+			long long a0 = runs[ri].first;
+			while (a0 < runs[ri].second) {
+				if (cta < nCta - 1 && mine >= tgt - 0.5) {          // this CTA is full: re-balance what is left over the rest
+					++cta;
+					mine = 0;
+					tgt = target(runs.size() - ri);
+				}
+				const double room = cta == nCta - 1 ? 1e300 : tgt - mine;
+				long long take = std::min<long long>(runs[ri].second - a0, maxSegTiles);
+				if ((double)take + segCharge > room) take = std::max<long long>(1, (long long)(room - segCharge + 0.5));
+				take = std::min<long long>(take, runs[ri].second - a0);
 				emit(a0, a0 + take);
 				a0 += take;
 			}
