@@ -217,8 +217,9 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 		const double segCharge = 4.0;
 		long long remTiles = totalTiles;
 		int cta = 0;
-		double mine = 0;                                        // cost dealt to the current CTA
-		auto target = [&](size_t runsLeft) { return ((double)remTiles + segCharge * (double)runsLeft) / (double)(nCta - cta); };
+		double mine = -segCharge;                               // cost dealt to the current CTA (its first segment is free:
+		                                                        // every CTA pays that one anyway)
+		auto target = [&](size_t runsLeft) { return ((double)remTiles + segCharge * (double)(runsLeft > 0 ? runsLeft - 1 : 0)) / (double)(nCta - cta); };
 		double tgt = target(runs.size());
 		auto emit = [&](long long a0, long long b0) {
 			PtpSegment sg = tiles[a0];
@@ -236,7 +237,7 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 			while (a0 < runs[ri].second) {
 				if (cta < nCta - 1 && mine >= tgt - 0.5) {          // this CTA is full: re-balance what is left over the rest
 					++cta;
-					mine = 0;
+					mine = -segCharge;
 					tgt = target(runs.size() - ri);
 				}
 				const double room = cta == nCta - 1 ? 1e300 : tgt - mine;
