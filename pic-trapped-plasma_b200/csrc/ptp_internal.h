@@ -70,6 +70,8 @@ struct ptp_trap {
 	double* dctInv = nullptr;    // [(Nz+1)^2]  C[m][k]  = cos(pi m k / Nz)
 	double* thInv = nullptr;     // [Nr][Nz+1]  1 / pivot of the r-tridiagonal of axial mode m
 	double* thCp = nullptr;      // [Nr][Nz+1]  upper / pivot
+	double* thR = nullptr;       // [Nr][Nz+1]  x_j / x_{j-1} above the outermost deposit row (factorisation from the wall)
+	double* thQ = nullptr;       // [Nr][Nz+1]  1 / (pivot + upper * thR[j+1]): closes the downward sweep at that row
 	double* thLower = nullptr;   // [Nr]        sub-diagonal of T_r
 	double* stLower = nullptr;   // [Nr] stencil r-lower   (operator apply / SOR)
 	double* stUpper = nullptr;   // [Nr] stencil r-upper
@@ -144,6 +146,10 @@ void ptp_solver_free(ptp_trap* t);
 // encBounds: per (species,row) touched node range as written by the push kernel (nullptr: scan rho for non-zeros).
 int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false, const uint2* encBounds = nullptr);
 int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
+// ptp_solve_wide.cu: the same direct solve organised for large grids
+bool ptp_solver_fft_fits(const ptp_trap* t);
+int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds);
+int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField);
 int ptp_node_field(ptp_trap* t);
 int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);
 int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi);

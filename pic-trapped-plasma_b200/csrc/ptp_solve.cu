@@ -475,41 +475,6 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 	}
 }
 
-// Inverse DCT-I of one grid row through an FFT, for long rows with a power-of-two number of cells (config 5: Nz = 4096,
-// where the dense transform would cost 17 GFMA per solve). The even extension of the row (length 2 Nz, real, symmetric)
-// has the real spectrum  X_k = a_0 + (-1)^k a_N + 2 sum_{m=1}^{N-1} a_m cos(pi m k / N), hence
-//   phi_k = sum_{m=0}^{N} a_m cos(pi m k / N) = X_k / 2 + (a_0 + (-1)^k a_N) / 2.
-// One CTA per row: the extension lives in shared memory as 2N complex values (128 KB at N = 4096), in-place radix-2
-// decimation-in-frequency passes with twiddles from a table computed in extended precision on the host; the result of
-// index k is read from the bit-reversed position.
-__global__ void __launch_bounds__(512) k_idct_fft(const double* __restrict__ alpha, double* __restrict__ phi,
-	const double2* __restrict__ tw, int N, int bits /* log2(2N) */)
-{
-	extern __shared__ double2 fb[];                             // [2N]
-	const int tid = threadIdx.x, T = blockDim.x, n1 = N + 1;
-	const double* a = alpha + (size_t)blockIdx.x * n1;
-	for (int k = tid; k < 2 * N; k += T) fb[k] = make_double2(a[k <= N ? k : 2 * N - k], 0.0);
-	const double a0 = a[0], aN = a[N];
-	__syncthreads();
-	for (int half = N; half >= 1; half >>= 1) {
-		const int stride = N / half;                            // twiddle exponent step: W_{2 half}^j = W_{2N}^{j stride}
-		for (int i = tid; i < N; i += T) {
-			const int j = i & (half - 1);
-			const int p = ((i - j) << 1) + j, q = p + half;
-			const double2 u = fb[p], v = fb[q], w = __ldg(&tw[j * stride]);
-			fb[p] = make_double2(u.x + v.x, u.y + v.y);
-			const double dx = u.x - v.x, dy = u.y - v.y;
-			fb[q] = make_double2(dx * w.x - dy * w.y, dx * w.y + dy * w.x);
-		}
-		__syncthreads();
-	}
-	double* out = phi + (size_t)blockIdx.x * n1;
-	for (int k = tid; k <= N; k += T) {
-		const unsigned int r = __brev((unsigned int)k) >> (32 - bits);
-		out[k] = 0.5 * fb[r].x + 0.5 * (a0 + ((k & 1) ? -aN : aN));
-	}
-}
-
 // PenningTrap::getEField(int,int), Source/PenningTrap.cpp:208-236: E = (sumPhi[idx-1] - sumPhi[idx+1]) / (2 hz),
 // zero at both axial ends, species added in registration order.
 __global__ void k_node_field(const double* __restrict__ phiTrap, const double* __restrict__ phiSelf, int nS,
@@ -640,7 +605,11 @@ int ptp_solver_build(ptp_trap* t)
 			inv[(size_t)m * n1 + k] = (double)c;
 		}
 	}
-	std::vector<double> thInv((size_t)Nr * n1), thCp((size_t)Nr * n1);
+	// thR / thQ: the same factorisation started from the wall (rows above the plasma carry no deposit):
+	//   r_j = -l_j / (d_m + u_j r_{j+1})  propagates x_j = r_j x_{j-1} above the outermost deposit row J,
+	//   q_J = 1 / (pivot_J + u_J r_{J+1}) closes the downward sweep at row J (k_thomas_wide, ptp_solve_wide.cu).
+	std::vector<double> thInv((size_t)Nr * n1), thCp((size_t)Nr * n1), thR((size_t)Nr * n1), thQ((size_t)Nr * n1);
+	std::vector<long double> piv((size_t)Nr);
 	for (int m = 0; m < n1; ++m) {
 		const long double dm = (long double)diag + 2.0L * (long double)hz2 * cosl(pi * (long double)m / (long double)Nz);
 		long double cpPrev = 0.0L;
@@ -648,8 +617,15 @@ int ptp_solver_build(ptp_trap* t)
 			const long double pivot = dm - (long double)lower[j] * cpPrev;
 			const long double pinv = 1.0L / pivot;
 			cpPrev = (long double)upper[j] * pinv;
+			piv[j] = pivot;
 			thInv[(size_t)j * n1 + m] = (double)pinv;
 			thCp[(size_t)j * n1 + m] = (double)cpPrev;
+		}
+		long double rNext = 0.0L;
+		for (int j = Nr - 1; j >= 0; --j) {
+			thQ[(size_t)j * n1 + m] = (double)(1.0L / (piv[j] + (long double)upper[j] * rNext));
+			rNext = -(long double)lower[j] / (dm + (long double)upper[j] * rNext);
+			thR[(size_t)j * n1 + m] = (double)rNext;
 		}
 	}
 	if (Nz >= 8 && (Nz & (Nz - 1)) == 0) {                      // power-of-two cell count: FFT path for the inverse transform
@@ -687,6 +663,10 @@ int ptp_solver_build(ptp_trap* t)
 			if (cudaStreamSetAttribute(t->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 		}
 	}
+	PTP_CUDA(cudaMalloc(&t->thR, gg));
+	PTP_CUDA(cudaMalloc(&t->thQ, gg));
+	PTP_CUDA(cudaMemcpy(t->thR, thR.data(), gg, cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMemcpy(t->thQ, thQ.data(), gg, cudaMemcpyHostToDevice));
 	PTP_CUDA(cudaMalloc(&t->thLower, Nr * sizeof(double)));
 	PTP_CUDA(cudaMalloc(&t->stLower, Nr * sizeof(double)));
 	PTP_CUDA(cudaMalloc(&t->stUpper, Nr * sizeof(double)));
@@ -703,7 +683,7 @@ int ptp_solver_build(ptp_trap* t)
 void ptp_solver_free(ptp_trap* t)
 {
 	cudaFree(t->solverConst); cudaFree(t->rowBounds); cudaFree(t->fftTw);
-	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper);
+	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper); cudaFree(t->thR); cudaFree(t->thQ);
 }
 
 int ptp_solver_reserve(ptp_trap* t, int nS)
@@ -730,35 +710,37 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	};
 	const int mb = smFwdBytes(16) <= t->smemMax ? 16 : 4;       // fewer modes per CTA when the radial tiles get large
 	const size_t smFwd = smFwdBytes(mb);
-	if (smFwd > t->smemMax) { ptp_set_error("direct solver: Nr too large for the shared-memory tiles of this build"); return PTP_EINVAL; }
-	const dim3 gridFwd((n1 + mb - 1) / mb, nS);
-	auto launchFwd = [&](auto kern, double fInv) -> cudaError_t {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd);
-		if (e != cudaSuccess) return e;
-		kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
-		return cudaGetLastError();
-	};
-	cudaError_t ef;
-	if (rhoIsFixed) ef = mb == 16 ? launchFwd(k_fwd_thomas<true, 16>, fixedInv) : launchFwd(k_fwd_thomas<true, 4>, fixedInv);
-	else ef = mb == 16 ? launchFwd(k_fwd_thomas<false, 16>, 1.0) : launchFwd(k_fwd_thomas<false, 4>, 1.0);
-	if (ef != cudaSuccess) return ptp_cuda_fail(ef, "k_fwd_thomas launch", __FILE__, __LINE__);
-	// inverse transform (+ node field): paired-mode kernel when its tiles fit in shared memory, chunked GEMM otherwise
+	// inverse transform (+ node field): paired-mode kernel when its tiles fit in shared memory, FFT for long power-of-two
+	// rows, chunked GEMM otherwise
 	const int stagesAll = ((n1 + 1) / 2 + 8 * INV_KS - 1) / (8 * INV_KS);    // stages that hold a warp's whole K-slice
 	auto smFieldBytes = [&](int st) { return ((size_t)INV_TM * (n1 | 1) + (size_t)8 * st * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double); };
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= t->smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const size_t smField = smFieldBytes(ringStages);
-	bool fieldDone = false;
-	const size_t smFft = (size_t)2 * t->Nz * sizeof(double2);
-	const bool useFft = t->fftTw && smFft <= t->smemMax && (t->solver == PTP_SOLVER_DIRECT_FFT || smField > t->smemMax);
-	if (useFft) {
-		int bits = 0;
-		while ((1 << bits) < 2 * t->Nz) ++bits;
-		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFft));
-		k_idct_fft<<<M, 512, smFft, t->stream>>>(spec, phi, t->fftTw, t->Nz, bits);
-		cudaError_t ei = cudaGetLastError();
-		if (ei != cudaSuccess) return ptp_cuda_fail(ei, "k_idct_fft launch", __FILE__, __LINE__);
+	const bool useFft = ptp_solver_fft_fits(t) && (t->solver == PTP_SOLVER_DIRECT_FFT || smField > t->smemMax);
+	// large grids (many radial nodes or long rows): separate forward transform + streamed radial solves (ptp_solve_wide.cu)
+	const bool wide = mb == 4 || useFft || smFwd > t->smemMax;
+	if (wide) {
+		PTP_TRY(ptp_solver_forward_wide(t, rho, rhoIsFixed, dScale, nS, spec, encBounds));
+		if (useFft) {
+			PTP_TRY(ptp_solver_inverse_fft(t, spec, phi, nS, withField));
+			if (withField) t->eNodesValid = true;
+			return PTP_OK;
+		}
 	}
-	else if (smField <= t->smemMax) {
+	else {
+		const dim3 gridFwd((n1 + mb - 1) / mb, nS);
+		auto launchFwd = [&](auto kern, double fInv) -> cudaError_t {
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd);
+			if (e != cudaSuccess) return e;
+			kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
+			return cudaGetLastError();
+		};
+		const cudaError_t ef = rhoIsFixed ? launchFwd(k_fwd_thomas<true, 16>, fixedInv) : launchFwd(k_fwd_thomas<false, 16>, 1.0);
+		if (ef != cudaSuccess) return ptp_cuda_fail(ef, "k_fwd_thomas launch", __FILE__, __LINE__);
+		t->lastLaunches++;
+	}
+	bool fieldDone = false;
+	if (smField <= t->smemMax) {
 		auto launchInv = [&](auto kern, bool field) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smField);
 			if (e != cudaSuccess) return e;
@@ -789,7 +771,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "solver launch", __FILE__, __LINE__);
-	t->lastLaunches += 2;
+	t->lastLaunches += 1;
 	if (withField) {
 		if (fieldDone) t->eNodesValid = true;
 		else return ptp_node_field(t);

@@ -1,0 +1,365 @@
+// K3 for large grids (config 5: Nz = 4096, Nr = 1024 -> 4.2 M unknowns, 33.6 MB per fp64 grid).
+//
+// Same direct solve as ptp_solve.cu - phi = DCT^-1 . Thomas_r . DCT (scale * rho), the matrix of
+// PenningTrap::generateSparse (Source/PenningTrap.cpp:94-162) solved as Plasma::solvePoisson does with
+// solver.solve (Source/Plasma.cpp:95-99) - but organised for grids whose radial extent no longer fits the fused
+// shared-memory kernel of the default grid:
+//   k_fwd_dct      forward DCT-I restricted to the touched rows and their touched axial range, as a tiled product
+//                  against the forward matrix (64 modes x 64 rows per CTA, 2 x 8 register tile per thread);
+//   k_thomas_wide  the radial solves, one warp per 32 axial modes, every coefficient row streamed through a deep
+//                  cp.async ring so that the only serial cost is one dependent FMA per row. The deposit is zero above
+//                  the plasma's outermost row J, so the rows above J are folded into one precomputed pivot
+//                  ("burn at both ends"): a forward sweep over rows J0..J-1 only, x_J from the folded pivot, the usual
+//                  back-substitution below J and a pure product chain x_j = r_j x_{j-1} above J. Identical to the plain
+//                  Thomas solve in exact arithmetic; 16 B instead of 40 B of traffic per node above J;
+//   k_idct_fft_field  inverse DCT-I of a whole grid row through ONE complex FFT of length Nz (the even extension of
+//                  the row is real, so its 2 Nz-point transform is obtained from an Nz-point complex transform of the
+//                  even/odd samples), all species of the row in one CTA, fused with the node field of
+//                  PenningTrap::getEField(int,int) (Source/PenningTrap.cpp:208-236).
+#include "ptp_internal.h"
+
+#include <limits.h>
+
+namespace {
+
+__device__ __forceinline__ void cpa8(void* smemDst, const void* gmemSrc, bool valid)
+{
+	const unsigned int d = (unsigned int)__cvta_generic_to_shared(smemDst);
+	const int bytes = valid ? 8 : 0;                            // src-size 0 -> zero fill
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmemSrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int2 row_bounds_of(const int2* bounds, const uint2* enc, int idx, int n1)
+{
+	if (enc) {                                                  // maxima written by the push kernel's flush: (Nz+2-kmin, kmax+1), 0 = untouched
+		const uint2 e = enc[idx];
+		return e.y ? make_int2(n1 + 1 - (int)e.x, (int)e.y - 1) : make_int2(INT_MAX, INT_MIN);
+	}
+	return bounds[idx];
+}
+
+// ---- forward DCT-I of the touched rows -------------------------------------------------------------------------
+constexpr int FD_M = 64;        // modes per CTA (2 per lane)
+constexpr int FD_R = 64;        // rows per CTA (8 per warp)
+constexpr int FD_K = 64;        // axial nodes staged per chunk
+
+template <bool A_FIXED>
+__global__ void __launch_bounds__(256) k_fwd_dct(const double* __restrict__ rho, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
+	const double* __restrict__ FT, const double* __restrict__ rowScale, double fixedInv, double* __restrict__ spec, int Nr, int n1)
+{
+	extern __shared__ double smw[];
+	double* sFT = smw;                                          // [FD_K][FD_M]
+	double* sRho = smw + FD_K * FD_M;                           // [FD_R][FD_K]
+	__shared__ int2 sBd[FD_R];
+	__shared__ int sLo, sHi;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int mBase = blockIdx.x * FD_M, jBase = blockIdx.y * FD_R, s = blockIdx.z;
+	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; }
+	__syncthreads();
+	if (tid < FD_R) {
+		int2 bd = make_int2(INT_MAX, INT_MIN);
+		if (jBase + tid < Nr) bd = row_bounds_of(bounds, encBounds, s * Nr + jBase + tid, n1);
+		sBd[tid] = bd;
+		if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); }
+	}
+	__syncthreads();
+	const int kLo = sLo, kHi = sHi;
+	if (kLo > kHi) return;                                      // nothing deposited in these rows
+	unsigned int active = 0;                                    // rows warp + 8 u of this tile that hold a deposit (uniform per warp)
+#pragma unroll
+	for (int u = 0; u < 8; ++u) active |= (sBd[warp + 8 * u].x <= sBd[warp + 8 * u].y ? 1u : 0u) << u;
+	const double* b = rho + (size_t)s * Nr * n1;
+	double acc0[8], acc1[8];
+#pragma unroll
+	for (int u = 0; u < 8; ++u) acc0[u] = acc1[u] = 0.0;
+	for (int k0 = kLo; k0 <= kHi; k0 += FD_K) {
+		const int kn = min(FD_K, kHi - k0 + 1);
+		__syncthreads();
+		for (int e = tid; e < kn * FD_M; e += 256) {
+			const int kk = e / FD_M, mm = e % FD_M;
+			const bool ok = mBase + mm < n1;
+			cpa8(&sFT[e], FT + (size_t)(k0 + kk) * n1 + (ok ? mBase + mm : 0), ok);
+		}
+		cpa_commit();
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+			if (!((active >> u) & 1u)) continue;
+			const int jj = warp + 8 * u;
+			const double* src = b + (size_t)(jBase + jj) * n1 + k0;
+			for (int kk = lane; kk < kn; kk += 32) {
+				// values outside a row's own range are exact zeros (the grid is cleared every step), so the whole chunk is loaded
+				const double raw = src[kk];
+				sRho[jj * FD_K + kk] = A_FIXED ? (double)__double_as_longlong(raw) : raw;
+			}
+		}
+		cpa_wait<0>();
+		__syncthreads();
+		for (int kk = 0; kk < kn; ++kk) {
+			const double f0 = sFT[kk * FD_M + lane], f1 = sFT[kk * FD_M + 32 + lane];
+#pragma unroll
+			for (int u = 0; u < 8; ++u) {
+				if (!((active >> u) & 1u)) continue;
+				const double val = sRho[(warp + 8 * u) * FD_K + kk];
+				acc0[u] = fma(val, f0, acc0[u]);
+				acc1[u] = fma(val, f1, acc1[u]);
+			}
+		}
+	}
+	const double scale = (rowScale ? rowScale[s] : 1.0) * (A_FIXED ? fixedInv : 1.0);
+	double* out = spec + (size_t)s * Nr * n1;
+#pragma unroll
+	for (int u = 0; u < 8; ++u) {
+		if (!((active >> u) & 1u)) continue;
+		const size_t row = (size_t)(jBase + warp + 8 * u) * n1;
+		if (mBase + lane < n1) out[row + mBase + lane] = acc0[u] * scale;
+		if (mBase + 32 + lane < n1) out[row + mBase + 32 + lane] = acc1[u] * scale;
+	}
+}
+
+// ---- radial solves -----------------------------------------------------------------------------------------------
+constexpr int TW_RS = 8;        // rows per ring stage
+constexpr int TW_ST = 16;       // stages: 15 x 4 KB in flight per warp
+
+// Visit rows jFirst, jFirst + DIR, ... (count rows) of one or two [Nr][n1] arrays for the 32 modes of this warp, each lane
+// copying and later reading only its own mode (no cross-lane hazards, so no barriers). a1 is read only where flag1 says
+// so (zero elsewhere). use(j, v0, v1) is called in row order - that is where the serial recurrence lives.
+template <int DIR, bool TWO, class Use>
+__device__ __forceinline__ void stream_rows(double* ring, int jFirst, int count, const double* __restrict__ a0, const double* __restrict__ a1,
+	const unsigned char* flag1, int n1, int m, bool mOk, int lane, Use use)
+{
+	const int nG = (count + TW_RS - 1) / TW_RS;
+	auto issue = [&](int g) {
+		if (g < nG) {
+			double* dst = ring + (size_t)(g % TW_ST) * 2 * TW_RS * 32 + lane;
+#pragma unroll
+			for (int r = 0; r < TW_RS; ++r) {
+				const int i = g * TW_RS + r;
+				if (i < count) {
+					const int j = jFirst + DIR * i;
+					const size_t off = (size_t)j * n1 + (mOk ? m : 0);
+					cpa8(dst + r * 32, a0 + off, mOk);
+					if (TWO) cpa8(dst + (TW_RS + r) * 32, a1 + off, mOk && (!flag1 || flag1[j]));
+				}
+			}
+		}
+		cpa_commit();
+	};
+#pragma unroll 1
+	for (int g = 0; g < TW_ST - 1; ++g) issue(g);
+#pragma unroll 1
+	for (int g = 0; g < nG; ++g) {
+		issue(g + TW_ST - 1);
+		cpa_wait<TW_ST - 1>();
+		const double* src = ring + (size_t)(g % TW_ST) * 2 * TW_RS * 32 + lane;
+		double v0[TW_RS], v1[TW_RS];
+#pragma unroll
+		for (int r = 0; r < TW_RS; ++r) {
+			v0[r] = src[r * 32];
+			v1[r] = TWO ? src[(TW_RS + r) * 32] : 0.0;
+		}
+#pragma unroll
+		for (int r = 0; r < TW_RS; ++r) {
+			const int i = g * TW_RS + r;
+			if (i < count) use(jFirst + DIR * i, v0[r], v1[r]);
+		}
+	}
+	cpa_wait<0>();
+}
+
+// spec holds beta (forward-transformed deposit) on the touched rows on entry and alpha = (T_r + lambda_m)^-1 beta on
+// all rows on exit. One warp per CTA and 32 modes; blockIdx.y = species.
+__global__ void __launch_bounds__(32) k_thomas_wide(double* __restrict__ specAll, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
+	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thR, const double* __restrict__ thQ,
+	const double* __restrict__ thLower, int Nr, int n1)
+{
+	extern __shared__ double smw[];
+	double* ring = smw;                                         // [TW_ST][2][TW_RS][32]
+	double* sLower = smw + (size_t)TW_ST * 2 * TW_RS * 32;      // [Nr]
+	unsigned char* sTouched = reinterpret_cast<unsigned char*>(sLower + Nr); // [Nr]
+	const int lane = threadIdx.x, s = blockIdx.y;
+	const int m = blockIdx.x * 32 + lane;
+	const bool mOk = m < n1;
+	double* spec = specAll + (size_t)s * Nr * n1;
+	int J0 = INT_MAX, J = INT_MIN;
+	for (int j = lane; j < Nr; j += 32) {
+		const int2 bd = row_bounds_of(bounds, encBounds, s * Nr + j, n1);
+		const bool touched = bd.x <= bd.y;
+		sTouched[j] = touched ? 1 : 0;
+		sLower[j] = thLower[j];
+		if (touched) { J0 = min(J0, j); J = max(J, j); }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		J0 = min(J0, __shfl_xor_sync(0xffffffffu, J0, o));
+		J = max(J, __shfl_xor_sync(0xffffffffu, J, o));
+	}
+	__syncwarp();
+	if (J < 0) {                                                // empty deposit: the potential is zero
+		if (mOk) for (int j = 0; j < Nr; ++j) spec[(size_t)j * n1 + m] = 0.0;
+		return;
+	}
+	// forward sweep over rows J0 .. J-1:  y_j = (beta_j - l_j y_{j-1}) / pivot_j
+	double y = 0.0;
+	stream_rows<1, true>(ring, J0, J - J0, thInv, spec, sTouched, n1, m, mOk, lane, [&](int j, double inv, double beta) {
+		const double g = beta * inv, c = -(sLower[j] * inv);
+		y = fma(c, y, g);
+		if (mOk) spec[(size_t)j * n1 + m] = y;
+	});
+	// row J closes the system: the rows above it carry no deposit and are folded into the pivot 1 / thQ
+	double xJ = 0.0;
+	if (mOk) {
+		const size_t o = (size_t)J * n1 + m;
+		xJ = (spec[o] - sLower[J] * y) * thQ[o];
+		spec[o] = xJ;
+	}
+	__threadfence_block();                                      // this lane's y values are read back through cp.async below
+	// back-substitution below J:  x_j = y_j - cp_j x_{j+1}   (y_j = 0 below the first touched row)
+	double x = xJ;
+	const unsigned char* fromJ0 = sTouched;                     // flag: row >= J0 (reuse the array: mark the whole range)
+	for (int j = J0 + lane; j < J; j += 32) sTouched[j] = 1;
+	__syncwarp();
+	stream_rows<-1, true>(ring, J - 1, J, thCp, spec, fromJ0, n1, m, mOk, lane, [&](int j, double cp, double yj) {
+		x = fma(-cp, x, yj);
+		if (mOk) spec[(size_t)j * n1 + m] = x;
+	});
+	// rows above J: homogeneous recurrence towards the wall
+	x = xJ;
+	stream_rows<1, false>(ring, J + 1, Nr - 1 - J, thR, nullptr, nullptr, n1, m, mOk, lane, [&](int j, double r, double) {
+		x = r * x;
+		if (mOk) spec[(size_t)j * n1 + m] = x;
+	});
+}
+
+// ---- inverse DCT-I through an Nz-point complex FFT + node field ---------------------------------------------
+// phi_k = sum_{m=0}^{N} a_m cos(pi m k / N) = X_k / 2 + (a_0 + (-1)^k a_N) / 2, where X is the 2N-point DFT of the even
+// extension e_n = a_n (n <= N), a_{2N-n} (n > N). With z_n = e_{2n} + i e_{2n+1} and Z = DFT_N(z):
+//   X_k = (Z_k + conj Z_{N-k}) / 2 + W_{2N}^k (Z_k - conj Z_{N-k}) / (2 i),   W_{2N} = exp(-i pi / N),
+// real for a symmetric e. The N-point transform runs in shared memory as radix-2 decimation-in-frequency passes fused
+// in pairs (four points per thread and pair of passes, same arithmetic as two radix-2 passes, half the barriers and half
+// the shared-memory traffic); Z_k is read from the bit-reversed slot. One CTA per grid row loops over the species.
+template <bool FIELD>
+__global__ void __launch_bounds__(512, 2) k_idct_fft_field(const double* __restrict__ alphaAll, double* __restrict__ phiAll, const double2* __restrict__ tw,
+	const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int N, int bits /* log2 N */, double hz)
+{
+	extern __shared__ double2 fbw[];                            // [N]
+	double* tot = reinterpret_cast<double*>(fbw + N);           // [N+1] running total potential of the row (FIELD)
+	const int tid = threadIdx.x, T = blockDim.x, n1 = N + 1;
+	const int row = blockIdx.x;
+	if (FIELD) for (int k = tid; k <= N; k += T) tot[k] = phiTrap[(size_t)row * n1 + k];
+	for (int sp = 0; sp < nS; ++sp) {
+		const double* a = alphaAll + ((size_t)sp * Nr + row) * n1;
+		__syncthreads();                                        // previous species is done with fbw
+		for (int n = tid; n < N; n += T) {
+			const int i0 = 2 * n, i1 = 2 * n + 1;
+			fbw[n] = make_double2(a[i0 <= N ? i0 : 2 * N - i0], a[i1 <= N ? i1 : 2 * N - i1]);
+		}
+		const double a0 = a[0], aN = a[N];
+		__syncthreads();
+		int h = N >> 1;
+		for (; h >= 2; h >>= 2) {                               // passes with half-sizes h and h/2, fused
+			const int q = h >> 1, sA = N / h;                   // twiddle steps: W_{2h}^j = tw[j * N / h]
+			for (int i = tid; i < (N >> 2); i += T) {
+				const int j0 = i & (q - 1);
+				const int b = ((i - j0) << 2) + j0;
+				const double2 x0 = fbw[b], x1 = fbw[b + q], x2 = fbw[b + h], x3 = fbw[b + h + q];
+				const double2 wa0 = __ldg(&tw[j0 * sA]), wa1 = __ldg(&tw[(j0 + q) * sA]), wb = __ldg(&tw[j0 * 2 * sA]);
+				const double2 u0 = make_double2(x0.x + x2.x, x0.y + x2.y), u1 = make_double2(x1.x + x3.x, x1.y + x3.y);
+				const double d2x = x0.x - x2.x, d2y = x0.y - x2.y, d3x = x1.x - x3.x, d3y = x1.y - x3.y;
+				const double2 u2 = make_double2(d2x * wa0.x - d2y * wa0.y, d2x * wa0.y + d2y * wa0.x);
+				const double2 u3 = make_double2(d3x * wa1.x - d3y * wa1.y, d3x * wa1.y + d3y * wa1.x);
+				fbw[b] = make_double2(u0.x + u1.x, u0.y + u1.y);
+				const double e1x = u0.x - u1.x, e1y = u0.y - u1.y;
+				fbw[b + q] = make_double2(e1x * wb.x - e1y * wb.y, e1x * wb.y + e1y * wb.x);
+				fbw[b + h] = make_double2(u2.x + u3.x, u2.y + u3.y);
+				const double e3x = u2.x - u3.x, e3y = u2.y - u3.y;
+				fbw[b + h + q] = make_double2(e3x * wb.x - e3y * wb.y, e3x * wb.y + e3y * wb.x);
+			}
+			__syncthreads();
+		}
+		if (h == 1) {                                           // odd number of passes: the last one on its own (twiddle 1)
+			for (int i = tid; i < (N >> 1); i += T) {
+				const double2 u = fbw[2 * i], v = fbw[2 * i + 1];
+				fbw[2 * i] = make_double2(u.x + v.x, u.y + v.y);
+				fbw[2 * i + 1] = make_double2(u.x - v.x, u.y - v.y);
+			}
+			__syncthreads();
+		}
+		double* out = phiAll + ((size_t)sp * Nr + row) * n1;
+		for (int k = tid; k <= N; k += T) {
+			const unsigned int ka = (unsigned int)(k & (N - 1)), kb = (unsigned int)((N - k) & (N - 1));
+			const double2 A = fbw[__brev(ka) >> (32 - bits)], B = fbw[__brev(kb) >> (32 - bits)];   // Z_k, Z_{N-k} (conjugated below)
+			const double2 w = k < N ? __ldg(&tw[k]) : make_double2(-1.0, 0.0);
+			const double dx = A.x - B.x, dy = A.y + B.y;            // Z_k - conj Z_{N-k}
+			const double X = 0.5 * (A.x + B.x) + 0.5 * (dy * w.x + dx * w.y);
+			const double v = 0.5 * X + 0.5 * (a0 + ((k & 1) ? -aN : aN));
+			out[k] = v;
+			if (FIELD) tot[k] = __dadd_rn(tot[k], v);
+		}
+	}
+	if (FIELD) {
+		__syncthreads();
+		for (int k = tid; k <= N; k += T) {
+			double e = 0.0;
+			if (k > 0 && k < N) e = __ddiv_rn(__dsub_rn(tot[k - 1], tot[k + 1]), __dmul_rn(2.0, hz));
+			eNodes[(size_t)row * n1 + k] = e;
+		}
+	}
+}
+
+} // namespace
+
+bool ptp_solver_fft_fits(const ptp_trap* t)
+{
+	return t->fftTw && (size_t)t->Nz * sizeof(double2) + (size_t)(t->Nz + 1) * sizeof(double) <= t->smemMax;
+}
+
+// beta -> alpha for nS grids: forward transform of the touched rows + radial solves. bounds / encBounds as in ptp_solver_run.
+int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds)
+{
+	const int n1 = t->Nz + 1, Nr = t->Nr;
+	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
+	const size_t smDct = (size_t)(FD_K * FD_M + FD_R * FD_K) * sizeof(double);
+	const dim3 gridDct((n1 + FD_M - 1) / FD_M, (Nr + FD_R - 1) / FD_R, nS);
+	if (rhoIsFixed) {
+		PTP_CUDA(cudaFuncSetAttribute(k_fwd_dct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smDct));
+		k_fwd_dct<true><<<gridDct, 256, smDct, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fixedInv, spec, Nr, n1);
+	}
+	else {
+		PTP_CUDA(cudaFuncSetAttribute(k_fwd_dct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smDct));
+		k_fwd_dct<false><<<gridDct, 256, smDct, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, 1.0, spec, Nr, n1);
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_fwd_dct launch", __FILE__, __LINE__);
+	const size_t smTh = (size_t)TW_ST * 2 * TW_RS * 32 * sizeof(double) + (size_t)Nr * sizeof(double) + (size_t)Nr;
+	if (smTh > t->smemMax) { ptp_set_error("direct solver: Nr too large for the radial-solve kernel of this build"); return PTP_EINVAL; }
+	PTP_CUDA(cudaFuncSetAttribute(k_thomas_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smTh));
+	k_thomas_wide<<<dim3((n1 + 31) / 32, nS), 32, smTh, t->stream>>>(spec, t->rowBounds, encBounds, t->thInv, t->thCp, t->thR, t->thQ, t->thLower, Nr, n1);
+	e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_wide launch", __FILE__, __LINE__);
+	t->lastLaunches += 2;
+	return PTP_OK;
+}
+
+// alpha -> phi for nS grids (+ node field when withField: nS covers all species and phi = phiSelfAll).
+int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField)
+{
+	const int N = t->Nz, Nr = t->Nr;
+	int bits = 0;
+	while ((1 << bits) < N) ++bits;
+	const size_t sm = (size_t)N * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
+	const int threads = N >= 2048 ? 512 : (N >= 1024 ? 256 : 128);
+	if (withField) {
+		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		k_idct_fft_field<true><<<Nr, threads, sm, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, N, bits, t->hz);
+	}
+	else {
+		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+		k_idct_fft_field<false><<<Nr, threads, sm, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, N, bits, t->hz);
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_idct_fft_field launch", __FILE__, __LINE__);
+	t->lastLaunches += 1;
+	return PTP_OK;
+}
