@@ -14,6 +14,8 @@
 // Row buckets are padded to this many ring slots so that every tile of the push kernel lies inside one
 // radial row and double2 accesses stay 16-byte aligned (8 rings/thread x 512 threads max).
 #define PTP_ROW_ALIGN 4096
+// Rows per block of the radial product tables of the large-grid solver (multiple of 8).
+#define PTP_THOMAS_BLOCK 32
 
 // One contiguous run of ring slots of ONE radial row, owned by one CTA of the push kernel.
 struct PtpSegment {
@@ -72,6 +74,10 @@ struct ptp_trap {
 	double* thCp = nullptr;      // [Nr][Nz+1]  upper / pivot
 	double* thR = nullptr;       // [Nr][Nz+1]  x_j / x_{j-1} above the outermost deposit row (factorisation from the wall)
 	double* thQ = nullptr;       // [Nr][Nz+1]  1 / (pivot + upper * thR[j+1]): closes the downward sweep at that row
+	double* thP = nullptr;       // [Nr][Nz+1]  product of thR over rows (block start .. j), blocks of PTP_THOMAS_BLOCK rows
+	double* wideXb = nullptr;    // [species][blocks][Nz+1] value entering each block above the deposit (k_thomas_wide -> k_thomas_expand)
+	int* wideJ = nullptr;        // [species] outermost deposit row of the last solve
+	int wideCap = 0;
 	double* thLower = nullptr;   // [Nr]        sub-diagonal of T_r
 	double* stLower = nullptr;   // [Nr] stencil r-lower   (operator apply / SOR)
 	double* stUpper = nullptr;   // [Nr] stencil r-upper

@@ -609,7 +609,8 @@ int ptp_solver_build(ptp_trap* t)
 	//   r_j = -l_j / (d_m + u_j r_{j+1})  propagates x_j = r_j x_{j-1} above the outermost deposit row J,
 	//   q_J = 1 / (pivot_J + u_J r_{J+1}) closes the downward sweep at row J (k_thomas_wide, ptp_solve_wide.cu).
 	std::vector<double> thInv((size_t)Nr * n1), thCp((size_t)Nr * n1), thR((size_t)Nr * n1), thQ((size_t)Nr * n1);
-	std::vector<long double> piv((size_t)Nr);
+	std::vector<double> thP((size_t)Nr * n1);
+	std::vector<long double> piv((size_t)Nr), rr((size_t)Nr);
 	for (int m = 0; m < n1; ++m) {
 		const long double dm = (long double)diag + 2.0L * (long double)hz2 * cosl(pi * (long double)m / (long double)Nz);
 		long double cpPrev = 0.0L;
@@ -626,6 +627,13 @@ int ptp_solver_build(ptp_trap* t)
 			thQ[(size_t)j * n1 + m] = (double)(1.0L / (piv[j] + (long double)upper[j] * rNext));
 			rNext = -(long double)lower[j] / (dm + (long double)upper[j] * rNext);
 			thR[(size_t)j * n1 + m] = (double)rNext;
+			rr[j] = rNext;
+		}
+		long double prod = 1.0L;
+		for (int j = 0; j < Nr; ++j) {                          // in-block prefix products of r (k_thomas_expand)
+			if (j % PTP_THOMAS_BLOCK == 0) prod = 1.0L;
+			prod *= rr[j];
+			thP[(size_t)j * n1 + m] = (double)prod;
 		}
 	}
 	if (Nz >= 8 && (Nz & (Nz - 1)) == 0) {                      // power-of-two cell count: FFT path for the inverse transform
@@ -667,6 +675,8 @@ int ptp_solver_build(ptp_trap* t)
 	PTP_CUDA(cudaMalloc(&t->thQ, gg));
 	PTP_CUDA(cudaMemcpy(t->thR, thR.data(), gg, cudaMemcpyHostToDevice));
 	PTP_CUDA(cudaMemcpy(t->thQ, thQ.data(), gg, cudaMemcpyHostToDevice));
+	PTP_CUDA(cudaMalloc(&t->thP, gg));
+	PTP_CUDA(cudaMemcpy(t->thP, thP.data(), gg, cudaMemcpyHostToDevice));
 	PTP_CUDA(cudaMalloc(&t->thLower, Nr * sizeof(double)));
 	PTP_CUDA(cudaMalloc(&t->stLower, Nr * sizeof(double)));
 	PTP_CUDA(cudaMalloc(&t->stUpper, Nr * sizeof(double)));
@@ -683,7 +693,7 @@ int ptp_solver_build(ptp_trap* t)
 void ptp_solver_free(ptp_trap* t)
 {
 	cudaFree(t->solverConst); cudaFree(t->rowBounds); cudaFree(t->fftTw);
-	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper); cudaFree(t->thR); cudaFree(t->thQ);
+	cudaFree(t->thLower); cudaFree(t->stLower); cudaFree(t->stUpper); cudaFree(t->thR); cudaFree(t->thQ); cudaFree(t->thP); cudaFree(t->wideXb); cudaFree(t->wideJ);
 }
 
 int ptp_solver_reserve(ptp_trap* t, int nS)
@@ -694,6 +704,14 @@ int ptp_solver_reserve(ptp_trap* t, int nS)
 		t->rowBounds = nullptr;
 		PTP_CUDA(cudaMalloc(&t->rowBounds, (size_t)M * sizeof(int2)));
 		t->rowBoundsCap = M;
+	}
+	if (t->wideCap < nS) {                                      // scratch of the large-grid radial solves
+		cudaFree(t->wideXb); cudaFree(t->wideJ);
+		t->wideXb = nullptr; t->wideJ = nullptr;
+		const size_t nB = (size_t)(t->Nr + PTP_THOMAS_BLOCK - 1) / PTP_THOMAS_BLOCK;
+		PTP_CUDA(cudaMalloc(&t->wideXb, (size_t)nS * nB * (t->Nz + 1) * sizeof(double)));
+		PTP_CUDA(cudaMalloc(&t->wideJ, (size_t)nS * sizeof(int)));
+		t->wideCap = nS;
 	}
 	return PTP_OK;
 }

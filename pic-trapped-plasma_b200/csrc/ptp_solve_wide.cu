@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) k_fwd_dct(const double* __restrict__ rho,
 // ---- radial solves -----------------------------------------------------------------------------------------------
 constexpr int TW_RS = 8;        // rows per ring stage
 constexpr int TW_ST = 16;       // stages: 15 x 4 KB in flight per warp
+constexpr int TW_BLK = PTP_THOMAS_BLOCK;   // rows per block of the product tables (thP)
 
 // Visit rows jFirst, jFirst + DIR, ... (count rows) of one or two [Nr][n1] arrays for the 32 modes of this warp, each lane
 // copying and later reading only its own mode (no cross-lane hazards, so no barriers). a1 is read only where flag1 says
@@ -170,66 +171,164 @@ __device__ __forceinline__ void stream_rows(double* ring, int jFirst, int count,
 }
 
 // spec holds beta (forward-transformed deposit) on the touched rows on entry and alpha = (T_r + lambda_m)^-1 beta on
-// all rows on exit. One warp per CTA and 32 modes; blockIdx.y = species.
-__global__ void __launch_bounds__(32) k_thomas_wide(double* __restrict__ specAll, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
+// all rows on exit (rows above the block of the outermost deposit row J are left to k_thomas_expand). 32 modes per CTA
+// (lane = mode), blockIdx.y = species.
+//   compact path (rows 0 .. end of J's block fit in shared memory - the usual case, a plasma near the axis): the four warps
+//   bring every coefficient of those rows in with one wave of cp.async, warp 0 runs the three short recurrences out of
+//   shared memory (7 instructions per row instead of ~40 for the streamed form), all warps write the rows back;
+//   streamed path (deposit reaching far out, e.g. the wall RHS of solveLaplace): warp 0 walks the rows through the ring.
+constexpr int TW_RCAP = 160;    // rows of the compact path: 3 x 160 x 256 B = 120 KB
+
+__global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAll, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
 	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thR, const double* __restrict__ thQ,
-	const double* __restrict__ thLower, int Nr, int n1)
+	const double* __restrict__ thP, const double* __restrict__ thLower, double* __restrict__ xbAll, int* __restrict__ wideJ, int Nr, int n1)
 {
 	extern __shared__ double smw[];
-	double* ring = smw;                                         // [TW_ST][2][TW_RS][32]
-	double* sLower = smw + (size_t)TW_ST * 2 * TW_RS * 32;      // [Nr]
+	double* ring = smw;                                         // streamed: [TW_ST][2][TW_RS][32]; compact: sInv | sB | sC, [TW_RCAP][32] each
+	double* sLower = smw + (size_t)3 * TW_RCAP * 32;            // [Nr]
 	unsigned char* sTouched = reinterpret_cast<unsigned char*>(sLower + Nr); // [Nr]
-	const int lane = threadIdx.x, s = blockIdx.y;
+	__shared__ int sJ0, sJ;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, s = blockIdx.y;
 	const int m = blockIdx.x * 32 + lane;
 	const bool mOk = m < n1;
 	double* spec = specAll + (size_t)s * Nr * n1;
-	int J0 = INT_MAX, J = INT_MIN;
-	for (int j = lane; j < Nr; j += 32) {
-		const int2 bd = row_bounds_of(bounds, encBounds, s * Nr + j, n1);
-		const bool touched = bd.x <= bd.y;
-		sTouched[j] = touched ? 1 : 0;
-		sLower[j] = thLower[j];
-		if (touched) { J0 = min(J0, j); J = max(J, j); }
+	if (tid == 0) { sJ0 = INT_MAX; sJ = INT_MIN; }
+	__syncthreads();
+	{
+		int lo = INT_MAX, hi = INT_MIN;
+		for (int j = tid; j < Nr; j += 128) {
+			const int2 bd = row_bounds_of(bounds, encBounds, s * Nr + j, n1);
+			const bool touched = bd.x <= bd.y;
+			sTouched[j] = touched ? 1 : 0;
+			sLower[j] = thLower[j];
+			if (touched) { lo = min(lo, j); hi = max(hi, j); }
+		}
+		if (lo <= hi) { atomicMin(&sJ0, lo); atomicMax(&sJ, hi); }
 	}
-	for (int o = 16; o > 0; o >>= 1) {
-		J0 = min(J0, __shfl_xor_sync(0xffffffffu, J0, o));
-		J = max(J, __shfl_xor_sync(0xffffffffu, J, o));
-	}
-	__syncwarp();
+	__syncthreads();
+	const int J0 = sJ0, J = sJ;
 	if (J < 0) {                                                // empty deposit: the potential is zero
-		if (mOk) for (int j = 0; j < Nr; ++j) spec[(size_t)j * n1 + m] = 0.0;
+		if (mOk) for (int j = warp; j < Nr; j += 4) spec[(size_t)j * n1 + m] = 0.0;
+		if (blockIdx.x == 0 && tid == 0) wideJ[s] = -1;
 		return;
 	}
-	// forward sweep over rows J0 .. J-1:  y_j = (beta_j - l_j y_{j-1}) / pivot_j
-	double y = 0.0;
-	stream_rows<1, true>(ring, J0, J - J0, thInv, spec, sTouched, n1, m, mOk, lane, [&](int j, double inv, double beta) {
-		const double g = beta * inv, c = -(sLower[j] * inv);
-		y = fma(c, y, g);
-		if (mOk) spec[(size_t)j * n1 + m] = y;
-	});
-	// row J closes the system: the rows above it carry no deposit and are folded into the pivot 1 / thQ
-	double xJ = 0.0;
-	if (mOk) {
-		const size_t o = (size_t)J * n1 + m;
-		xJ = (spec[o] - sLower[J] * y) * thQ[o];
-		spec[o] = xJ;
+	// rows above J: homogeneous recurrence towards the wall, x_j = r_j x_{j-1}. Only the rest of J's block of TW_BLK rows is
+	// walked here; for the blocks above, the value entering each block is propagated with the precomputed block products
+	// (thP at a block's last row) and k_thomas_expand fills the rows in parallel from thP's in-block prefix products.
+	const int jEnd = min(Nr - 1, (J / TW_BLK) * TW_BLK + TW_BLK - 1);
+	double x = 0.0;                                             // warp 0: alpha at row jEnd
+	if (jEnd < TW_RCAP) {
+		double* sInv = smw;
+		double* sB = smw + TW_RCAP * 32;
+		double* sC = smw + 2 * TW_RCAP * 32;
+		const double q = (warp == 0 && mOk) ? thQ[(size_t)J * n1 + m] : 0.0;
+		for (int j = warp; j <= jEnd; j += 4) {
+			const size_t off = (size_t)j * n1 + (mOk ? m : 0);
+			if (j <= J) {
+				cpa8(&sB[j * 32 + lane], spec + off, mOk && sTouched[j]);
+				if (j >= J0 && j < J) cpa8(&sInv[j * 32 + lane], thInv + off, mOk);
+				if (j < J) cpa8(&sC[j * 32 + lane], thCp + off, mOk);
+			}
+			else cpa8(&sC[j * 32 + lane], thR + off, mOk);
+		}
+		cpa_commit();
+		cpa_wait<0>();
+		__syncthreads();
+		if (warp == 0) {
+			// forward sweep over rows J0 .. J-1:  y_j = (beta_j - l_j y_{j-1}) / pivot_j
+			double y = 0.0;
+#pragma unroll 4
+			for (int j = J0; j < J; ++j) {
+				const double inv = sInv[j * 32 + lane];
+				const double g = sB[j * 32 + lane] * inv, c = -(sLower[j] * inv);
+				y = fma(c, y, g);
+				sB[j * 32 + lane] = y;
+			}
+			// row J closes the system: the rows above it carry no deposit and are folded into the pivot 1 / thQ
+			const double xJ = (sB[J * 32 + lane] - sLower[J] * y) * q;
+			sB[J * 32 + lane] = xJ;
+			// back-substitution below J:  x_j = y_j - cp_j x_{j+1}   (y_j = 0 below the first touched row: sB was zero-filled)
+			x = xJ;
+#pragma unroll 4
+			for (int j = J - 1; j >= 0; --j) {
+				x = fma(-sC[j * 32 + lane], x, sB[j * 32 + lane]);
+				sB[j * 32 + lane] = x;
+			}
+			x = xJ;
+#pragma unroll 4
+			for (int j = J + 1; j <= jEnd; ++j) {
+				x = sC[j * 32 + lane] * x;
+				sB[j * 32 + lane] = x;
+			}
+		}
+		__syncthreads();
+		if (mOk) for (int j = warp; j <= jEnd; j += 4) spec[(size_t)j * n1 + m] = sB[j * 32 + lane];
 	}
-	__threadfence_block();                                      // this lane's y values are read back through cp.async below
-	// back-substitution below J:  x_j = y_j - cp_j x_{j+1}   (y_j = 0 below the first touched row)
-	double x = xJ;
-	const unsigned char* fromJ0 = sTouched;                     // flag: row >= J0 (reuse the array: mark the whole range)
-	for (int j = J0 + lane; j < J; j += 32) sTouched[j] = 1;
-	__syncwarp();
-	stream_rows<-1, true>(ring, J - 1, J, thCp, spec, fromJ0, n1, m, mOk, lane, [&](int j, double cp, double yj) {
-		x = fma(-cp, x, yj);
-		if (mOk) spec[(size_t)j * n1 + m] = x;
-	});
-	// rows above J: homogeneous recurrence towards the wall
-	x = xJ;
-	stream_rows<1, false>(ring, J + 1, Nr - 1 - J, thR, nullptr, nullptr, n1, m, mOk, lane, [&](int j, double r, double) {
-		x = r * x;
-		if (mOk) spec[(size_t)j * n1 + m] = x;
-	});
+	else if (warp == 0) {
+		double y = 0.0;
+		stream_rows<1, true>(ring, J0, J - J0, thInv, spec, sTouched, n1, m, mOk, lane, [&](int j, double inv, double beta) {
+			const double g = beta * inv, c = -(sLower[j] * inv);
+			y = fma(c, y, g);
+			if (mOk) spec[(size_t)j * n1 + m] = y;
+		});
+		double xJ = 0.0;
+		if (mOk) {
+			const size_t o = (size_t)J * n1 + m;
+			xJ = (spec[o] - sLower[J] * y) * thQ[o];
+			spec[o] = xJ;
+		}
+		__threadfence_block();                                  // this lane's y values are read back through cp.async below
+		x = xJ;
+		for (int j = J0 + lane; j < J; j += 32) sTouched[j] = 1;    // from here on the flag means "row >= J0": y was stored there
+		__syncwarp();
+		stream_rows<-1, true>(ring, J - 1, J, thCp, spec, sTouched, n1, m, mOk, lane, [&](int j, double cp, double yj) {
+			x = fma(-cp, x, yj);
+			if (mOk) spec[(size_t)j * n1 + m] = x;
+		});
+		x = xJ;
+		stream_rows<1, false>(ring, J + 1, jEnd - J, thR, nullptr, nullptr, n1, m, mOk, lane, [&](int j, double r, double) {
+			x = r * x;
+			if (mOk) spec[(size_t)j * n1 + m] = x;
+		});
+	}
+	if (warp != 0) return;
+	const int nB = (Nr + TW_BLK - 1) / TW_BLK, bFirst = J / TW_BLK + 1;
+	double* xb = xbAll + (size_t)s * nB * n1;
+	if (blockIdx.x == 0 && lane == 0) wideJ[s] = J;
+	for (int b0 = bFirst; b0 < nB; b0 += 16) {
+		double pb[16];
+#pragma unroll
+		for (int u = 0; u < 16; ++u) {
+			const int b = b0 + u;
+			pb[u] = (b < nB && mOk) ? thP[(size_t)min(Nr - 1, b * TW_BLK + TW_BLK - 1) * n1 + m] : 0.0;
+		}
+#pragma unroll
+		for (int u = 0; u < 16; ++u) {
+			const int b = b0 + u;
+			if (b < nB && mOk) xb[(size_t)b * n1 + m] = x;
+			x = pb[u] * x;
+		}
+	}
+}
+
+// Rows above the block of the outermost deposit row: alpha[j][m] = (value entering the block) * (in-block prefix product).
+__global__ void __launch_bounds__(256) k_thomas_expand(double* __restrict__ specAll, const double* __restrict__ xbAll, const int* __restrict__ wideJ,
+	const double* __restrict__ thP, int Nr, int n1)
+{
+	const int s = blockIdx.z, J = wideJ[s];
+	const int j0 = blockIdx.y * 8;
+	if (J < 0 || j0 <= min(Nr - 1, (J / TW_BLK) * TW_BLK + TW_BLK - 1)) return;   // TW_BLK is a multiple of 8: the whole group is on one side
+	const int m = blockIdx.x * 256 + threadIdx.x;
+	if (m >= n1) return;
+	const int nB = (Nr + TW_BLK - 1) / TW_BLK;
+	const double xin = xbAll[((size_t)s * nB + j0 / TW_BLK) * n1 + m];
+	double* spec = specAll + (size_t)s * Nr * n1;
+	double p[8];
+#pragma unroll
+	for (int u = 0; u < 8; ++u) p[u] = j0 + u < Nr ? thP[(size_t)(j0 + u) * n1 + m] : 0.0;
+#pragma unroll
+	for (int u = 0; u < 8; ++u)
+		if (j0 + u < Nr) spec[(size_t)(j0 + u) * n1 + m] = xin * p[u];
 }
 
 // ---- inverse DCT-I through an Nz-point complex FFT + node field ---------------------------------------------
@@ -243,17 +342,22 @@ template <bool FIELD>
 __global__ void __launch_bounds__(512, 2) k_idct_fft_field(const double* __restrict__ alphaAll, double* __restrict__ phiAll, const double2* __restrict__ tw,
 	const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int N, int bits /* log2 N */, double hz)
 {
-	extern __shared__ double2 fbw[];                            // [N]
+	extern __shared__ double2 fbw[];                            // [N], swizzled
 	double* tot = reinterpret_cast<double*>(fbw + N);           // [N+1] running total potential of the row (FIELD)
 	const int tid = threadIdx.x, T = blockDim.x, n1 = N + 1;
 	const int row = blockIdx.x;
+	// Element p lives at p ^ f(p >> 3): the 16-byte bank group (p & 7) is mixed with the next three index bits (the late
+	// passes touch 4 q-strided points per thread with q < 8) and with the three bits that the bit-reversed read-out makes
+	// vary from lane to lane. Without it the last three pass pairs and the read-out are 4- to 32-way bank conflicted.
+	const int sh = bits >= 9 ? bits - 5 : 3;
+	auto SW = [sh](int p) { return p ^ (((p >> 3) ^ (p >> sh)) & 7); };
 	if (FIELD) for (int k = tid; k <= N; k += T) tot[k] = phiTrap[(size_t)row * n1 + k];
 	for (int sp = 0; sp < nS; ++sp) {
 		const double* a = alphaAll + ((size_t)sp * Nr + row) * n1;
 		__syncthreads();                                        // previous species is done with fbw
 		for (int n = tid; n < N; n += T) {
 			const int i0 = 2 * n, i1 = 2 * n + 1;
-			fbw[n] = make_double2(a[i0 <= N ? i0 : 2 * N - i0], a[i1 <= N ? i1 : 2 * N - i1]);
+			fbw[SW(n)] = make_double2(a[i0 <= N ? i0 : 2 * N - i0], a[i1 <= N ? i1 : 2 * N - i1]);
 		}
 		const double a0 = a[0], aN = a[N];
 		__syncthreads();
@@ -263,33 +367,36 @@ __global__ void __launch_bounds__(512, 2) k_idct_fft_field(const double* __restr
 			for (int i = tid; i < (N >> 2); i += T) {
 				const int j0 = i & (q - 1);
 				const int b = ((i - j0) << 2) + j0;
-				const double2 x0 = fbw[b], x1 = fbw[b + q], x2 = fbw[b + h], x3 = fbw[b + h + q];
-				const double2 wa0 = __ldg(&tw[j0 * sA]), wa1 = __ldg(&tw[(j0 + q) * sA]), wb = __ldg(&tw[j0 * 2 * sA]);
+				const int p0 = SW(b), p1 = SW(b + q), p2 = SW(b + h), p3 = SW(b + h + q);
+				const double2 x0 = fbw[p0], x1 = fbw[p1], x2 = fbw[p2], x3 = fbw[p3];
+				// W_{2h}^{j0 + h/2} = -i W_{2h}^{j0}; the second pass' twiddle W_{h}^{j0} comes from the table as well (exactly rounded)
+				const double2 wa = __ldg(&tw[j0 * sA]), wb = __ldg(&tw[j0 * 2 * sA]);
 				const double2 u0 = make_double2(x0.x + x2.x, x0.y + x2.y), u1 = make_double2(x1.x + x3.x, x1.y + x3.y);
 				const double d2x = x0.x - x2.x, d2y = x0.y - x2.y, d3x = x1.x - x3.x, d3y = x1.y - x3.y;
-				const double2 u2 = make_double2(d2x * wa0.x - d2y * wa0.y, d2x * wa0.y + d2y * wa0.x);
-				const double2 u3 = make_double2(d3x * wa1.x - d3y * wa1.y, d3x * wa1.y + d3y * wa1.x);
-				fbw[b] = make_double2(u0.x + u1.x, u0.y + u1.y);
+				const double2 u2 = make_double2(d2x * wa.x - d2y * wa.y, d2x * wa.y + d2y * wa.x);
+				const double2 u3 = make_double2(d3x * wa.y + d3y * wa.x, d3y * wa.y - d3x * wa.x);   // (d3x + i d3y) (wa.y - i wa.x)
+				fbw[p0] = make_double2(u0.x + u1.x, u0.y + u1.y);
 				const double e1x = u0.x - u1.x, e1y = u0.y - u1.y;
-				fbw[b + q] = make_double2(e1x * wb.x - e1y * wb.y, e1x * wb.y + e1y * wb.x);
-				fbw[b + h] = make_double2(u2.x + u3.x, u2.y + u3.y);
+				fbw[p1] = make_double2(e1x * wb.x - e1y * wb.y, e1x * wb.y + e1y * wb.x);
+				fbw[p2] = make_double2(u2.x + u3.x, u2.y + u3.y);
 				const double e3x = u2.x - u3.x, e3y = u2.y - u3.y;
-				fbw[b + h + q] = make_double2(e3x * wb.x - e3y * wb.y, e3x * wb.y + e3y * wb.x);
+				fbw[p3] = make_double2(e3x * wb.x - e3y * wb.y, e3x * wb.y + e3y * wb.x);
 			}
 			__syncthreads();
 		}
 		if (h == 1) {                                           // odd number of passes: the last one on its own (twiddle 1)
 			for (int i = tid; i < (N >> 1); i += T) {
-				const double2 u = fbw[2 * i], v = fbw[2 * i + 1];
-				fbw[2 * i] = make_double2(u.x + v.x, u.y + v.y);
-				fbw[2 * i + 1] = make_double2(u.x - v.x, u.y - v.y);
+				const int p0 = SW(2 * i), p1 = SW(2 * i + 1);
+				const double2 u = fbw[p0], v = fbw[p1];
+				fbw[p0] = make_double2(u.x + v.x, u.y + v.y);
+				fbw[p1] = make_double2(u.x - v.x, u.y - v.y);
 			}
 			__syncthreads();
 		}
 		double* out = phiAll + ((size_t)sp * Nr + row) * n1;
 		for (int k = tid; k <= N; k += T) {
 			const unsigned int ka = (unsigned int)(k & (N - 1)), kb = (unsigned int)((N - k) & (N - 1));
-			const double2 A = fbw[__brev(ka) >> (32 - bits)], B = fbw[__brev(kb) >> (32 - bits)];   // Z_k, Z_{N-k} (conjugated below)
+			const double2 A = fbw[SW((int)(__brev(ka) >> (32 - bits)))], B = fbw[SW((int)(__brev(kb) >> (32 - bits)))];   // Z_k, Z_{N-k}
 			const double2 w = k < N ? __ldg(&tw[k]) : make_double2(-1.0, 0.0);
 			const double dx = A.x - B.x, dy = A.y + B.y;            // Z_k - conj Z_{N-k}
 			const double X = 0.5 * (A.x + B.x) + 0.5 * (dy * w.x + dx * w.y);
@@ -332,13 +439,18 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_fwd_dct launch", __FILE__, __LINE__);
-	const size_t smTh = (size_t)TW_ST * 2 * TW_RS * 32 * sizeof(double) + (size_t)Nr * sizeof(double) + (size_t)Nr;
+	static_assert(3 * TW_RCAP >= TW_ST * 2 * TW_RS, "the ring of the streamed path lives in the compact path's tiles");
+	const size_t smTh = (size_t)3 * TW_RCAP * 32 * sizeof(double) + (size_t)Nr * sizeof(double) + (size_t)Nr;
 	if (smTh > t->smemMax) { ptp_set_error("direct solver: Nr too large for the radial-solve kernel of this build"); return PTP_EINVAL; }
 	PTP_CUDA(cudaFuncSetAttribute(k_thomas_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smTh));
-	k_thomas_wide<<<dim3((n1 + 31) / 32, nS), 32, smTh, t->stream>>>(spec, t->rowBounds, encBounds, t->thInv, t->thCp, t->thR, t->thQ, t->thLower, Nr, n1);
+	k_thomas_wide<<<dim3((n1 + 31) / 32, nS), 128, smTh, t->stream>>>(spec, t->rowBounds, encBounds, t->thInv, t->thCp, t->thR, t->thQ, t->thP, t->thLower,
+		t->wideXb, t->wideJ, Nr, n1);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_wide launch", __FILE__, __LINE__);
-	t->lastLaunches += 2;
+	k_thomas_expand<<<dim3((n1 + 255) / 256, (Nr + 7) / 8, nS), 256, 0, t->stream>>>(spec, t->wideXb, t->wideJ, t->thP, Nr, n1);
+	e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_expand launch", __FILE__, __LINE__);
+	t->lastLaunches += 3;
 	return PTP_OK;
 }
 
