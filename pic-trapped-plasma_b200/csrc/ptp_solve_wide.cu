@@ -42,17 +42,20 @@ __device__ __forceinline__ int2 row_bounds_of(const int2* bounds, const uint2* e
 }
 
 // ---- forward DCT-I of the touched rows -------------------------------------------------------------------------
-constexpr int FD_M = 64;        // modes per CTA (2 per lane)
-constexpr int FD_R = 64;        // rows per CTA (8 per warp)
+constexpr int FD_M = 64;        // modes per CTA (lane -> modes 2 lane, 2 lane + 1)
+constexpr int FD_R = 32;        // rows per CTA (warp -> rows 4 warp .. 4 warp + 3)
 constexpr int FD_K = 64;        // axial nodes staged per chunk
+constexpr int FD_RP = FD_R + 2; // padded row count of the transposed deposit tile (keeps 16-byte alignment)
 
+// beta[j][m] = scale * sum_k rho[j][k] FT[k][m] over the union of the touched axial ranges of the tile's rows. Chunks of
+// 64 nodes are double-buffered through cp.async; per node a lane reads its two matrix entries with one 16-byte load and
+// the warp's four deposit values with two 16-byte broadcasts for 8 FMAs.
 template <bool A_FIXED>
-__global__ void __launch_bounds__(256) k_fwd_dct(const double* __restrict__ rho, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
+__global__ void __launch_bounds__(256, 2) k_fwd_dct(const double* __restrict__ rho, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
 	const double* __restrict__ FT, const double* __restrict__ rowScale, double fixedInv, double* __restrict__ spec, int Nr, int n1)
 {
-	extern __shared__ double smw[];
-	double* sFT = smw;                                          // [FD_K][FD_M]
-	double* sRho = smw + FD_K * FD_M;                           // [FD_R][FD_K]
+	extern __shared__ __align__(16) double smw[];
+	constexpr int BUF = FD_K * FD_M + FD_K * FD_RP;             // doubles per buffer: sFT [FD_K][FD_M] | sRho [FD_K][FD_RP]
 	__shared__ int2 sBd[FD_R];
 	__shared__ int sLo, sHi;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -68,54 +71,68 @@ __global__ void __launch_bounds__(256) k_fwd_dct(const double* __restrict__ rho,
 	__syncthreads();
 	const int kLo = sLo, kHi = sHi;
 	if (kLo > kHi) return;                                      // nothing deposited in these rows
-	unsigned int active = 0;                                    // rows warp + 8 u of this tile that hold a deposit (uniform per warp)
-#pragma unroll
-	for (int u = 0; u < 8; ++u) active |= (sBd[warp + 8 * u].x <= sBd[warp + 8 * u].y ? 1u : 0u) << u;
+	unsigned int rowsActive = 0;                                // bit jj: row jBase + jj holds a deposit
+	for (int jj = 0; jj < FD_R; ++jj) rowsActive |= (sBd[jj].x <= sBd[jj].y ? 1u : 0u) << jj;
+	const bool warpActive = ((rowsActive >> (4 * warp)) & 15u) != 0u;
 	const double* b = rho + (size_t)s * Nr * n1;
-	double acc0[8], acc1[8];
-#pragma unroll
-	for (int u = 0; u < 8; ++u) acc0[u] = acc1[u] = 0.0;
-	for (int k0 = kLo; k0 <= kHi; k0 += FD_K) {
-		const int kn = min(FD_K, kHi - k0 + 1);
-		__syncthreads();
-		for (int e = tid; e < kn * FD_M; e += 256) {
+	const int nC = (kHi - kLo + FD_K) / FD_K;
+	auto issue = [&](int c) {
+		double* sFT = smw + (size_t)(c & 1) * BUF;
+		double* sRho = sFT + FD_K * FD_M;
+		const int k0 = kLo + c * FD_K, kn = min(FD_K, kHi - k0 + 1);
+		for (int e = tid; e < FD_K * FD_M; e += 256) {
 			const int kk = e / FD_M, mm = e % FD_M;
-			const bool ok = mBase + mm < n1;
-			cpa8(&sFT[e], FT + (size_t)(k0 + kk) * n1 + (ok ? mBase + mm : 0), ok);
+			const bool ok = kk < kn && mBase + mm < n1;
+			cpa8(&sFT[e], FT + (ok ? (size_t)(k0 + kk) * n1 + mBase + mm : 0), ok);
+		}
+		// deposit tile, transposed to [node][row]: values outside a row's own range are exact zeros (the grid is cleared
+		// every step), rows without a deposit and nodes past the end of the range are zero-filled
+		for (int e = tid; e < FD_K * FD_R; e += 256) {
+			const int jj = e / FD_K, kk = e % FD_K;
+			const bool ok = kk < kn && ((rowsActive >> jj) & 1u);
+			cpa8(&sRho[kk * FD_RP + jj], b + (ok ? (size_t)(jBase + jj) * n1 + k0 + kk : 0), ok);
 		}
 		cpa_commit();
+	};
+	double acc[4][2];
 #pragma unroll
-		for (int u = 0; u < 8; ++u) {
-			if (!((active >> u) & 1u)) continue;
-			const int jj = warp + 8 * u;
-			const double* src = b + (size_t)(jBase + jj) * n1 + k0;
-			for (int kk = lane; kk < kn; kk += 32) {
-				// values outside a row's own range are exact zeros (the grid is cleared every step), so the whole chunk is loaded
-				const double raw = src[kk];
-				sRho[jj * FD_K + kk] = A_FIXED ? (double)__double_as_longlong(raw) : raw;
+	for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+	issue(0);
+	for (int c = 0; c < nC; ++c) {
+		if (c + 1 < nC) { issue(c + 1); cpa_wait<1>(); }
+		else cpa_wait<0>();
+		double* sFT = smw + (size_t)(c & 1) * BUF;
+		double* sRho = sFT + FD_K * FD_M;
+		if (A_FIXED) {                                          // int64 accumulators -> double, each thread its own copies
+			for (int e = tid; e < FD_K * FD_R; e += 256) {
+				double* q = &sRho[(e % FD_K) * FD_RP + e / FD_K];
+				*q = (double)__double_as_longlong(*q);
 			}
 		}
-		cpa_wait<0>();
 		__syncthreads();
-		for (int kk = 0; kk < kn; ++kk) {
-			const double f0 = sFT[kk * FD_M + lane], f1 = sFT[kk * FD_M + 32 + lane];
-#pragma unroll
-			for (int u = 0; u < 8; ++u) {
-				if (!((active >> u) & 1u)) continue;
-				const double val = sRho[(warp + 8 * u) * FD_K + kk];
-				acc0[u] = fma(val, f0, acc0[u]);
-				acc1[u] = fma(val, f1, acc1[u]);
+		if (warpActive) {
+#pragma unroll 4
+			for (int kk = 0; kk < FD_K; ++kk) {
+				const double2 f = *reinterpret_cast<const double2*>(&sFT[kk * FD_M + 2 * lane]);
+				const double2 r01 = *reinterpret_cast<const double2*>(&sRho[kk * FD_RP + 4 * warp]);
+				const double2 r23 = *reinterpret_cast<const double2*>(&sRho[kk * FD_RP + 4 * warp + 2]);
+				acc[0][0] = fma(r01.x, f.x, acc[0][0]); acc[0][1] = fma(r01.x, f.y, acc[0][1]);
+				acc[1][0] = fma(r01.y, f.x, acc[1][0]); acc[1][1] = fma(r01.y, f.y, acc[1][1]);
+				acc[2][0] = fma(r23.x, f.x, acc[2][0]); acc[2][1] = fma(r23.x, f.y, acc[2][1]);
+				acc[3][0] = fma(r23.y, f.x, acc[3][0]); acc[3][1] = fma(r23.y, f.y, acc[3][1]);
 			}
 		}
+		__syncthreads();                                        // this buffer is refilled by the next iteration's issue
 	}
 	const double scale = (rowScale ? rowScale[s] : 1.0) * (A_FIXED ? fixedInv : 1.0);
 	double* out = spec + (size_t)s * Nr * n1;
 #pragma unroll
-	for (int u = 0; u < 8; ++u) {
-		if (!((active >> u) & 1u)) continue;
-		const size_t row = (size_t)(jBase + warp + 8 * u) * n1;
-		if (mBase + lane < n1) out[row + mBase + lane] = acc0[u] * scale;
-		if (mBase + 32 + lane < n1) out[row + mBase + 32 + lane] = acc1[u] * scale;
+	for (int u = 0; u < 4; ++u) {
+		const int jj = 4 * warp + u;
+		if (!((rowsActive >> jj) & 1u)) continue;
+		const size_t row = (size_t)(jBase + jj) * n1;
+		if (mBase + 2 * lane < n1) out[row + mBase + 2 * lane] = acc[u][0] * scale;
+		if (mBase + 2 * lane + 1 < n1) out[row + mBase + 2 * lane + 1] = acc[u][1] * scale;
 	}
 }
 
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAl
 	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thR, const double* __restrict__ thQ,
 	const double* __restrict__ thP, const double* __restrict__ thLower, double* __restrict__ xbAll, int* __restrict__ wideJ, int Nr, int n1)
 {
-	extern __shared__ double smw[];
+	extern __shared__ __align__(16) double smw[];
 	double* ring = smw;                                         // streamed: [TW_ST][2][TW_RS][32]; compact: sInv | sB | sC, [TW_RCAP][32] each
 	double* sLower = smw + (size_t)3 * TW_RCAP * 32;            // [Nr]
 	unsigned char* sTouched = reinterpret_cast<unsigned char*>(sLower + Nr); // [Nr]
@@ -339,18 +356,19 @@ __global__ void __launch_bounds__(256) k_thomas_expand(double* __restrict__ spec
 // in pairs (four points per thread and pair of passes, same arithmetic as two radix-2 passes, half the barriers and half
 // the shared-memory traffic); Z_k is read from the bit-reversed slot. One CTA per grid row loops over the species.
 template <bool FIELD>
-__global__ void __launch_bounds__(512, 2) k_idct_fft_field(const double* __restrict__ alphaAll, double* __restrict__ phiAll, const double2* __restrict__ tw,
+__global__ void __launch_bounds__(256, 2) k_idct_fft_field(const double* __restrict__ alphaAll, double* __restrict__ phiAll, const double2* __restrict__ tw,
 	const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int N, int bits /* log2 N */, double hz)
 {
 	extern __shared__ double2 fbw[];                            // [N], swizzled
 	double* tot = reinterpret_cast<double*>(fbw + N);           // [N+1] running total potential of the row (FIELD)
 	const int tid = threadIdx.x, T = blockDim.x, n1 = N + 1;
 	const int row = blockIdx.x;
-	// Element p lives at p ^ f(p >> 3): the 16-byte bank group (p & 7) is mixed with the next three index bits (the late
-	// passes touch 4 q-strided points per thread with q < 8) and with the three bits that the bit-reversed read-out makes
-	// vary from lane to lane. Without it the last three pass pairs and the read-out are 4- to 32-way bank conflicted.
-	const int sh = bits >= 9 ? bits - 5 : 3;
-	auto SW = [sh](int p) { return p ^ (((p >> 3) ^ (p >> sh)) & 7); };
+	// Element p lives at p ^ f(p >> 3). 16-byte accesses are served a quarter-warp at a time, so the 8 lanes of a quarter
+	// must hit the 8 distinct 16-byte bank groups (p & 7). The late passes touch q-strided points with q < 8, which moves the
+	// lane index into bits 3..5 of p, and the bit-reversed read-out moves it into the top three bits: both fields are folded
+	// into the group (bits 3, 4 twice so that every small stride stays a bijection on the quarter-warp).
+	const int sh = bits >= 9 ? bits - 3 : 31;
+	auto SW = [sh](int p) { const int x = p >> 3; return p ^ ((x ^ ((x & 3) << 1) ^ (p >> sh)) & 7); };
 	if (FIELD) for (int k = tid; k <= N; k += T) tot[k] = phiTrap[(size_t)row * n1 + k];
 	for (int sp = 0; sp < nS; ++sp) {
 		const double* a = alphaAll + ((size_t)sp * Nr + row) * n1;
@@ -364,23 +382,36 @@ __global__ void __launch_bounds__(512, 2) k_idct_fft_field(const double* __restr
 		int h = N >> 1;
 		for (; h >= 2; h >>= 2) {                               // passes with half-sizes h and h/2, fused
 			const int q = h >> 1, sA = N / h;                   // twiddle steps: W_{2h}^j = tw[j * N / h]
-			for (int i = tid; i < (N >> 2); i += T) {
-				const int j0 = i & (q - 1);
-				const int b = ((i - j0) << 2) + j0;
-				const int p0 = SW(b), p1 = SW(b + q), p2 = SW(b + h), p3 = SW(b + h + q);
-				const double2 x0 = fbw[p0], x1 = fbw[p1], x2 = fbw[p2], x3 = fbw[p3];
-				// W_{2h}^{j0 + h/2} = -i W_{2h}^{j0}; the second pass' twiddle W_{h}^{j0} comes from the table as well (exactly rounded)
-				const double2 wa = __ldg(&tw[j0 * sA]), wb = __ldg(&tw[j0 * 2 * sA]);
-				const double2 u0 = make_double2(x0.x + x2.x, x0.y + x2.y), u1 = make_double2(x1.x + x3.x, x1.y + x3.y);
-				const double d2x = x0.x - x2.x, d2y = x0.y - x2.y, d3x = x1.x - x3.x, d3y = x1.y - x3.y;
-				const double2 u2 = make_double2(d2x * wa.x - d2y * wa.y, d2x * wa.y + d2y * wa.x);
-				const double2 u3 = make_double2(d3x * wa.y + d3y * wa.x, d3y * wa.y - d3x * wa.x);   // (d3x + i d3y) (wa.y - i wa.x)
-				fbw[p0] = make_double2(u0.x + u1.x, u0.y + u1.y);
-				const double e1x = u0.x - u1.x, e1y = u0.y - u1.y;
-				fbw[p1] = make_double2(e1x * wb.x - e1y * wb.y, e1x * wb.y + e1y * wb.x);
-				fbw[p2] = make_double2(u2.x + u3.x, u2.y + u3.y);
-				const double e3x = u2.x - u3.x, e3y = u2.y - u3.y;
-				fbw[p3] = make_double2(e3x * wb.x - e3y * wb.y, e3x * wb.y + e3y * wb.x);
+			for (int i0 = tid; i0 < (N >> 2); i0 += 2 * T) {    // two items per thread in flight
+				int p[2][4];
+				double2 x[2][4], wa[2], wb[2];
+#pragma unroll
+				for (int u = 0; u < 2; ++u) {
+					const int i = min(i0 + u * T, (N >> 2) - 1);
+					const int j0 = i & (q - 1);
+					const int b = ((i - j0) << 2) + j0;
+					p[u][0] = SW(b); p[u][1] = SW(b + q); p[u][2] = SW(b + h); p[u][3] = SW(b + h + q);
+					// W_{2h}^{j0 + h/2} = -i W_{2h}^{j0}; the second pass' twiddle W_{h}^{j0} comes from the table (exactly rounded)
+					wa[u] = __ldg(&tw[j0 * sA]);
+					wb[u] = __ldg(&tw[j0 * 2 * sA]);
+#pragma unroll
+					for (int c = 0; c < 4; ++c) x[u][c] = fbw[p[u][c]];
+				}
+#pragma unroll
+				for (int u = 0; u < 2; ++u) {
+					if (i0 + u * T >= (N >> 2)) continue;
+					const double2 x0 = x[u][0], x1 = x[u][1], x2 = x[u][2], x3 = x[u][3];
+					const double2 u0 = make_double2(x0.x + x2.x, x0.y + x2.y), u1 = make_double2(x1.x + x3.x, x1.y + x3.y);
+					const double d2x = x0.x - x2.x, d2y = x0.y - x2.y, d3x = x1.x - x3.x, d3y = x1.y - x3.y;
+					const double2 u2 = make_double2(d2x * wa[u].x - d2y * wa[u].y, d2x * wa[u].y + d2y * wa[u].x);
+					const double2 u3 = make_double2(d3x * wa[u].y + d3y * wa[u].x, d3y * wa[u].y - d3x * wa[u].x);   // (d3x + i d3y) (wa.y - i wa.x)
+					fbw[p[u][0]] = make_double2(u0.x + u1.x, u0.y + u1.y);
+					const double e1x = u0.x - u1.x, e1y = u0.y - u1.y;
+					fbw[p[u][1]] = make_double2(e1x * wb[u].x - e1y * wb[u].y, e1x * wb[u].y + e1y * wb[u].x);
+					fbw[p[u][2]] = make_double2(u2.x + u3.x, u2.y + u3.y);
+					const double e3x = u2.x - u3.x, e3y = u2.y - u3.y;
+					fbw[p[u][3]] = make_double2(e3x * wb[u].x - e3y * wb[u].y, e3x * wb[u].y + e3y * wb[u].x);
+				}
 			}
 			__syncthreads();
 		}
@@ -427,7 +458,7 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 {
 	const int n1 = t->Nz + 1, Nr = t->Nr;
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
-	const size_t smDct = (size_t)(FD_K * FD_M + FD_R * FD_K) * sizeof(double);
+	const size_t smDct = (size_t)2 * (FD_K * FD_M + FD_K * FD_RP) * sizeof(double);
 	const dim3 gridDct((n1 + FD_M - 1) / FD_M, (Nr + FD_R - 1) / FD_R, nS);
 	if (rhoIsFixed) {
 		PTP_CUDA(cudaFuncSetAttribute(k_fwd_dct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smDct));
@@ -461,7 +492,7 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 	int bits = 0;
 	while ((1 << bits) < N) ++bits;
 	const size_t sm = (size_t)N * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
-	const int threads = N >= 2048 ? 512 : (N >= 1024 ? 256 : 128);
+	const int threads = N >= 1024 ? 256 : 128;
 	if (withField) {
 		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
 		k_idct_fft_field<true><<<Nr, threads, sm, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, N, bits, t->hz);
