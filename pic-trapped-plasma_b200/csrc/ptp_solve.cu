@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -657,7 +658,10 @@ int ptp_solver_build(ptp_trap* t)
 	{
 		cudaDeviceProp prop;
 		PTP_CUDA(cudaGetDeviceProperties(&prop, t->device));
-		if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+		// only when the whole set fits: on large grids (config 5: 335 MB of tables) a partial carve-out would just take most
+		// of L2 away from the push kernel's prefetch stream without making the solve any faster
+		if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0 && constBytes <= (size_t)prop.persistingL2CacheMaxSize / 2 &&
+			!getenv("PTP_NO_L2_PERSIST")) {
 			const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, constBytes);
 			size_t current = 0;
 			cudaDeviceGetLimit(&current, cudaLimitPersistingL2CacheSize);
