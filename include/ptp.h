@@ -130,6 +130,17 @@ int ptp_plasma_destroy(ptp_plasma* p);
  * {r[i] in [0,Nr), z[i], v[i]} in any order; ring i keeps id i. macroChargeDensity as in
  * Source/Plasma.cpp:494. Does not deposit or solve. */
 int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* z, const double* v, double macroChargeDensity);
+/* Ring placement of Plasma::loadDensityFile / Plasma::loadProfile (Source/Plasma.cpp:464-526 = :558-620) on the device:
+ * density[G] (host) is the expected charge density; the cumulative charge per row, chargeMacro (:492) and the rings per
+ * row (:496,499) are evaluated on the host in the reference's serial order, the quantile inversion (:512-523, positions
+ * bit-identical) and the Maxwellian speeds run on the device. The speeds reproduce the deviate stream of the reference's
+ * freshly seeded std::default_random_engine + std::normal_distribution (:508-509, libstdc++: minstd_rand0 and the polar
+ * method) ring for ring; values agree to the last bits of log(). Shard `shard` of `nShards` keeps rings i = shard
+ * (mod nShards) of every row (the multi-GPU partition); ring ids count the shard's rings in (row, i) order.
+ * chargeMacro / nAtRow[Nr] (rings per row over all shards) / nLoaded (rings of this shard) may be NULL.
+ * Does not deposit or solve (call ptp_plasma_deposit_solve, as both loaders do at :528,622). */
+int ptp_plasma_load_density(ptp_plasma* p, const double* density, double temperature, int64_t numMacro, int shard, int nShards,
+	double* chargeMacro, int64_t* nAtRow, int64_t* nLoaded);
 /* Plasma::solvePoisson (Source/Plasma.cpp:95-99): deposit this plasma's RHS and solve its self potential. */
 int ptp_plasma_deposit_solve(ptp_plasma* p);
 /* Plasma::updateRHS alone (Source/Plasma.cpp:77-94). */

@@ -71,6 +71,7 @@ SIGNATURES = {
     "ptp_plasma_create": (_i, [_vp, _pvp, _d, _d]),
     "ptp_plasma_destroy": (_i, [_vp]),
     "ptp_plasma_upload": (_i, [_vp, _i64, _vp, _vp, _vp, _d]),
+    "ptp_plasma_load_density": (_i, [_vp, _vp, _d, _i64, _i, _i, C.POINTER(_d), _vp, C.POINTER(_i64)]),
     "ptp_plasma_deposit_solve": (_i, [_vp]),
     "ptp_plasma_deposit": (_i, [_vp]),
     "ptp_plasma_count": (_i, [_vp, C.POINTER(_i64)]),
@@ -312,6 +313,24 @@ class Plasma:
         self.massMacro = self.chargeMacro * self.mass / self.charge
         self.macroChargeDensity = 4 * self.chargeMacro / (PI * t.hz * t.hr * t.hr)
         _check(lib().ptp_plasma_upload(self.h, len(r), _ptr(r), _ptr(z), _ptr(v), self.macroChargeDensity))
+
+    def loadDensity(self, density, temperature, numMacro, shard=0, nShards=1, solve=True):
+        """Placement + speeds of Plasma::loadDensityFile / loadProfile on the device (Source/Plasma.cpp:464-528) from the
+        expected density grid; returns (rings loaded on this shard, rings per row over all shards)."""
+        t = self.refTrap
+        density = _f64(density)
+        if density.size != t.G:
+            raise ValueError("The number of grid points in the file do not match this trap.")   # Source/Plasma.cpp:556
+        cm, n = C.c_double(), C.c_int64()
+        per_row = np.zeros(t.Nr, np.int64)
+        _check(lib().ptp_plasma_load_density(self.h, _ptr(density), float(temperature), int(numMacro), int(shard), int(nShards),
+                                             C.byref(cm), _ptr(per_row), C.byref(n)))
+        self.chargeMacro = cm.value
+        self.massMacro = self.chargeMacro * self.mass / self.charge
+        self.macroChargeDensity = 4 * self.chargeMacro / (PI * t.hz * t.hr * t.hr)
+        if solve:
+            self.solvePoisson()
+        return n.value, per_row
 
     def solvePoisson(self):  # Source/Plasma.cpp:95-99
         _check(lib().ptp_plasma_deposit_solve(self.h))

@@ -169,6 +169,7 @@ int ptp_push_configure(ptp_trap* t);
 
 // ---- ptp_particles.cu ----------------------------------------------------------------------------
 int ptp_build_segments(ptp_trap* t, ptp_plasma* p);
+int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, int64_t n, double macroChargeDensity);
 int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p);
 
 // ---- ptp_comm.cu ---------------------------------------------------------------------------------

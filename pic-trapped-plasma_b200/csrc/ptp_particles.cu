@@ -312,6 +312,62 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 	return ptp_build_segments(t, p);
 }
 
+// Row-bucketed storage for count[j] rings in row j (n in total): bucket offsets, (re)allocation, the empty-slot pattern in
+// every bucket's padding, the species' RHS factor, a cleared loss counter and the fixed-point scale. The caller fills the
+// live prefix of every bucket (z, v, id) and then builds the segments.
+int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, int64_t n, double macroChargeDensity)
+{
+	ptp_trap* t = p->trap;
+	const int Nr = t->Nr;
+	++t->cfgEpoch;                                               // ring buffers / segment tables change: cached step graph is stale
+	p->rowOff.assign(Nr + 1, 0);
+	p->rowLive.assign(Nr, 0);
+	for (int j = 0; j < Nr; ++j) {
+		p->rowLive[j] = count[j];
+		p->rowOff[j + 1] = p->rowOff[j] + (count[j] + PTP_ROW_ALIGN - 1) / PTP_ROW_ALIGN * PTP_ROW_ALIGN;
+	}
+	const long long newCap = p->rowOff[Nr];
+	if (newCap != p->cap) {                                    // same-size reloads keep their buffers
+		cudaFree(p->z); cudaFree(p->v); cudaFree(p->id);
+		p->z = p->v = nullptr; p->id = nullptr;
+	}
+	cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
+	p->zAlt = p->vAlt = nullptr; p->idAlt = nullptr; p->dRowOff = nullptr;
+	p->cap = newCap;
+	p->nUploaded = n;
+	p->nAlive = n;
+	p->macroChargeDensity = macroChargeDensity;
+	const double scale = -macroChargeDensity / 8.8541878128e-12;     // Source/Plasma.cpp:91-92, Source/Constants.hpp:12
+	PTP_CUDA(cudaMemcpyAsync(t->dScale + p->index, &scale, sizeof(double), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
+	PTP_CUDA(cudaMalloc(&p->dRowOff, (Nr + 1) * sizeof(long long)));
+	PTP_CUDA(cudaMemcpyAsync(p->dRowOff, p->rowOff.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));                  // `scale` is a stack variable
+	if (p->cap > 0) {
+		if (!p->z) {
+			PTP_CUDA(cudaMalloc(&p->z, p->cap * sizeof(double)));
+			PTP_CUDA(cudaMalloc(&p->v, p->cap * sizeof(double)));
+			PTP_CUDA(cudaMalloc(&p->id, p->cap * sizeof(long long)));
+		}
+		// only the padding at the end of every bucket needs the empty-slot pattern (all-ones = NaN / id -1)
+		for (int j = 0; j < Nr; ++j) {
+			const long long padBegin = p->rowOff[j] + count[j], padLen = p->rowOff[j + 1] - padBegin;
+			if (padLen <= 0) continue;
+			PTP_CUDA(cudaMemsetAsync(p->z + padBegin, 0xFF, padLen * sizeof(double), t->stream));
+			PTP_CUDA(cudaMemsetAsync(p->v + padBegin, 0, padLen * sizeof(double), t->stream));
+			PTP_CUDA(cudaMemsetAsync(p->id + padBegin, 0xFF, padLen * sizeof(long long), t->stream));
+		}
+	}
+	// fixed-point scale: node sums stay below 2^62 for the whole (multi-GPU) population
+	long long total = 0;
+	for (ptp_plasma* q : t->plasmas) total += q->nUploaded;
+	total *= ptp_comm_size(t);
+	int bits = 0;
+	while ((1LL << bits) < total + 1) ++bits;
+	t->fixedBits = std::min(40, 62 - bits);
+	return PTP_OK;
+}
+
 // ---- C ABI: particle-side entry points ---------------------------------------------------------------
 extern "C" {
 
@@ -354,44 +410,9 @@ int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* 
 	}
 	if (bad) { ptp_set_error("ptp_plasma_upload: radial index outside [0, Nr)"); return PTP_EINVAL; }
 	std::vector<long long> rowSrc(Nr + 1, 0);
-	p->rowOff.assign(Nr + 1, 0);
-	p->rowLive.assign(Nr, 0);
-	for (int j = 0; j < Nr; ++j) {
-		rowSrc[j + 1] = rowSrc[j] + count[j];
-		p->rowLive[j] = count[j];
-		p->rowOff[j + 1] = p->rowOff[j] + (count[j] + PTP_ROW_ALIGN - 1) / PTP_ROW_ALIGN * PTP_ROW_ALIGN;
-	}
-	const long long newCap = p->rowOff[Nr];
-	if (newCap != p->cap) {                                    // same-size reloads keep their buffers
-		cudaFree(p->z); cudaFree(p->v); cudaFree(p->id);
-		p->z = p->v = nullptr; p->id = nullptr;
-	}
-	cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
-	p->zAlt = p->vAlt = nullptr; p->idAlt = nullptr; p->dRowOff = nullptr;
-	p->cap = newCap;
-	p->nUploaded = n;
-	p->nAlive = n;
-	p->macroChargeDensity = macroChargeDensity;
-	const double scale = -macroChargeDensity / 8.8541878128e-12;     // Source/Plasma.cpp:91-92, Source/Constants.hpp:12
-	PTP_CUDA(cudaMemcpyAsync(t->dScale + p->index, &scale, sizeof(double), cudaMemcpyHostToDevice, t->stream));
-	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
-	PTP_CUDA(cudaMalloc(&p->dRowOff, (Nr + 1) * sizeof(long long)));
-	PTP_CUDA(cudaMemcpyAsync(p->dRowOff, p->rowOff.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
-	PTP_CUDA(cudaStreamSynchronize(t->stream));                  // `scale` is a stack variable
+	for (int j = 0; j < Nr; ++j) rowSrc[j + 1] = rowSrc[j] + count[j];
+	PTP_TRY(ptp_plasma_set_layout(p, count, n, macroChargeDensity));
 	if (p->cap > 0) {
-		if (!p->z) {
-			PTP_CUDA(cudaMalloc(&p->z, p->cap * sizeof(double)));
-			PTP_CUDA(cudaMalloc(&p->v, p->cap * sizeof(double)));
-			PTP_CUDA(cudaMalloc(&p->id, p->cap * sizeof(long long)));
-		}
-		// only the padding at the end of every bucket needs the empty-slot pattern (all-ones = NaN / id -1)
-		for (int j = 0; j < Nr; ++j) {
-			const long long padBegin = p->rowOff[j] + count[j], padLen = p->rowOff[j + 1] - padBegin;
-			if (padLen <= 0) continue;
-			PTP_CUDA(cudaMemsetAsync(p->z + padBegin, 0xFF, padLen * sizeof(double), t->stream));
-			PTP_CUDA(cudaMemsetAsync(p->v + padBegin, 0, padLen * sizeof(double), t->stream));
-			PTP_CUDA(cudaMemsetAsync(p->id + padBegin, 0xFF, padLen * sizeof(long long), t->stream));
-		}
 		if (sorted) {
 			// loaders emit rows in ascending order (Source/Plasma.cpp:510-526): each bucket is one contiguous copy
 			for (int j = 0; j < Nr; ++j) {
@@ -423,13 +444,6 @@ int ptp_plasma_upload(ptp_plasma* p, int64_t n, const int32_t* r, const double* 
 			PTP_CUDA(cudaStreamSynchronize(t->stream));
 		}
 	}
-	// fixed-point scale: node sums stay below 2^62 for the whole (multi-GPU) population
-	long long total = 0;
-	for (ptp_plasma* q : t->plasmas) total += q->nUploaded;
-	total *= ptp_comm_size(t);
-	int bits = 0;
-	while ((1LL << bits) < total + 1) ++bits;
-	t->fixedBits = std::min(40, 62 - bits);
 	return ptp_build_segments(t, p);
 }
 

@@ -375,6 +375,48 @@ def test_edge_cases():
     t.close()
 
 
+# ------------------------------------------------------------------------------------------ loaders on the device (f-1)
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("num_macro,mass", [(4000, ptp.massE), (100000, ptp.massE), (1000003, ptp.massP)])
+def test_device_loader_matches_reference_loader(density_files, num_macro, mass):
+    """ptp_plasma_load_density against Plasma::loadDensityFile of the compiled reference (Source/Plasma.cpp:558-622):
+    ring counts per row and chargeMacro exact, positions bit-identical, speeds = the reference's own deviate stream
+    (minstd_rand0 + polar method reproduced in parallel) to the last bits of log(), first deposit and solve within the
+    step tolerances; shards partition the load ring for ring."""
+    dens = np.loadtxt(density_files[0])
+    rt = ref.default_trap()
+    rp = rt.plasma("Species", mass, -ref.E_POS)
+    rp.load_density_file(density_files[0], 150.0, num_macro)
+    r0, z0, v0 = rp.rings()
+    t = ptp.default_trap()
+    p = ptp.Plasma(t, "Species", mass, -ptp.ePos)
+    n, per_row = p.loadDensity(dens, 150.0, num_macro)
+    assert n == rp.count() == p.getNumMacro() == int(per_row.sum())
+    assert np.array_equal(per_row, np.bincount(r0, minlength=t.Nr))
+    par = rp.params()
+    assert p.chargeMacro == par["chargeMacro"] and p.macroChargeDensity == par["macroChargeDensity"]
+    r, z, v, ids = _by_id(p)
+    assert np.array_equal(ids, np.arange(n))
+    assert np.array_equal(r, r0)
+    assert np.array_equal(z, z0)                                     # bit-identical positions
+    assert np.max(np.abs(v - v0) / np.abs(v0)) < 2e-15               # same deviates; log() may differ in the last bit
+    assert np.mean(v != v0) < 0.35
+    assert rel_l2(p.rhs(), rp.rhs()) < 1e-12
+    assert rel_l2(p.selfPotential(), rp.self_potential()) < 1e-10
+    # shards: rings i = s (mod S) of every row, same values
+    S = 3
+    within = np.concatenate([np.arange(c) for c in per_row if c > 0])    # index of a ring inside its row, reference order
+    for sh in range(S):
+        q = ptp.Plasma(t, "Shard", mass, -ptp.ePos)
+        ns, _ = q.loadDensity(dens, 150.0, num_macro, shard=sh, nShards=S, solve=False)
+        sel = within % S == sh
+        assert ns == int(sel.sum())
+        rs, zs, vs, _ = _by_id(q)
+        assert np.array_equal(rs, r0[sel]) and np.array_equal(zs, z0[sel]) and np.array_equal(vs, v[sel])
+    t.close()
+    rt.close()
+
+
 # ------------------------------------------------------------------------------------------ other grid shapes
 @pytest.mark.parametrize("Nz,Nr,solver,fixed", [(1024, 96, 0, 0), (2048, 16, 0, 0), (1500, 12, 0, 0), (301, 130, 0, 0), (48, 420, 0, 0),
                                                 (256, 24, 2, 0), (256, 24, 2, 1), (64, 300, 2, 0), (128, 5, 2, 0), (8, 70, 2, 0)])
