@@ -8,6 +8,7 @@
 #include "ptp.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 namespace {
@@ -277,6 +278,30 @@ void Plasma::loadRings(const std::vector<int>& r, const std::vector<double>& z, 
 // (freshly seeded for every load, so every species sees the same deviate sequence scaled by its sigma).
 void Plasma::placeRings(int numMacro)
 {
+	// Large loads are placed on the device (ptp_plasma_load_density: same counts, bit-identical positions, the same deviate
+	// stream to the last bits of log()); small ones stay here so that their speeds are bit-identical too.
+	// PTP_DEVICE_LOADER=1 / 0 forces one or the other.
+	const char* force = std::getenv("PTP_DEVICE_LOADER");
+	if (force ? force[0] == '1' : numMacro >= 2000000) {
+		std::vector<std::int64_t> perRowDevice((std::size_t)refTrap.Nr);
+		std::int64_t loaded = 0;
+		double newChargeMacro = 0;
+		check(ptp_plasma_load_density(device, initialDensity.data(), temperature, numMacro, 0, 1, &newChargeMacro, perRowDevice.data(), &loaded));
+		chargeMacro = newChargeMacro;
+		massMacro = chargeMacro * mass / charge;
+		macroChargeDensity = 4 * chargeMacro / (PI * refTrap.hz * refTrap.hr * refTrap.hr);
+		ringR.clear();
+		ringR.reserve((std::size_t)loaded);
+		for (int j = 0; j < refTrap.Nr; ++j) ringR.insert(ringR.end(), (std::size_t)perRowDevice[(std::size_t)j], j);
+		ringAlive.assign(ringR.size(), 1);
+		historyZ.assign(ringR.size(), std::vector<double>());
+		historySpeed.assign(ringR.size(), std::vector<double>());
+		order.resize(ringR.size());
+		std::iota(order.begin(), order.end(), (std::int64_t)0);
+		std::cout << "Loading " << ringR.size() << " macro-particles from which " << perRowDevice[0] << " are at r=0.\n";
+		solvePoisson();
+		return;
+	}
 	const int Nz = refTrap.Nz, Nr = refTrap.Nr, n1 = Nz + 1;
 	const double hz = refTrap.hz, hr = refTrap.hr;
 	std::vector<std::vector<double>> cumulative((std::size_t)Nr, std::vector<double>((std::size_t)n1));

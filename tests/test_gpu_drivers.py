@@ -28,8 +28,9 @@ def _have():
     return all(os.path.exists(os.path.join(DRV, "driver_" + c)) for c in "ABCD")
 
 
-def _run(letter, cwd):
-    p = subprocess.run([os.path.join(DRV, "driver_" + letter)], cwd=cwd, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=900)
+def _run(letter, cwd, **env):
+    p = subprocess.run([os.path.join(DRV, "driver_" + letter)], cwd=cwd, stdin=subprocess.DEVNULL, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, **env))
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stdout
 
@@ -79,6 +80,25 @@ def test_driver_b_loading(work):
     for name in ("Z Electron Parameters.csv", "Z Antiproton Parameters.csv", "Z NumOfMacros.txt", "Z Times.csv",
                  "Z PositionsElectrons.csv", "Z PositionsAntiprotons.csv", "Z SpeedsElectrons.csv", "Z SpeedsAntiprotons.csv"):
         assert _text(os.path.join(data, name)) == _gold(name), name
+    pe = float(_text(os.path.join(data, "Z PotentialEnergies.csv")))
+    assert pe == pytest.approx(float(_gold("Z PotentialEnergies.csv")), rel=1e-8)
+
+
+def test_driver_b_loading_on_the_device(work, tmp_path):
+    """Same program with the placement forced onto the GPU (what the host classes do by themselves from 2 M rings up):
+    same ring counts and positions as text, speeds from the same deviate stream to the last bits of log()."""
+    d = str(tmp_path / "dev")
+    shutil.copytree(work, d)
+    out = _run("B", d, PTP_DEVICE_LOADER="1")
+    data = os.path.join(d, DATA)
+    assert out.count("Loading 4001 macro-particles from which 777 are at r=0.") == 2
+    for name in ("Z Electron Parameters.csv", "Z Antiproton Parameters.csv", "Z NumOfMacros.txt", "Z PositionsElectrons.csv", "Z PositionsAntiprotons.csv"):
+        assert _text(os.path.join(data, name)) == _gold(name), name
+    for name in ("Z SpeedsElectrons.csv", "Z SpeedsAntiprotons.csv"):
+        mine = np.array([[float(x) for x in line.split(",")] for line in _text(os.path.join(data, name)).splitlines()])
+        gold = np.array([[float(x) for x in line.split(",")] for line in _gold(name).splitlines()])
+        assert mine.shape == gold.shape
+        assert np.max(np.abs(mine - gold) / np.maximum(np.abs(gold), 1e-300)) < 1e-13
     pe = float(_text(os.path.join(data, "Z PotentialEnergies.csv")))
     assert pe == pytest.approx(float(_gold("Z PotentialEnergies.csv")), rel=1e-8)
 
