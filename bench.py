@@ -213,7 +213,7 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=0)
-    ap.add_argument("--allreduce", default="peer", choices=["nccl", "peer"], help="exchange step for N > 1")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer"], help="exchange step for N > 1 (auto: peer memory up to 2^20 grid nodes)")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -278,7 +278,10 @@ def main():
         uid = [ptp.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         trap.comm_init(uid[0], world, rank)
+        if args.allreduce == "auto":
+            args.allreduce = "peer" if trap.G <= (1 << 20) else "nccl"
         trap.set_allreduce(1 if args.allreduce == "peer" else 0)
+        config["exchange"] = "peer-memory push fused into the deposit flush + flag barrier" if args.allreduce == "peer" else "NCCL all-reduce"
     trap.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64 if args.deposit == "fixed" else ptp.PTP_DEPOSIT_FP64)
     if args.threads or args.window or args.ctas >= 0 or args.rings:
         trap.set_tuning(args.threads, args.window, args.ctas, args.rings)

@@ -116,7 +116,9 @@ int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ring
 /* 128-byte NCCL unique id; rank 0 creates it, the launcher broadcasts it (torch.distributed / MPI / file). */
 int ptp_comm_unique_id(void* id128);
 int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank);
-/* 0: NCCL all-reduce, 1: one-shot peer-memory all-reduce kernel (needs ptp_trap_comm_init). */
+/* Exchange of the deposit grids between the ranks (needs ptp_trap_comm_init): 0 = NCCL all-reduce; 1 = peer memory, the
+ * push kernel's flush adds into every rank's grid over NVLink and a flag barrier replaces the collective; 2 = choose by
+ * grid size (peer memory up to 2^20 nodes). */
 int ptp_trap_set_allreduce(ptp_trap* t, int kind);
 
 /* ---- plasma ------------------------------------------------------------------------------- */
