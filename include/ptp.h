@@ -69,6 +69,18 @@ int ptp_trap_destroy(ptp_trap* t);
  * and solves for phi_trap. */
 int ptp_trap_set_wall(ptp_trap* t, const double* vWall);
 
+/* Time-dependent electrode programmes (PenningTrap::setPotential before every step, as in
+ * Diagnostics/D) Useless Boundary Test.txt:120-134; Source/PenningTrap.cpp:313-317 = updateRHS + solveLaplace each time).
+ * phi_trap is linear in the wall potential and the wall of PenningTrap::updateRHS (:169-197) is linear in the electrode
+ * potentials (the gap ramps of :184 included), so phi_trap = sum_i V_i phi_i with phi_i the Laplace solution for "electrode
+ * i at 1 V, all others grounded". ptp_trap_set_wall_basis registers nBasis wall profiles walls[nBasis][Nz+1] (one solve
+ * each, once); ptp_trap_set_wall_weights then replaces a setPotential call by one axpy kernel (no solve, no wall upload),
+ * and ptp_trap_step_programme runs nSteps steps with weights[s][nBasis] applied before step s without returning to the
+ * host in between. Equal to the per-step solve up to the re-association of the sum (~1e-16 relative). */
+int ptp_trap_set_wall_basis(ptp_trap* t, int nBasis, const double* walls);
+int ptp_trap_set_wall_weights(ptp_trap* t, const double* weights);
+int ptp_trap_step_programme(ptp_trap* t, double dt, int nSteps, const double* weights);
+
 /* solver.solve(b) (Source/PenningTrap.cpp:202, Source/Plasma.cpp:98,389,412): phi = A^-1 rhs, host buffers of G. */
 int ptp_trap_solve(ptp_trap* t, const double* rhs, double* phi);
 /* y = A x with the assembled operator (coefficients * vector, Source/PenningTrap.cpp:250). */

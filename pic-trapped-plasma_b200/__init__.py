@@ -47,6 +47,9 @@ SIGNATURES = {
     "ptp_trap_create": (_i, [_pvp, _i, _i, _d, _d, _d, _d, _i]),
     "ptp_trap_destroy": (_i, [_vp]),
     "ptp_trap_set_wall": (_i, [_vp, _vp]),
+    "ptp_trap_set_wall_basis": (_i, [_vp, _i, _vp]),
+    "ptp_trap_set_wall_weights": (_i, [_vp, _vp]),
+    "ptp_trap_step_programme": (_i, [_vp, _d, _i, _vp]),
     "ptp_trap_solve": (_i, [_vp, _vp, _vp]),
     "ptp_trap_apply": (_i, [_vp, _vp, _vp]),
     "ptp_trap_get_phi": (_i, [_vp, _vp]),
@@ -151,6 +154,7 @@ class PenningTrap:
         self.hr = self.trapRadius / self.Nr         # :52
         self.G = (self.Nz + 1) * self.Nr
         self.plasmas = []
+        self.basis = False
         h = C.c_void_p()
         _check(lib().ptp_trap_create(C.byref(h), self.Nz, self.Nr, self.hz, self.hr, self.lengthTrap, self.trapRadius, device))
         self.h = h
@@ -187,7 +191,36 @@ class PenningTrap:
 
     def setPotential(self, indexElectrode, newPotential):  # Source/PenningTrap.cpp:313-317
         self.electrodes[indexElectrode].setPotential(newPotential)
-        self.solveLaplace()
+        if self.basis:
+            w = np.array([e.getPotential() for e in self.electrodes])
+            _check(lib().ptp_trap_set_wall_weights(self.h, _ptr(w)))
+        else:
+            self.solveLaplace()
+
+    def useElectrodeBasis(self):
+        """Electrode programmes: one Laplace solution per electrode at 1 V is kept on the device, after which
+        setPotential is one axpy kernel and movePlasmasProgramme runs a whole voltage schedule without host round trips."""
+        saved = [e.getPotential() for e in self.electrodes]
+        walls = []
+        for i in range(len(self.electrodes)):
+            for j, e in enumerate(self.electrodes):
+                e.setPotential(1.0 if i == j else 0.0)
+            walls.append(self.wallPotential())
+        for e, v in zip(self.electrodes, saved):
+            e.setPotential(v)
+        walls = _f64(np.stack(walls))
+        _check(lib().ptp_trap_set_wall_basis(self.h, len(self.electrodes), _ptr(walls)))
+        self.basis = True
+        _check(lib().ptp_trap_set_wall_weights(self.h, _ptr(np.array(saved, dtype=np.float64))))
+
+    def movePlasmasProgramme(self, deltaT, potentials):
+        """potentials[s][i] = potential of electrode i during step s (setPotential calls + movePlasmas of the driver-D loop)."""
+        w = _f64(potentials)
+        if w.ndim != 2 or w.shape[1] != len(self.electrodes) or not self.basis:
+            raise ValueError("movePlasmasProgramme: needs useElectrodeBasis() and potentials[steps][electrodes]")
+        _check(lib().ptp_trap_step_programme(self.h, float(deltaT), w.shape[0], _ptr(w)))
+        for e, v in zip(self.electrodes, w[-1]):
+            e.setPotential(float(v))
 
     def getLength(self):
         return self.lengthTrap

@@ -6,6 +6,27 @@
 #include <cstring>
 
 namespace {
+
+// phi_trap = sum_i w_i phi_i over the registered wall basis (electrode programmes): fixed summation order.
+__global__ void k_combine_basis(const double* __restrict__ basisPhi, const double* __restrict__ weights, int nBasis, long long G, double* __restrict__ phiTrap)
+{
+	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= G) return;
+	double s = __dmul_rn(weights[0], basisPhi[idx]);
+	for (int i = 1; i < nBasis; ++i) s = __dadd_rn(s, __dmul_rn(weights[i], basisPhi[(size_t)i * G + idx]));
+	phiTrap[idx] = s;
+}
+
+int combine_basis(ptp_trap* t, const double* dWeights)
+{
+	k_combine_basis<<<(unsigned)((t->G + 255) / 256), 256, 0, t->stream>>>(t->basisPhi, dWeights, t->nBasis, t->G, t->phiTrap);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_combine_basis launch", __FILE__, __LINE__);
+	t->lastLaunches++;
+	t->eNodesValid = false;
+	return PTP_OK;
+}
+
 thread_local std::string g_error;
 }
 
@@ -180,6 +201,7 @@ int ptp_trap_destroy(ptp_trap* t)
 	for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : t->evPool) cudaEventDestroy(ev);
 	if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
+	cudaFree(t->basisPhi); cudaFree(t->dWeights);
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return PTP_OK;
@@ -225,6 +247,51 @@ int ptp_trap_set_wall(ptp_trap* t, const double* vWall)
 	t->eNodesValid = false;
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
 	return PTP_OK;
+}
+
+int ptp_trap_set_wall_basis(ptp_trap* t, int nBasis, const double* walls)
+{
+	if (!t || nBasis < 1 || nBasis > 256 || !walls) { ptp_set_error("ptp_trap_set_wall_basis: bad arguments"); return PTP_EINVAL; }
+	if (t->solver == PTP_SOLVER_SOR) { ptp_set_error("ptp_trap_set_wall_basis: needs the direct solver"); return PTP_ESTATE; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	const int n1 = t->Nz + 1;
+	cudaFree(t->basisPhi); cudaFree(t->dWeights);
+	t->basisPhi = nullptr; t->dWeights = nullptr; t->nBasis = 0; t->weightsCap = 0;
+	PTP_CUDA(cudaMalloc(&t->basisPhi, (size_t)nBasis * t->G * sizeof(double)));
+	for (int i = 0; i < nBasis; ++i) {                        // one Laplace solve per basis wall, as ptp_trap_set_wall does
+		PTP_CUDA(cudaMemcpyAsync(t->tmpSpec, walls + (size_t)i * n1, (size_t)n1 * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+		PTP_TRY(ptp_wall_rhs(t, t->tmpSpec, t->tmpA));
+		PTP_TRY(ptp_solver_run(t, t->tmpA, false, nullptr, 1, t->tmpSpec, t->basisPhi + (size_t)i * t->G));
+	}
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	t->nBasis = nBasis;
+	return PTP_OK;
+}
+
+namespace {
+int upload_weights(ptp_trap* t, const double* weights, size_t count)
+{
+	if (t->weightsCap < count) {
+		cudaFree(t->dWeights);
+		t->dWeights = nullptr;
+		PTP_CUDA(cudaMalloc(&t->dWeights, count * sizeof(double)));
+		t->weightsCap = count;
+	}
+	PTP_CUDA(cudaMemcpyAsync(t->dWeights, weights, count * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));               // the caller's buffer may be reused right away
+	return PTP_OK;
+}
+} // namespace
+
+int ptp_trap_set_wall_weights(ptp_trap* t, const double* weights)
+{
+	if (!t || !weights) { ptp_set_error("ptp_trap_set_wall_weights: null argument"); return PTP_EINVAL; }
+	if (t->nBasis < 1) { ptp_set_error("ptp_trap_set_wall_weights: call ptp_trap_set_wall_basis first"); return PTP_ESTATE; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	PTP_TRY(upload_weights(t, weights, (size_t)t->nBasis));
+	return combine_basis(t, t->dWeights);
 }
 
 int ptp_trap_get_phi(ptp_trap* t, double* phi)
@@ -371,6 +438,26 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	else PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
 	for (int s = done; s < nSteps; ++s) {
 		PTP_TRY(one_step(t, dt, s < timed ? &t->evPool[4 * s] : nullptr));
+		if (t->sortInterval > 0 && t->stepCount % t->sortInterval == 0)
+			for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
+	}
+	PTP_CUDA(cudaEventRecord(t->ev[4], t->stream));
+	return PTP_OK;
+}
+
+int ptp_trap_step_programme(ptp_trap* t, double dt, int nSteps, const double* weights)
+{
+	if (!t || nSteps < 0 || (nSteps > 0 && !weights)) { ptp_set_error("ptp_trap_step_programme: bad arguments"); return PTP_EINVAL; }
+	if (t->nBasis < 1) { ptp_set_error("ptp_trap_step_programme: call ptp_trap_set_wall_basis first"); return PTP_ESTATE; }
+	PTP_CUDA(cudaSetDevice(t->device));
+	t->lastLaunches = 0;
+	t->evSteps = 0;
+	if (nSteps > 0) PTP_TRY(upload_weights(t, weights, (size_t)nSteps * t->nBasis));
+	PTP_TRY(begin_exchange(t));
+	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
+	for (int s = 0; s < nSteps; ++s) {
+		PTP_TRY(combine_basis(t, t->dWeights + (size_t)s * t->nBasis));   // setPotential(...) of this step; the node field follows in the push
+		PTP_TRY(one_step(t, dt, nullptr));
 		if (t->sortInterval > 0 && t->stepCount % t->sortInterval == 0)
 			for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
 	}

@@ -86,6 +86,10 @@ struct ptp_trap {
 	int2* rowBounds = nullptr;   // [species x Nr] non-zero axial range of each deposit row (forward transform)
 	int rowBoundsCap = 0;
 
+	double* basisPhi = nullptr;  // [nBasis][G] Laplace solutions of the registered wall basis (electrode programmes)
+	double* dWeights = nullptr;  // [weightsCap] weights of the programme's steps
+	int nBasis = 0;
+	size_t weightsCap = 0;
 	double* phiTrap = nullptr;   // [G]
 	double* eNodes = nullptr;    // [G]
 	double* tmpA = nullptr;      // [G] scratch (host-RHS solves, wall RHS)

@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 		__syncthreads();
 		for (int o = tid; o < INV_TM * (INV_TN - 2); o += 256) {
 			const int r = o / (INV_TN - 2), c = 1 + o % (INV_TN - 2), col = c0 + c;
-			if (j0 + r >= Nr || col >= n1) continue;
+			if (j0 + r >= Nr || col < 0 || col >= n1) continue;     // the first tile starts at column -2
 			double e = 0.0;
 			if (col > 0 && col < n1 - 1)
 				e = __ddiv_rn(__dsub_rn(sTot[r * INV_TN + c - 1], sTot[r * INV_TN + c + 1]), __dmul_rn(2.0, hz));

@@ -79,6 +79,18 @@ def test_set_potential_every_step_protocol(trap, c1_kat):
     pt.close()
 
 
+def test_steps_leave_trap_potential_untouched(c1_kat):
+    """Regression: the fused inverse-transform + node-field kernel once wrote E = 0 one element in front of the node-field
+    array (column -1 of its first tile), which is the last node of phi_trap when the two allocations are adjacent."""
+    t, el, ap = _fresh_c1(c1_kat)
+    el.solvePoisson()
+    ap.solvePoisson()
+    before = t.phi()
+    t.movePlasmas(float(c1_kat["dt"]), 3)
+    assert np.array_equal(t.phi(), before)
+    t.close()
+
+
 def test_self_potential_of_reference_rhs(trap, c1_kat):
     for tag in ("e", "p"):
         assert rel_l2(trap.solve(c1_kat[f"{tag}_rhs0"]), c1_kat[f"{tag}_phi0"]) < 1e-10
@@ -226,6 +238,52 @@ def test_driver_d_loss_counts(c1_kat):
     t.sort()
     assert el.getNumMacro() == 3965
     t.close()
+
+
+def test_electrode_programme_matches_per_step_solves(c1_kat):
+    """the driver-D voltage ramp run as a device-side programme (phi_trap = sum_i V_i phi_i over the electrode
+    basis, one axpy per step, no host round trip) against the same ramp with setPotential + Laplace solve before every
+    step: phi_trap to rounding, loss counts and surviving rings identical, the golden loss counts reproduced."""
+    gold = json.load(open(os.path.join(GOLDEN, "driver_d_counts.json")))
+    dt = gold["dt"]
+
+    def changed_voltage(Vi, Vf, duration, compression, tt):
+        return (Vf - Vi) * (1 + math.exp(-(tt - duration / 2) * compression * 2 / duration)) ** -1 + Vi
+
+    ramp = []
+    i = 1
+    while i * dt <= 10e-9:
+        ramp.append(changed_voltage(-70, -51, 10e-9, 4.5, i * dt))
+        i += 1
+    # reference protocol: one solve per step
+    ta, ea, aa = _fresh_c1(c1_kat)
+    ea.solvePoisson()
+    aa.solvePoisson()
+    for v in ramp:
+        ta.setPotential(1, v)
+        ta.movePlasmas(dt)
+    # programme: basis fields, all steps queued in one call
+    tb, eb, ab = _fresh_c1(c1_kat)
+    eb.solvePoisson()
+    ab.solvePoisson()
+    tb.useElectrodeBasis()
+    assert rel_l2(tb.phi(), c1_kat["phi_trap"]) < 1e-12
+    sched = np.tile(np.array([0.0, -70.0, -15.0, -70.0, 0.0]), (len(ramp), 1))
+    sched[:, 1] = ramp
+    tb.movePlasmasProgramme(dt, sched)
+    assert rel_l2(tb.phi(), ta.phi()) < 1e-13
+    assert [eb.getNumMacro(), ab.getNumMacro()] == [ea.getNumMacro(), aa.getNumMacro()] == gold["counts"][len(ramp)]
+    for pa, pb in ((ea, eb), (aa, ab)):
+        ra, za, va, ia = _by_id(pa)
+        rb, zb, vb, ib = _by_id(pb)
+        assert np.array_equal(ia, ib)
+        assert np.max(np.abs(za - zb) / za) < 1e-11
+    # single setPotential calls go through the basis too
+    tb.setPotential(1, -51.0)
+    ta.setPotential(1, -51.0)
+    assert rel_l2(tb.phi(), ta.phi()) < 1e-13
+    ta.close()
+    tb.close()
 
 
 def test_losses_match_oracle_ring_by_ring():
