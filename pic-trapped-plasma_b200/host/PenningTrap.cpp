@@ -4,6 +4,8 @@
 // comparisons, which node belongs to which electrode, so it is evaluated on the host exactly as the
 // reference does, Source/PenningTrap.cpp:169-197), the well limits and the text writers.
 #include "PenningTrap.hpp"
+
+#include <cstdlib>
 #include "Plasma.hpp"
 
 #include "ptp.h"
@@ -237,7 +239,46 @@ void PenningTrap::extractTrapParameters(std::string filename) const
 void PenningTrap::setPotential(int indexElectrode, double newPotential)
 {
 	electrodes[indexElectrode].setPotential(newPotential);
-	solveLaplace();
+	if (!electrodeBasis) {
+		const char* env = std::getenv("PTP_ELECTRODE_BASIS");
+		if (env && env[0] == '1') useElectrodeBasis();
+	}
+	if (electrodeBasis) {
+		std::vector<double> weights;
+		for (const Electrode& e : electrodes) weights.push_back(e.getPotential());
+		check(ptp_trap_set_wall_weights(device, weights.data()));
+	}
+	else solveLaplace();
+}
+
+void PenningTrap::useElectrodeBasis()
+{
+	// wall profile of "electrode i at 1 V, the others grounded" through the same node loop as every other wall
+	std::vector<double> saved, walls;
+	for (const Electrode& e : electrodes) saved.push_back(e.getPotential());
+	for (std::size_t i = 0; i < electrodes.size(); ++i) {
+		for (std::size_t j = 0; j < electrodes.size(); ++j) electrodes[j].setPotential(i == j ? 1.0 : 0.0);
+		const std::vector<double> wall = wallPotential();
+		walls.insert(walls.end(), wall.begin(), wall.end());
+	}
+	for (std::size_t j = 0; j < electrodes.size(); ++j) electrodes[j].setPotential(saved[j]);
+	check(ptp_trap_set_wall_basis(device, (int)electrodes.size(), walls.data()));
+	check(ptp_trap_set_wall_weights(device, saved.data()));
+	electrodeBasis = true;
+}
+
+void PenningTrap::movePlasmas(double deltaT, const std::vector<std::vector<double>>& potentials)
+{
+	if (potentials.empty()) return;
+	if (!electrodeBasis) useElectrodeBasis();
+	std::vector<double> flat;
+	for (const std::vector<double>& step : potentials) {
+		if (step.size() != electrodes.size()) throw std::logic_error("movePlasmas: one potential per electrode and step");
+		flat.insert(flat.end(), step.begin(), step.end());
+	}
+	check(ptp_trap_step_programme(device, deltaT, (int)potentials.size(), flat.data()));
+	for (std::size_t j = 0; j < electrodes.size(); ++j) electrodes[j].setPotential(potentials.back()[j]);
+	for (Plasma& p : plasmas) p.refreshAlive();
 }
 
 double PenningTrap::getLength() const { return lengthTrap; }

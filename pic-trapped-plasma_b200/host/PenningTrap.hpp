@@ -55,6 +55,7 @@ private:
 	std::vector<int> limitRight;
 	std::vector<std::reference_wrapper<Plasma>> plasmas;
 	ptp_trap* device; // GPU twin (operator, phi_trap, node field, per-species grids)
+	bool electrodeBasis = false;
 
 	void addPlasma(Plasma&);
 	void solveLaplace();                       // wall potential -> device Laplace solve
@@ -86,6 +87,11 @@ public:
 
 	// Extensions (not in the reference): several steps per call, device selection, raw handle.
 	void movePlasmas(double deltaT, int numSteps);
+	// Electrode programmes: keep one Laplace solution per electrode on the device; setPotential then costs one axpy
+	// kernel instead of a solve (also switched on by PTP_ELECTRODE_BASIS=1), and a schedule potentials[step][electrode]
+	// runs without returning to the host between steps.
+	void useElectrodeBasis();
+	void movePlasmas(double deltaT, const std::vector<std::vector<double>>& potentials);
 	ptp_trap* deviceHandle() const { return device; }
 	static void selectDevice(int cudaOrdinal); // device used by traps constructed afterwards (default 0 / $PTP_DEVICE)
 };

@@ -125,3 +125,12 @@ def test_driver_c_evolution(work):
 def test_driver_d_ekick_losses(work):
     out = _run("D", work)
     assert out.strip().endswith(_gold("driver_D_stdout.txt").strip())
+
+
+def test_driver_d_with_electrode_basis(work, tmp_path):
+    """Driver D unchanged, its per-step setPotential calls served from the electrode basis fields (one axpy instead of a
+    Laplace solve per call): same losses, same text."""
+    d = str(tmp_path / "basis")
+    shutil.copytree(work, d)
+    out = _run("D", d, PTP_ELECTRODE_BASIS="1")
+    assert out.strip().endswith(_gold("driver_D_stdout.txt").strip())
