@@ -402,6 +402,56 @@ def test_large_load_properties(c1_kat, mode):
     t.close()
 
 
+def test_fine_grid_full_size_properties(c1_kat):
+    """BASELINE config 5 grid (Nz = 4096, Nr = 1024: 4.2 M unknowns - far beyond what the LU oracle can factorise) through
+    size-independent properties: the direct solver's phi satisfies A phi = b for the operator applied by the independent
+    stencil kernel (PenningTrap::generateSparse coefficients), for a random right-hand side and for the deposit of a
+    5 M-ring load placed by the device loader; the deposit conserves the ring count; the node field is the centred
+    difference of the total potential; fixed-point deposits give the same grid for 148 and 37 CTAs bit for bit."""
+    from bench import density_on
+    Nz, Nr = 4096, 1024
+    el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
+    t = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
+    n1 = Nz + 1
+    rng = np.random.default_rng(11)
+    b = rng.standard_normal(t.G)
+    assert rel_l2(t.apply(t.solve(b)), b) < 1e-11
+    wall_rhs = t.apply(t.phi())                      # = the wall RHS: zero except on the last row
+    assert np.max(np.abs(wall_rhs[: (Nr - 1) * n1])) < 1e-6 * np.max(np.abs(wall_rhs))
+    dens = density_on(Nz, Nr)
+    p = ptp.Plasma(t, "Antiprotons", ptp.massP, -ptp.ePos)
+    n, per_row = p.loadDensity(dens, 150.0, 5_000_000)
+    assert n == int(per_row.sum()) and abs(n - 5_000_000) < 2000
+    scale = -p.macroChargeDensity / ptp.epsilon
+    rhs = p.rhs()
+    assert abs(rhs.sum() / scale - n) < 1e-6 * n
+    assert rel_l2(t.apply(p.selfPotential()), rhs) < 1e-10
+    dt = float(c1_kat["dt"])
+    t.movePlasmas(dt, 3)
+    assert p.getNumMacro() == n
+    rhs = p.rhs()
+    phi = p.selfPotential()
+    assert abs(rhs.sum() / scale - n) < 1e-6 * n
+    assert rel_l2(t.apply(phi), rhs) < 1e-10
+    tot = (t.phi() + phi).reshape(Nr, n1)
+    e = np.zeros_like(tot)
+    e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * t.hz)
+    assert np.array_equal(t.enodes().reshape(Nr, n1), e)            # same expression, same rounding (Source/PenningTrap.cpp:226-233)
+    # fixed point: independent of how the segments are dealt to CTAs
+    grids = []
+    for ctas in (0, 37):
+        tf = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
+        tf.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64)
+        tf.set_tuning(ctas=ctas)
+        q = ptp.Plasma(tf, "Antiprotons", ptp.massP, -ptp.ePos)
+        q.loadDensity(dens, 150.0, 1_000_000)
+        tf.movePlasmas(dt, 2)
+        grids.append((q.rhs(), q.selfPotential()))
+        tf.close()
+    assert np.array_equal(grids[0][0], grids[1][0]) and np.array_equal(grids[0][1], grids[1][1])
+    t.close()
+
+
 def test_edge_cases():
     t = ptp.default_trap()
     p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
