@@ -63,7 +63,7 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	}
 	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
 	t->rhoStore = rho; t->rhoParity = 0; t->rhoAll = rho; t->peerStale = true; t->spanDoubles = span;
-	++t->cfgEpoch;
+	++t->cfgEpoch; ++t->layoutEpoch;
 	t->phiSelfAll = phi; t->specAll = spec; t->dScale = scale;
 	t->capS = cap;
 	return PTP_OK;
@@ -82,7 +82,8 @@ int solve_species(ptp_trap* t, int first, int count, bool withField = false)
 	// one GPU, or peer-memory mode inside a step; an NCCL-reduced grid is scanned instead
 	const bool trust = ptp_comm_size(t) == 1 || (withField && ptp_peer_mode(t));
 	const uint2* enc = trust ? reinterpret_cast<const uint2*>(t->rhoAll + (size_t)t->capS * t->G) + (size_t)first * t->Nr : nullptr;
-	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField, enc);
+	const int rowLimit = t->extentEpoch == t->layoutEpoch ? t->rowExtent : -1;
+	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField, enc, rowLimit);
 }
 
 // Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
@@ -98,7 +99,16 @@ int push_deposit_all(ptp_trap* t, double dt)
 		t->rhoAll = t->rhoStore + (size_t)t->rhoParity * span;
 		PTP_CUDA(cudaMemsetAsync(t->rhoStore + (size_t)(t->rhoParity ^ 1) * span, 0, span * sizeof(double), t->stream));
 	}
-	else PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, span * sizeof(double), t->stream));   // grids and row bounds of all species
+	else if (t->G >= (1LL << 20) && t->cleanEpoch == t->layoutEpoch && t->extentEpoch == t->layoutEpoch) {
+		// large grid: only the rows that can hold a deposit, plus the row bounds (the rest is still zero from the last full clear)
+		const size_t rowsBytes = (size_t)t->rowExtent * (t->Nz + 1) * sizeof(double);
+		for (int s = 0; s < nS; ++s) PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)s * t->G, 0, rowsBytes, t->stream));
+		PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)t->capS * t->G, 0, (size_t)t->capS * t->Nr * sizeof(double), t->stream));
+	}
+	else {
+		PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, span * sizeof(double), t->stream));   // grids and row bounds of all species
+		t->cleanEpoch = t->layoutEpoch;
+	}
 	for (ptp_plasma* p : t->plasmas) {
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 		PTP_TRY(ptp_push_launch(t, p, dt, true));
@@ -112,7 +122,13 @@ int reduce_rho(ptp_trap* t)
 {
 	const int nS = (int)t->plasmas.size();
 	if (ptp_peer_mode(t)) return ptp_peer_barrier(t);
-	return ptp_comm_allreduce(t, t->rhoAll, (size_t)nS * t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
+	if (ptp_comm_size(t) == 1) return PTP_OK;
+	int extent = t->Nr;
+	PTP_TRY(ptp_row_extent(t, &extent));
+	if (extent == t->Nr) return ptp_comm_allreduce(t, t->rhoAll, (size_t)nS * t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
+	for (int s = 0; s < nS; ++s)                                 // rows >= extent are zero on every rank
+		PTP_TRY(ptp_comm_allreduce(t, t->rhoAll + (size_t)s * t->G, (size_t)extent * (t->Nz + 1), t->depositMode == PTP_DEPOSIT_FIXED64));
+	return PTP_OK;
 }
 
 // Peer-memory mode, once per ptp_trap_step / ptp_trap_push_deposit call: map the peers, start from two clean parities.
@@ -373,6 +389,7 @@ int capture_step_graph(ptp_trap* t, double dt)
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	PTP_TRY(ptp_solver_reserve(t, (int)t->plasmas.size()));
+	{ int extent; PTP_TRY(ptp_row_extent(t, &extent)); }       // may synchronise: not inside the capture
 	const int unit = ptp_peer_mode(t) ? 2 : 1;
 	const int parity0 = t->rhoParity;
 	const long long steps0 = t->stepCount;
@@ -419,6 +436,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 		t->evPool.push_back(e);
 	}
 	t->evSteps = timed;
+	if (!ptp_peer_mode(t)) { int extent; PTP_TRY(ptp_row_extent(t, &extent)); }
 	PTP_TRY(begin_exchange(t));
 	int done = 0;
 	if (graph && nSteps > 0) {
@@ -592,7 +610,7 @@ int ptp_plasma_destroy(ptp_plasma* p)
 {
 	if (!p) return PTP_OK;
 	ptp_trap* t = p->trap;
-	++t->cfgEpoch;
+	++t->cfgEpoch; ++t->layoutEpoch;
 	cudaSetDevice(t->device);
 	cudaStreamSynchronize(t->stream);
 	// later species move down one slice so that slices stay contiguous and in registration order
@@ -622,7 +640,9 @@ int ptp_plasma_deposit(ptp_plasma* p)
 	PTP_CUDA(cudaMemsetAsync(rho, 0, (size_t)t->G * sizeof(double), t->stream));
 	PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)t->capS * t->G + (size_t)p->index * t->Nr, 0, (size_t)t->Nr * sizeof(double), t->stream));
 	PTP_TRY(ptp_push_launch(t, p, 0.0, false));
-	return ptp_comm_allreduce(t, rho, (size_t)t->G, t->depositMode == PTP_DEPOSIT_FIXED64);
+	int extent = t->Nr;
+	if (ptp_comm_size(t) > 1) PTP_TRY(ptp_row_extent(t, &extent));
+	return ptp_comm_allreduce(t, rho, (size_t)extent * (t->Nz + 1), t->depositMode == PTP_DEPOSIT_FIXED64);
 }
 
 int ptp_plasma_deposit_solve(ptp_plasma* p)

@@ -180,6 +180,35 @@ int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64)
 	return PTP_OK;
 }
 
+int ptp_comm_max_int(ptp_trap* t, int* value)
+{
+	if (!t->comm || t->comm->nRanks == 1) return PTP_OK;
+	int* dV = nullptr;
+	PTP_CUDA(cudaMalloc(&dV, sizeof(int)));
+	PTP_CUDA(cudaMemcpyAsync(dV, value, sizeof(int), cudaMemcpyHostToDevice, t->stream));
+	ncclResult_t r = g_nccl.AllReduce(dV, dV, 1, ncclInt32, ncclMax, t->comm->comm, t->stream);
+	if (r != ncclSuccess) { cudaFree(dV); return nccl_fail(r, "ncclAllReduce(max)"); }
+	PTP_CUDA(cudaMemcpyAsync(value, dV, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dV);
+	return PTP_OK;
+}
+
+int ptp_row_extent(ptp_trap* t, int* extent)
+{
+	if (t->extentEpoch != t->layoutEpoch) {
+		int ext = 0;
+		for (const ptp_plasma* p : t->plasmas)
+			for (int j = (int)p->rowLive.size() - 1; j >= ext; --j)
+				if (p->rowLive[j] > 0) { ext = j + 1; break; }
+		PTP_TRY(ptp_comm_max_int(t, &ext));
+		t->rowExtent = ext;
+		t->extentEpoch = t->layoutEpoch;
+	}
+	*extent = t->rowExtent;
+	return PTP_OK;
+}
+
 void ptp_comm_free(ptp_trap* t)
 {
 	if (t->comm) {

@@ -123,6 +123,13 @@ struct ptp_trap {
 
 	PtpComm* comm = nullptr;
 	int allreduceKind = 0;
+	// Rings never change their radial row (posR is immutable, Source/Plasma.hpp:22-24), so deposits can only land in rows
+	// below rowExtent = 1 + the outermost populated row over all species and ranks: the all-reduce and (on large grids) the
+	// per-step clearing of the deposit grids are restricted to those rows.
+	long long layoutEpoch = 0;       // bumped by every (re)load of rings
+	long long extentEpoch = -1;      // layoutEpoch rowExtent was computed for
+	int rowExtent = 0;
+	long long cleanEpoch = -1;       // layoutEpoch for which the rows >= rowExtent of rhoStore are known to be zero
 
 	// CUDA-graph replay of the step (ptp_trap_set_graph)
 	bool useGraph = false;
@@ -154,7 +161,8 @@ void ptp_solver_free(ptp_trap* t);
 // phi[s] = A^-1 (scale[s] * rho[s]) for nS consecutive grids; rho is double weights or int64 fixed point.
 // withField: nS covers ALL species (phi = phiSelfAll) and the node field is produced too (fused when possible).
 // encBounds: per (species,row) touched node range as written by the push kernel (nullptr: scan rho for non-zeros).
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false, const uint2* encBounds = nullptr);
+// rowLimit: radial rows >= rowLimit of rho are known to be zero (deposit grids: no ring lives there); -1 = unknown.
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false, const uint2* encBounds = nullptr, int rowLimit = -1);
 int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
 // ptp_solve_wide.cu: the same direct solve organised for large grids
 bool ptp_solver_fft_fits(const ptp_trap* t);
@@ -178,6 +186,8 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p);
 
 // ---- ptp_comm.cu ---------------------------------------------------------------------------------
 int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64);
+int ptp_comm_max_int(ptp_trap* t, int* value);                   // collective max over the ranks (synchronises the stream)
+int ptp_row_extent(ptp_trap* t, int* extent);                    // collective on the first call after a (re)load, cached afterwards
 void ptp_comm_free(ptp_trap* t);
 int ptp_comm_size(ptp_trap* t);
 int ptp_comm_rank(ptp_trap* t);

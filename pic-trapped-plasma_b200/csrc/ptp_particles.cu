@@ -320,6 +320,7 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 	ptp_trap* t = p->trap;
 	const int Nr = t->Nr;
 	++t->cfgEpoch;                                               // ring buffers / segment tables change: cached step graph is stale
+	++t->layoutEpoch;                                            // ... and so is the outermost populated row
 	p->rowOff.assign(Nr + 1, 0);
 	p->rowLive.assign(Nr, 0);
 	for (int j = 0; j < Nr; ++j) {

@@ -32,11 +32,15 @@ constexpr int INV_KC = 1024;    // modes staged in shared memory per chunk
 
 // Per radial row: first / last axial node with a non-zero deposit (lo > hi: empty row). Deposits are exact
 // zeros outside the plasma, so skipping them in the forward transform changes nothing bitwise.
-__global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ rho, int rows, int n1, int2* __restrict__ bounds)
+__global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ rho, int rows, int n1, int2* __restrict__ bounds, int Nr, int rowLimit)
 {
 	const int lane = threadIdx.x & 31;
 	const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
 	if (row >= rows) return;
+	if (row % Nr >= rowLimit) {                                 // no ring lives in this radial row: nothing to scan
+		if (lane == 0) bounds[row] = make_int2(INT_MAX, INT_MIN);
+		return;
+	}
 	const unsigned long long* w = reinterpret_cast<const unsigned long long*>(rho) + (size_t)row * n1;
 	int lo = INT_MAX, hi = INT_MIN;
 	constexpr int UB = 20;                                      // one wave of loads covers a row of up to 640 nodes
@@ -720,13 +724,13 @@ int ptp_solver_reserve(ptp_trap* t, int nS)
 	return PTP_OK;
 }
 
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds)
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds, int rowLimit)
 {
 	if (nS <= 0) return PTP_OK;
 	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
 	PTP_TRY(ptp_solver_reserve(t, nS));
-	if (!encBounds) { k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds); t->lastLaunches++; }
+	if (!encBounds) { k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds, Nr, rowLimit < 0 ? Nr : rowLimit); t->lastLaunches++; }
 	auto smFwdBytes = [&](int mb) {
 		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB + (size_t)Nr) * sizeof(double) + (size_t)Nr * sizeof(int2);
 	};
