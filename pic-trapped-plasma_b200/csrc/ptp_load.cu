@@ -162,6 +162,17 @@ __global__ void __launch_bounds__(256) k_rng_emit(long long nAttempts, const uns
 	}
 }
 
+// Device temporaries of one load, released on every exit path.
+struct LoadScratch {
+	double* normals = nullptr;
+	unsigned int* blockCount = nullptr;
+	unsigned long long* blockOffset = nullptr;
+	double* cum = nullptr;
+	void* rows = nullptr;
+	void dropStream() { cudaFree(normals); cudaFree(blockCount); cudaFree(blockOffset); normals = nullptr; blockCount = nullptr; blockOffset = nullptr; }
+	~LoadScratch() { dropStream(); cudaFree(cum); cudaFree(rows); }
+};
+
 struct PlaceRow {
 	int row, pad;
 	long long perRow;       // rings of the row over all shards (numAtR)
@@ -259,45 +270,38 @@ extern "C" int ptp_plasma_load_density(ptp_plasma* p, const double* density, dou
 	// deviate stream: accepted pairs needed = ceil(total / 2); acceptance probability pi / 4
 	const long long pairs = (total + 1) / 2;
 	long long nAttempts = (long long)std::ceil((double)pairs * 1.2732395447351628 * 1.002) + 4096;
-	double* dNormals = nullptr;
-	unsigned int* dBlockCount = nullptr;
-	unsigned long long* dBlockOffset = nullptr;
-	auto freeTmp = [&]() { cudaFree(dNormals); cudaFree(dBlockCount); cudaFree(dBlockOffset); dNormals = nullptr; dBlockCount = nullptr; dBlockOffset = nullptr; };
+	LoadScratch tmp;
 	for (int tries = 0;; ++tries) {
 		const long long nThreads = (nAttempts + RNG_CH - 1) / RNG_CH;
 		const int nBlocks = (int)((nThreads + 255) / 256);
-		PTP_CUDA(cudaMalloc(&dBlockCount, (size_t)nBlocks * sizeof(unsigned int)));
-		PTP_CUDA(cudaMalloc(&dBlockOffset, ((size_t)nBlocks + 1) * sizeof(unsigned long long)));
-		k_rng_count<<<nBlocks, 256, 0, t->stream>>>(nAttempts, dBlockCount);
-		k_rng_scan<<<1, 1024, 0, t->stream>>>(dBlockCount, dBlockOffset, nBlocks);
+		PTP_CUDA(cudaMalloc(&tmp.blockCount, (size_t)nBlocks * sizeof(unsigned int)));
+		PTP_CUDA(cudaMalloc(&tmp.blockOffset, ((size_t)nBlocks + 1) * sizeof(unsigned long long)));
+		k_rng_count<<<nBlocks, 256, 0, t->stream>>>(nAttempts, tmp.blockCount);
+		k_rng_scan<<<1, 1024, 0, t->stream>>>(tmp.blockCount, tmp.blockOffset, nBlocks);
 		unsigned long long accepted = 0;
-		PTP_CUDA(cudaMemcpyAsync(&accepted, dBlockOffset + nBlocks, sizeof(accepted), cudaMemcpyDeviceToHost, t->stream));
+		PTP_CUDA(cudaMemcpyAsync(&accepted, tmp.blockOffset + nBlocks, sizeof(accepted), cudaMemcpyDeviceToHost, t->stream));
 		PTP_CUDA(cudaStreamSynchronize(t->stream));
 		if ((long long)accepted >= pairs) {
-			PTP_CUDA(cudaMalloc(&dNormals, (size_t)total * sizeof(double)));
-			k_rng_emit<<<nBlocks, 256, 0, t->stream>>>(nAttempts, dBlockOffset, dNormals, total);
+			PTP_CUDA(cudaMalloc(&tmp.normals, (size_t)total * sizeof(double)));
+			k_rng_emit<<<nBlocks, 256, 0, t->stream>>>(nAttempts, tmp.blockOffset, tmp.normals, total);
 			break;
 		}
-		freeTmp();
+		tmp.dropStream();
 		if (tries > 8) { ptp_set_error("ptp_plasma_load_density: deviate stream came up short"); return PTP_ESTATE; }
 		nAttempts = nAttempts + nAttempts / 16 + 4096;
 	}
-	double* dCum = nullptr;
-	PlaceRow* dRows = nullptr;
-	PTP_CUDA(cudaMalloc(&dCum, cum.size() * sizeof(double)));
-	PTP_CUDA(cudaMalloc(&dRows, rows.size() * sizeof(PlaceRow)));
-	PTP_CUDA(cudaMemcpyAsync(dCum, cum.data(), cum.size() * sizeof(double), cudaMemcpyHostToDevice, t->stream));
-	PTP_CUDA(cudaMemcpyAsync(dRows, rows.data(), rows.size() * sizeof(PlaceRow), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaMalloc(&tmp.cum, cum.size() * sizeof(double)));
+	PTP_CUDA(cudaMalloc(&tmp.rows, rows.size() * sizeof(PlaceRow)));
+	PTP_CUDA(cudaMemcpyAsync(tmp.cum, cum.data(), cum.size() * sizeof(double), cudaMemcpyHostToDevice, t->stream));
+	PTP_CUDA(cudaMemcpyAsync(tmp.rows, rows.data(), rows.size() * sizeof(PlaceRow), cudaMemcpyHostToDevice, t->stream));
 	long long maxLocal = 0;
 	for (const PlaceRow& pr : rows) maxLocal = std::max(maxLocal, pr.local);
 	const double sigma = std::sqrt(KB * temperature / p->mass);              // :509
 	const dim3 grid((unsigned)std::min<long long>((maxLocal + 255) / 256, 4096), (unsigned)rows.size());
-	k_place<<<grid, 256, 0, t->stream>>>(dRows, dCum, dNormals, n1, hz, sigma, shard, nShards, p->z, p->v, p->id);
+	k_place<<<grid, 256, 0, t->stream>>>(static_cast<const PlaceRow*>(tmp.rows), tmp.cum, tmp.normals, n1, hz, sigma, shard, nShards, p->z, p->v, p->id);
 	cudaError_t e = cudaGetLastError();
-	PTP_CUDA(cudaStreamSynchronize(t->stream));
-	freeTmp();
-	cudaFree(dCum); cudaFree(dRows);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "loader launch", __FILE__, __LINE__);
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
 	t->lastLaunches = 4;
 	return ptp_build_segments(t, p);
 }
