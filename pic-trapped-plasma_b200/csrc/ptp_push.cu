@@ -304,11 +304,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 #pragma unroll
 				for (int i = 0; i < R; ++i)
 					if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)W) {
-						for (int pr = 0; pr < a.nRho; ++pr) {
-							unsigned int* bd = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(a.rho[pr]) + a.bndOffset) + 2 * seg.row;
-							atomicMax(bd, (unsigned int)(a.Nz + 2 - k[i]));
-							atomicMax(bd + 1, (unsigned int)(k[i] + 2));
-						}
+						// (the row's touched node range is widened to the segment's whole cell range in the epilogue)
 						if (FIXED) {
 							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 							const unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
@@ -334,6 +330,19 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 						st_ring(z2w + p0 + (long long)j * T, make_double2(z[2 * j], z[2 * j + 1]));
 						st_ring(v2w + p0 + (long long)j * T, make_double2(v[2 * j], v[2 * j + 1]));
 					}
+			}
+		}
+
+		// the CTA's next segment starts with cold loads: pull its first tiles into L2 while this segment's epilogue runs
+		if (PTP_L2_PREFETCH_TILES > 0 && s + 1 < a.ctaSegBegin[blockIdx.x + 1]) {
+			const PtpSegment nx = a.segs[s + 1];
+			for (int u = 0; u < PTP_L2_PREFETCH_TILES && nx.begin + u * tile < nx.end; ++u) {
+				const long long pf = ((nx.begin + u * tile) >> 1) + tid;
+#pragma unroll
+				for (int j = 0; j < NV; ++j) {
+					prefetch_l2(z2 + pf + (long long)j * T);
+					if (PUSH) prefetch_l2(v2 + pf + (long long)j * T);
+				}
 			}
 		}
 
@@ -396,13 +405,14 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 						for (int pr = 0; pr < a.nRho; ++pr) atomicAdd(reinterpret_cast<double*>(a.rho[pr]) + rowBase + k0 + i, val);
 				}
 			}
-			// nodes k0+lo .. k0+hi+1 of this row were touched: keep the row's range for the solver's forward transform
-			// (both ends stored as maxima so that a memset(0) resets them: Nz+2-kmin and kmax+1)
+			// nodes gMin .. gMax+1 of this row were touched - by the flush above or, for rings outside the window, by their own
+			// global adds: keep the row's range for the solver's forward transform, one pair of atomics per segment
+			// (both ends stored as maxima so that a memset(0) resets them: Nz+2-kmin and kmax+2)
 			if (tid == 0)
 				for (int pr = 0; pr < a.nRho; ++pr) {
 					unsigned int* bd = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(a.rho[pr]) + a.bndOffset) + 2 * seg.row;
-					atomicMax(bd, (unsigned int)(a.Nz + 2 - (k0 + lo)));
-					atomicMax(bd + 1, (unsigned int)(k0 + hi + 2));
+					atomicMax(bd, (unsigned int)(a.Nz + 2 - gMin));
+					atomicMax(bd + 1, (unsigned int)(gMax + 2));
 				}
 		}
 		if (a.nRho > 1 && a.pad1) {                      // remote adds performed before the grid can be declared complete:

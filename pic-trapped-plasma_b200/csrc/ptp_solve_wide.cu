@@ -20,6 +20,12 @@
 
 #include <limits.h>
 
+#include <cstdlib>
+
+#ifndef PTP_FFT_R16_DEFAULT
+#define PTP_FFT_R16_DEFAULT 0
+#endif
+
 namespace {
 
 __device__ __forceinline__ void cpa8(void* smemDst, const void* gmemSrc, bool valid)
@@ -446,6 +452,153 @@ __global__ void __launch_bounds__(256, 2) k_idct_fft_field(const double* __restr
 	}
 }
 
+
+// ---- the same transform for N = 4096 in three register-resident radix-16 stages ------------------------------------
+// 4096 = 16^3: with n = 256 n2 + 16 n1 + n0 and k = k0 + 16 k1 + 256 k2 the N-point transform is three rounds of 256
+// independent 16-point transforms (over n2, n1, n0), each done by one thread in registers, with a twiddle W_N^{(16 n1 + n0) k0}
+// after the first round and W_256^{n0 k1} after the second. The rounds exchange their data through a [16][257] buffer
+// (row stride 257 sixteen-byte elements: every access of every round is conflict-free for the quarter-warps that serve
+// 16-byte accesses). Shared-memory traffic per row and species: 6 x 64 KB (three writes, three reads) against 15 x 64 KB for
+// the radix-2 pass pairs, and five barriers against eight. The read-out forms phi_k and phi_{N-k} from the same pair
+// (Z_k, Z_{N-k}). tools/fft16_model.py is a thread-level model of this kernel (index maps, twiddles, bank groups).
+// [r16-begin] (tools/emu_r16.sh compiles the text between these markers for the host and runs it on 256 CPU threads)
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// 4-point transform, exp(-2 pi i j k / 4), in place
+__device__ __forceinline__ void fft4(double2& a0, double2& a1, double2& a2, double2& a3)
+{
+	const double2 s0 = make_double2(a0.x + a2.x, a0.y + a2.y), s1 = make_double2(a0.x - a2.x, a0.y - a2.y);
+	const double2 s2 = make_double2(a1.x + a3.x, a1.y + a3.y), s3 = make_double2(a1.x - a3.x, a1.y - a3.y);
+	a0 = make_double2(s0.x + s2.x, s0.y + s2.y);
+	a2 = make_double2(s0.x - s2.x, s0.y - s2.y);
+	a1 = make_double2(s1.x + s3.y, s1.y - s3.x);                // s1 - i s3
+	a3 = make_double2(s1.x - s3.y, s1.y + s3.x);                // s1 + i s3
+}
+
+// y[k] = sum_j x[j] exp(-2 pi i j k / 16), natural order in and out: j = 4 j1 + j0, k = k0 + 4 k1
+__device__ __forceinline__ void fft16(double2 (&x)[16])
+{
+	constexpr double C8 = 0.92387953251128675613, S8 = 0.38268343236508977173, R2 = 0.70710678118654752440;
+	double2 t[16];                                              // t[4 j0 + k0]
+#pragma unroll
+	for (int j0 = 0; j0 < 4; ++j0) {
+		t[4 * j0] = x[j0]; t[4 * j0 + 1] = x[4 + j0]; t[4 * j0 + 2] = x[8 + j0]; t[4 * j0 + 3] = x[12 + j0];
+		fft4(t[4 * j0], t[4 * j0 + 1], t[4 * j0 + 2], t[4 * j0 + 3]);
+	}
+	const double2 W1 = make_double2(C8, -S8), W3 = make_double2(S8, -C8);
+	t[5] = cmul(t[5], W1);                                                      // W_16^{j0 k0}
+	t[6] = make_double2(R2 * (t[6].x + t[6].y), R2 * (t[6].y - t[6].x));        // W^2 = (1 - i) / sqrt 2
+	t[7] = cmul(t[7], W3);
+	t[9] = make_double2(R2 * (t[9].x + t[9].y), R2 * (t[9].y - t[9].x));        // W^2
+	t[10] = make_double2(t[10].y, -t[10].x);                                    // W^4 = -i
+	t[11] = make_double2(R2 * (t[11].y - t[11].x), -R2 * (t[11].x + t[11].y));  // W^6 = -(1 + i) / sqrt 2
+	t[13] = cmul(t[13], W3);
+	t[14] = make_double2(R2 * (t[14].y - t[14].x), -R2 * (t[14].x + t[14].y));  // W^6
+	{ const double2 m = cmul(t[15], W1); t[15] = make_double2(-m.x, -m.y); }    // W^9 = -W^1
+#pragma unroll
+	for (int k0 = 0; k0 < 4; ++k0) {
+		fft4(t[k0], t[4 + k0], t[8 + k0], t[12 + k0]);
+		x[k0] = t[k0]; x[k0 + 4] = t[4 + k0]; x[k0 + 8] = t[8 + k0]; x[k0 + 12] = t[12 + k0];
+	}
+}
+
+// x[k] *= w1^k, the powers by binary splitting (at most four products deep)
+__device__ __forceinline__ void twiddle16(double2 (&x)[16], double2 w1)
+{
+	double2 w[8];
+	w[1] = w1;
+	w[2] = cmul(w1, w1);
+	w[3] = cmul(w[2], w1);
+	w[4] = cmul(w[2], w[2]);
+	w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+	const double2 w8 = cmul(w[4], w[4]);
+#pragma unroll
+	for (int k = 1; k < 8; ++k) x[k] = cmul(x[k], w[k]);
+	x[8] = cmul(x[8], w8);
+#pragma unroll
+	for (int k = 1; k < 8; ++k) x[8 + k] = cmul(x[8 + k], cmul(w8, w[k]));
+}
+
+constexpr int R16_N = 4096, R16_RS = 257;
+
+template <bool FIELD>
+__global__ void __launch_bounds__(256, 2) k_idct_r16_field(const double* __restrict__ alphaAll, double* __restrict__ phiAll, const double2* __restrict__ tw,
+	const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, double hz)
+{
+	constexpr int N = R16_N, n1 = N + 1, RS = R16_RS;
+	extern __shared__ double2 fbw[];                            // [16][RS] exchange buffer; natural-order Z after the third round
+	double* tot = reinterpret_cast<double*>(fbw + 16 * RS);     // [N+1] running total potential of the row (FIELD)
+	const int t = threadIdx.x, row = blockIdx.x;
+	if (FIELD) for (int k = t; k <= N; k += 256) tot[k] = phiTrap[(size_t)row * n1 + k];
+	const double2 wA = __ldg(&tw[2 * t]);                       // W_N^t      (tw[j] = exp(-i pi j / N))
+	const double2 wB = __ldg(&tw[32 * (t & 15)]);               // W_256^n0
+	for (int sp = 0; sp < nS; ++sp) {
+		const double* a = alphaAll + ((size_t)sp * Nr + row) * n1;
+		double2 x[16];
+		// round 1 (over n2): thread t = 16 n1 + n0 owns the samples n = t + 256 j of z_n = e_2n + i e_2n+1 (even extension of a)
+#pragma unroll
+		for (int j = 0; j < 16; ++j) {
+			const int i0 = 2 * (t + 256 * j), i1 = i0 + 1;
+			x[j] = make_double2(a[i0 <= N ? i0 : 2 * N - i0], a[i1 <= N ? i1 : 2 * N - i1]);
+		}
+		const double a0 = a[0], aN = a[N];
+		fft16(x);
+		twiddle16(x, wA);
+		__syncthreads();                                        // the previous species' read-out is done with fbw
+#pragma unroll
+		for (int k0 = 0; k0 < 16; ++k0) fbw[(t >> 4) * RS + k0 * 16 + (t & 15)] = x[k0];
+		__syncthreads();
+		// round 2 (over n1): thread t = 16 k0 + n0
+#pragma unroll
+		for (int j = 0; j < 16; ++j) x[j] = fbw[j * RS + t];
+		fft16(x);
+		twiddle16(x, wB);
+		__syncthreads();                                        // every read of this round precedes its writes (other layout)
+#pragma unroll
+		for (int k1 = 0; k1 < 16; ++k1) fbw[(t & 15) * RS + (t >> 4) + 16 * k1] = x[k1];
+		__syncthreads();
+		// round 3 (over n0): thread t = k0 + 16 k1 ends up with Z[t + 256 k2]
+#pragma unroll
+		for (int j = 0; j < 16; ++j) x[j] = fbw[j * RS + t];
+		fft16(x);
+		__syncthreads();
+#pragma unroll
+		for (int k2 = 0; k2 < 16; ++k2) fbw[t + 256 * k2] = x[k2];
+		__syncthreads();
+		// read-out: phi_k and phi_{N-k} from the pair (Z_k, Z_{N-k});  W_2N^{N-k} = -conj W_2N^k
+		double* out = phiAll + ((size_t)sp * Nr + row) * n1;
+		const double half0 = 0.5 * (a0 + aN), half1 = 0.5 * (a0 - aN);
+		auto emit = [&](int k, double2 A, double2 B, double2 w) {
+			const double dx = A.x - B.x, dy = A.y + B.y;            // Z_k - conj Z_{N-k}
+			const double X = 0.5 * (A.x + B.x) + 0.5 * (dy * w.x + dx * w.y);
+			const double v = 0.5 * X + ((k & 1) ? half1 : half0);
+			out[k] = v;
+			if (FIELD) tot[k] = __dadd_rn(tot[k], v);
+		};
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const int k = t + 256 * j;
+			const double2 A = fbw[k], B = fbw[(N - k) & (N - 1)];
+			const double2 w = __ldg(&tw[k]);
+			emit(k, A, B, w);
+			emit(N - k, B, A, make_double2(-w.x, w.y));
+		}
+		if (t == 0) {
+			const double2 A = fbw[N / 2];
+			emit(N / 2, A, A, __ldg(&tw[N / 2]));
+		}
+	}
+	if (FIELD) {
+		__syncthreads();
+		for (int k = t; k <= N; k += 256) {
+			double e = 0.0;
+			if (k > 0 && k < N) e = __ddiv_rn(__dsub_rn(tot[k - 1], tot[k + 1]), __dmul_rn(2.0, hz));
+			eNodes[(size_t)row * n1 + k] = e;
+		}
+	}
+}
+// [r16-end]
+
 } // namespace
 
 bool ptp_solver_fft_fits(const ptp_trap* t)
@@ -491,6 +644,23 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 	const int N = t->Nz, Nr = t->Nr;
 	int bits = 0;
 	while ((1 << bits) < N) ++bits;
+	// N = 4096: three radix-16 rounds in registers (PTP_FFT_R16=1 selects it, =0 the radix-2 pass pairs)
+	static const int r16 = [] { const char* e = std::getenv("PTP_FFT_R16"); return e ? std::atoi(e) : PTP_FFT_R16_DEFAULT; }();
+	if (N == R16_N && r16) {
+		const size_t sm16 = (size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
+		if (withField) {
+			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+			k_idct_r16_field<true><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz);
+		}
+		else {
+			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
+			k_idct_r16_field<false><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, t->hz);
+		}
+		const cudaError_t e16 = cudaGetLastError();
+		if (e16 != cudaSuccess) return ptp_cuda_fail(e16, "k_idct_r16_field launch", __FILE__, __LINE__);
+		t->lastLaunches += 1;
+		return PTP_OK;
+	}
 	const size_t sm = (size_t)N * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
 	const int threads = N >= 1024 ? 256 : 128;
 	if (withField) {
