@@ -645,7 +645,8 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 	int bits = 0;
 	while ((1 << bits) < N) ++bits;
 	// N = 4096: three radix-16 rounds in registers (PTP_FFT_R16=1 selects it, =0 the radix-2 pass pairs)
-	static const int r16 = [] { const char* e = std::getenv("PTP_FFT_R16"); return e ? std::atoi(e) : PTP_FFT_R16_DEFAULT; }();
+	const char* r16env = std::getenv("PTP_FFT_R16");               // read per call: tests switch it inside one process
+	const int r16 = r16env ? std::atoi(r16env) : PTP_FFT_R16_DEFAULT;
 	if (N == R16_N && r16) {
 		const size_t sm16 = (size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
 		if (withField) {

@@ -402,13 +402,16 @@ def test_large_load_properties(c1_kat, mode):
     t.close()
 
 
-def test_fine_grid_full_size_properties(c1_kat):
-    """BASELINE config 5 grid (Nz = 4096, Nr = 1024: 4.2 M unknowns - far beyond what the LU oracle can factorise) through
+@pytest.mark.parametrize("r16", ["0", "1"])
+def test_fine_grid_full_size_properties(c1_kat, r16, monkeypatch):
+    """(r16: inverse transform of the 4096-node rows by radix-2 pass pairs / by three register-resident radix-16 rounds.)
+    BASELINE config 5 grid (Nz = 4096, Nr = 1024: 4.2 M unknowns - far beyond what the LU oracle can factorise) through
     size-independent properties: the direct solver's phi satisfies A phi = b for the operator applied by the independent
     stencil kernel (PenningTrap::generateSparse coefficients), for a random right-hand side and for the deposit of a
     5 M-ring load placed by the device loader; the deposit conserves the ring count; the node field is the centred
     difference of the total potential; fixed-point deposits give the same grid for 148 and 37 CTAs bit for bit."""
     from bench import density_on
+    monkeypatch.setenv("PTP_FFT_R16", r16)
     Nz, Nr = 4096, 1024
     el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
     t = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
@@ -529,6 +532,34 @@ def test_device_loader_matches_reference_loader(density_files, num_macro, mass):
 @pytest.mark.parametrize("Nz,Nr,solver,fixed", [(1024, 96, 0, 0), (2048, 16, 0, 0), (1500, 12, 0, 0), (301, 130, 0, 0), (48, 420, 0, 0),
                                                 (256, 24, 2, 0), (256, 24, 2, 1), (64, 300, 2, 0), (128, 5, 2, 0), (8, 70, 2, 0)])
 def test_solver_and_step_on_other_grids(Nz, Nr, solver, fixed):
+    _other_grid_case(Nz, Nr, solver, fixed)
+
+
+@pytest.mark.parametrize("r16", ["0", "1"])
+@pytest.mark.parametrize("Nr,fixed", [(12, 0), (40, 1)])
+def test_4096_node_rows_both_inverse_kernels(Nr, fixed, r16, monkeypatch):
+    """Rows of config 5's length (Nz = 4096) on grids small enough for the LU oracle: k_idct_fft_field (PTP_FFT_R16=0)
+    and k_idct_r16_field (=1) against the oracle - trap potential, a random right-hand side, deposits, three steps."""
+    monkeypatch.setenv("PTP_FFT_R16", r16)
+    _other_grid_case(4096, Nr, 2, fixed)
+
+
+def test_radix16_and_radix2_inverse_agree(monkeypatch):
+    """Same spectrum through both inverse-transform kernels on a 4096 x 64 grid: potentials agree to rounding."""
+    args = (0.012, [0.02, 0.03, 0.02], [0.0, -50.0, 0.0], [0.001, 0.001], 4096, 64)
+    rng = np.random.default_rng(5)
+    out = []
+    for r16 in ("0", "1"):
+        monkeypatch.setenv("PTP_FFT_R16", r16)
+        t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], args[4], args[5])
+        x = np.random.default_rng(5).standard_normal(t.G)
+        out.append((t.phi(), t.solve(x), t.enodes()))
+        t.close()
+    for a, b in zip(out[0], out[1]):
+        assert rel_l2(b, a) < 1e-13
+
+
+def _other_grid_case(Nz, Nr, solver, fixed):
     """Grid shapes that take the other code paths of the solver against the CPU oracle: odd Nz+1 (8-byte copies), pipelined
     cosine ring (1024), chunked inverse GEMM + separate node field for long rows that are not a power of two (1500), and
     the large-grid organisation (ptp_solve_wide.cu): tiled forward transform + streamed radial solves for many radial
