@@ -212,7 +212,7 @@ def main():
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
-    ap.add_argument("--sort-interval", type=int, default=0)
+    ap.add_argument("--sort-interval", type=int, default=-1, help="> 0: re-sort every so many steps; 0: never; -1: adaptive (library default)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer"], help="exchange step for N > 1 (auto: peer memory up to 2^20 grid nodes)")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -321,11 +321,13 @@ def main():
     sampler.start()
     alive_before = sum_over_ranks(sum(p.getNumMacro() for p in plasmas))
     barrier()
+    sorts_before = trap.sorts_done()
     trap.movePlasmas(DT, args.steps)
     trap.sync()
     barrier()
     times = trap.last_times()
     launches = trap.last_launches()
+    sorts_timed = trap.sorts_done() - sorts_before
     clocks = sampler.stop()
     ms_total = max_over_ranks(float(times[0]))
     ms_push = max_over_ranks(float(times[1]))
@@ -405,7 +407,8 @@ def main():
                                        "solve_node_field": float(times[3]) / args.steps},
                 "phases_ms_per_step_per_rank[whole,push,exchange,solve]": per_rank,
                 "load": {"how": "ptp_plasma_load_density (device-side Plasma::loadDensityFile placement + deviate stream)", "seconds_rank0": t_load},
-                "tuning": {"threads": args.threads or 512, "window": args.window or 44, "ctas": args.ctas, "rings_per_thread": args.rings or 4}}
+                "tuning": {"threads": args.threads or 512, "window": args.window or 44, "ctas": args.ctas, "rings_per_thread": args.rings or 4,
+                           "sort_interval": args.sort_interval, "sorts_in_run_rank0": sorts_timed}}
         print(json.dumps(line))
     trap.close()
     if world > 1:

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ptp_trap_last_launches": (_i64, [_vp]),
     "ptp_trap_sort": (_i, [_vp]),
     "ptp_trap_set_sort_interval": (_i, [_vp, _i]),
+    "ptp_trap_sorts_done": (_i64, [_vp]),
     "ptp_trap_set_deposit_mode": (_i, [_vp, _i]),
     "ptp_trap_set_arith_mode": (_i, [_vp, _i]),
     "ptp_trap_set_solver": (_i, [_vp, _i, _d, _i]),
@@ -295,7 +296,11 @@ class PenningTrap:
         _check(lib().ptp_trap_set_graph(self.h, 1 if on else 0))
 
     def set_sort_interval(self, interval):
+        """> 0: re-sort every `interval` steps; 0: never; -1 (default): adaptive (see include/ptp.h)."""
         _check(lib().ptp_trap_set_sort_interval(self.h, interval))
+
+    def sorts_done(self):
+        return int(lib().ptp_trap_sorts_done(self.h))
 
     def set_allreduce(self, kind):
         """0: NCCL all-reduce of the deposit grids; 1: peer-memory mode (the push kernel adds into every rank's grid)."""

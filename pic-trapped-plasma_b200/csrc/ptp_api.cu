@@ -2,7 +2,9 @@
 // (reference Source/PenningTrap.cpp:352-363) on one CUDA stream per trap.
 #include "ptp_internal.h"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -186,6 +188,8 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 	PTP_CUDA(cudaGetDeviceProperties(&prop, device));
 	t->smCount = prop.multiProcessorCount;
 	t->smemMax = prop.sharedMemPerBlockOptin;
+	if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
+	if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));
 	PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
 	for (auto& ev : t->ev) PTP_CUDA(cudaEventCreate(&ev));
 	const size_t gb = (size_t)t->G * sizeof(double);
@@ -373,6 +377,36 @@ int one_step(ptp_trap* t, double dt, cudaEvent_t* e)
 	return PTP_OK;
 }
 
+// K5 policy after a step. Fixed interval: every sortInterval steps. Adaptive (sortInterval < 0): the push kernel counts the
+// deposits that missed the thread-private window (rings that drifted away from the cell range their segment was planned
+// for - long plasmas on fine grids); every sortCheckSteps steps the counters are read back, and a species whose miss rate
+// exceeds sortFarFraction is re-sorted by axial cell, which also re-plans its segments.
+int maintain_order(ptp_trap* t)
+{
+	if (t->sortInterval > 0) {
+		if (t->stepCount % t->sortInterval == 0)
+			for (ptp_plasma* p : t->plasmas) { PTP_TRY(ptp_sort_plasma(t, p)); ++t->sortsDone; }
+		return PTP_OK;
+	}
+	if (t->sortInterval == 0 || ++t->stepsSinceCheck < t->sortCheckSteps) return PTP_OK;
+	const int steps = t->stepsSinceCheck;
+	t->stepsSinceCheck = 0;
+	const size_t nS = t->plasmas.size();
+	std::vector<unsigned long long> h(2 * nS, 0ULL);
+	for (size_t s = 0; s < nS; ++s)
+		PTP_CUDA(cudaMemcpyAsync(&h[2 * s], t->plasmas[s]->dLost, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	for (size_t s = 0; s < nS; ++s) {
+		ptp_plasma* p = t->plasmas[s];
+		const unsigned long long far = h[2 * s + 1];
+		if (!far) continue;
+		const double alive = (double)(p->nUploaded - (int64_t)h[2 * s]);
+		if ((double)far > t->sortFarFraction * alive * steps) { PTP_TRY(ptp_sort_plasma(t, p)); ++t->sortsDone; }   // clears the counters
+		else PTP_CUDA(cudaMemsetAsync(p->dLost + 1, 0, sizeof(unsigned long long), t->stream));
+	}
+	return PTP_OK;
+}
+
 void drop_graph(ptp_trap* t)
 {
 	if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
@@ -427,7 +461,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	if (!t || nSteps < 0) { ptp_set_error("ptp_trap_step: bad arguments"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
-	const bool graph = t->useGraph && t->sortInterval == 0 && t->solver != PTP_SOLVER_SOR && !t->plasmas.empty();
+	const bool graph = t->useGraph && t->sortInterval <= 0 && t->solver != PTP_SOLVER_SOR && !t->plasmas.empty();   // (no adaptive re-sort under replay)
 	// phase events for every step (up to a bound), so that callers can report the mean kernel time
 	const int timed = (!graph && nSteps <= 4096) ? nSteps : 0;
 	while ((int)t->evPool.size() < 4 * timed) {
@@ -456,8 +490,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	else PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
 	for (int s = done; s < nSteps; ++s) {
 		PTP_TRY(one_step(t, dt, s < timed ? &t->evPool[4 * s] : nullptr));
-		if (t->sortInterval > 0 && t->stepCount % t->sortInterval == 0)
-			for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
+		PTP_TRY(maintain_order(t));
 	}
 	PTP_CUDA(cudaEventRecord(t->ev[4], t->stream));
 	return PTP_OK;
@@ -476,8 +509,7 @@ int ptp_trap_step_programme(ptp_trap* t, double dt, int nSteps, const double* we
 	for (int s = 0; s < nSteps; ++s) {
 		PTP_TRY(combine_basis(t, t->dWeights + (size_t)s * t->nBasis));   // setPotential(...) of this step; the node field follows in the push
 		PTP_TRY(one_step(t, dt, nullptr));
-		if (t->sortInterval > 0 && t->stepCount % t->sortInterval == 0)
-			for (ptp_plasma* p : t->plasmas) PTP_TRY(ptp_sort_plasma(t, p));
+		PTP_TRY(maintain_order(t));
 	}
 	PTP_CUDA(cudaEventRecord(t->ev[4], t->stream));
 	return PTP_OK;
@@ -531,10 +563,13 @@ int ptp_trap_sort(ptp_trap* t)
 
 int ptp_trap_set_sort_interval(ptp_trap* t, int interval)
 {
-	if (!t || interval < 0) { ptp_set_error("ptp_trap_set_sort_interval: bad arguments"); return PTP_EINVAL; }
+	if (!t || interval < -1) { ptp_set_error("ptp_trap_set_sort_interval: bad arguments"); return PTP_EINVAL; }
 	t->sortInterval = interval;
+	t->stepsSinceCheck = 0;
 	return PTP_OK;
 }
+
+int64_t ptp_trap_sorts_done(ptp_trap* t) { return t ? t->sortsDone : 0; }
 
 int ptp_trap_set_deposit_mode(ptp_trap* t, int mode)
 {
@@ -595,8 +630,8 @@ int ptp_plasma_create(ptp_trap* t, ptp_plasma** out, double mass, double charge)
 	p->charge = charge;
 	p->rowOff.assign(t->Nr + 1, 0);
 	p->rowLive.assign(t->Nr, 0);
-	PTP_CUDA(cudaMalloc(&p->dLost, sizeof(unsigned long long)));
-	PTP_CUDA(cudaMemset(p->dLost, 0, sizeof(unsigned long long)));
+	PTP_CUDA(cudaMalloc(&p->dLost, 2 * sizeof(unsigned long long)));
+	PTP_CUDA(cudaMemset(p->dLost, 0, 2 * sizeof(unsigned long long)));
 	const size_t gb = (size_t)t->G * sizeof(double);
 	PTP_CUDA(cudaMemset(t->rhoAll + (size_t)p->index * t->G, 0, gb));
 	PTP_CUDA(cudaMemset(t->phiSelfAll + (size_t)p->index * t->G, 0, gb));

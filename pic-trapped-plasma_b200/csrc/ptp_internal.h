@@ -46,7 +46,7 @@ struct ptp_plasma {
 	int* dCtaSegBegin = nullptr;
 	int4* dSegBounds = nullptr;      // per segment: min / max / mean axial cell of its live rings (x, y, z)
 	int nCta = 0;
-	unsigned long long* dLost = nullptr; // rings lost since upload (device counter)
+	unsigned long long* dLost = nullptr; // [2] device counters: rings lost since upload; deposits outside the private window since the last check
 	bool boundsValid = false;
 };
 
@@ -117,7 +117,11 @@ struct ptp_trap {
 	int sorMaxIter = 20000;
 	int fixedBits = 40;
 	int threads = 512, window = 44, ctas = 0, ringsPerThread = 4;
-	int sortInterval = 0;
+	int sortInterval = -1;           // > 0: re-sort every so many steps; 0: never; -1: when the push kernel reports too many out-of-window deposits
+	int stepsSinceCheck = 0;         // adaptive mode: steps since the out-of-window counters were last read
+	int sortCheckSteps = 64;         // adaptive mode: steps between two reads of the counters (PTP_SORT_CHECK_STEPS)
+	double sortFarFraction = 0.02;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
+	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)
 	long long stepCount = 0;
 	bool eNodesValid = false;
 
@@ -177,6 +181,7 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push);
 int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p);
 int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& tiles, std::vector<int2>& tileBounds, int64_t* nLive);
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window);
+int ptp_push_field_window(const ptp_trap* t);
 int ptp_push_configure(ptp_trap* t);
 
 // ---- ptp_particles.cu ----------------------------------------------------------------------------

@@ -307,7 +307,7 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 	long long total = 0;
 	for (int r = 0; r < Nr; ++r) { p->rowLive[r] = (long long)live[r]; total += (long long)live[r]; }
 	p->nAlive = total;
-	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
+	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, 2 * sizeof(unsigned long long), t->stream));
 	p->nUploaded = total;                                  // loss counter restarts from the compacted population
 	return ptp_build_segments(t, p);
 }
@@ -340,7 +340,7 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 	p->macroChargeDensity = macroChargeDensity;
 	const double scale = -macroChargeDensity / 8.8541878128e-12;     // Source/Plasma.cpp:91-92, Source/Constants.hpp:12
 	PTP_CUDA(cudaMemcpyAsync(t->dScale + p->index, &scale, sizeof(double), cudaMemcpyHostToDevice, t->stream));
-	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, sizeof(unsigned long long), t->stream));
+	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, 2 * sizeof(unsigned long long), t->stream));
 	PTP_CUDA(cudaMalloc(&p->dRowOff, (Nr + 1) * sizeof(long long)));
 	PTP_CUDA(cudaMemcpyAsync(p->dRowOff, p->rowOff.data(), (Nr + 1) * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));                  // `scale` is a stack variable

@@ -39,7 +39,7 @@ constexpr unsigned long long kPackBias = 0x4320000000000000ULL; // bits(2^52 + x
 constexpr unsigned long long kSumMask = (1ULL << 52) - 1;
 
 struct PushArgs {
-	int Nz, W, fixedBits, pad0;
+	int Nz, W, fixedBits, WE;   // W: cells of the thread-private deposit window, WE: cells of the (wider) field window
 	double hz, invHz, eps, epsHi, length;
 	double dt, charge, mass, invMass;
 	double fixedScale;          // 2^fixedBits
@@ -52,7 +52,7 @@ struct PushArgs {
 	void* rho[8];               // [G] double weights or int64 fixed point: this rank's grid, or every rank's (peer-memory mode)
 	int nRho, pad1;
 	long long bndOffset;        // (uint2*)((double*)rho[r] + bndOffset) = this species' touched-node range per row (encoded maxima)
-	unsigned long long* lost;
+	unsigned long long* lost;   // [0] rings lost since upload, [1] deposits that missed the private window (re-sort trigger)
 };
 
 // Axial cell of a position: bit-exact (int)floor(z / hz) (Source/Plasma.cpp:87, Source/PenningTrap.cpp:328).
@@ -141,14 +141,14 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
 	constexpr int NV = R / 2;
 	extern __shared__ __align__(16) unsigned char smem[];
-	const int W = a.W;
-	double2* eTile = reinterpret_cast<double2*>(smem);                       // [W] (E[k], E[k+1]) of cell k0+i
-	unsigned long long* redC = reinterpret_cast<unsigned long long*>(eTile + W); // [W]
+	const int W = a.W, WE = a.WE;
+	double2* eTile = reinterpret_cast<double2*>(smem);                       // [WE] (E[k], E[k+1]) of cell kE0+i
+	unsigned long long* redC = reinterpret_cast<unsigned long long*>(eTile + WE); // [W]
 	unsigned long long* redS = redC + W;                                     // [W] u64 (fixed) or double bits
 	unsigned long long* bins = redS + W;                                     // [W][T] packed words / double sums
 	unsigned short* cnts = reinterpret_cast<unsigned short*>(bins + (size_t)W * T); // [W][T] fp64 mode only (a thread sees < 4096 rings per segment)
 	__shared__ int sKmin, sKmax;
-	__shared__ unsigned int sLost;
+	__shared__ unsigned int sLost, sFar;
 	__shared__ long long sKsum[T / 32];
 	__shared__ unsigned int sNdep[T / 32];
 
@@ -166,23 +166,26 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		const int span = bounds.y - bounds.x + 1;
 		int k0 = span <= W ? bounds.x - ((W - span) >> 1) : bounds.z - (W >> 1);
 		k0 = max(0, min(k0, a.Nz - W));
+		// the field window is wider than the deposit window (16 B per cell instead of 10 B per cell and thread): rings that
+		// have drifted out of the deposit window still gather from shared memory - a global load there would stall the warp
+		const int kE0 = max(0, min(k0 + (W >> 1) - (WE >> 1), a.Nz - WE));
 		for (int i = 0; i < W; ++i) {
 			bins[(size_t)i * T + tid] = 0ULL;
 			if (!FIXED) cnts[(size_t)i * T + tid] = 0;
 		}
 		if (PUSH) {
-			for (int i = tid; i < W; i += T) {
-				const int node = k0 + i;
+			for (int i = tid; i < WE; i += T) {
+				const int node = kE0 + i;
 				const double eL = node <= a.Nz ? a.eNodes[rowBase + node] : 0.0;
 				const double eR = node + 1 <= a.Nz ? a.eNodes[rowBase + node + 1] : 0.0;
 				eTile[i] = make_double2(eL, eR);
 			}
 		}
-		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLost = 0u; }
+		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLost = 0u; sFar = 0u; }
 		__syncthreads();
 
 		int kMin = INT_MAX, kMax = INT_MIN;
-		unsigned int lost = 0, nDep = 0;
+		unsigned int lost = 0, nDep = 0, nFar = 0;
 		long long kSum = 0;
 
 		const double2* z2 = reinterpret_cast<const double2*>(a.z);
@@ -243,8 +246,8 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				bool far = false;
 #pragma unroll
 				for (int i = 0; i < R; ++i) {
-					const unsigned int io = (unsigned int)(k[i] - k0);
-					const bool in = io < (unsigned int)W;
+					const unsigned int io = (unsigned int)(k[i] - kE0);
+					const bool in = io < (unsigned int)WE;
 					far |= live[i] && !in;
 					const double2 e = eTile[in ? io : 0u];
 					eL[i] = e.x; eR[i] = e.y;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				if (far) {
 #pragma unroll
 					for (int i = 0; i < R; ++i)
-						if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)W) {
+						if (live[i] && (unsigned int)(k[i] - kE0) >= (unsigned int)WE) {
 							eL[i] = a.eNodes[rowBase + k[i]];
 							eR[i] = a.eNodes[rowBase + k[i] + 1];
 						}
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				const unsigned int io = (unsigned int)(k[i] - k0);
 				const bool in = live[i] && io < (unsigned int)W;
 				farD |= live[i] && io >= (unsigned int)W;
+				nFar += (live[i] && io >= (unsigned int)W) ? 1u : 0u;
 				if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
 				if (in) {
 					if (FIXED) {
@@ -352,11 +356,13 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			kMax = max(kMax, __shfl_xor_sync(0xffffffffu, kMax, o));
 		}
 		lost = warp_sum(lost);
+		nFar = warp_sum(nFar);
 		kSum = warp_sum(kSum);
 		nDep = warp_sum(nDep);
 		if (lane == 0) {
 			if (kMin <= kMax) { atomicMin(&sKmin, kMin); atomicMax(&sKmax, kMax); }
 			if (lost) atomicAdd(&sLost, lost);
+			if (nFar) atomicAdd(&sFar, nFar);
 			sKsum[warp] = kSum;
 			sNdep[warp] = nDep;
 		}
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			for (int w = 0; w < T / 32; ++w) { ks += sKsum[w]; nd += sNdep[w]; }
 			a.segBounds[s] = make_int4(gMin, gMax, nd ? (int)(ks / nd) : 0, 0);   // next step's window (this CTA owns the segment)
 			if (sLost) atomicAdd(a.lost, (unsigned long long)sLost);
+			if (sFar) atomicAdd(a.lost + 1, (unsigned long long)sFar);
 		}
 		__syncthreads();
 	}
@@ -499,6 +506,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	PushArgs a{};
 	a.Nz = t->Nz;
 	a.W = t->window < t->Nz ? t->window : t->Nz;
+	a.WE = ptp_push_field_window(t);
 	a.fixedBits = t->fixedBits;
 	a.hz = t->hz;
 	a.invHz = 1.0 / t->hz;
@@ -532,11 +540,24 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 
 } // namespace
 
+// Cells of the field window: as many as fit beside the deposit bins, at most 256 and never fewer than the deposit window.
+int ptp_push_field_window(const ptp_trap* t)
+{
+	const size_t w = (size_t)(t->window < t->Nz ? t->window : t->Nz);
+	const size_t perBin = t->depositMode == PTP_DEPOSIT_FIXED64 ? 8 : 10;
+	const size_t fixedPart = w * 16 + w * (size_t)t->threads * perBin + 1024;   // reduction rows + bins + static shared memory
+	size_t we = t->smemMax > fixedPart ? (t->smemMax - fixedPart) / 16 : 0;
+	if (we > 256) we = 256;
+	if (we > (size_t)t->Nz) we = (size_t)t->Nz;
+	if (we < w) we = w;
+	return (int)we;
+}
+
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window)
 {
 	size_t w = (size_t)(window < t->Nz ? window : t->Nz);
 	size_t perBin = t->depositMode == PTP_DEPOSIT_FIXED64 ? 8 : 10;
-	return w * 16 + w * 16 + w * (size_t)threads * perBin;
+	return (size_t)ptp_push_field_window(t) * 16 + w * 16 + w * (size_t)threads * perBin;
 }
 
 int ptp_push_configure(ptp_trap* t)

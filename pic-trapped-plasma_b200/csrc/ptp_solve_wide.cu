@@ -23,7 +23,7 @@
 #include <cstdlib>
 
 #ifndef PTP_FFT_R16_DEFAULT
-#define PTP_FFT_R16_DEFAULT 0
+#define PTP_FFT_R16_DEFAULT 1
 #endif
 
 namespace {

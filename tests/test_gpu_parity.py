@@ -455,6 +455,34 @@ def test_fine_grid_full_size_properties(c1_kat, r16, monkeypatch):
     t.close()
 
 
+def test_adaptive_resort_keeps_results_and_triggers(monkeypatch, c1_kat):
+    """Electrons on a fine grid (1.6 cells of drift per step) leave the cell ranges their segments were planned for within a
+    few steps. The adaptive policy (ptp_trap_set_sort_interval(-1), the default) must notice the out-of-window deposits and
+    re-sort; with fixed-point deposits the whole trajectory is bitwise independent of the ring order, so the run with
+    re-sorts equals the run without (interval 0) ring by ring."""
+    from bench import density_on
+    monkeypatch.setenv("PTP_SORT_CHECK_STEPS", "8")
+    Nz, Nr = 4096, 64
+    el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
+    dens = density_on(Nz, Nr)
+    dt = float(c1_kat["dt"])
+    res = []
+    for interval in (0, -1):
+        t = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
+        t.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64)
+        t.set_sort_interval(interval)
+        p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+        n, _ = p.loadDensity(dens, 150.0, 400_000)
+        t.movePlasmas(dt, 60)
+        r, z, v, ids = _by_id(p)
+        res.append((r, z, v, ids, p.rhs(), p.selfPotential(), t.sorts_done(), p.getNumMacro()))
+        t.close()
+    assert res[0][6] == 0 and res[1][6] >= 1, (res[0][6], res[1][6])
+    assert res[0][7] == res[1][7]
+    for a, b in zip(res[0][:6], res[1][:6]):
+        assert np.array_equal(a, b)
+
+
 def test_edge_cases():
     t = ptp.default_trap()
     p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
