@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -188,6 +189,7 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 	PTP_CUDA(cudaGetDeviceProperties(&prop, device));
 	t->smCount = prop.multiProcessorCount;
 	t->smemMax = prop.sharedMemPerBlockOptin;
+	if (const char* e = std::getenv("PTP_PLAN_SLACK")) t->planSlack = std::atoi(e);
 	if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
 	if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));
 	PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
@@ -546,6 +548,18 @@ int ptp_trap_last_times(ptp_trap* t, double* ms4)
 			sum[ph] += ms;
 		}
 	ms4[0] = whole; ms4[1] = sum[0]; ms4[2] = sum[1]; ms4[3] = sum[2];
+	if (const char* path = std::getenv("PTP_STEP_TIMES_FILE")) {   // diagnostics: per-step phase times of the last call as CSV
+		if (FILE* f = std::fopen(path, "w")) {
+			std::fprintf(f, "step,push_deposit_ms,exchange_ms,solve_ms\n");
+			for (int s = 0; s < t->evSteps; ++s) {
+				float ms[3] = { 0, 0, 0 };
+				for (int ph = 0; ph < 3; ++ph)
+					if (cudaEventElapsedTime(&ms[ph], t->evPool[4 * s + ph], t->evPool[4 * s + ph + 1]) != cudaSuccess) cudaGetLastError();
+				std::fprintf(f, "%d,%.5f,%.5f,%.5f\n", s, ms[0], ms[1], ms[2]);
+			}
+			std::fclose(f);
+		}
+	}
 	return PTP_OK;
 }
 
@@ -658,7 +672,7 @@ int ptp_plasma_destroy(ptp_plasma* p)
 	}
 	t->plasmas.erase(t->plasmas.begin() + p->index);
 	t->eNodesValid = false;
-	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt);
+	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->sortScratch);
 	cudaFree(p->dRowOff); cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds); cudaFree(p->dLost);
 	delete p;
 	return PTP_OK;

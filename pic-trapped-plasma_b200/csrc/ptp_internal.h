@@ -37,6 +37,9 @@ struct ptp_plasma {
 	double* zAlt = nullptr;      // sort ping-pong buffers (allocated on first sort)
 	double* vAlt = nullptr;
 	long long* idAlt = nullptr;
+	std::vector<long long> altDirty; // [Nr] slots at the start of each bucket of the alternate buffers that do not hold the empty-slot pattern
+	void* sortScratch = nullptr;  // counters, cursors and chunk table of the sort (kept between sorts)
+	size_t sortScratchBytes = 0;
 	std::vector<long long> rowOff;   // [Nr+1] slot offset of each row bucket (host)
 	std::vector<long long> rowLive;  // [Nr] slots of the bucket that may hold live rings (prefix of the bucket)
 	long long* dRowOff = nullptr;
@@ -121,6 +124,8 @@ struct ptp_trap {
 	int stepsSinceCheck = 0;         // adaptive mode: steps since the out-of-window counters were last read
 	int sortCheckSteps = 64;         // adaptive mode: steps between two reads of the counters (PTP_SORT_CHECK_STEPS)
 	double sortFarFraction = 0.02;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
+	int planSlack = -1;              // cells of the deposit window left free when segments are planned (room for the rings' drift until
+	                                 // the next re-sort); -1: max(2, window / 8) (PTP_PLAN_SLACK)
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)
 	long long stepCount = 0;
 	bool eNodesValid = false;

@@ -75,25 +75,42 @@ __global__ void k_central_well(const double* __restrict__ z, const PtpSegment* _
 }
 
 // ---- K5: per-row counting sort by axial cell ---------------------------------------------------------
-// pass 1: histogram of live rings per (row, cell); shared-memory histogram per CTA chunk, then global adds.
-__global__ void __launch_bounds__(256) k_sort_count(const double* __restrict__ z, const long long* __restrict__ rowOff,
-	int Nr, int Nz, double hz, unsigned int* __restrict__ counts, int chunksPerRow)
+// The live prefix of every row bucket is cut into chunks of SORT_CHUNK slots (host table); one CTA per chunk. Rings arrive
+// nearly sorted (the loaders emit them in z order and a re-sort happens long before they mix), so most of a warp shares
+// one cell: ranks are formed per warp with match.any - one shared-memory atomic per distinct cell and warp instruction
+// instead of 32 colliding ones.
+constexpr int SORT_CHUNK = 32768;
+struct SortChunk { int row, pad; long long begin, end; };
+
+// rank of this lane among the lanes of the warp with the same key + the counter's value before the warp's update
+__device__ __forceinline__ unsigned int warp_claim(unsigned int* hist, int k, bool valid, int lane)
+{
+	const unsigned int peers = __match_any_sync(0xffffffffu, valid ? k : -1);
+	const int leader = __ffs(peers) - 1;
+	unsigned int base = 0;
+	if (valid && lane == leader) base = atomicAdd(&hist[k], (unsigned int)__popc(peers));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+}
+
+// pass 1: histogram of live rings per (row, cell)
+__global__ void __launch_bounds__(256) k_sort_count(const double* __restrict__ z, const SortChunk* __restrict__ chunks,
+	int Nz, double hz, unsigned int* __restrict__ counts)
 {
 	extern __shared__ unsigned int hist[];                 // [Nz]
-	const int r = blockIdx.x / chunksPerRow, chunk = blockIdx.x % chunksPerRow;
-	const long long b = rowOff[r], e = rowOff[r + 1];
-	if (b == e) return;
-	const long long len = (e - b + chunksPerRow - 1) / chunksPerRow;
-	const long long cb = b + chunk * len, ce = min(e, cb + len);
+	const SortChunk c = chunks[blockIdx.x];
+	const int lane = threadIdx.x & 31;
 	for (int i = threadIdx.x; i < Nz; i += blockDim.x) hist[i] = 0;
 	__syncthreads();
-	for (long long i = cb + threadIdx.x; i < ce; i += blockDim.x) {
-		const double zz = z[i];
-		if (zz == zz) atomicAdd(&hist[exact_cell(zz, hz, Nz)], 1u);
+	for (long long i0 = c.begin; i0 < c.end; i0 += blockDim.x) {
+		const long long i = i0 + threadIdx.x;
+		const double zz = i < c.end ? z[i] : __longlong_as_double(0x7ff8000000000000LL);
+		const bool valid = zz == zz;
+		warp_claim(hist, valid ? exact_cell(zz, hz, Nz) : 0, valid, lane);
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < Nz; i += blockDim.x)
-		if (hist[i]) atomicAdd(&counts[(size_t)r * Nz + i], hist[i]);
+		if (hist[i]) atomicAdd(&counts[(size_t)c.row * Nz + i], hist[i]);
 }
 
 // pass 2: exclusive scan of each row's cell counts -> cursor[row][cell] (slot offsets inside the bucket), live[row].
@@ -118,41 +135,57 @@ __global__ void __launch_bounds__(256) k_sort_scan(const unsigned int* __restric
 	for (int i = b; i < e; ++i) { cursor[(size_t)r * Nz + i] = run; run += counts[(size_t)r * Nz + i]; }
 }
 
-// pass 3: scatter. One CTA per (row, chunk); ranks inside the CTA from a shared histogram, one global
-// atomic per (CTA, non-empty cell) to reserve the destination range.
+// pass 3: scatter. Ranks inside the chunk from the shared histogram, one global atomic per (chunk, non-empty cell) to
+// reserve the destination range.
 __global__ void __launch_bounds__(256) k_sort_scatter(const double* __restrict__ z, const double* __restrict__ v,
 	const long long* __restrict__ id, double* __restrict__ zOut, double* __restrict__ vOut, long long* __restrict__ idOut,
-	const long long* __restrict__ rowOff, int Nr, int Nz, double hz, unsigned long long* __restrict__ cursor, int chunksPerRow)
+	const long long* __restrict__ rowOff, const SortChunk* __restrict__ chunks, int Nz, double hz, unsigned long long* __restrict__ cursor)
 {
 	extern __shared__ unsigned int sh[];                   // hist[Nz] then base (as 2 x u32 per cell)
 	unsigned int* hist = sh;
 	unsigned long long* base = reinterpret_cast<unsigned long long*>(sh + ((Nz + 1) & ~1));
-	const int r = blockIdx.x / chunksPerRow, chunk = blockIdx.x % chunksPerRow;
-	const long long b = rowOff[r], e = rowOff[r + 1];
-	if (b == e) return;
-	const long long len = (e - b + chunksPerRow - 1) / chunksPerRow;
-	const long long cb = b + chunk * len, ce = min(e, cb + len);
+	const SortChunk c = chunks[blockIdx.x];
+	const int lane = threadIdx.x & 31;
+	const long long b = rowOff[c.row];
 	for (int i = threadIdx.x; i < Nz; i += blockDim.x) hist[i] = 0;
 	__syncthreads();
-	for (long long i = cb + threadIdx.x; i < ce; i += blockDim.x) {
-		const double zz = z[i];
-		if (zz == zz) atomicAdd(&hist[exact_cell(zz, hz, Nz)], 1u);
+	for (long long i0 = c.begin; i0 < c.end; i0 += blockDim.x) {
+		const long long i = i0 + threadIdx.x;
+		const double zz = i < c.end ? z[i] : __longlong_as_double(0x7ff8000000000000LL);
+		const bool valid = zz == zz;
+		warp_claim(hist, valid ? exact_cell(zz, hz, Nz) : 0, valid, lane);
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < Nz; i += blockDim.x) {
-		const unsigned int c = hist[i];
-		base[i] = c ? atomicAdd(&cursor[(size_t)r * Nz + i], (unsigned long long)c) : 0ULL;
+		const unsigned int n = hist[i];
+		base[i] = n ? atomicAdd(&cursor[(size_t)c.row * Nz + i], (unsigned long long)n) : 0ULL;
 		hist[i] = 0;
 	}
 	__syncthreads();
-	for (long long i = cb + threadIdx.x; i < ce; i += blockDim.x) {
-		const double zz = z[i];
-		if (!(zz == zz)) continue;
-		const int k = exact_cell(zz, hz, Nz);
-		const long long dst = b + (long long)base[k] + atomicAdd(&hist[k], 1u);
-		zOut[dst] = zz;
-		vOut[dst] = v[i];
-		idOut[dst] = id[i];
+	for (long long i0 = c.begin; i0 < c.end; i0 += blockDim.x) {
+		const long long i = i0 + threadIdx.x;
+		const double zz = i < c.end ? z[i] : __longlong_as_double(0x7ff8000000000000LL);
+		const bool valid = zz == zz;
+		const int k = valid ? exact_cell(zz, hz, Nz) : 0;
+		const unsigned int rank = warp_claim(hist, k, valid, lane);
+		if (valid) {
+			const long long dst = b + (long long)base[k] + rank;
+			zOut[dst] = zz;
+			vOut[dst] = v[i];
+			idOut[dst] = id[i];
+		}
+	}
+}
+
+// Slots of every bucket behind its (new) live prefix get the empty-slot pattern: NaN position, zero speed, id -1.
+__global__ void __launch_bounds__(256) k_sort_pad(double* __restrict__ z, double* __restrict__ v, long long* __restrict__ id,
+	const long long* __restrict__ rowOff, const unsigned long long* __restrict__ live, const long long* __restrict__ oldLive)
+{
+	const int r = blockIdx.y;
+	const long long b = rowOff[r] + (long long)live[r], e = rowOff[r] + oldLive[r];   // slots beyond the mark already hold the pattern
+	const double nan = __longlong_as_double(-1LL);
+	for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x) {
+		z[i] = nan; v[i] = 0.0; id[i] = -1LL;
 	}
 }
 
@@ -184,7 +217,8 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 	int nCta = t->ctas > 0 ? t->ctas : t->smCount;
 	if (totalTiles < nCta) nCta = (int)totalTiles;
 	const int W = t->window < t->Nz ? t->window : t->Nz;
-	const int limit = std::max(1, W - std::max(2, W / 8));      // cells a planned segment may span
+	const int slack = t->planSlack >= 0 ? t->planSlack : std::max(2, W / 8);
+	const int limit = std::max(1, W - slack);                   // cells a planned segment may span
 	p->segs.clear();
 	p->ctaSegBegin.assign(1, 0);
 	p->nCta = nCta;
@@ -267,45 +301,71 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 }
 
 // K5. Rings of each row are re-ordered by axial cell into the alternate buffers (lost rings dropped), the
-// buffers are swapped and the segment tables rebuilt on the shrunken live ranges.
+// buffers are swapped and the segment tables rebuilt on the shrunken live ranges. Scratch (alternate ring buffers, the
+// per-(row, cell) counters) is allocated on the first sort and kept.
 int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 {
 	if (p->cap == 0) return PTP_OK;
 	++t->cfgEpoch;
 	const int Nr = t->Nr, Nz = t->Nz;
-	if (!p->zAlt) {
+	const bool freshAlt = !p->zAlt;
+	if (freshAlt) {
 		PTP_CUDA(cudaMalloc(&p->zAlt, p->cap * sizeof(double)));
 		PTP_CUDA(cudaMalloc(&p->vAlt, p->cap * sizeof(double)));
 		PTP_CUDA(cudaMalloc(&p->idAlt, p->cap * sizeof(long long)));
+		// padding pattern everywhere once; later sorts only rewrite the slots between the new and the old live prefix
+		PTP_CUDA(cudaMemsetAsync(p->zAlt, 0xFF, p->cap * sizeof(double), t->stream));
+		PTP_CUDA(cudaMemsetAsync(p->vAlt, 0, p->cap * sizeof(double), t->stream));
+		PTP_CUDA(cudaMemsetAsync(p->idAlt, 0xFF, p->cap * sizeof(long long), t->stream));
+		p->altDirty.assign(Nr, 0);
 	}
-	unsigned int* dCounts = nullptr;
-	unsigned long long* dCursor = nullptr;
-	PTP_CUDA(cudaMalloc(&dCounts, (size_t)Nr * Nz * sizeof(unsigned int)));
-	PTP_CUDA(cudaMalloc(&dCursor, ((size_t)Nr * Nz + Nr) * sizeof(unsigned long long)));
-	unsigned long long* dLive = dCursor + (size_t)Nr * Nz;
-	PTP_CUDA(cudaMemsetAsync(dCounts, 0, (size_t)Nr * Nz * sizeof(unsigned int), t->stream));
-	PTP_CUDA(cudaMemsetAsync(p->zAlt, 0xFF, p->cap * sizeof(double), t->stream));
-	PTP_CUDA(cudaMemsetAsync(p->vAlt, 0, p->cap * sizeof(double), t->stream));
-	PTP_CUDA(cudaMemsetAsync(p->idAlt, 0xFF, p->cap * sizeof(long long), t->stream));
-	long long maxRow = 0;
-	for (int r = 0; r < Nr; ++r) maxRow = std::max(maxRow, p->rowOff[r + 1] - p->rowOff[r]);
-	int chunksPerRow = (int)std::min<long long>(std::max<long long>(1, maxRow / 16384), 4096);
+	std::vector<SortChunk> chunks;
+	for (int r = 0; r < Nr; ++r)
+		for (long long b = 0; b < p->rowLive[r]; b += SORT_CHUNK) {
+			SortChunk c;
+			c.row = r; c.pad = 0;
+			c.begin = p->rowOff[r] + b;
+			c.end = p->rowOff[r] + std::min<long long>(p->rowLive[r], b + SORT_CHUNK);
+			chunks.push_back(c);
+		}
+	// scratch: counts [Nr][Nz] u32 | cursor [Nr][Nz] u64 | live [Nr] u64 | oldLive [Nr] i64 | chunk table
+	const size_t nCells = (size_t)Nr * Nz;
+	const size_t need = nCells * sizeof(unsigned int) + (nCells + 2 * (size_t)Nr) * sizeof(unsigned long long) + (chunks.size() + 1) * sizeof(SortChunk) + 64;
+	if (p->sortScratchBytes < need) {
+		cudaFree(p->sortScratch);
+		p->sortScratch = nullptr; p->sortScratchBytes = 0;
+		PTP_CUDA(cudaMalloc(&p->sortScratch, need));
+		p->sortScratchBytes = need;
+	}
+	unsigned long long* dCursor = reinterpret_cast<unsigned long long*>(p->sortScratch);
+	unsigned long long* dLive = dCursor + nCells;
+	long long* dOldLive = reinterpret_cast<long long*>(dLive + Nr);
+	SortChunk* dChunks = reinterpret_cast<SortChunk*>(dOldLive + Nr);
+	unsigned int* dCounts = reinterpret_cast<unsigned int*>(dChunks + chunks.size() + 1);
+	PTP_CUDA(cudaMemsetAsync(dCounts, 0, nCells * sizeof(unsigned int), t->stream));
+	PTP_CUDA(cudaMemcpyAsync(dOldLive, p->altDirty.data(), (size_t)Nr * sizeof(long long), cudaMemcpyHostToDevice, t->stream));
+	if (!chunks.empty()) PTP_CUDA(cudaMemcpyAsync(dChunks, chunks.data(), chunks.size() * sizeof(SortChunk), cudaMemcpyHostToDevice, t->stream));
 	const size_t smCount = (size_t)Nz * sizeof(unsigned int);
 	const size_t smScatter = (size_t)((Nz + 1) & ~1) * sizeof(unsigned int) + (size_t)Nz * sizeof(unsigned long long);
-	k_sort_count<<<Nr * chunksPerRow, 256, smCount, t->stream>>>(p->z, p->dRowOff, Nr, Nz, t->hz, dCounts, chunksPerRow);
+	if (smScatter > t->smemMax) { ptp_set_error("ptp_trap_sort: Nz too large for the sort kernels of this build"); return PTP_EINVAL; }
+	PTP_CUDA(cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smCount));
+	PTP_CUDA(cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smScatter));
+	const unsigned int nChunks = (unsigned int)chunks.size();
+	if (nChunks) k_sort_count<<<nChunks, 256, smCount, t->stream>>>(p->z, dChunks, Nz, t->hz, dCounts);
 	k_sort_scan<<<Nr, 256, 0, t->stream>>>(dCounts, Nz, dCursor, dLive);
-	k_sort_scatter<<<Nr * chunksPerRow, 256, smScatter, t->stream>>>(p->z, p->v, p->id, p->zAlt, p->vAlt, p->idAlt,
-		p->dRowOff, Nr, Nz, t->hz, dCursor, chunksPerRow);
+	if (nChunks) k_sort_scatter<<<nChunks, 256, smScatter, t->stream>>>(p->z, p->v, p->id, p->zAlt, p->vAlt, p->idAlt, p->dRowOff, dChunks, Nz, t->hz, dCursor);
+	// the alternate buffers hold the empty-slot pattern beyond altDirty (what they held when they were last the primary
+	// ones): only the slots between the new live prefix and that mark need it again
+	k_sort_pad<<<dim3(32, Nr), 256, 0, t->stream>>>(p->zAlt, p->vAlt, p->idAlt, p->dRowOff, dLive, dOldLive);
 	cudaError_t e = cudaGetLastError();
-	if (e != cudaSuccess) { cudaFree(dCounts); cudaFree(dCursor); return ptp_cuda_fail(e, "sort launch", __FILE__, __LINE__); }
-	t->lastLaunches += 3;
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "sort launch", __FILE__, __LINE__);
+	t->lastLaunches += 4;
 	std::vector<unsigned long long> live(Nr);
 	PTP_CUDA(cudaMemcpyAsync(live.data(), dLive, Nr * sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
-	cudaFree(dCounts); cudaFree(dCursor);
 	std::swap(p->z, p->zAlt); std::swap(p->v, p->vAlt); std::swap(p->id, p->idAlt);
 	long long total = 0;
-	for (int r = 0; r < Nr; ++r) { p->rowLive[r] = (long long)live[r]; total += (long long)live[r]; }
+	for (int r = 0; r < Nr; ++r) { p->altDirty[r] = p->rowLive[r]; p->rowLive[r] = (long long)live[r]; total += (long long)live[r]; }
 	p->nAlive = total;
 	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, 2 * sizeof(unsigned long long), t->stream));
 	p->nUploaded = total;                                  // loss counter restarts from the compacted population

@@ -529,7 +529,10 @@ __global__ void __launch_bounds__(256, 2) k_idct_r16_field(const double* __restr
 	extern __shared__ double2 fbw[];                            // [16][RS] exchange buffer; natural-order Z after the third round
 	double* tot = reinterpret_cast<double*>(fbw + 16 * RS);     // [N+1] running total potential of the row (FIELD)
 	const int t = threadIdx.x, row = blockIdx.x;
-	if (FIELD) for (int k = t; k <= N; k += 256) tot[k] = phiTrap[(size_t)row * n1 + k];
+	if (FIELD) {                                                // asynchronous: needed only at the first read-out
+		for (int k = t; k <= N; k += 256) cpa8(&tot[k], phiTrap + (size_t)row * n1 + k, true);
+		cpa_commit();
+	}
 	const double2 wA = __ldg(&tw[2 * t]);                       // W_N^t      (tw[j] = exp(-i pi j / N))
 	const double2 wB = __ldg(&tw[32 * (t & 15)]);               // W_256^n0
 	for (int sp = 0; sp < nS; ++sp) {
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(256, 2) k_idct_r16_field(const double* __restr
 		const double a0 = a[0], aN = a[N];
 		fft16(x);
 		twiddle16(x, wA);
+		if (FIELD && sp == 0) cpa_wait<0>();                    // this thread's part of tot has landed; the barriers below publish it
 		__syncthreads();                                        // the previous species' read-out is done with fbw
 #pragma unroll
 		for (int k0 = 0; k0 < 16; ++k0) fbw[(t >> 4) * RS + k0 * 16 + (t & 15)] = x[k0];

@@ -27,6 +27,9 @@ static thread_local Idx threadIdx;
 static thread_local Idx blockIdx;
 static std::barrier<>* g_bar;
 static inline void __syncthreads() { g_bar->arrive_and_wait(); }
+static inline void cpa8(void* dst, const void* src, bool valid) { *(double*)dst = valid ? *(const double*)src : 0.0; }
+static inline void cpa_commit() {}
+template <int N> static inline void cpa_wait() {}
 static double2* fbw;   // "extern __shared__ double2 fbw[];" in the kernel becomes a redeclaration of this pointer
 #define extern_shared_fbw
 
