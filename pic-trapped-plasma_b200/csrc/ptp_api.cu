@@ -672,7 +672,7 @@ int ptp_plasma_destroy(ptp_plasma* p)
 	}
 	t->plasmas.erase(t->plasmas.begin() + p->index);
 	t->eNodesValid = false;
-	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->sortScratch);
+	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->sortScratch); cudaFree(p->planScratch);
 	cudaFree(p->dRowOff); cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds); cudaFree(p->dLost);
 	delete p;
 	return PTP_OK;

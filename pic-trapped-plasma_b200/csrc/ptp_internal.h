@@ -48,6 +48,9 @@ struct ptp_plasma {
 	PtpSegment* dSegs = nullptr;
 	int* dCtaSegBegin = nullptr;
 	int4* dSegBounds = nullptr;      // per segment: min / max / mean axial cell of its live rings (x, y, z)
+	size_t segCap = 0, ctaCap = 0;   // allocated entries of dSegs / dSegBounds and of dCtaSegBegin (grow-only: re-plans are frequent)
+	void* planScratch = nullptr;     // tile list, tile bounds and counters of ptp_tile_bounds (grow-only)
+	size_t planScratchBytes = 0;
 	int nCta = 0;
 	unsigned long long* dLost = nullptr; // [2] device counters: rings lost since upload; deposits outside the private window since the last check
 	bool boundsValid = false;
@@ -122,10 +125,10 @@ struct ptp_trap {
 	int threads = 512, window = 44, ctas = 0, ringsPerThread = 4;
 	int sortInterval = -1;           // > 0: re-sort every so many steps; 0: never; -1: when the push kernel reports too many out-of-window deposits
 	int stepsSinceCheck = 0;         // adaptive mode: steps since the out-of-window counters were last read
-	int sortCheckSteps = 64;         // adaptive mode: steps between two reads of the counters (PTP_SORT_CHECK_STEPS)
-	double sortFarFraction = 0.02;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
-	int planSlack = -1;              // cells of the deposit window left free when segments are planned (room for the rings' drift until
-	                                 // the next re-sort); -1: max(2, window / 8) (PTP_PLAN_SLACK)
+	int sortCheckSteps = 16;         // adaptive mode: steps between two reads of the counters (PTP_SORT_CHECK_STEPS)
+	double sortFarFraction = 1e-4;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
+	int planSlack = -1;              // rows whose rings span more cells than the deposit window are cut into segments that leave this many
+	                                 // cells of the window free (room for the rings' drift until the next re-sort); -1: window / 2 (PTP_PLAN_SLACK)
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)
 	long long stepCount = 0;
 	bool eNodesValid = false;

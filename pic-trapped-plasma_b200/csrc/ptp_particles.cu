@@ -217,8 +217,21 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 	int nCta = t->ctas > 0 ? t->ctas : t->smCount;
 	if (totalTiles < nCta) nCta = (int)totalTiles;
 	const int W = t->window < t->Nz ? t->window : t->Nz;
-	const int slack = t->planSlack >= 0 ? t->planSlack : std::max(2, W / 8);
-	const int limit = std::max(1, W - slack);                   // cells a planned segment may span
+	// A row whose rings fit the window with a little room to spare is never split by cell range: wherever its rings drift
+	// inside that range, the window covers them (the reference's default plasma: 37 cells in a 44-cell window). Wider rows are
+	// cut into segments that use only part of the window, so that rings can drift for many steps before any of them leaves
+	// its segment's window - an out-of-window deposit costs a global atomic on a contended node, ~10^3 x an in-window one.
+	const int fitLimit = std::max(1, W - std::max(2, W / 8));
+	const int wideLimit = std::max(1, W - (t->planSlack >= 0 ? t->planSlack : W / 2));
+	std::vector<int> rowLimit(t->Nr, fitLimit);
+	{
+		std::vector<int> rlo(t->Nr, INT_MAX), rhi(t->Nr, INT_MIN);
+		for (size_t q = 0; q < tiles.size(); ++q)
+			if (tb[q].x <= tb[q].y) { rlo[tiles[q].row] = std::min(rlo[tiles[q].row], tb[q].x); rhi[tiles[q].row] = std::max(rhi[tiles[q].row], tb[q].y); }
+		for (int r = 0; r < t->Nr; ++r)
+			if (rlo[r] <= rhi[r] && rhi[r] - rlo[r] + 1 > fitLimit) rowLimit[r] = std::min(fitLimit, wideLimit);
+	}
+	const int limit = fitLimit;                                 // cells a tile may span before it counts as wide
 	p->segs.clear();
 	p->ctaSegBegin.assign(1, 0);
 	p->nCta = nCta;
@@ -239,7 +252,7 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 			const bool alone = !mostlyWide && isWide(i);
 			while (!alone && i + n < totalTiles && tiles[i + n].row == tiles[i].row) {
 				const int nlo = std::min(lo, tb[i + n].x), nhi = std::max(hi, tb[i + n].y);
-				if (!mostlyWide && nlo <= nhi && nhi - nlo + 1 > limit) break;
+				if (!mostlyWide && nlo <= nhi && nhi - nlo + 1 > rowLimit[tiles[i].row]) break;
 				lo = nlo; hi = nhi;
 				++n;
 			}
@@ -284,12 +297,22 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 		}
 		while ((int)p->ctaSegBegin.size() < nCta + 1) p->ctaSegBegin.push_back((int)p->segs.size());
 	}
-	cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds);
-	p->dSegs = nullptr; p->dCtaSegBegin = nullptr; p->dSegBounds = nullptr;
+	if (p->segs.size() > p->segCap) {
+		cudaFree(p->dSegs); cudaFree(p->dSegBounds);
+		p->dSegs = nullptr; p->dSegBounds = nullptr; p->segCap = 0;
+		const size_t cap = p->segs.size() + p->segs.size() / 2 + 64;
+		PTP_CUDA(cudaMalloc(&p->dSegs, cap * sizeof(PtpSegment)));
+		PTP_CUDA(cudaMalloc(&p->dSegBounds, cap * sizeof(int4)));
+		p->segCap = cap;
+	}
+	if (p->ctaSegBegin.size() > p->ctaCap) {
+		cudaFree(p->dCtaSegBegin);
+		p->dCtaSegBegin = nullptr; p->ctaCap = 0;
+		const size_t cap = p->ctaSegBegin.size() + 64;
+		PTP_CUDA(cudaMalloc(&p->dCtaSegBegin, cap * sizeof(int)));
+		p->ctaCap = cap;
+	}
 	if (!p->segs.empty()) {
-		PTP_CUDA(cudaMalloc(&p->dSegs, p->segs.size() * sizeof(PtpSegment)));
-		PTP_CUDA(cudaMalloc(&p->dCtaSegBegin, p->ctaSegBegin.size() * sizeof(int)));
-		PTP_CUDA(cudaMalloc(&p->dSegBounds, p->segs.size() * sizeof(int4)));
 		PTP_CUDA(cudaMemcpyAsync(p->dSegs, p->segs.data(), p->segs.size() * sizeof(PtpSegment), cudaMemcpyHostToDevice, t->stream));
 		PTP_CUDA(cudaMemcpyAsync(p->dCtaSegBegin, p->ctaSegBegin.data(), p->ctaSegBegin.size() * sizeof(int), cudaMemcpyHostToDevice, t->stream));
 		PTP_CUDA(cudaMemcpyAsync(p->dSegBounds, segBounds.data(), segBounds.size() * sizeof(int4), cudaMemcpyHostToDevice, t->stream));

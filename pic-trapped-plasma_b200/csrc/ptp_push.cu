@@ -600,13 +600,17 @@ int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& t
 	if (tiles.empty()) return PTP_OK;
 	const PushArgs a = make_args(t, p, 0.0);
 	const int n = (int)tiles.size();
-	PtpSegment* dTiles = nullptr;
-	int2* dB = nullptr;
-	unsigned long long* dLive = nullptr;
-	PTP_CUDA(cudaMalloc(&dTiles, (size_t)n * sizeof(PtpSegment)));
-	PTP_CUDA(cudaMalloc(&dB, (size_t)n * sizeof(int2)));
-	PTP_CUDA(cudaMalloc(&dLive, sizeof(unsigned long long) + 2 * sizeof(int)));
+	const size_t need = (size_t)n * (sizeof(PtpSegment) + sizeof(int2)) + 64;
+	if (p->planScratchBytes < need) {
+		cudaFree(p->planScratch);
+		p->planScratch = nullptr; p->planScratchBytes = 0;
+		PTP_CUDA(cudaMalloc(&p->planScratch, need + need / 2));
+		p->planScratchBytes = need + need / 2;
+	}
+	unsigned long long* dLive = static_cast<unsigned long long*>(p->planScratch);   // counter + two flags in the first 64 bytes
 	int* dInvalid = reinterpret_cast<int*>(dLive + 1);
+	PtpSegment* dTiles = reinterpret_cast<PtpSegment*>(static_cast<char*>(p->planScratch) + 64);
+	int2* dB = reinterpret_cast<int2*>(dTiles + n);
 	PTP_CUDA(cudaMemcpyAsync(dTiles, tiles.data(), (size_t)n * sizeof(PtpSegment), cudaMemcpyHostToDevice, t->stream));
 	PTP_CUDA(cudaMemsetAsync(dLive, 0, sizeof(unsigned long long) + 2 * sizeof(int), t->stream));
 	const int grid = n < t->smCount * 32 ? n : t->smCount * 32;
@@ -618,7 +622,6 @@ int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& t
 	if (e == cudaSuccess) e = cudaMemcpyAsync(&live, dLive, sizeof(live), cudaMemcpyDeviceToHost, t->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(&invalid, dInvalid, sizeof(int), cudaMemcpyDeviceToHost, t->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
-	cudaFree(dTiles); cudaFree(dB); cudaFree(dLive);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_tile_bounds", __FILE__, __LINE__);
 	t->lastLaunches++;
 	if (invalid) { ptp_set_error("ring position outside (0, trap length)"); return PTP_EINVAL; }
