@@ -112,8 +112,8 @@ int ptp_trap_sort(ptp_trap* t);
 /* Re-sort policy inside ptp_trap_step / ptp_trap_step_programme. interval > 0: every `interval` steps; 0: never;
  * -1 (default): adaptive - the push kernel counts the deposits that missed its thread-private cell window (rings that
  * drifted out of the cell range their segment was planned for: long plasmas on fine grids), the counters are read every
- * PTP_SORT_CHECK_STEPS steps (environment, default 64) and a species is re-sorted when more than PTP_SORT_FAR_FRACTION
- * (default 0.02) of its deposits missed. The reference keeps its rings in one std::vector in load order
+ * PTP_SORT_CHECK_STEPS steps (environment, default 16) and a species is re-sorted when its miss rate has risen by more
+ * than PTP_SORT_FAR_FRACTION (default 5e-5 per ring-step) over the rate measured right after its last load or sort. The reference keeps its rings in one std::vector in load order
  * (Source/Plasma.hpp:46); ring identities survive a sort (ptp_plasma_download returns the upload index of every ring).
  * CUDA-graph replay (ptp_trap_set_graph) runs without the adaptive check. */
 int ptp_trap_set_sort_interval(ptp_trap* t, int interval);

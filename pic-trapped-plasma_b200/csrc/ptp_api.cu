@@ -382,7 +382,9 @@ int one_step(ptp_trap* t, double dt, cudaEvent_t* e)
 // K5 policy after a step. Fixed interval: every sortInterval steps. Adaptive (sortInterval < 0): the push kernel counts the
 // deposits that missed the thread-private window (rings that drifted away from the cell range their segment was planned
 // for - long plasmas on fine grids); every sortCheckSteps steps the counters are read back, and a species whose miss rate
-// exceeds sortFarFraction is re-sorted by axial cell, which also re-plans its segments.
+// has risen by more than sortFarFraction (and by more than half) over the rate measured right after its last load / sort
+// is re-sorted by axial cell, which also re-plans its segments. Measured on the 4096 x 1024 grid: 1e-4 misses per
+// ring-step already cost the push kernel 18 % (same-node global atomics), 5e-3 make it 4.6 x slower.
 int maintain_order(ptp_trap* t)
 {
 	if (t->sortInterval > 0) {
@@ -390,9 +392,10 @@ int maintain_order(ptp_trap* t)
 			for (ptp_plasma* p : t->plasmas) { PTP_TRY(ptp_sort_plasma(t, p)); ++t->sortsDone; }
 		return PTP_OK;
 	}
-	if (t->sortInterval == 0 || ++t->stepsSinceCheck < t->sortCheckSteps) return PTP_OK;
+	if (t->sortInterval == 0 || ++t->stepsSinceCheck < std::min(t->nextCheckSteps, t->sortCheckSteps)) return PTP_OK;
 	const int steps = t->stepsSinceCheck;
 	t->stepsSinceCheck = 0;
+	t->nextCheckSteps = t->sortCheckSteps;
 	const size_t nS = t->plasmas.size();
 	std::vector<unsigned long long> h(2 * nS, 0ULL);
 	for (size_t s = 0; s < nS; ++s)
@@ -401,10 +404,20 @@ int maintain_order(ptp_trap* t)
 	for (size_t s = 0; s < nS; ++s) {
 		ptp_plasma* p = t->plasmas[s];
 		const unsigned long long far = h[2 * s + 1];
-		if (!far) continue;
 		const double alive = (double)(p->nUploaded - (int64_t)h[2 * s]);
-		if ((double)far > t->sortFarFraction * alive * steps) { PTP_TRY(ptp_sort_plasma(t, p)); ++t->sortsDone; }   // clears the counters
-		else PTP_CUDA(cudaMemsetAsync(p->dLost + 1, 0, sizeof(unsigned long long), t->stream));
+		const double rate = alive > 0 ? (double)far / (alive * steps) : 0.0;
+		bool sort;
+		if (p->farBaseline < 0) {                               // first reading after a load / sort: what is left is not the drift's doing,
+			sort = rate > 0.05;                                 // unless the rings came in unordered
+			if (!sort) p->farBaseline = rate;
+		}
+		else sort = rate > p->farBaseline + std::max(t->sortFarFraction, 0.5 * p->farBaseline);
+		if (sort) {
+			PTP_TRY(ptp_sort_plasma(t, p));                     // clears the counters and the baseline
+			++t->sortsDone;
+			t->nextCheckSteps = 4;
+		}
+		else if (far) PTP_CUDA(cudaMemsetAsync(p->dLost + 1, 0, sizeof(unsigned long long), t->stream));
 	}
 	return PTP_OK;
 }

@@ -37,6 +37,8 @@ struct ptp_plasma {
 	double* zAlt = nullptr;      // sort ping-pong buffers (allocated on first sort)
 	double* vAlt = nullptr;
 	long long* idAlt = nullptr;
+	double farBaseline = -1.0;    // out-of-window deposits per ring-step right after the last load / sort (what a sort cannot remove:
+	                              // the sparse tails of a row, whose tiles are wider than the window); < 0: not measured yet
 	std::vector<long long> altDirty; // [Nr] slots at the start of each bucket of the alternate buffers that do not hold the empty-slot pattern
 	void* sortScratch = nullptr;  // counters, cursors and chunk table of the sort (kept between sorts)
 	size_t sortScratchBytes = 0;
@@ -125,8 +127,9 @@ struct ptp_trap {
 	int threads = 512, window = 44, ctas = 0, ringsPerThread = 4;
 	int sortInterval = -1;           // > 0: re-sort every so many steps; 0: never; -1: when the push kernel reports too many out-of-window deposits
 	int stepsSinceCheck = 0;         // adaptive mode: steps since the out-of-window counters were last read
+	int nextCheckSteps = 4;          // adaptive mode: steps until the next read (short right after a load / sort: measures the baseline)
 	int sortCheckSteps = 16;         // adaptive mode: steps between two reads of the counters (PTP_SORT_CHECK_STEPS)
-	double sortFarFraction = 1e-4;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
+	double sortFarFraction = 5e-5;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
 	int planSlack = -1;              // rows whose rings span more cells than the deposit window are cut into segments that leave this many
 	                                 // cells of the window free (room for the rings' drift until the next re-sort); -1: window / 2 (PTP_PLAN_SLACK)
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)

@@ -392,6 +392,7 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 	p->nAlive = total;
 	PTP_CUDA(cudaMemsetAsync(p->dLost, 0, 2 * sizeof(unsigned long long), t->stream));
 	p->nUploaded = total;                                  // loss counter restarts from the compacted population
+	p->farBaseline = -1.0;
 	return ptp_build_segments(t, p);
 }
 
@@ -418,6 +419,9 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 	cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
 	p->zAlt = p->vAlt = nullptr; p->idAlt = nullptr; p->dRowOff = nullptr;
 	p->cap = newCap;
+	p->farBaseline = -1.0;
+	t->stepsSinceCheck = 0;
+	t->nextCheckSteps = 4;
 	p->nUploaded = n;
 	p->nAlive = n;
 	p->macroChargeDensity = macroChargeDensity;
