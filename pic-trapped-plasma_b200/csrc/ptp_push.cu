@@ -34,6 +34,7 @@
 
 namespace {
 
+// [emu-begin] (tests/emu/emu_push.sh compiles the text between these markers for the host: tests/emu/emu_push.cpp)
 constexpr double kMagic = 6755399441055744.0;            // 2^52 + 2^51: floor via add.rm, integer in the low word
 constexpr unsigned long long kPackBias = 0x4320000000000000ULL; // bits(2^52 + x) - bias = (1 << 52) | x
 constexpr unsigned long long kSumMask = (1ULL << 52) - 1;
@@ -126,7 +127,11 @@ __device__ __forceinline__ void st_ring(double2* p, double2 v) { *p = v; }
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
+#ifndef PTP_HOST_EMU
 	asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+#else
+	(void)p;
+#endif
 }
 
 template <typename T> __device__ __forceinline__ T warp_sum(T x)
@@ -436,6 +441,8 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		__syncthreads();
 	}
 }
+
+// [emu-end]
 
 // Axial cell range and live count of every tile (window planning at upload / after a sort) and validation of the
 // positions. One CTA per tile; tiles[] lists them as one-tile segments.

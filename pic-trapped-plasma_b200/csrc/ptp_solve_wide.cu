@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(256, 2) k_idct_fft_field(const double* __restr
 // 16-byte accesses). Shared-memory traffic per row and species: 6 x 64 KB (three writes, three reads) against 15 x 64 KB for
 // the radix-2 pass pairs, and five barriers against eight. The read-out forms phi_k and phi_{N-k} from the same pair
 // (Z_k, Z_{N-k}). tools/fft16_model.py is a thread-level model of this kernel (index maps, twiddles, bank groups).
-// [r16-begin] (tools/emu_r16.sh compiles the text between these markers for the host and runs it on 256 CPU threads)
+// [r16-begin] (tests/emu/emu_r16.sh compiles the text between these markers for the host and runs it on 256 CPU threads)
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // 4-point transform, exp(-2 pi i j k / 4), in place

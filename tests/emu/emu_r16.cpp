@@ -1,37 +1,10 @@
 // Host emulation of k_idct_r16_field: the kernel text between the [r16-begin] / [r16-end] markers of
 // pic-trapped-plasma_b200/csrc/ptp_solve_wide.cu is compiled unchanged for the CPU (CUDA keywords shimmed below) and run
 // as one CTA of 256 std::threads with a std::barrier for __syncthreads(). Checks phi against the DCT-I sum in long double
-// and the node field against its definition. Build + run: tools/emu_r16.sh
-#include <barrier>
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <thread>
-#include <vector>
+// and the node field against its definition. Build + run: tests/emu/emu_r16.sh
+#include "cuda_host_shim.h"
 
-struct double2 { double x, y; };
-static inline double2 make_double2(double x, double y) { return double2{ x, y }; }
-#define __device__
-#define __forceinline__ inline
-#define __global__
-#define __restrict__
-#define __launch_bounds__(...)
-#define __shared__
-template <class T> static inline T __ldg(const T* p) { return *p; }
-static inline double __dadd_rn(double a, double b) { return a + b; }
-static inline double __dsub_rn(double a, double b) { return a - b; }
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __ddiv_rn(double a, double b) { return a / b; }
-struct Idx { int x; };
-static thread_local Idx threadIdx;
-static thread_local Idx blockIdx;
-static std::barrier<>* g_bar;
-static inline void __syncthreads() { g_bar->arrive_and_wait(); }
-static inline void cpa8(void* dst, const void* src, bool valid) { *(double*)dst = valid ? *(const double*)src : 0.0; }
-static inline void cpa_commit() {}
-template <int N> static inline void cpa_wait() {}
-static double2* fbw;   // "extern __shared__ double2 fbw[];" in the kernel becomes a redeclaration of this pointer
-#define extern_shared_fbw
+static double2* fbw;   // "extern __shared__ double2 fbw[];" in the kernel becomes a use of this pointer
 
 #include "r16_snippet.inc"
 
@@ -48,15 +21,10 @@ int main()
 	std::vector<double2> smem(16 * 257 + (N + 1) / 2 + 8);
 	fbw = smem.data();
 	const double hz = 1.6625e-5;
-	std::barrier<> bar(256);
-	g_bar = &bar;
-	std::vector<std::thread> th;
-	for (int t = 0; t < 256; ++t)
-		th.emplace_back([&, t] {
-			threadIdx.x = t; blockIdx.x = row;
-			k_idct_r16_field<true>(alpha.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), nS, Nr, hz);
-		});
-	for (auto& x : th) x.join();
+	emu_launch(1, 256, [&] {
+		blockIdx.x = row;
+		k_idct_r16_field<true>(alpha.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), nS, Nr, hz);
+	});
 	// reference: phi_k = sum_m a_m cos(pi m k / N) in long double with exact argument reduction (m k mod 2N)
 	double worst = 0, norm = 0, err = 0;
 	std::vector<long double> tot(n1);

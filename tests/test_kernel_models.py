@@ -1,5 +1,5 @@
 """CPU checks of device code that needs no GPU: the radix-16 inverse-DCT kernel's index maps / bank groups (numpy model)
-and the kernel's own source text compiled for the host and run as one CTA of 256 threads (tools/emu_r16.cpp)."""
+and the kernel's own source text compiled for the host and run as one CTA of 256 threads (tests/emu/emu_r16.cpp)."""
 import os
 import shutil
 import subprocess
@@ -8,6 +8,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_BUILT = {}
 
 
 def test_radix16_thread_model_matches_dct_and_is_conflict_free():
@@ -18,6 +19,103 @@ def test_radix16_thread_model_matches_dct_and_is_conflict_free():
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
 def test_radix16_kernel_text_on_host_threads():
-    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "emu_r16.sh")], capture_output=True, text=True, timeout=600)
+    r = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_r16.sh")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "other rows untouched: yes" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------ K1 on host threads
+def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, fixed_bits=40, seg_tiles=2, n_cta=3):
+    import numpy as np
+    exe = os.path.join(ROOT, "build", "emu", "emu_push")
+    if not _BUILT.get("push"):
+        b = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_push.sh")], capture_output=True, text=True, timeout=600)
+        assert b.returncode == 0, b.stdout + b.stderr
+        _BUILT["push"] = True
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
+    with open(case, "wb") as f:
+        f.write(np.array([trap.Nz, trap.Nr, W, WE, fixed, exact, fixed_bits, seg_tiles, n_cta, 0], np.int32).tobytes())
+        f.write(np.array([len(r)], np.int64).tobytes())
+        f.write(np.array([trap.hz, trap.length, dt, charge, mass], np.float64).tobytes())
+        for a, t in ((enodes, np.float64), (r, np.int32), (z, np.float64), (v, np.float64)):
+            f.write(np.ascontiguousarray(a, dtype=t).tobytes())
+    p = subprocess.run([exe, case, out], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = open(out, "rb").read()
+    n, G = len(r), trap.G
+    n_seg = int(np.frombuffer(raw, np.int64, 1, 0)[0])
+    lost = np.frombuffer(raw, np.uint64, 2, 8)
+    zo = np.frombuffer(raw, np.float64, n, 24)
+    vo = np.frombuffer(raw, np.float64, n, 24 + 8 * n)
+    grid = raw[24 + 16 * n: 24 + 16 * n + 8 * G]
+    bnd = np.frombuffer(raw, np.uint32, 2 * trap.Nr, 24 + 16 * n + 8 * G).reshape(trap.Nr, 2)
+    seg_bounds = np.frombuffer(raw, np.int32, 4 * n_seg, 24 + 16 * n + 8 * (G + trap.Nr)).reshape(n_seg, 4)
+    return zo, vo, grid, bnd, lost, seg_bounds
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+@pytest.mark.parametrize("W,WE,fixed,exact", [(44, 256, 0, 1), (44, 256, 0, 0), (44, 256, 1, 1), (6, 12, 0, 1), (6, 6, 1, 0)])
+def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed, exact):
+    """The source text of k_push_deposit (pic-trapped-plasma_b200/csrc/ptp_push.cu) compiled for the host and run CTA by CTA
+    on 512 threads, against the oracle on the C1 electrons plus fast rings near both trap ends (losses): positions / speeds
+    ring by ring (EXACT arithmetic: bit for bit; FAST: 1e-14), loss count, deposit (fp64 1e-12; fixed point 2^-40 per ring),
+    the touched node range per row. W = 6 forces most rings through the out-of-window paths (global gather / atomics)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    kat = np.load(os.path.join(ROOT, "tests", "golden", "c1_step_kat.npz"))
+    dt, mass, charge = float(kat["dt"]), 9.1093837015e-31, -1.602176634e-19
+    trap = port.default_trap()
+    pl = trap.plasma("Electrons", mass, charge)
+    rng = np.random.default_rng(3)
+    extra = 300
+    r = np.concatenate([kat["e_r0"], rng.integers(0, 5, extra).astype(np.int32)])
+    edge = 2e-5 * (1 + 0.1 * rng.random(extra))
+    z = np.concatenate([kat["e_z0"], np.where(rng.random(extra) < 0.5, edge, trap.length - edge)])
+    v = np.concatenate([kat["e_v0"], rng.normal(0, 2e5, extra)])
+    order = np.argsort(r, kind="stable")
+    r, z, v = r[order], z[order], v[order]
+    pl.set_rings(r, z, v, float(kat["e_chargeMacro"]))
+    pl.solve_poisson()
+    enodes = trap.enodes()
+    zo, vo, grid, bnd, lost, seg_bounds = _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact)
+    # the reference's ring update, expression by expression (Source/PenningTrap.cpp:328-333, Source/Plasma.cpp:105-108)
+    hz, n1 = trap.hz, trap.Nz + 1
+    k = np.floor(z / hz).astype(np.int64)
+    w = (z - k * hz) / hz
+    e = (1 - w) * enodes[n1 * r + k] + w * enodes[n1 * r + k + 1]
+    vn = dt * e * charge / mass + v
+    zn = dt * vn + z
+    keep = (zn < trap.length) & (zn > 0)
+    assert int(lost[0]) == int((~keep).sum()) and int(lost[0]) > 0
+    assert np.array_equal(np.isnan(zo), ~keep)
+    if exact:
+        assert np.array_equal(zo[keep], zn[keep]) and np.array_equal(vo[keep], vn[keep])
+    else:
+        assert np.max(np.abs(zo[keep] - zn[keep]) / zn[keep]) < 1e-14
+        assert np.max(np.abs(vo[keep] - vn[keep]) / np.abs(vn[keep]).max()) < 1e-14
+    # ... and the same survivors as the oracle's swap-with-back loop
+    pl.move_rings(dt, enodes)
+    assert pl.count() == int(keep.sum())
+    assert np.array_equal(np.sort(pl.z), np.sort(zn[keep]))
+    # deposit at the new positions in units of one ring; the oracle's RHS carries -rho_macro / eps0 (Source/Plasma.cpp:91-92)
+    pl.update_rhs()
+    scale = -pl.macro_charge_density / 8.8541878128e-12
+    if fixed:
+        got = np.frombuffer(grid, np.int64).astype(np.float64) / 2.0 ** 40
+        tol = 1e-9
+    else:
+        got = np.frombuffer(grid, np.float64)
+        tol = 1e-12
+    assert np.linalg.norm(got * scale - pl.rhs) / np.linalg.norm(pl.rhs) < tol
+    assert abs(got.sum() - keep.sum()) < 1e-6
+    # touched node range per row = [min cell, max cell + 1] of its survivors, encoded as (Nz + 2 - kmin, kmax + 2)
+    kn = np.minimum(np.floor(zn[keep] / hz).astype(np.int64), trap.Nz - 1)
+    for row in np.unique(r[keep]):
+        kk = kn[r[keep] == row]
+        assert tuple(bnd[row]) == (trap.Nz + 2 - kk.min(), kk.max() + 2)
+    assert not bnd[np.setdiff1d(np.arange(trap.Nr), r[keep])].any()
+    # out-of-window counter: nothing misses a 44-cell window around a 37-cell plasma except the rings parked at the trap ends
+    if W == 6:
+        assert int(lost[1]) > 1000
+    trap.close()
