@@ -75,6 +75,7 @@ __global__ void k_central_well(const double* __restrict__ z, const PtpSegment* _
 }
 
 // ---- K5: per-row counting sort by axial cell ---------------------------------------------------------
+// [emu-begin] (tests/emu/emu_sort.cpp runs the text between these markers on host threads)
 // The live prefix of every row bucket is cut into chunks of SORT_CHUNK slots (host table); one CTA per chunk. Rings arrive
 // nearly sorted (the loaders emit them in z order and a re-sort happens long before they mix), so most of a warp shares
 // one cell: ranks are formed per warp with match.any - one shared-memory atomic per distinct cell and warp instruction
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(256) k_sort_pad(double* __restrict__ z, double
 		z[i] = nan; v[i] = 0.0; id[i] = -1LL;
 	}
 }
+// [emu-end]
 
 } // namespace
 

@@ -132,22 +132,23 @@ static inline void cpa8(void* dst, const void* src, bool valid) { *(double*)dst 
 static inline void cpa_commit() {}
 template <int N> static inline void cpa_wait() {}
 
-// Run body() as the threads of one CTA (blockDim.x threads, a multiple of 32), for every block index in [0, grid).
-static inline void emu_launch(int grid, int threads, const std::function<void()>& body)
+// Run body() as the threads of one CTA (blockDim.x threads, a multiple of 32), for every block index of a gridX x gridY grid.
+static inline void emu_launch(int gridX, int threads, const std::function<void()>& body, int gridY = 1)
 {
-	blockDim.x = threads; gridDim.x = grid;
-	for (int b = 0; b < grid; ++b) {
-		std::barrier<> bar(threads);
-		g_ctaBarrier = &bar;
-		std::vector<std::unique_ptr<EmuWarp>> warps;
-		for (int w = 0; w < threads / 32; ++w) warps.emplace_back(new EmuWarp);
-		std::vector<std::thread> th;
-		for (int t = 0; t < threads; ++t)
-			th.emplace_back([&, t, b] {
-				threadIdx.x = t; blockIdx.x = b;
-				g_warp = warps[t / 32].get(); g_lane = t & 31;
-				body();
-			});
-		for (auto& x : th) x.join();
-	}
+	blockDim.x = threads; gridDim.x = gridX; gridDim.y = gridY;
+	for (int by = 0; by < gridY; ++by)
+		for (int b = 0; b < gridX; ++b) {
+			std::barrier<> bar(threads);
+			g_ctaBarrier = &bar;
+			std::vector<std::unique_ptr<EmuWarp>> warps;
+			for (int w = 0; w < threads / 32; ++w) warps.emplace_back(new EmuWarp);
+			std::vector<std::thread> th;
+			for (int t = 0; t < threads; ++t)
+				th.emplace_back([&, t, b, by] {
+					threadIdx.x = t; blockIdx.x = b; blockIdx.y = by;
+					g_warp = warps[t / 32].get(); g_lane = t & 31;
+					body();
+				});
+			for (auto& x : th) x.join();
+		}
 }

@@ -119,3 +119,13 @@ def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed,
     if W == 6:
         assert int(lost[1]) > 1000
     trap.close()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+def test_sort_kernel_text_on_host_threads():
+    """K5's four kernels (count / scan / scatter / pad, pic-trapped-plasma_b200/csrc/ptp_particles.cu) on host threads, driven
+    like ptp_sort_plasma over three rounds with losses in between: rows ordered by axial cell, ring multiset intact (z, v
+    travel with their id), live counts, empty-slot pattern behind every live prefix of the re-used alternate buffers."""
+    r = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_sort.sh")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("padding clean") == 3
