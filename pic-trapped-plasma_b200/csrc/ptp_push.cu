@@ -174,31 +174,13 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		// the field window is wider than the deposit window (16 B per cell instead of 10 B per cell and thread): rings that
 		// have drifted out of the deposit window still gather from shared memory - a global load there would stall the warp
 		const int kE0 = max(0, min(k0 + (W >> 1) - (WE >> 1), a.Nz - WE));
-		for (int i = 0; i < W; ++i) {
-			bins[(size_t)i * T + tid] = 0ULL;
-			if (!FIXED) cnts[(size_t)i * T + tid] = 0;
-		}
-		if (PUSH) {
-			for (int i = tid; i < WE; i += T) {
-				const int node = kE0 + i;
-				const double eL = node <= a.Nz ? a.eNodes[rowBase + node] : 0.0;
-				const double eR = node + 1 <= a.Nz ? a.eNodes[rowBase + node + 1] : 0.0;
-				eTile[i] = make_double2(eL, eR);
-			}
-		}
-		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLost = 0u; sFar = 0u; }
-		__syncthreads();
-
-		int kMin = INT_MAX, kMax = INT_MIN;
-		unsigned int lost = 0, nDep = 0, nFar = 0;
-		long long kSum = 0;
-
+		// The segment's first global loads go out before anything else - the first tile of rings and this thread's entry of
+		// the field window (WE <= 256 <= T) - so that their latency overlaps the clearing of the bins.
 		const double2* z2 = reinterpret_cast<const double2*>(a.z);
 		const double2* v2 = reinterpret_cast<const double2*>(a.v);
 		double2* z2w = reinterpret_cast<double2*>(a.z);
 		double2* v2w = reinterpret_cast<double2*>(a.v);
 		const long long tile = (long long)R * T;
-
 		double2 zzN[NV], vvN[NV];
 		{
 			const long long p0 = (seg.begin >> 1) + tid;
@@ -209,6 +191,24 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				for (int j = 0; j < NV; ++j) vvN[j] = ld_ring(v2 + p0 + (long long)j * T);
 			}
 		}
+		double eL0 = 0.0, eR0 = 0.0;
+		if (PUSH && tid < WE) {
+			const int node = kE0 + tid;
+			if (node <= a.Nz) eL0 = a.eNodes[rowBase + node];
+			if (node + 1 <= a.Nz) eR0 = a.eNodes[rowBase + node + 1];
+		}
+		for (int i = 0; i < W; ++i) {
+			bins[(size_t)i * T + tid] = 0ULL;
+			if (!FIXED) cnts[(size_t)i * T + tid] = 0;
+		}
+		if (PUSH && tid < WE) eTile[tid] = make_double2(eL0, eR0);
+		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLost = 0u; sFar = 0u; }
+		__syncthreads();
+
+		int kMin = INT_MAX, kMax = INT_MIN;
+		unsigned int lost = 0, nDep = 0, nFar = 0;
+		long long kSum = 0;
+
 		for (long long t0 = seg.begin; t0 < seg.end; t0 += tile) {
 			const long long p0 = (t0 >> 1) + tid;
 			double z[R], v[R];
