@@ -181,8 +181,10 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
 // ptp_solve_wide.cu: the same direct solve organised for large grids
 bool ptp_solver_fft_fits(const ptp_trap* t);
-int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds);
-int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField);
+// expand = false: rows above the block of the outermost deposit row are left to the inverse transform (rowsFormed = false there)
+int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand = true);
+bool ptp_solver_inverse_forms_rows(const ptp_trap* t);
+int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed = true);
 int ptp_node_field(ptp_trap* t);
 int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);
 int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi);

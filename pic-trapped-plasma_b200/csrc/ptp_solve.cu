@@ -746,9 +746,10 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	// large grids (many radial nodes or long rows): separate forward transform + streamed radial solves (ptp_solve_wide.cu)
 	const bool wide = mb == 4 || useFft || smFwd > t->smemMax;
 	if (wide) {
-		PTP_TRY(ptp_solver_forward_wide(t, rho, rhoIsFixed, dScale, nS, spec, encBounds));
+		const bool formInInverse = useFft && ptp_solver_inverse_forms_rows(t);
+		PTP_TRY(ptp_solver_forward_wide(t, rho, rhoIsFixed, dScale, nS, spec, encBounds, !formInInverse));
 		if (useFft) {
-			PTP_TRY(ptp_solver_inverse_fft(t, spec, phi, nS, withField));
+			PTP_TRY(ptp_solver_inverse_fft(t, spec, phi, nS, withField, !formInInverse));
 			if (withField) t->eNodesValid = true;
 			return PTP_OK;
 		}

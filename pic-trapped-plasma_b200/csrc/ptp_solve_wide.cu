@@ -25,6 +25,9 @@
 #ifndef PTP_FFT_R16_DEFAULT
 #define PTP_FFT_R16_DEFAULT 1
 #endif
+#ifndef PTP_FFT_FORM_ROWS_DEFAULT
+#define PTP_FFT_FORM_ROWS_DEFAULT 1
+#endif
 
 namespace {
 
@@ -521,9 +524,12 @@ __device__ __forceinline__ void twiddle16(double2 (&x)[16], double2 w1)
 
 constexpr int R16_N = 4096, R16_RS = 257;
 
+// Rows above the block of the outermost deposit row can be formed on the fly instead of being read from alphaAll (xbAll != nullptr):
+// alpha[j][m] = (value entering the row's block, xbAll) * (in-block prefix product, thP) - what k_thomas_expand would have written.
 template <bool FIELD>
 __global__ void __launch_bounds__(256, 2) k_idct_r16_field(const double* __restrict__ alphaAll, double* __restrict__ phiAll, const double2* __restrict__ tw,
-	const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, double hz)
+	const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, double hz,
+	const double* __restrict__ xbAll, const int* __restrict__ wideJ, const double* __restrict__ thP, int blockRows)
 {
 	constexpr int N = R16_N, n1 = N + 1, RS = R16_RS;
 	extern __shared__ double2 fbw[];                            // [16][RS] exchange buffer; natural-order Z after the third round
@@ -538,13 +544,34 @@ __global__ void __launch_bounds__(256, 2) k_idct_r16_field(const double* __restr
 	for (int sp = 0; sp < nS; ++sp) {
 		const double* a = alphaAll + ((size_t)sp * Nr + row) * n1;
 		double2 x[16];
-		// round 1 (over n2): thread t = 16 n1 + n0 owns the samples n = t + 256 j of z_n = e_2n + i e_2n+1 (even extension of a)
-#pragma unroll
-		for (int j = 0; j < 16; ++j) {
-			const int i0 = 2 * (t + 256 * j), i1 = i0 + 1;
-			x[j] = make_double2(a[i0 <= N ? i0 : 2 * N - i0], a[i1 <= N ? i1 : 2 * N - i1]);
+		double a0, aN;
+		bool formed = false;                                    // uniform over the CTA
+		if (xbAll) {
+			const int J = wideJ[sp];
+			formed = J >= 0 && row > min(Nr - 1, (J / blockRows) * blockRows + blockRows - 1);
 		}
-		const double a0 = a[0], aN = a[N];
+		// round 1 (over n2): thread t = 16 n1 + n0 owns the samples n = t + 256 j of z_n = e_2n + i e_2n+1 (even extension of a)
+		if (!formed) {
+#pragma unroll
+			for (int j = 0; j < 16; ++j) {
+				const int i0 = 2 * (t + 256 * j), i1 = i0 + 1;
+				x[j] = make_double2(a[i0 <= N ? i0 : 2 * N - i0], a[i1 <= N ? i1 : 2 * N - i1]);
+			}
+			a0 = a[0]; aN = a[N];
+		}
+		else {
+			const int nB = (Nr + blockRows - 1) / blockRows;
+			const double* xin = xbAll + ((size_t)sp * nB + row / blockRows) * n1;
+			const double* pp = thP + (size_t)row * n1;
+#pragma unroll
+			for (int j = 0; j < 16; ++j) {
+				int i0 = 2 * (t + 256 * j), i1 = i0 + 1;
+				i0 = i0 <= N ? i0 : 2 * N - i0;
+				i1 = i1 <= N ? i1 : 2 * N - i1;
+				x[j] = make_double2(xin[i0] * pp[i0], xin[i1] * pp[i1]);
+			}
+			a0 = xin[0] * pp[0]; aN = xin[N] * pp[N];
+		}
 		fft16(x);
 		twiddle16(x, wA);
 		if (FIELD && sp == 0) cpa_wait<0>();                    // this thread's part of tot has landed; the barriers below publish it
@@ -611,7 +638,7 @@ bool ptp_solver_fft_fits(const ptp_trap* t)
 }
 
 // beta -> alpha for nS grids: forward transform of the touched rows + radial solves. bounds / encBounds as in ptp_solver_run.
-int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds)
+int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand)
 {
 	const int n1 = t->Nz + 1, Nr = t->Nr;
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
@@ -635,15 +662,27 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 		t->wideXb, t->wideJ, Nr, n1);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_wide launch", __FILE__, __LINE__);
+	t->lastLaunches += 2;
+	if (!expand) return PTP_OK;                                 // the inverse transform forms the rows above the deposit itself
 	k_thomas_expand<<<dim3((n1 + 255) / 256, (Nr + 7) / 8, nS), 256, 0, t->stream>>>(spec, t->wideXb, t->wideJ, t->thP, Nr, n1);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_expand launch", __FILE__, __LINE__);
-	t->lastLaunches += 3;
+	t->lastLaunches += 1;
 	return PTP_OK;
 }
 
 // alpha -> phi for nS grids (+ node field when withField: nS covers all species and phi = phiSelfAll).
-int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField)
+// Does the inverse transform of this trap form the rows above the deposit itself (no k_thomas_expand needed)?
+bool ptp_solver_inverse_forms_rows(const ptp_trap* t)
+{
+	const char* r16env = std::getenv("PTP_FFT_R16");
+	const int r16 = r16env ? std::atoi(r16env) : PTP_FFT_R16_DEFAULT;
+	const char* fe = std::getenv("PTP_FFT_FORM_ROWS");
+	const int form = fe ? std::atoi(fe) : PTP_FFT_FORM_ROWS_DEFAULT;
+	return t->Nz == R16_N && r16 && form;
+}
+
+int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed)
 {
 	const int N = t->Nz, Nr = t->Nr;
 	int bits = 0;
@@ -655,11 +694,13 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 		const size_t sm16 = (size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
 		if (withField) {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-			k_idct_r16_field<true><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz);
+			k_idct_r16_field<true><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz,
+				rowsFormed ? nullptr : t->wideXb, t->wideJ, t->thP, TW_BLK);
 		}
 		else {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-			k_idct_r16_field<false><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, t->hz);
+			k_idct_r16_field<false><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, t->hz,
+				rowsFormed ? nullptr : t->wideXb, t->wideJ, t->thP, TW_BLK);
 		}
 		const cudaError_t e16 = cudaGetLastError();
 		if (e16 != cudaSuccess) return ptp_cuda_fail(e16, "k_idct_r16_field launch", __FILE__, __LINE__);

@@ -21,9 +21,21 @@ int main()
 	std::vector<double2> smem(16 * 257 + (N + 1) / 2 + 8);
 	fbw = smem.data();
 	const double hz = 1.6625e-5;
+	// second species: its row is not read from alpha but formed as (value entering the row's block) x (in-block prefix
+	// product), the way the kernel does for rows above the outermost deposit row; alpha keeps the product for the reference
+	const int blockRows = 1, nB = Nr;
+	std::vector<double> xb((size_t)nS * nB * n1, 0.0), thP((size_t)Nr * n1, 0.0);
+	std::vector<int> wideJ = { Nr - 1, 0 };                     // species 0: every row read; species 1: rows > 0 formed
+	for (int k = 0; k <= N; ++k) {
+		thP[(size_t)row * n1 + k] = 0.5 + rand() / (double)RAND_MAX;
+		xb[((size_t)1 * nB + row) * n1 + k] = (rand() / (double)RAND_MAX - 0.5) * 2;
+		alpha[((size_t)1 * Nr + row) * n1 + k] = xb[((size_t)1 * nB + row) * n1 + k] * thP[(size_t)row * n1 + k];
+	}
+	std::vector<double> alphaSeen = alpha;
+	for (int k = 0; k <= N; ++k) alphaSeen[((size_t)1 * Nr + row) * n1 + k] = 1e300;   // must not be read
 	emu_launch(1, 256, [&] {
 		blockIdx.x = row;
-		k_idct_r16_field<true>(alpha.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), nS, Nr, hz);
+		k_idct_r16_field<true>(alphaSeen.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), nS, Nr, hz, xb.data(), wideJ.data(), thP.data(), blockRows);
 	});
 	// reference: phi_k = sum_m a_m cos(pi m k / N) in long double with exact argument reduction (m k mod 2N)
 	double worst = 0, norm = 0, err = 0;

@@ -402,16 +402,18 @@ def test_large_load_properties(c1_kat, mode):
     t.close()
 
 
-@pytest.mark.parametrize("r16", ["0", "1"])
+@pytest.mark.parametrize("r16", ["0", "1", "1x"])
 def test_fine_grid_full_size_properties(c1_kat, r16, monkeypatch):
-    """(r16: inverse transform of the 4096-node rows by radix-2 pass pairs / by three register-resident radix-16 rounds.)
+    """(r16: inverse transform of the 4096-node rows by radix-2 pass pairs "0" / by three register-resident radix-16 rounds
+    that form the rows above the plasma themselves "1" (default) / radix-16 after k_thomas_expand "1x".)
     BASELINE config 5 grid (Nz = 4096, Nr = 1024: 4.2 M unknowns - far beyond what the LU oracle can factorise) through
     size-independent properties: the direct solver's phi satisfies A phi = b for the operator applied by the independent
     stencil kernel (PenningTrap::generateSparse coefficients), for a random right-hand side and for the deposit of a
     5 M-ring load placed by the device loader; the deposit conserves the ring count; the node field is the centred
     difference of the total potential; fixed-point deposits give the same grid for 148 and 37 CTAs bit for bit."""
     from bench import density_on
-    monkeypatch.setenv("PTP_FFT_R16", r16)
+    monkeypatch.setenv("PTP_FFT_R16", r16[0])
+    monkeypatch.setenv("PTP_FFT_FORM_ROWS", "0" if r16 == "1x" else "1")
     Nz, Nr = 4096, 1024
     el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
     t = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
