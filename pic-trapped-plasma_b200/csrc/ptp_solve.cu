@@ -577,6 +577,7 @@ __global__ void k_norm2(const double* __restrict__ rho, const double* __restrict
 // Thomas factors in extended precision.
 int ptp_solver_build(ptp_trap* t)
 {
+	// [tables-begin] (pure host arithmetic up to [tables-end]: tests/emu/emu_wide.cpp includes this text to feed the kernels it emulates)
 	const int Nz = t->Nz, Nr = t->Nr, n1 = Nz + 1;
 	const double hz = t->hz, hr = t->hr;
 	const double hz2 = std::pow(hz, -2);                                   // Source/PenningTrap.cpp:97
@@ -641,6 +642,7 @@ int ptp_solver_build(ptp_trap* t)
 			thP[(size_t)j * n1 + m] = (double)prod;
 		}
 	}
+	// [tables-end]
 	if (Nz >= 8 && (Nz & (Nz - 1)) == 0) {                      // power-of-two cell count: FFT path for the inverse transform
 		std::vector<double2> tw((size_t)Nz);
 		for (int j = 0; j < Nz; ++j) {

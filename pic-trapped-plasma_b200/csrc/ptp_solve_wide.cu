@@ -41,6 +41,7 @@ __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// [wide-begin] (tests/emu/emu_wide.cpp runs the kernels from here to [r16-end] on host threads)
 __device__ __forceinline__ int2 row_bounds_of(const int2* bounds, const uint2* enc, int idx, int n1)
 {
 	if (enc) {                                                  // maxima written by the push kernel's flush: (Nz+2-kmin, kmax+1), 0 = untouched

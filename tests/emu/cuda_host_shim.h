@@ -76,6 +76,12 @@ static inline unsigned int __match_any_sync(unsigned, int key)
 	g_warp->bar.arrive_and_wait();
 	return m;
 }
+static inline unsigned int __brev(unsigned int x)
+{
+	unsigned int r = 0;
+	for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+	return r;
+}
 static inline int __ffs(unsigned int x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
 

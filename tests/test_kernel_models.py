@@ -129,3 +129,48 @@ def test_sort_kernel_text_on_host_threads():
     r = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_sort.sh")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("padding clean") == 3
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+@pytest.mark.parametrize("Nz,Nr,rows,k_lo,k_hi", [(256, 40, range(0, 10), 100, 160),       # compact radial path, radix-2 inverse
+                                                  (256, 200, [3, 180, 199], 0, 256),       # streamed radial path (deposit reaching the wall row)
+                                                  (4096, 40, range(0, 7), 1900, 2200)])    # radix-16 inverse, rows 32..39 formed in the inverse
+def test_large_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, Nr, rows, k_lo, k_hi):
+    """The shipped table builder (ptp_solver_build) and the kernels of ptp_solve_wide.cu - forward DCT of the touched rows,
+    radial solves with the rows above the deposit folded into one pivot, block-product expansion, FFT inverse + node field -
+    run on host threads in launch order, against the oracle's LU solve of the reference matrix (phi rel-L2 <= 1e-10); the
+    node field must be the centred difference of phi_trap + phi bit for bit (Source/PenningTrap.cpp:226-233)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    if not _BUILT.get("wide"):
+        b = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_wide.sh")], capture_output=True, text=True, timeout=900)
+        assert b.returncode == 0, b.stdout + b.stderr
+        _BUILT["wide"] = True
+    pt = port.PortTrap(0.012, [0.02, 0.03, 0.02], [0.0, -50.0, 0.0], [0.001, 0.001], Nz, Nr)
+    n1 = Nz + 1
+    rng = np.random.default_rng(Nz + Nr)
+    rho = np.zeros((Nr, n1))
+    for j in rows:
+        lo = k_lo + int(rng.integers(0, 5))
+        rho[j, lo:k_hi + 1] = -1e6 * rng.random(k_hi + 1 - lo)
+    rho = rho.reshape(-1)
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
+    with open(case, "wb") as f:
+        f.write(np.array([Nz, Nr], np.int32).tobytes())
+        f.write(np.array([pt.hz, pt.hr, pt.radius], np.float64).tobytes())
+        f.write(rho.tobytes())
+        f.write(np.ascontiguousarray(pt.phi).tobytes())
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_wide"), case, out], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = np.fromfile(out, np.float64)
+    G = pt.G
+    phi, en, phi_formed = raw[:G], raw[G:2 * G], raw[2 * G:3 * G]
+    want = pt.solve(rho)
+    assert np.linalg.norm(phi - want) / np.linalg.norm(want) < 1e-10
+    assert np.linalg.norm(phi_formed - phi) / np.linalg.norm(phi) < 1e-13
+    tot = (pt.phi + phi).reshape(Nr, n1)
+    e = np.zeros_like(tot)
+    e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * pt.hz)
+    assert np.array_equal(en.reshape(Nr, n1), e)
+    pt.close()
