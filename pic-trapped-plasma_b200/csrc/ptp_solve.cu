@@ -26,6 +26,7 @@
 
 namespace {
 
+// [solve-begin] (tests/emu/emu_solve.cpp runs the kernels from here to [solve-end] on host threads)
 constexpr int INV_TM = 16;      // output rows (radial nodes) per CTA of the inverse kernel
 constexpr int INV_TN = 40;      // output columns (axial nodes) per CTA
 constexpr int INV_KC = 1024;    // modes staged in shared memory per chunk
@@ -520,6 +521,8 @@ __global__ void k_wall_rhs(const double* __restrict__ wall, double* __restrict__
 	const long long first = G - n1;
 	rhs[idx] = idx >= first ? __dmul_rn(__dmul_rn(-1.0, factor), wall[idx - first]) : 0.0;
 }
+
+// [solve-end]
 
 // Red-black SOR sweep (cross-check solver): one colour of  A phi = b.
 template <bool A_FIXED>

@@ -174,3 +174,52 @@ def test_large_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, 
     e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * pt.hz)
     assert np.array_equal(en.reshape(Nr, n1), e)
     pt.close()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+@pytest.mark.parametrize("Nz,Nr,rows,k_lo,k_hi", [(585, 128, range(0, 12), 274, 311),     # the reference's default grid: fused inverse + node field
+                                                  (300, 20, [0, 5, 19], 3, 297),           # odd row length: 8-byte copies
+                                                  (1500, 12, range(0, 4), 700, 800)])      # long rows, not a power of two: chunked inverse GEMM + k_node_field
+def test_default_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, Nr, rows, k_lo, k_hi):
+    """The shipped table builder and the kernels of ptp_solve.cu (row-bounds scan, forward DCT fused with the Thomas solves,
+    paired-mode inverse DCT fused with the node field / chunked inverse GEMM, stencil apply, wall right-hand side) on host
+    threads with ptp_solver_run's launch arithmetic, against the oracle: phi vs the LU solve (rel-L2 <= 1e-10), A phi = b through
+    k_apply, node field bit for bit, wall right-hand side equal to the oracle's (Source/PenningTrap.cpp:163-198)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    if not _BUILT.get("solve"):
+        b = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_solve.sh")], capture_output=True, text=True, timeout=900)
+        assert b.returncode == 0, b.stdout + b.stderr
+        _BUILT["solve"] = True
+    pt = port.PortTrap(0.01488, [0.01322] * 5, [0, -70, -15, -70, 0], [0.0005] * 4, Nz, Nr)
+    n1 = Nz + 1
+    rng = np.random.default_rng(Nz + Nr)
+    rho = np.zeros((Nr, n1))
+    for j in rows:
+        lo = k_lo + int(rng.integers(0, 3))
+        rho[j, lo:k_hi + 1] = -1e6 * rng.random(k_hi + 1 - lo)
+    rho = rho.reshape(-1)
+    wall = pt.wall_potential()
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
+    with open(case, "wb") as f:
+        f.write(np.array([Nz, Nr], np.int32).tobytes())
+        f.write(np.array([pt.hz, pt.hr, pt.radius], np.float64).tobytes())
+        f.write(rho.tobytes())
+        f.write(np.ascontiguousarray(pt.phi).tobytes())
+        f.write(np.ascontiguousarray(wall).tobytes())
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_solve"), case, out], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = np.fromfile(out, np.float64)
+    G = pt.G
+    phi, en, aphi, wall_rhs = raw[:G], raw[G:2 * G], raw[2 * G:3 * G], raw[3 * G:4 * G]
+    want = pt.solve(rho)
+    assert np.linalg.norm(phi - want) / np.linalg.norm(want) < 1e-10
+    assert np.linalg.norm(aphi - rho) / np.linalg.norm(rho) < 1e-10
+    assert np.linalg.norm(aphi - pt.apply(phi)) / np.linalg.norm(rho) < 1e-13
+    tot = (pt.phi + phi).reshape(Nr, n1)
+    e = np.zeros_like(tot)
+    e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * pt.hz)
+    assert np.array_equal(en.reshape(Nr, n1), e)
+    assert np.array_equal(wall_rhs, pt.wall_rhs())
+    pt.close()
