@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAl
 		}
 		__threadfence_block();                                  // this lane's y values are read back through cp.async below
 		x = xJ;
+		__syncwarp();                                           // every lane is done reading the flags in their first meaning
 		for (int j = J0 + lane; j < J; j += 32) sTouched[j] = 1;    // from here on the flag means "row >= J0": y was stored there
 		__syncwarp();
 		stream_rows<-1, true>(ring, J - 1, J, thCp, spec, sTouched, n1, m, mOk, lane, [&](int j, double cp, double yj) {
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(256, 2) k_idct_fft_field(const double* __restr
 					wa[u] = __ldg(&tw[j0 * sA]);
 					wb[u] = __ldg(&tw[j0 * 2 * sA]);
 #pragma unroll
-					for (int c = 0; c < 4; ++c) x[u][c] = fbw[p[u][c]];
+					for (int c = 0; c < 4; ++c) x[u][c] = (i0 + u * T < (N >> 2)) ? fbw[p[u][c]] : make_double2(0.0, 0.0);   // (a clamped item is another thread's: not even read)
 				}
 #pragma unroll
 				for (int u = 0; u < 2; ++u) {
