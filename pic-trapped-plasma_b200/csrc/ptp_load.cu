@@ -26,6 +26,7 @@
 
 namespace {
 
+// [emu-begin] (tests/emu/emu_rng.cpp runs the deviate-stream kernels on host threads against libstdc++'s own engine)
 constexpr unsigned long long kM = 2147483647ULL;            // 2^31 - 1
 constexpr unsigned long long kA = 16807ULL;
 constexpr int RNG_CH = 16;                                  // attempts per thread
@@ -161,6 +162,8 @@ __global__ void __launch_bounds__(256) k_rng_emit(long long nAttempts, const uns
 		++slot;
 	}
 }
+
+// [emu-end]
 
 // Device temporaries of one load, released on every exit path.
 struct LoadScratch {

@@ -67,6 +67,7 @@ template <class T> static inline T emu_exchange(T x, int src)
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T x, int o) { return emu_exchange(x, g_lane ^ o); }
 template <class T> static inline T __shfl_sync(unsigned, T x, int src) { return emu_exchange(x, src); }
+template <class T> static inline T __shfl_up_sync(unsigned, T x, int d) { return emu_exchange(x, g_lane >= d ? g_lane - d : g_lane); }
 static inline unsigned int __match_any_sync(unsigned, int key)
 {
 	g_warp->buf[g_lane] = (unsigned long long)(unsigned int)key;
@@ -116,6 +117,7 @@ static inline double __dsub_rn(double a, double b) { volatile double r = a - b; 
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline double __dsqrt_rn(double a) { volatile double r = std::sqrt(a); return r; }
 static inline double __dadd_rd(double a, double b)
 {
 	std::fesetround(FE_DOWNWARD);
@@ -132,6 +134,8 @@ static inline int max(int a, int b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 using std::floor;
+using std::log;
+using std::fabs;
 
 // cp.async helpers of ptp_solve_wide.cu (synchronous on the host)
 static inline void cpa8(void* dst, const void* src, bool valid) { *(double*)dst = valid ? *(const double*)src : 0.0; }

@@ -6,13 +6,13 @@
 set -e
 cd "$(dirname "$0")/../.."
 CASES=${1:-/tmp/pytest-of-$(id -un)/pytest-current}
-bash tests/emu/emu_push.sh; bash tests/emu/emu_wide.sh; bash tests/emu/emu_solve.sh; bash tests/emu/emu_sort.sh > /dev/null; bash tests/emu/emu_r16.sh > /dev/null
+bash tests/emu/emu_push.sh; bash tests/emu/emu_wide.sh; bash tests/emu/emu_solve.sh; bash tests/emu/emu_sort.sh > /dev/null; bash tests/emu/emu_r16.sh > /dev/null; bash tests/emu/emu_rng.sh > /dev/null
 rc=0
 for SAN in thread address; do
-  for H in push wide solve sort r16; do
+  for H in push wide solve sort r16 rng; do
     g++ -std=c++20 -O1 -g -pthread -fsanitize=$SAN -ffp-contract=off -frounding-math -Ibuild/emu -Itests/emu -o build/emu/emu_${H}_$SAN tests/emu/emu_$H.cpp
   done
-  for H in sort r16; do
+  for H in sort r16 rng; do
     if ! TSAN_OPTIONS="exitcode=66" ASAN_OPTIONS="exitcode=66:detect_leaks=0" build/emu/emu_${H}_$SAN > build/emu/san_${H}_$SAN.log 2>&1; then echo "$SAN $H: FAILED"; tail -20 build/emu/san_${H}_$SAN.log; rc=1; else echo "$SAN $H: clean"; fi
   done
   for H in push wide solve; do

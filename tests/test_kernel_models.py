@@ -223,3 +223,13 @@ def test_default_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz
     assert np.array_equal(en.reshape(Nr, n1), e)
     assert np.array_equal(wall_rhs, pt.wall_rhs())
     pt.close()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+def test_loader_deviate_stream_text_on_host_threads_equals_libstdcxx():
+    """k_rng_count / k_rng_scan / k_rng_emit (ptp_load.cu) on host threads: the parallel, jump-ahead reproduction of the
+    reference's speed deviates - std::default_random_engine + std::normal_distribution<double>, Source/Plasma.cpp:508-509 -
+    against libstdc++'s own objects, bit for bit, for 1, 2, 4097 and 100001 deviates."""
+    r = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_rng.sh")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("identical to std::normal_distribution") == 4
