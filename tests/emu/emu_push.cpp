@@ -77,8 +77,8 @@ int main(int argc, char** argv)
 	std::vector<double> rho(G + h.Nr, 0.0);                  // grid + per-row touched-node range (two u32 per row)
 	unsigned long long lost[2] = { 0, 0 };
 	const size_t perBin = h.fixed ? 8 : 10;
-	std::vector<unsigned char> smem((size_t)h.WE * 16 + (size_t)h.W * 16 + (size_t)h.W * 512 * perBin + 64);
-	g_smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+	std::vector<unsigned char> smem((size_t)h.WE * 16 + (size_t)h.W * 16 + (size_t)h.W * 512 * perBin);   // = ptp_push_smem_bytes, to the byte (AddressSanitizer)
+	g_smem = smem.data();
 
 	PushArgs a{};
 	a.Nz = h.Nz; a.W = h.W; a.fixedBits = h.fixedBits; a.WE = h.WE;

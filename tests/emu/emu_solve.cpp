@@ -33,8 +33,8 @@ int main(int argc, char** argv)
 #include "tables_snippet.inc"
 	(void)thR; (void)thQ; (void)thP; (void)hr; (void)hr2;
 	const size_t smemMax = 232448;
-	std::vector<unsigned char> smem(smemMax + 64);
-	g_smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+	std::vector<unsigned char> smem;                            // exactly the dynamic shared memory each launch requests (AddressSanitizer)
+	auto dynSmem = [&](size_t bytes) { smem.assign(bytes, 0); g_smem = smem.data(); };
 	const int nS = 1, M = nS * Nr;
 
 	// ---- as ptp_solver_run ----
@@ -43,6 +43,7 @@ int main(int argc, char** argv)
 	auto smFwdBytes = [&](int mb) { return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB + (size_t)Nr) * sizeof(double) + (size_t)Nr * sizeof(int2); };
 	if (smFwdBytes(16) > smemMax) { std::printf("emu_solve: grid belongs to the large-grid path (emu_wide)\n"); return 6; }
 	std::vector<double> spec(G, 0.0), phi(G, 0.0), eN(G, -1.0);
+	dynSmem(smFwdBytes(16));
 	emu_launch((n1 + 15) / 16, 256, [&] {
 		blockIdx.y = 0;
 		k_fwd_thomas<false, 16>(rho.data(), bounds.data(), nullptr, fwd.data(), nullptr, 1.0, thInv.data(), thCp.data(), lower.data(), spec.data(), Nr, n1);
@@ -54,6 +55,7 @@ int main(int argc, char** argv)
 	const char* path;
 	if (smFieldBytes(ringStages) <= smemMax) {
 		path = "k_inv_field";
+		dynSmem(smFieldBytes(ringStages));
 		const int gx = (n1 + 1 + INV_TN - 3) / (INV_TN - 2), gy = (Nr + INV_TM - 1) / INV_TM;
 		for (int by = 0; by < gy; ++by)
 			emu_launch(gx, 256, [&] {
@@ -64,6 +66,12 @@ int main(int argc, char** argv)
 	}
 	else {
 		path = "k_inv_gemm + k_node_field";
+		{
+			const int kc = n1 < INV_KC ? n1 : INV_KC;
+			size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
+			if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);
+			dynSmem(smInv);
+		}
 		const int gx = (n1 + INV_TN - 1) / INV_TN, gy = (M + INV_TM - 1) / INV_TM;
 		for (int by = 0; by < gy; ++by)
 			emu_launch(gx, 256, [&] {

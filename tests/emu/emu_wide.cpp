@@ -47,21 +47,24 @@ int main(int argc, char** argv)
 			if (rho[(size_t)j * n1 + k] != 0.0) { lo = std::min(lo, k); hi = std::max(hi, k); }
 		bounds[j] = make_int2(lo, hi);
 	}
-	std::vector<unsigned char> smem(240 * 1024);
-	g_smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
-	fbw = reinterpret_cast<double2*>(g_smem);
+	// dynamic shared memory: exactly the bytes the launch code requests for each kernel (heap blocks, so that
+	// AddressSanitizer sees an access past the end)
+	std::vector<unsigned char> smem;
+	auto dynSmem = [&](size_t bytes) { smem.assign(bytes, 0); g_smem = smem.data(); fbw = reinterpret_cast<double2*>(g_smem); };
 	std::vector<double> spec(G, 0.0);
 	const int nB = (Nr + TW_BLK - 1) / TW_BLK;
 	std::vector<double> xb((size_t)nB * n1, 0.0);
 	std::vector<int> wideJ(1, -7);
 
 	// forward transform of the touched rows: grid (modes / 64, rows / 32, species)
+	dynSmem((size_t)2 * (FD_K * FD_M + FD_K * FD_RP) * sizeof(double));
 	for (int by = 0; by < (Nr + FD_R - 1) / FD_R; ++by)
 		emu_launch((n1 + FD_M - 1) / FD_M, 256, [&] {
 			blockIdx.y = by;
 			k_fwd_dct<false>(rho.data(), bounds.data(), nullptr, fwd.data(), nullptr, 1.0, spec.data(), Nr, n1);
 		});
 	// radial solves: grid (modes / 32, species), 128 threads
+	dynSmem((size_t)3 * TW_RCAP * 32 * sizeof(double) + (size_t)Nr * sizeof(double) + (size_t)Nr);
 	emu_launch((n1 + 31) / 32, 128, [&] {
 		blockIdx.y = 0;
 		k_thomas_wide(spec.data(), bounds.data(), nullptr, thInv.data(), thCp.data(), thR.data(), thQ.data(), thP.data(), lower.data(),
@@ -77,6 +80,7 @@ int main(int argc, char** argv)
 	std::vector<double> phi(G, 0.0), eN(G, 0.0), phiFormed(G, 0.0), eN2(G, 0.0);
 	const int threads = N >= 1024 ? 256 : 128;
 	if (N == R16_N) {
+		dynSmem((size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double));
 		emu_launch(Nr, 256, [&] { k_idct_r16_field<true>(spec.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), 1, Nr, hz, nullptr, nullptr, nullptr, TW_BLK); });
 		for (int j = 0; j < Nr; ++j)                            // rows the inverse must form itself: poison what expand would have written
 			if (wideJ[0] >= 0 && j > std::min(Nr - 1, (wideJ[0] / TW_BLK) * TW_BLK + TW_BLK - 1))
@@ -84,6 +88,7 @@ int main(int argc, char** argv)
 		emu_launch(Nr, 256, [&] { k_idct_r16_field<true>(specLazy.data(), phiFormed.data(), tw.data(), phiTrap.data(), eN2.data(), 1, Nr, hz, xb.data(), wideJ.data(), thP.data(), TW_BLK); });
 	}
 	else {
+		dynSmem((size_t)N * sizeof(double2) + (size_t)(N + 1) * sizeof(double));
 		emu_launch(Nr, threads, [&] { k_idct_fft_field<true>(spec.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), 1, Nr, N, bits, hz); });
 		phiFormed = phi;
 	}
