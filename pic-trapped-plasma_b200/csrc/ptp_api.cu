@@ -100,7 +100,14 @@ int push_deposit_all(ptp_trap* t, double dt)
 		// sums, already consumed by its solve - is zeroed now, ahead of the step that will push into it
 		t->rhoParity ^= 1;
 		t->rhoAll = t->rhoStore + (size_t)t->rhoParity * span;
-		PTP_CUDA(cudaMemsetAsync(t->rhoStore + (size_t)(t->rhoParity ^ 1) * span, 0, span * sizeof(double), t->stream));
+		double* other = t->rhoStore + (size_t)(t->rhoParity ^ 1) * span;
+		if (t->G >= (1LL << 20) && t->extentEpoch == t->layoutEpoch) {
+			// large grid: begin_exchange cleared both parities in full, and no rank ever deposits above the (global) row extent
+			const size_t rowsBytes = (size_t)t->rowExtent * (t->Nz + 1) * sizeof(double);
+			for (int s = 0; s < nS; ++s) PTP_CUDA(cudaMemsetAsync(other + (size_t)s * t->G, 0, rowsBytes, t->stream));
+			PTP_CUDA(cudaMemsetAsync(other + (size_t)t->capS * t->G, 0, (size_t)t->capS * t->Nr * sizeof(double), t->stream));
+		}
+		else PTP_CUDA(cudaMemsetAsync(other, 0, span * sizeof(double), t->stream));
 	}
 	else if (t->G >= (1LL << 20) && t->cleanEpoch == t->layoutEpoch && t->extentEpoch == t->layoutEpoch) {
 		// large grid: only the rows that can hold a deposit, plus the row bounds (the rest is still zero from the last full clear)
@@ -485,7 +492,8 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 		t->evPool.push_back(e);
 	}
 	t->evSteps = timed;
-	if (!ptp_peer_mode(t)) { int extent; PTP_TRY(ptp_row_extent(t, &extent)); }
+	// collective on the first call after a (re)load, cached afterwards; peer-memory mode needs it only on large grids
+	if (!ptp_peer_mode(t) || t->G >= (1LL << 20)) { int extent; PTP_TRY(ptp_row_extent(t, &extent)); }
 	PTP_TRY(begin_exchange(t));
 	int done = 0;
 	if (graph && nSteps > 0) {
