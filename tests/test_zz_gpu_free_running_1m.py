@@ -1,0 +1,65 @@
+"""Free-running ensemble parity at BASELINE configs 2 / 3 scale (runs last: the file name sorts behind the other GPU tests)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from oracle import port
+
+ptp = importlib.import_module("pic-trapped-plasma_b200")
+pytestmark = pytest.mark.gpu
+PERIODS = int(os.environ.get("PTP_TEST_PERIODS", "5"))
+
+
+def _by_id(p):
+    r, z, v, ids = p.download()
+    o = np.argsort(ids)
+    return r[o], z[o], v[o], ids[o]
+
+
+@pytest.mark.parametrize("species", [(("Antiprotons", "massP", 1.0, 1_000_000),),
+                                     (("Electrons", "massE", 0.5, 500_000), ("Antiprotons", "massP", 0.5, 500_000))])
+def test_free_running_million_rings_vs_oracle(c1_kat, species):
+    """BASELINE configs 2 and 3 in shape (antiproton plasma / co-trapped e- + pbar on the default trap, 1 M macro-rings, fp64),
+    free-running for five plasma periods (175 steps, Diagnostics/C) Visualise Evolution.txt:34-36) beside the CPU oracle on
+    the same rings, the ensemble diagnostics compared every period: alive counts equal, potential energy
+    (Plasma::getPotentialEnergy, Source/Plasma.cpp:244-252) rel <= 1e-8 (1e-7 with electrons in the trap), kinetic sum with
+    the ring masses of Source/Plasma.cpp:212-228 rel <= 1e-6, on-axis and radially summed density profiles rel-L2 <= 1e-5,
+    and at the end the rings themselves: z rel-L2 <= 1e-9 for antiprotons alone; with electrons, whose orbits amplify a
+    1e-12 solver-level difference ~1e5 x over this horizon (SURVEY A-8), 1e-6 for them and 1e-8 for the antiprotons."""
+    from bench import expected_density
+    dens = expected_density()
+    t, ot = ptp.default_trap(), port.default_trap()
+    pairs = []
+    for name, mkey, share, num in species:
+        g = ptp.Plasma(t, name, getattr(ptp, mkey), -ptp.ePos)
+        n, _ = g.loadDensity(dens * share, 150.0, num, solve=False)
+        r, z, v, ids = _by_id(g)
+        assert len(z) == n and np.array_equal(ids, np.arange(n))
+        o = ot.plasma(name, getattr(ptp, mkey), -ptp.ePos)
+        o.set_rings(r, z, v, g.chargeMacro)
+        pairs.append((g, o, n))
+    for g, o, n in pairs:
+        g.solvePoisson()
+        o.solve_poisson()
+        assert rel_l2(g.rhs(), o.rhs) < 1e-12 and rel_l2(g.selfPotential(), o.self_potential) < 1e-10
+    dt = float(c1_kat["dt"])
+    n1 = t.Nz + 1
+    for period in range(PERIODS):
+        t.movePlasmas(dt, 35)
+        ot.move_plasmas(dt, 35)
+        for g, o, n in pairs:
+            assert g.getNumMacro() == o.count() == n           # nothing leaves the well at 150 K: ring order is unchanged
+            assert g.getPotentialEnergy() == pytest.approx(o.potential_energy(), rel=1e-8 if len(species) == 1 else 1e-7)
+            r, z, v, _ = _by_id(g)
+            w = np.where(r == 0, 1.0, 8.0 * r)
+            assert float(np.sum(w * v * v)) == pytest.approx(float(np.sum(w * o.v * o.v)), rel=1e-6)
+            dg, do = g.rhs().reshape(t.Nr, n1), o.rhs.reshape(t.Nr, n1)
+            assert rel_l2(dg[0], do[0]) < 1e-5 and rel_l2(dg.sum(axis=0), do.sum(axis=0)) < 1e-5
+    for (g, o, n), (name, _, _, _) in zip(pairs, species):
+        _, z, _, _ = _by_id(g)
+        assert rel_l2(z, o.z) < (1e-6 if name == "Electrons" else 1e-9 if len(species) == 1 else 1e-8)
+    t.close()
+    ot.close()
