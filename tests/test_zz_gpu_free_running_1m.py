@@ -25,10 +25,11 @@ def test_free_running_million_rings_vs_oracle(c1_kat, species):
     """BASELINE configs 2 and 3 in shape (antiproton plasma / co-trapped e- + pbar on the default trap, 1 M macro-rings, fp64),
     free-running for five plasma periods (175 steps, Diagnostics/C) Visualise Evolution.txt:34-36) beside the CPU oracle on
     the same rings, the ensemble diagnostics compared every period: alive counts equal, potential energy
-    (Plasma::getPotentialEnergy, Source/Plasma.cpp:244-252) rel <= 1e-8 (1e-7 with electrons in the trap), kinetic sum with
-    the ring masses of Source/Plasma.cpp:212-228 rel <= 1e-6, on-axis and radially summed density profiles rel-L2 <= 1e-5,
-    and at the end the rings themselves: z rel-L2 <= 1e-9 for antiprotons alone; with electrons, whose orbits amplify a
-    1e-12 solver-level difference ~1e5 x over this horizon (SURVEY A-8), 1e-6 for them and 1e-8 for the antiprotons."""
+    (Plasma::getPotentialEnergy, Source/Plasma.cpp:244-252) rel <= 1e-8, kinetic sum with the ring masses of
+    Source/Plasma.cpp:212-228 rel <= 1e-6, on-axis and radially summed density profiles rel-L2 <= 1e-6, and at the end the
+    rings themselves: z rel-L2 <= 1e-9 for antiprotons, 1e-7 for electrons. (Measured on the CPU between the two oracles, whose
+    solves differ by 8e-14: 7e-13 for the electrons' z, 3e-15 for the antiprotons', 8e-12 for the density after five periods
+    - at this ring count the orbits amplify a solver-level difference ~10 x, not the ~1e5 x of the 4 k-ring case.)"""
     from bench import expected_density
     dens = expected_density()
     t, ot = ptp.default_trap(), port.default_trap()
@@ -52,14 +53,14 @@ def test_free_running_million_rings_vs_oracle(c1_kat, species):
         ot.move_plasmas(dt, 35)
         for g, o, n in pairs:
             assert g.getNumMacro() == o.count() == n           # nothing leaves the well at 150 K: ring order is unchanged
-            assert g.getPotentialEnergy() == pytest.approx(o.potential_energy(), rel=1e-8 if len(species) == 1 else 1e-7)
+            assert g.getPotentialEnergy() == pytest.approx(o.potential_energy(), rel=1e-8)
             r, z, v, _ = _by_id(g)
             w = np.where(r == 0, 1.0, 8.0 * r)
             assert float(np.sum(w * v * v)) == pytest.approx(float(np.sum(w * o.v * o.v)), rel=1e-6)
             dg, do = g.rhs().reshape(t.Nr, n1), o.rhs.reshape(t.Nr, n1)
-            assert rel_l2(dg[0], do[0]) < 1e-5 and rel_l2(dg.sum(axis=0), do.sum(axis=0)) < 1e-5
+            assert rel_l2(dg[0], do[0]) < 1e-6 and rel_l2(dg.sum(axis=0), do.sum(axis=0)) < 1e-6
     for (g, o, n), (name, _, _, _) in zip(pairs, species):
         _, z, _, _ = _by_id(g)
-        assert rel_l2(z, o.z) < (1e-6 if name == "Electrons" else 1e-9 if len(species) == 1 else 1e-8)
+        assert rel_l2(z, o.z) < (1e-7 if name == "Electrons" else 1e-9)
     t.close()
     ot.close()
