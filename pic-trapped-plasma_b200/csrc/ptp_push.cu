@@ -52,6 +52,7 @@ struct PushArgs {
 	int4* segBounds;            // per segment: (min cell, max cell, mean cell, -) of its live rings, updated every step
 	void* rho[8];               // [G] double weights or int64 fixed point: this rank's grid, or every rank's (peer-memory mode)
 	int nRho, pad1;
+	int mergeBins, pad2;        // consecutive rings of a thread that fall into the same cell share one read-modify-write of the bin
 	long long bndOffset;        // (uint2*)((double*)rho[r] + bndOffset) = this species' touched-node range per row (encoded maxima)
 	unsigned long long* lost;   // [0] rings lost since upload, [1] deposits that missed the private window (re-sort trigger)
 };
@@ -125,6 +126,9 @@ __device__ __forceinline__ void st_ring(double2* p, double2 v) { *p = v; }
 #ifndef PTP_L2_PREFETCH_TILES
 #define PTP_L2_PREFETCH_TILES 2
 #endif
+#ifndef PTP_MERGE_BINS_DEFAULT
+#define PTP_MERGE_BINS_DEFAULT 0
+#endif
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
 #ifndef PTP_HOST_EMU
@@ -141,7 +145,7 @@ template <typename T> __device__ __forceinline__ T warp_sum(T x)
 	return x;
 }
 
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE = false>
 __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
 	constexpr int NV = R / 2;
@@ -288,25 +292,62 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			// ---- deposit at the (new) position: Plasma::updateRHS body (Source/Plasma.cpp:86-92) -----------
 			cells_of<R, EXACT>(z, live, a, k, w);
 			bool farD = false;
+			if constexpr (!MERGE) {
 #pragma unroll
-			for (int i = 0; i < R; ++i) {
-				const unsigned int io = (unsigned int)(k[i] - k0);
-				const bool in = live[i] && io < (unsigned int)W;
-				farD |= live[i] && io >= (unsigned int)W;
-				nFar += (live[i] && io >= (unsigned int)W) ? 1u : 0u;
-				if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
-				if (in) {
-					if (FIXED) {
-						// round(w * 2^F) lands in the mantissa of (2^52 + x); subtracting the bias leaves (1 << 52) | x
-						const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
-						bins[(size_t)io * T + tid] += (unsigned long long)__double_as_longlong(t) - kPackBias;
-					}
-					else {
-						double* b = reinterpret_cast<double*>(bins) + (size_t)io * T + tid;
-						*b = __dadd_rn(*b, w[i]);
-						cnts[(size_t)io * T + tid] += 1;
+				for (int i = 0; i < R; ++i) {
+					const unsigned int io = (unsigned int)(k[i] - k0);
+					const bool in = live[i] && io < (unsigned int)W;
+					farD |= live[i] && io >= (unsigned int)W;
+					nFar += (live[i] && io >= (unsigned int)W) ? 1u : 0u;
+					if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
+					if (in) {
+						if (FIXED) {
+							// round(w * 2^F) lands in the mantissa of (2^52 + x); subtracting the bias leaves (1 << 52) | x
+							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
+							bins[(size_t)io * T + tid] += (unsigned long long)__double_as_longlong(t) - kPackBias;
+						}
+						else {
+							double* b = reinterpret_cast<double*>(bins) + (size_t)io * T + tid;
+							*b = __dadd_rn(*b, w[i]);
+							cnts[(size_t)io * T + tid] += 1;
+						}
 					}
 				}
+			}
+			else {
+				// MERGE (PTP_MERGE_BINS=1, 512 x 4 push kernels; off by default until measured): a thread's rings are neighbours in a
+				// z-ordered row and mostly share a cell; their weights are summed in registers and the bin sees one read-modify-write
+				// per run instead of one per ring (a dependent shared-memory round trip each). Same sums in fixed point; in fp64 the
+				// association changes at rounding level.
+				unsigned int pendIo = 0xffffffffu, pendC = 0;
+				double pendW = 0.0;
+				unsigned long long pendWord = 0ULL;
+				auto flushPending = [&]() {
+					if (pendIo == 0xffffffffu) return;
+					if (FIXED) bins[(size_t)pendIo * T + tid] += pendWord;
+					else {
+						double* b = reinterpret_cast<double*>(bins) + (size_t)pendIo * T + tid;
+						*b = __dadd_rn(*b, pendW);
+						cnts[(size_t)pendIo * T + tid] += (unsigned short)pendC;
+					}
+				};
+#pragma unroll
+				for (int i = 0; i < R; ++i) {
+					const unsigned int io = (unsigned int)(k[i] - k0);
+					const bool in = live[i] && io < (unsigned int)W;
+					farD |= live[i] && io >= (unsigned int)W;
+					nFar += (live[i] && io >= (unsigned int)W) ? 1u : 0u;
+					if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
+					if (in) {
+						if (io != pendIo) { flushPending(); pendIo = io; pendC = 0; pendW = 0.0; pendWord = 0ULL; }
+						if (FIXED) {
+							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
+							pendWord += (unsigned long long)__double_as_longlong(t) - kPackBias;
+						}
+						else { pendW = pendC ? __dadd_rn(pendW, w[i]) : w[i]; ++pendC; }
+					}
+				}
+				flushPending();
 			}
 			if (farD) {
 				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
@@ -489,6 +530,13 @@ __global__ void __launch_bounds__(256) k_tile_bounds(const PushArgs a, const Ptp
 template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st)
 	{
+		if (a.mergeBins && PUSH && T == 512 && R == 4) {            // the variant exists for the default tuning only
+			auto kernM = k_push_deposit<512, 4, true, FIXED, EXACT, true>;
+			cudaError_t eM = cudaFuncSetAttribute(kernM, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (eM != cudaSuccess) return eM;
+			kernM<<<grid, 512, smem, st>>>(a);
+			return cudaGetLastError();
+		}
 		auto kern = k_push_deposit<T, R, PUSH, FIXED, EXACT>;
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
@@ -538,6 +586,8 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 		// adds one system fence per CTA after the flush anyway (measured cost: ~12 us per step at 4 GPUs).
 		static const int fence = std::getenv("PTP_PEER_FENCE") ? 1 : 0;
 		a.pad1 = fence;
+		const char* mb = std::getenv("PTP_MERGE_BINS");             // read per call: tests switch it inside one process
+		a.mergeBins = mb ? std::atoi(mb) : PTP_MERGE_BINS_DEFAULT;
 	}
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
 	a.bndOffset = (long long)((size_t)t->capS * t->G - (size_t)p->index * t->G + (size_t)p->index * t->Nr);

@@ -17,14 +17,15 @@ static unsigned char* g_smem;
 #include "push_snippet.inc"
 
 struct CaseHeader {
-	int Nz, Nr, W, WE, fixed, exact, fixedBits, segTiles, nCta, pad;
+	int Nz, Nr, W, WE, fixed, exact, fixedBits, segTiles, nCta, mergeBins;
 	long long n;
 	double hz, length, dt, charge, mass;
 };
 
 template <bool FIXED, bool EXACT> static void run(const PushArgs& a, int nCta)
 {
-	emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT>(a); });
+	if (a.mergeBins) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, true>(a); });
+	else emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT>(a); });
 }
 
 int main(int argc, char** argv)
@@ -87,7 +88,7 @@ int main(int argc, char** argv)
 	a.fixedScale = (double)(1ULL << h.fixedBits);
 	a.eNodes = eNodes.data(); a.z = bz.data(); a.v = bv.data();
 	a.segs = segs.data(); a.ctaSegBegin = ctaSegBegin.data(); a.segBounds = bounds.data();
-	a.rho[0] = rho.data(); a.nRho = 1; a.pad1 = 0; a.bndOffset = G; a.lost = lost;
+	a.rho[0] = rho.data(); a.nRho = 1; a.pad1 = 0; a.mergeBins = h.mergeBins; a.bndOffset = G; a.lost = lost;
 	if (h.fixed) { if (h.exact) run<true, true>(a, nCta); else run<true, false>(a, nCta); }
 	else { if (h.exact) run<false, true>(a, nCta); else run<false, false>(a, nCta); }
 

@@ -25,7 +25,7 @@ def test_radix16_kernel_text_on_host_threads():
 
 
 # ------------------------------------------------------------------------------------------ K1 on host threads
-def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, fixed_bits=40, seg_tiles=2, n_cta=3):
+def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, fixed_bits=40, seg_tiles=2, n_cta=3, merge=0):
     import numpy as np
     exe = os.path.join(ROOT, "build", "emu", "emu_push")
     if not _BUILT.get("push"):
@@ -34,7 +34,7 @@ def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixe
         _BUILT["push"] = True
     case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
     with open(case, "wb") as f:
-        f.write(np.array([trap.Nz, trap.Nr, W, WE, fixed, exact, fixed_bits, seg_tiles, n_cta, 0], np.int32).tobytes())
+        f.write(np.array([trap.Nz, trap.Nr, W, WE, fixed, exact, fixed_bits, seg_tiles, n_cta, merge], np.int32).tobytes())
         f.write(np.array([len(r)], np.int64).tobytes())
         f.write(np.array([trap.hz, trap.length, dt, charge, mass], np.float64).tobytes())
         for a, t in ((enodes, np.float64), (r, np.int32), (z, np.float64), (v, np.float64)):
@@ -54,8 +54,9 @@ def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixe
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
-@pytest.mark.parametrize("W,WE,fixed,exact", [(44, 256, 0, 1), (44, 256, 0, 0), (44, 256, 1, 1), (6, 12, 0, 1), (6, 6, 1, 0)])
-def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed, exact):
+@pytest.mark.parametrize("W,WE,fixed,exact,merge", [(44, 256, 0, 1, 0), (44, 256, 0, 0, 0), (44, 256, 1, 1, 0), (6, 12, 0, 1, 0), (6, 6, 1, 0, 0),
+                                                    (44, 256, 0, 1, 1), (44, 256, 1, 0, 1), (6, 12, 0, 0, 1)])
+def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed, exact, merge):
     """The source text of k_push_deposit (pic-trapped-plasma_b200/csrc/ptp_push.cu) compiled for the host and run CTA by CTA
     on 512 threads, against the oracle on the C1 electrons plus fast rings near both trap ends (losses): positions / speeds
     ring by ring (EXACT arithmetic: bit for bit; FAST: 1e-14), loss count, deposit (fp64 1e-12; fixed point 2^-40 per ring),
@@ -78,7 +79,7 @@ def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed,
     pl.set_rings(r, z, v, float(kat["e_chargeMacro"]))
     pl.solve_poisson()
     enodes = trap.enodes()
-    zo, vo, grid, bnd, lost, seg_bounds = _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact)
+    zo, vo, grid, bnd, lost, seg_bounds = _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, merge=merge)
     # the reference's ring update, expression by expression (Source/PenningTrap.cpp:328-333, Source/Plasma.cpp:105-108)
     hz, n1 = trap.hz, trap.Nz + 1
     k = np.floor(z / hz).astype(np.int64)
