@@ -376,8 +376,8 @@ def main():
         e2e_steps = args.steps
         for _ in range(e2e_steps):
             trap.movePlasmas(DT, 1)
-        counts = [p.getNumMacro() for p in plasmas]        # D2H: the step's metric
-        d2h += 8 * len(plasmas)
+            counts = [p.getNumMacro() for p in plasmas]    # D2H every step: the step's metric (alive rings per species)
+            d2h += 8 * len(plasmas)
         t3 = time.perf_counter()
         rhs = plasmas[0].rhs()                             # D2H: density grid (the diagnostics' input)
         d2h += rhs.nbytes
@@ -388,7 +388,7 @@ def main():
         e2e_phases = {"upload_h2d": t1 - t0, "first_deposit_solve": t2 - t1, "steps_and_counts": t3 - t2, "readback_grid": t4 - t3}
         e2e = {"value": sum_over_ranks(float(sum(counts))) * e2e_steps / sec, "unit": "particle-steps/s",
                "h2d_bytes_per_step": h2d / e2e_steps, "d2h_bytes_per_step": d2h / e2e_steps,
-               "protocol": "upload rings from pinned host (H2D, %d B/ring) + first deposit/solve + %d x movePlasmas + read back alive counts and the density grid; "
+               "protocol": "upload rings from pinned host (H2D, %d B/ring) + first deposit/solve + %d x (movePlasmas + read back of the alive counts) + read back of the density grid; "
                            "rings stay resident between steps as in the reference's API (movePlasmas(dt) takes no ring data)" % (20, e2e_steps),
                "phases_s_rank0": e2e_phases}
 
