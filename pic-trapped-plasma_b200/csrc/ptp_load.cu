@@ -176,6 +176,7 @@ struct LoadScratch {
 	~LoadScratch() { dropStream(); cudaFree(cum); cudaFree(rows); }
 };
 
+// [place-begin] (tests/emu/emu_place.cpp: the placement kernel and, further down, the host arithmetic in front of it)
 struct PlaceRow {
 	int row, pad;
 	long long perRow;       // rings of the row over all shards (numAtR)
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(256) k_place(const PlaceRow* __restrict__ rows
 		id[pr.slot0 + q] = pr.id0 + q;
 	}
 }
+// [place-end]
 
 } // namespace
 
@@ -223,6 +225,7 @@ extern "C" int ptp_plasma_load_density(ptp_plasma* p, const double* density, dou
 	}
 	ptp_trap* t = p->trap;
 	PTP_CUDA(cudaSetDevice(t->device));
+	// [counts-begin] (pure host arithmetic up to [counts-end])
 	const int Nr = t->Nr, n1 = t->Nz + 1;
 	const double hz = t->hz, hr = t->hr;
 	const double PI = 3.141592653589793238463, KB = 1.380649e-23;          // Source/Constants.hpp:15-16
@@ -264,6 +267,7 @@ extern "C" int ptp_plasma_load_density(ptp_plasma* p, const double* density, dou
 		total += perRow[j];
 		local += count[j];
 	}
+	// [counts-end]
 	if (chargeMacroOut) *chargeMacroOut = chargeMacro;
 	if (nLoaded) *nLoaded = local;
 	PTP_TRY(ptp_plasma_set_layout(p, count, local, mcd));

@@ -234,3 +234,51 @@ def test_loader_deviate_stream_text_on_host_threads_equals_libstdcxx():
     r = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_rng.sh")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("identical to std::normal_distribution") == 4
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+@pytest.mark.parametrize("num_macro,mass,shard,n_shards", [(4000, 9.1093837015e-31, 0, 1), (100000, 1.67262192369e-27, 0, 1), (100000, 1.67262192369e-27, 2, 3)])
+def test_loader_text_on_host_threads_matches_reference_loader(tmp_path, density_files, num_macro, mass, shard, n_shards):
+    """ptp_plasma_load_density's host arithmetic and its placement kernel k_place (ptp_load.cu) on host threads against
+    Plasma::loadDensityFile of the compiled reference (Source/Plasma.cpp:558-622): rings per row and chargeMacro exact,
+    positions and speeds bit for bit (the host shares glibc's log with the reference), shard s of S = rings i = s (mod S) of
+    every row."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    if not _BUILT.get("place"):
+        b = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_place.sh")], capture_output=True, text=True, timeout=600)
+        assert b.returncode == 0, b.stdout + b.stderr
+        _BUILT["place"] = True
+    dens = np.loadtxt(density_files[0])
+    rt = ref.default_trap()
+    rp = rt.plasma("Species", mass, -ref.E_POS)
+    rp.load_density_file(density_files[0], 150.0, num_macro)
+    r0, z0, v0 = rp.rings()
+    par = rp.params()
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
+    with open(case, "wb") as f:
+        f.write(np.array([rt.Nz, rt.Nr, shard, n_shards], np.int32).tobytes())
+        f.write(np.array([num_macro], np.int64).tobytes())
+        f.write(np.array([rt.hz, rt.hr, 150.0, mass], np.float64).tobytes())
+        f.write(np.ascontiguousarray(dens, dtype=np.float64).tobytes())
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_place"), case, out], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = open(out, "rb").read()
+    n = int(np.frombuffer(raw, np.int64, 1, 0)[0])
+    charge_macro = float(np.frombuffer(raw, np.float64, 1, 8)[0])
+    per_row = np.frombuffer(raw, np.int64, rt.Nr, 16)
+    o = 16 + 8 * rt.Nr
+    r = np.frombuffer(raw, np.int32, n, o)
+    z = np.frombuffer(raw, np.float64, n, o + 4 * n)
+    v = np.frombuffer(raw, np.float64, n, o + 12 * n)
+    ids = np.frombuffer(raw, np.int64, n, o + 20 * n)
+    assert charge_macro == par["chargeMacro"]
+    assert np.array_equal(per_row, np.bincount(r0, minlength=rt.Nr))
+    within = np.concatenate([np.arange(c) for c in per_row if c > 0])        # index of a ring inside its row, reference order
+    mine = within % n_shards == shard
+    assert n == int(mine.sum()) and np.array_equal(ids, np.arange(n))
+    assert np.array_equal(r, r0[mine]) and np.array_equal(z, z0[mine]) and np.array_equal(v, v0[mine])
+    rt.close()
