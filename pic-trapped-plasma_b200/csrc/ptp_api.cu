@@ -196,6 +196,9 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 	PTP_CUDA(cudaGetDeviceProperties(&prop, device));
 	t->smCount = prop.multiProcessorCount;
 	t->smemMax = prop.sharedMemPerBlockOptin;
+	if (const char* e = std::getenv("PTP_FFT_R16")) t->fftR16 = std::atoi(e);
+	if (const char* e = std::getenv("PTP_FFT_FORM_ROWS")) t->fftFormRows = std::atoi(e);
+	if (const char* e = std::getenv("PTP_MERGE_BINS")) t->mergeBins = std::atoi(e);
 	if (const char* e = std::getenv("PTP_PLAN_SLACK")) t->planSlack = std::atoi(e);
 	if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
 	if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));

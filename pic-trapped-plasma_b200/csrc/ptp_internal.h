@@ -130,6 +130,10 @@ struct ptp_trap {
 	int nextCheckSteps = 4;          // adaptive mode: steps until the next read (short right after a load / sort: measures the baseline)
 	int sortCheckSteps = 16;         // adaptive mode: steps between two reads of the counters (PTP_SORT_CHECK_STEPS)
 	double sortFarFraction = 5e-5;   // adaptive mode: re-sort a species when more than this fraction of its deposits missed the window (PTP_SORT_FAR_FRACTION)
+	// kernel variants, read from the environment once, when the trap is created
+	int fftR16 = 1;                  // PTP_FFT_R16: rows of 4096 nodes go through the radix-16 inverse (0: radix-2 pass pairs)
+	int fftFormRows = 1;             // PTP_FFT_FORM_ROWS: the radix-16 inverse forms the rows above the plasma itself (0: k_thomas_expand)
+	int mergeBins = 0;               // PTP_MERGE_BINS: push kernel variant that merges a thread's same-cell rings (never timed: off)
 	int planSlack = -1;              // rows whose rings span more cells than the deposit window are cut into segments that leave this many
 	                                 // cells of the window free (room for the rings' drift until the next re-sort); -1: window / 2 (PTP_PLAN_SLACK)
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)

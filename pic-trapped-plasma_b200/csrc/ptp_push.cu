@@ -126,9 +126,7 @@ __device__ __forceinline__ void st_ring(double2* p, double2 v) { *p = v; }
 #ifndef PTP_L2_PREFETCH_TILES
 #define PTP_L2_PREFETCH_TILES 2
 #endif
-#ifndef PTP_MERGE_BINS_DEFAULT
-#define PTP_MERGE_BINS_DEFAULT 0
-#endif
+
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
 #ifndef PTP_HOST_EMU
@@ -586,8 +584,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 		// adds one system fence per CTA after the flush anyway (measured cost: ~12 us per step at 4 GPUs).
 		static const int fence = std::getenv("PTP_PEER_FENCE") ? 1 : 0;
 		a.pad1 = fence;
-		const char* mb = std::getenv("PTP_MERGE_BINS");             // read per call: tests switch it inside one process
-		a.mergeBins = mb ? std::atoi(mb) : PTP_MERGE_BINS_DEFAULT;
+		a.mergeBins = t->mergeBins;
 	}
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
 	a.bndOffset = (long long)((size_t)t->capS * t->G - (size_t)p->index * t->G + (size_t)p->index * t->Nr);

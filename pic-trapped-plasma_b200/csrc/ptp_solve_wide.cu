@@ -22,13 +22,6 @@
 
 #include <cstdlib>
 
-#ifndef PTP_FFT_R16_DEFAULT
-#define PTP_FFT_R16_DEFAULT 1
-#endif
-#ifndef PTP_FFT_FORM_ROWS_DEFAULT
-#define PTP_FFT_FORM_ROWS_DEFAULT 1
-#endif
-
 namespace {
 
 __device__ __forceinline__ void cpa8(void* smemDst, const void* gmemSrc, bool valid)
@@ -677,11 +670,7 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 // Does the inverse transform of this trap form the rows above the deposit itself (no k_thomas_expand needed)?
 bool ptp_solver_inverse_forms_rows(const ptp_trap* t)
 {
-	const char* r16env = std::getenv("PTP_FFT_R16");
-	const int r16 = r16env ? std::atoi(r16env) : PTP_FFT_R16_DEFAULT;
-	const char* fe = std::getenv("PTP_FFT_FORM_ROWS");
-	const int form = fe ? std::atoi(fe) : PTP_FFT_FORM_ROWS_DEFAULT;
-	return t->Nz == R16_N && r16 && form;
+	return t->Nz == R16_N && t->fftR16 && t->fftFormRows;
 }
 
 int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed)
@@ -689,10 +678,8 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 	const int N = t->Nz, Nr = t->Nr;
 	int bits = 0;
 	while ((1 << bits) < N) ++bits;
-	// N = 4096: three radix-16 rounds in registers (PTP_FFT_R16=1 selects it, =0 the radix-2 pass pairs)
-	const char* r16env = std::getenv("PTP_FFT_R16");               // read per call: tests switch it inside one process
-	const int r16 = r16env ? std::atoi(r16env) : PTP_FFT_R16_DEFAULT;
-	if (N == R16_N && r16) {
+	// N = 4096: three radix-16 rounds in registers (PTP_FFT_R16=0 at trap creation selects the radix-2 pass pairs instead)
+	if (N == R16_N && t->fftR16) {
 		const size_t sm16 = (size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
 		if (withField) {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
