@@ -52,18 +52,25 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	const size_t bytes = (size_t)cap * t->G * sizeof(double), old = (size_t)t->capS * t->G * sizeof(double);
 	double *rho = nullptr, *phi = nullptr, *spec = nullptr, *scale = nullptr;
 	const size_t span = (size_t)cap * t->G + (size_t)cap * t->Nr;       // doubles per parity: grids + row bounds
-	PTP_CUDA(cudaMalloc(&rho, 2 * span * sizeof(double) + 64 * sizeof(unsigned long long)));
-	PTP_CUDA(cudaMalloc(&phi, bytes));
-	PTP_CUDA(cudaMalloc(&spec, bytes));
-	PTP_CUDA(cudaMalloc(&scale, cap * sizeof(double)));
-	PTP_CUDA(cudaMemset(rho, 0, 2 * span * sizeof(double) + 64 * sizeof(unsigned long long)));
-	PTP_CUDA(cudaMemset(phi, 0, bytes));
-	PTP_CUDA(cudaMemset(scale, 0, cap * sizeof(double)));
-	if (t->capS) {
-		PTP_CUDA(cudaMemcpy(rho, t->rhoAll, old, cudaMemcpyDeviceToDevice));
-		PTP_CUDA(cudaMemcpy(phi, t->phiSelfAll, old, cudaMemcpyDeviceToDevice));
-		PTP_CUDA(cudaMemcpy(scale, t->dScale, t->capS * sizeof(double), cudaMemcpyDeviceToDevice));
+	const size_t storeBytes = 2 * span * sizeof(double) + 64 * sizeof(unsigned long long);
+	cudaError_t e = cudaMalloc(&rho, storeBytes);
+	if (e == cudaSuccess) e = cudaMalloc(&phi, bytes);
+	if (e == cudaSuccess) e = cudaMalloc(&spec, bytes);
+	if (e == cudaSuccess) e = cudaMalloc(&scale, cap * sizeof(double));
+	if (e == cudaSuccess) e = cudaMemset(rho, 0, storeBytes);
+	if (e == cudaSuccess) e = cudaMemset(phi, 0, bytes);
+	if (e == cudaSuccess) e = cudaMemset(spec, 0, bytes);
+	if (e == cudaSuccess) e = cudaMemset(scale, 0, cap * sizeof(double));
+	if (e == cudaSuccess && t->capS) {
+		e = cudaMemcpy(rho, t->rhoAll, old, cudaMemcpyDeviceToDevice);
+		if (e == cudaSuccess) e = cudaMemcpy(phi, t->phiSelfAll, old, cudaMemcpyDeviceToDevice);
+		if (e == cudaSuccess) e = cudaMemcpy(scale, t->dScale, t->capS * sizeof(double), cudaMemcpyDeviceToDevice);
 	}
+	if (e != cudaSuccess) {                                      // nothing of the trap has been touched yet
+		cudaFree(rho); cudaFree(phi); cudaFree(spec); cudaFree(scale);
+		return ptp_cuda_fail(e, "ensure_species_capacity", __FILE__, __LINE__);
+	}
+	for (ptp_plasma* p : t->plasmas) p->encValid = false;       // the touched-node ranges were not carried over: the solver scans
 	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
 	t->rhoStore = rho; t->rhoParity = 0; t->rhoAll = rho; t->peerStale = true; t->spanDoubles = span;
 	++t->cfgEpoch; ++t->layoutEpoch;
@@ -72,21 +79,27 @@ int ensure_species_capacity(ptp_trap* t, int need)
 	return PTP_OK;
 }
 
-int solve_species(ptp_trap* t, int first, int count, bool withField = false)
+// rowsWanted > 0 (only with withField, i.e. all species): the leading rows the caller needs; t->phiRows is updated.
+int solve_species(ptp_trap* t, int first, int count, bool withField = false, int rowsWanted = 0)
 {
 	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64;
 	const double* rho = t->rhoAll + (size_t)first * t->G;
 	double* phi = t->phiSelfAll + (size_t)first * t->G;
 	if (t->solver == PTP_SOLVER_SOR) {
 		PTP_TRY(ptp_sor_run(t, rho, fixed, t->dScale + first, count, phi));
+		if (withField) t->phiRows = t->Nr;
 		return withField ? ptp_node_field(t) : PTP_OK;
 	}
-	// the touched node range per row comes from the push kernel's flush when it has seen every deposit of the grid:
-	// one GPU, or peer-memory mode inside a step; an NCCL-reduced grid is scanned instead
-	const bool trust = ptp_comm_size(t) == 1 || (withField && ptp_peer_mode(t));
+	// the touched node range per row comes from the push kernel's flush when it has seen every deposit of the grid (one GPU,
+	// or peer-memory mode inside a step) and nothing has replaced the grids since; otherwise the grid is scanned
+	bool trust = ptp_comm_size(t) == 1 || (withField && ptp_peer_mode(t));
+	for (int s = first; s < first + count && trust; ++s) trust = t->plasmas[s]->encValid;
 	const uint2* enc = trust ? reinterpret_cast<const uint2*>(t->rhoAll + (size_t)t->capS * t->G) + (size_t)first * t->Nr : nullptr;
 	const int rowLimit = t->extentEpoch == t->layoutEpoch ? t->rowExtent : -1;
-	return ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField, enc, rowLimit);
+	int rowsDone = t->Nr;
+	PTP_TRY(ptp_solver_run(t, rho, fixed, t->dScale + first, count, t->specAll + (size_t)first * t->G, phi, withField, enc, rowLimit, rowsWanted, &rowsDone));
+	if (withField) t->phiRows = rowsDone;
+	return PTP_OK;
 }
 
 // Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
@@ -94,6 +107,7 @@ int push_deposit_all(ptp_trap* t, double dt)
 {
 	const int nS = (int)t->plasmas.size();
 	const size_t span = t->spanDoubles;
+	if (t->phiRows < t->rowExtent) PTP_TRY(ptp_materialize_fields(t));   // rings were loaded into rows the last solve left out
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	if (ptp_peer_mode(t)) {
 		// this step's target parity was zeroed one step ago (or at the start of the call); the other one - last step's
@@ -122,6 +136,7 @@ int push_deposit_all(ptp_trap* t, double dt)
 	for (ptp_plasma* p : t->plasmas) {
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 		PTP_TRY(ptp_push_launch(t, p, dt, true));
+		p->encValid = true;
 	}
 	return PTP_OK;
 }
@@ -141,23 +156,41 @@ int reduce_rho(ptp_trap* t)
 	return PTP_OK;
 }
 
-// Peer-memory mode, once per ptp_trap_step / ptp_trap_push_deposit call: map the peers, start from two clean parities.
+// Peer-memory mode, at the start of every ptp_trap_step / ptp_trap_push_deposit call. The step keeps the invariant "the
+// parity that is not in use is zero on every rank" by itself (push_deposit_all), so the collective part - mapping the peers'
+// grids, clearing both parities and a barrier behind the clearing - runs only when the grids were (re)allocated or rings were
+// (re)loaded; per-step callers (the host classes call ptp_trap_step(dt, 1) from movePlasmas) pay nothing here.
 int begin_exchange(ptp_trap* t)
 {
 	if (!ptp_peer_mode(t)) return PTP_OK;
 	PTP_TRY(ptp_peer_prepare(t));
+	if (t->peerCleanEpoch == t->layoutEpoch) return PTP_OK;
 	const size_t span = t->spanDoubles;
 	PTP_CUDA(cudaMemsetAsync(t->rhoStore, 0, 2 * span * sizeof(double), t->stream));
+	for (ptp_plasma* p : t->plasmas) p->encValid = false;
+	t->peerCleanEpoch = t->layoutEpoch;
 	return ptp_peer_barrier(t);
 }
 
 int solve_all(ptp_trap* t)
 {
-	if (t->plasmas.empty()) return ptp_node_field(t);
-	return solve_species(t, 0, (int)t->plasmas.size(), true);
+	if (t->plasmas.empty()) { t->phiRows = t->Nr; return ptp_node_field(t); }
+	const bool lazy = t->lazyRows && t->extentEpoch == t->layoutEpoch && t->rowExtent > 0;
+	return solve_species(t, 0, (int)t->plasmas.size(), true, lazy ? t->rowExtent : 0);
 }
 
 } // namespace
+
+// Whole-grid potentials and node field from the deposit grids as they stand (the sums of the last step, or of the last
+// stand-alone deposit): what the reference holds in Plasma::selfPotential after every solvePoisson (Source/Plasma.cpp:98).
+// The arithmetic per row is the same as in the step's solve (same fold row, same transforms), so the rows the push used do
+// not change by a bit.
+int ptp_materialize_fields(ptp_trap* t)
+{
+	if (t->phiRows >= t->Nr) return PTP_OK;
+	if (t->plasmas.empty()) { t->phiRows = t->Nr; return PTP_OK; }
+	return solve_species(t, 0, (int)t->plasmas.size(), true, 0);   // (no collective here: a getter may run on one rank only)
+}
 
 extern "C" {
 
@@ -192,30 +225,39 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 	t->device = device;
 	t->Nz = Nz; t->Nr = Nr; t->G = (long long)(Nz + 1) * Nr;
 	t->hz = hz; t->hr = hr; t->length = length; t->radius = radius;
-	cudaDeviceProp prop;
-	PTP_CUDA(cudaGetDeviceProperties(&prop, device));
-	t->smCount = prop.multiProcessorCount;
-	t->smemMax = prop.sharedMemPerBlockOptin;
-	if (const char* e = std::getenv("PTP_FFT_R16")) t->fftR16 = std::atoi(e);
-	if (const char* e = std::getenv("PTP_FFT_FORM_ROWS")) t->fftFormRows = std::atoi(e);
-	if (const char* e = std::getenv("PTP_MERGE_BINS")) t->mergeBins = std::atoi(e);
-	if (const char* e = std::getenv("PTP_PLAN_SLACK")) t->planSlack = std::atoi(e);
-	if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
-	if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));
-	PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
-	for (auto& ev : t->ev) PTP_CUDA(cudaEventCreate(&ev));
-	const size_t gb = (size_t)t->G * sizeof(double);
-	PTP_CUDA(cudaMalloc(&t->phiTrap, gb));
-	PTP_CUDA(cudaMalloc(&t->eNodes, gb));
-	PTP_CUDA(cudaMalloc(&t->tmpA, gb));
-	PTP_CUDA(cudaMalloc(&t->tmpB, gb));
-	PTP_CUDA(cudaMalloc(&t->tmpSpec, gb));
-	PTP_CUDA(cudaMemset(t->phiTrap, 0, gb));
-	PTP_CUDA(cudaMemset(t->eNodes, 0, gb));
-	int rc = ptp_solver_build(t);
-	if (rc != PTP_OK) { ptp_trap_destroy(t); return rc; }
-	rc = ensure_species_capacity(t, 2);
-	if (rc != PTP_OK) { ptp_trap_destroy(t); return rc; }
+	t->phiRows = Nr;
+	auto init = [&]() -> int {
+		cudaDeviceProp prop;
+		PTP_CUDA(cudaGetDeviceProperties(&prop, device));
+		t->smCount = prop.multiProcessorCount;
+		t->smemMax = prop.sharedMemPerBlockOptin;
+		if (const char* e = std::getenv("PTP_FFT_R16")) t->fftR16 = std::atoi(e);
+		if (const char* e = std::getenv("PTP_FFT_FORM_ROWS")) t->fftFormRows = std::atoi(e);
+		if (const char* e = std::getenv("PTP_MERGE_BINS")) t->mergeBins = std::atoi(e);
+		if (const char* e = std::getenv("PTP_PLAN_SLACK")) t->planSlack = std::atoi(e);
+		if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
+		if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));
+		if (const char* e = std::getenv("PTP_FULL_SOLVE")) t->lazyRows = std::atoi(e) == 0;
+		PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+		for (auto& ev : t->ev) PTP_CUDA(cudaEventCreate(&ev));
+		const size_t gb = (size_t)t->G * sizeof(double);
+		PTP_CUDA(cudaMalloc(&t->phiTrap, gb));
+		PTP_CUDA(cudaMalloc(&t->eNodes, gb));
+		PTP_CUDA(cudaMalloc(&t->tmpA, gb));
+		PTP_CUDA(cudaMalloc(&t->tmpB, gb));
+		PTP_CUDA(cudaMalloc(&t->tmpSpec, gb));
+		PTP_CUDA(cudaMemset(t->phiTrap, 0, gb));
+		PTP_CUDA(cudaMemset(t->eNodes, 0, gb));
+		PTP_TRY(ptp_solver_build(t));
+		return ensure_species_capacity(t, 2);
+	};
+	const int rc = init();
+	if (rc != PTP_OK) {                                          // one cleanup path: whatever was created so far is released
+		const std::string why = g_error;
+		ptp_trap_destroy(t);
+		g_error = why;
+		return rc;
+	}
 	*out = t;
 	return PTP_OK;
 }
@@ -349,6 +391,7 @@ int ptp_trap_get_enodes(ptp_trap* t, double* eNodes)
 {
 	if (!t || !eNodes) { ptp_set_error("ptp_trap_get_enodes: null argument"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_TRY(ptp_materialize_fields(t));
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	PTP_CUDA(cudaMemcpyAsync(eNodes, t->eNodes, (size_t)t->G * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
@@ -360,6 +403,7 @@ int ptp_trap_push_deposit(ptp_trap* t, double dt)
 	if (!t) { ptp_set_error("ptp_trap_push_deposit: null trap"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
+	PTP_TRY(ptp_layout_sync(t));
 	PTP_TRY(begin_exchange(t));
 	PTP_TRY(push_deposit_all(t, dt));
 	PTP_TRY(reduce_rho(t));
@@ -448,7 +492,8 @@ int capture_step_graph(ptp_trap* t, double dt)
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	PTP_TRY(ptp_solver_reserve(t, (int)t->plasmas.size()));
-	{ int extent; PTP_TRY(ptp_row_extent(t, &extent)); }       // may synchronise: not inside the capture
+	PTP_TRY(ptp_layout_sync(t));                                  // may synchronise: not inside the capture
+	if (t->phiRows < t->rowExtent) PTP_TRY(ptp_materialize_fields(t));
 	const int unit = ptp_peer_mode(t) ? 2 : 1;
 	const int parity0 = t->rhoParity;
 	const long long steps0 = t->stepCount;
@@ -495,8 +540,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 		t->evPool.push_back(e);
 	}
 	t->evSteps = timed;
-	// collective on the first call after a (re)load, cached afterwards; peer-memory mode needs it only on large grids
-	if (!ptp_peer_mode(t) || t->G >= (1LL << 20)) { int extent; PTP_TRY(ptp_row_extent(t, &extent)); }
+	PTP_TRY(ptp_layout_sync(t));                                 // collective on the first call after a (re)load, cached afterwards
 	PTP_TRY(begin_exchange(t));
 	int done = 0;
 	if (graph && nSteps > 0) {
@@ -530,6 +574,7 @@ int ptp_trap_step_programme(ptp_trap* t, double dt, int nSteps, const double* we
 	t->lastLaunches = 0;
 	t->evSteps = 0;
 	if (nSteps > 0) PTP_TRY(upload_weights(t, weights, (size_t)nSteps * t->nBasis));
+	PTP_TRY(ptp_layout_sync(t));
 	PTP_TRY(begin_exchange(t));
 	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
 	for (int s = 0; s < nSteps; ++s) {
@@ -695,6 +740,7 @@ int ptp_plasma_destroy(ptp_plasma* p)
 		t->plasmas[s]->index = (int)s - 1;
 	}
 	t->plasmas.erase(t->plasmas.begin() + p->index);
+	for (ptp_plasma* q : t->plasmas) q->encValid = false;       // the touched-node ranges were not moved with the grids
 	t->eNodesValid = false;
 	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->sortScratch); cudaFree(p->planScratch);
 	cudaFree(p->dRowOff); cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds); cudaFree(p->dLost);
@@ -708,14 +754,15 @@ int ptp_plasma_deposit(ptp_plasma* p)
 	ptp_trap* t = p->trap;
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
+	PTP_TRY(ptp_layout_sync(t));                                 // row extent and fixed-point scale (collective after a (re)load)
 	if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 	void* rho = t->rhoAll + (size_t)p->index * t->G;
 	PTP_CUDA(cudaMemsetAsync(rho, 0, (size_t)t->G * sizeof(double), t->stream));
 	PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)t->capS * t->G + (size_t)p->index * t->Nr, 0, (size_t)t->Nr * sizeof(double), t->stream));
 	PTP_TRY(ptp_push_launch(t, p, 0.0, false));
-	int extent = t->Nr;
-	if (ptp_comm_size(t) > 1) PTP_TRY(ptp_row_extent(t, &extent));
-	return ptp_comm_allreduce(t, rho, (size_t)extent * (t->Nz + 1), t->depositMode == PTP_DEPOSIT_FIXED64);
+	// the kernel saw this rank's rings only: its touched-node ranges describe the grid on one GPU, not the all-reduced one
+	p->encValid = ptp_comm_size(t) == 1;
+	return ptp_comm_allreduce(t, rho, (size_t)t->rowExtent * (t->Nz + 1), t->depositMode == PTP_DEPOSIT_FIXED64);
 }
 
 int ptp_plasma_deposit_solve(ptp_plasma* p)
@@ -753,6 +800,7 @@ int ptp_plasma_get_self_potential(ptp_plasma* p, double* phi)
 	if (!p || !phi) { ptp_set_error("ptp_plasma_get_self_potential: null argument"); return PTP_EINVAL; }
 	ptp_trap* t = p->trap;
 	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_TRY(ptp_materialize_fields(t));
 	PTP_CUDA(cudaMemcpyAsync(phi, t->phiSelfAll + (size_t)p->index * t->G, (size_t)t->G * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
 	return PTP_OK;
@@ -763,6 +811,7 @@ int ptp_plasma_set_self_potential(ptp_plasma* p, const double* phi)
 	if (!p || !phi) { ptp_set_error("ptp_plasma_set_self_potential: null argument"); return PTP_EINVAL; }
 	ptp_trap* t = p->trap;
 	PTP_CUDA(cudaSetDevice(t->device));
+	PTP_TRY(ptp_materialize_fields(t));                          // the other species' grids in full before this one is replaced
 	PTP_CUDA(cudaMemcpyAsync(t->phiSelfAll + (size_t)p->index * t->G, phi, (size_t)t->G * sizeof(double), cudaMemcpyHostToDevice, t->stream));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
 	t->eNodesValid = false;

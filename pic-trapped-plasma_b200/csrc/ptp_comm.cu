@@ -10,6 +10,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
+#include <cstring>
+
 struct PtpComm {
 	ncclComm_t comm = nullptr;
 	int nRanks = 1, rank = 0;
@@ -105,17 +108,12 @@ bool ptp_peer_mode(ptp_trap* t) { return t->comm && t->comm->nRanks > 1 && t->al
 int ptp_peer_prepare(ptp_trap* t)
 {
 	PtpComm* c = t->comm;
-	// the decision to remap must be collective too: any rank stale -> everybody remaps
+	// Remapping is a collective (all-gather of the IPC handles): ranks must agree on when it happens. They do when every rank
+	// issues the same sequence of calls (SPMD use: same species created in the same order), which include/ptp.h requires of
+	// multi-rank callers - the allocation is replaced only when a species is added beyond the reserved capacity.
+	if (!t->peerStale && c->mapped) return PTP_OK;
 	int* dFlag = nullptr;
-	PTP_CUDA(cudaMalloc(&dFlag, sizeof(int)));
-	int stale = (t->peerStale || !c->mapped) ? 1 : 0;
-	PTP_CUDA(cudaMemcpyAsync(dFlag, &stale, sizeof(int), cudaMemcpyHostToDevice, t->stream));
-	ncclResult_t r = g_nccl.AllReduce(dFlag, dFlag, 1, ncclInt32, ncclMax, c->comm, t->stream);
-	if (r != ncclSuccess) { cudaFree(dFlag); return nccl_fail(r, "ncclAllReduce(stale)"); }
-	PTP_CUDA(cudaMemcpyAsync(&stale, dFlag, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-	PTP_CUDA(cudaStreamSynchronize(t->stream));
-	cudaFree(dFlag);
-	if (!stale) return PTP_OK;
+	ncclResult_t r;
 	if (c->nRanks > 8) { ptp_set_error("peer-memory mode supports at most 8 ranks"); return PTP_EINVAL; }
 	unmap_peers(t);
 	cudaIpcMemHandle_t mine;
@@ -140,6 +138,7 @@ int ptp_peer_prepare(ptp_trap* t)
 	c->mapped = true;
 	c->spanDoubles = t->spanDoubles;
 	t->peerStale = false;
+	t->peerCleanEpoch = -1;
 	// every rank restarts its barrier generation and flags at zero; nobody may signal before everybody has done so
 	if (!c->dEpoch) PTP_CUDA(cudaMalloc(&c->dEpoch, sizeof(unsigned long long)));
 	PTP_CUDA(cudaMemsetAsync(c->dEpoch, 0, sizeof(unsigned long long), t->stream));
@@ -180,31 +179,53 @@ int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64)
 	return PTP_OK;
 }
 
-int ptp_comm_max_int(ptp_trap* t, int* value)
+int ptp_comm_max_int(ptp_trap* t, int* value, int n)
 {
 	if (!t->comm || t->comm->nRanks == 1) return PTP_OK;
 	int* dV = nullptr;
-	PTP_CUDA(cudaMalloc(&dV, sizeof(int)));
-	PTP_CUDA(cudaMemcpyAsync(dV, value, sizeof(int), cudaMemcpyHostToDevice, t->stream));
-	ncclResult_t r = g_nccl.AllReduce(dV, dV, 1, ncclInt32, ncclMax, t->comm->comm, t->stream);
+	PTP_CUDA(cudaMalloc(&dV, n * sizeof(int)));
+	cudaError_t e = cudaMemcpyAsync(dV, value, n * sizeof(int), cudaMemcpyHostToDevice, t->stream);
+	if (e != cudaSuccess) { cudaFree(dV); return ptp_cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__); }
+	ncclResult_t r = g_nccl.AllReduce(dV, dV, n, ncclInt32, ncclMax, t->comm->comm, t->stream);
 	if (r != ncclSuccess) { cudaFree(dV); return nccl_fail(r, "ncclAllReduce(max)"); }
-	PTP_CUDA(cudaMemcpyAsync(value, dV, sizeof(int), cudaMemcpyDeviceToHost, t->stream));
-	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	e = cudaMemcpyAsync(value, dV, n * sizeof(int), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
 	cudaFree(dV);
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "ptp_comm_max_int", __FILE__, __LINE__);
+	return PTP_OK;
+}
+
+// Quantities every rank must agree on after a (re)load, settled by one small collective per load: the outermost populated
+// row (rows above it never receive a deposit) and the fixed-point scale 2^F of the deposit sums. F follows from the GLOBAL
+// ring count (F = min(40, 62 - ceil(log2(N + 1))): node sums stay below 2^62); shards are unequal, so every rank derives
+// its bit count from its own rings times the rank count and the maximum over the ranks decides - otherwise ranks near a power
+// of two would scale the same grid differently.
+int ptp_layout_sync(ptp_trap* t)
+{
+	if (t->extentEpoch == t->layoutEpoch) return PTP_OK;
+	int ext = 0;
+	long long total = 0;
+	for (const ptp_plasma* p : t->plasmas) {
+		total += p->nUploaded;
+		for (int j = (int)p->rowLive.size() - 1; j >= ext; --j)
+			if (p->rowLive[j] > 0) { ext = j + 1; break; }
+	}
+	total *= ptp_comm_size(t);
+	int bits = 0;
+	while ((1LL << bits) < total + 1) ++bits;
+	int both[2] = { ext, bits };
+	PTP_TRY(ptp_comm_max_int(t, both, 2));
+	ext = both[0]; bits = both[1];
+	const int fixedBits = std::min(40, 62 - bits);
+	if (fixedBits != t->fixedBits) { t->fixedBits = fixedBits; ++t->cfgEpoch; }
+	t->rowExtent = ext;
+	t->extentEpoch = t->layoutEpoch;
 	return PTP_OK;
 }
 
 int ptp_row_extent(ptp_trap* t, int* extent)
 {
-	if (t->extentEpoch != t->layoutEpoch) {
-		int ext = 0;
-		for (const ptp_plasma* p : t->plasmas)
-			for (int j = (int)p->rowLive.size() - 1; j >= ext; --j)
-				if (p->rowLive[j] > 0) { ext = j + 1; break; }
-		PTP_TRY(ptp_comm_max_int(t, &ext));
-		t->rowExtent = ext;
-		t->extentEpoch = t->layoutEpoch;
-	}
+	PTP_TRY(ptp_layout_sync(t));
 	*extent = t->rowExtent;
 	return PTP_OK;
 }

@@ -56,6 +56,8 @@ struct ptp_plasma {
 	int nCta = 0;
 	unsigned long long* dLost = nullptr; // [2] device counters: rings lost since upload; deposits outside the private window since the last check
 	bool boundsValid = false;
+	bool encValid = false;       // the touched-node range per row kept next to this species' deposit grid (written by the push kernel's
+	                             // flush) describes the grid's present content
 };
 
 struct PtpComm; // ptp_comm.cu
@@ -139,6 +141,11 @@ struct ptp_trap {
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)
 	long long stepCount = 0;
 	bool eNodesValid = false;
+	// The push reads the node field only in rows that hold rings, and rings never change their row: a step solves for the
+	// populated rows only (lazyRows; PTP_FULL_SOLVE=1 turns that off). phiRows = leading rows of phiSelfAll / eNodes that are
+	// current; the whole grids are produced on demand from the deposit grids (ptp_materialize_fields) when a getter asks.
+	bool lazyRows = true;
+	int phiRows = 0;
 
 	PtpComm* comm = nullptr;
 	int allreduceKind = 0;
@@ -149,6 +156,8 @@ struct ptp_trap {
 	long long extentEpoch = -1;      // layoutEpoch rowExtent was computed for
 	int rowExtent = 0;
 	long long cleanEpoch = -1;       // layoutEpoch for which the rows >= rowExtent of rhoStore are known to be zero
+	long long peerCleanEpoch = -1;   // peer-memory mode: layoutEpoch for which both parities were cleared collectively (the invariant
+	                                 // "the parity not in use is zero" then carries over from call to call)
 
 	// CUDA-graph replay of the step (ptp_trap_set_graph)
 	bool useGraph = false;
@@ -181,14 +190,15 @@ void ptp_solver_free(ptp_trap* t);
 // withField: nS covers ALL species (phi = phiSelfAll) and the node field is produced too (fused when possible).
 // encBounds: per (species,row) touched node range as written by the push kernel (nullptr: scan rho for non-zeros).
 // rowLimit: radial rows >= rowLimit of rho are known to be zero (deposit grids: no ring lives there); -1 = unknown.
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false, const uint2* encBounds = nullptr, int rowLimit = -1);
+// rowsWanted > 0: only the first rowsWanted radial rows of phi (and of the node field) are needed; *rowsDone = rows produced.
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField = false, const uint2* encBounds = nullptr, int rowLimit = -1, int rowsWanted = 0, int* rowsDone = nullptr);
 int ptp_solver_apply(ptp_trap* t, const double* x, double* y);
 // ptp_solve_wide.cu: the same direct solve organised for large grids
 bool ptp_solver_fft_fits(const ptp_trap* t);
 // expand = false: rows above the block of the outermost deposit row are left to the inverse transform (rowsFormed = false there)
-int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand = true);
+int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand = true, int rowLimit = -1, int rowsOut = 0);
 bool ptp_solver_inverse_forms_rows(const ptp_trap* t);
-int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed = true);
+int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed = true, int rowsOut = 0);
 int ptp_node_field(ptp_trap* t);
 int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);
 int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi);
@@ -208,8 +218,10 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p);
 
 // ---- ptp_comm.cu ---------------------------------------------------------------------------------
 int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64);
-int ptp_comm_max_int(ptp_trap* t, int* value);                   // collective max over the ranks (synchronises the stream)
+int ptp_comm_max_int(ptp_trap* t, int* value, int n = 1);        // collective element-wise max over the ranks (synchronises the stream)
 int ptp_row_extent(ptp_trap* t, int* extent);                    // collective on the first call after a (re)load, cached afterwards
+int ptp_layout_sync(ptp_trap* t);                                // row extent + fixed-point scale agreed between the ranks (same caching)
+int ptp_materialize_fields(ptp_trap* t);                         // ptp_api.cu: whole-grid potentials and node field when only the populated rows are current
 void ptp_comm_free(ptp_trap* t);
 int ptp_comm_size(ptp_trap* t);
 int ptp_comm_rank(ptp_trap* t);

@@ -448,13 +448,8 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 			PTP_CUDA(cudaMemsetAsync(p->id + padBegin, 0xFF, padLen * sizeof(long long), t->stream));
 		}
 	}
-	// fixed-point scale: node sums stay below 2^62 for the whole (multi-GPU) population
-	long long total = 0;
-	for (ptp_plasma* q : t->plasmas) total += q->nUploaded;
-	total *= ptp_comm_size(t);
-	int bits = 0;
-	while ((1LL << bits) < total + 1) ++bits;
-	t->fixedBits = std::min(40, 62 - bits);
+	// (the fixed-point scale follows from the global ring count: ptp_layout_sync, first use after this load)
+	p->encValid = false;
 	return PTP_OK;
 }
 
@@ -607,6 +602,8 @@ int ptp_plasma_potential_energy(ptp_plasma* p, double chargeMacro, double* pe)
 	PTP_CUDA(cudaSetDevice(t->device));
 	*pe = 0.0;
 	if (p->segs.empty()) return PTP_OK;
+	for (int j = t->Nr - 1; j >= t->phiRows; --j)               // rings in rows the last step's solve left out (loaded since)
+		if (p->rowLive[j] > 0) { PTP_TRY(ptp_materialize_fields(t)); break; }
 	double* dOut = nullptr;
 	PTP_CUDA(cudaMalloc(&dOut, sizeof(double)));
 	PTP_CUDA(cudaMemsetAsync(dOut, 0, sizeof(double), t->stream));

@@ -143,6 +143,20 @@ template <typename T> __device__ __forceinline__ T warp_sum(T x)
 	return x;
 }
 
+// Grid adds of the flush. In peer-memory mode (nRho > 1) several GPUs add to the same node of the same grid over NVLink:
+// the operation must be atomic at system scope (red.relaxed.sys) - a .gpu-scope atomic is only defined among the threads of
+// one device. On one GPU the narrower scope is kept.
+template <typename V> __device__ __forceinline__ void grid_add(V* p, V val, bool sys)
+{
+	if (sys) atomicAdd_system(p, val);
+	else atomicAdd(p, val);
+}
+__device__ __forceinline__ void grid_max(unsigned int* p, unsigned int val, bool sys)
+{
+	if (sys) atomicMax_system(p, val);
+	else atomicMax(p, val);
+}
+
 template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE = false>
 __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
@@ -161,6 +175,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int n1 = a.Nz + 1;
+	const bool sys = a.nRho > 1;                 // remote grids are among the targets: system-scope atomics
 	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
 
 	for (int s = a.ctaSegBegin[blockIdx.x]; s < a.ctaSegBegin[blockIdx.x + 1]; ++s) {
@@ -358,15 +373,15 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 							const unsigned long long wq = (unsigned long long)__double_as_longlong(t) & kSumMask;
 							for (int pr = 0; pr < a.nRho; ++pr) {
 								unsigned long long* g = reinterpret_cast<unsigned long long*>(a.rho[pr]) + rowBase + k[i];
-								atomicAdd(g, (1ULL << a.fixedBits) - wq);
-								atomicAdd(g + 1, wq);
+								grid_add(g, (1ULL << a.fixedBits) - wq, sys);
+								grid_add(g + 1, wq, sys);
 							}
 						}
 						else {
 							for (int pr = 0; pr < a.nRho; ++pr) {
 								double* g = reinterpret_cast<double*>(a.rho[pr]) + rowBase + k[i];
-								atomicAdd(g, __dsub_rn(1.0, w[i]));
-								atomicAdd(g + 1, w[i]);
+								grid_add(g, __dsub_rn(1.0, w[i]), sys);
+								grid_add(g + 1, w[i], sys);
 							}
 						}
 					}
@@ -445,14 +460,14 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 					if (i <= hi) val += (redC[i] << a.fixedBits) - redS[i];
 					if (i > lo) val += redS[i - 1];
 					if (val)
-						for (int pr = 0; pr < a.nRho; ++pr) atomicAdd(reinterpret_cast<unsigned long long*>(a.rho[pr]) + rowBase + k0 + i, val);
+						for (int pr = 0; pr < a.nRho; ++pr) grid_add(reinterpret_cast<unsigned long long*>(a.rho[pr]) + rowBase + k0 + i, val, sys);
 				}
 				else {
 					double val = 0.0;
 					if (i <= hi) val = (double)redC[i] - __longlong_as_double((long long)redS[i]);
 					if (i > lo) val += __longlong_as_double((long long)redS[i - 1]);
 					if (val != 0.0)
-						for (int pr = 0; pr < a.nRho; ++pr) atomicAdd(reinterpret_cast<double*>(a.rho[pr]) + rowBase + k0 + i, val);
+						for (int pr = 0; pr < a.nRho; ++pr) grid_add(reinterpret_cast<double*>(a.rho[pr]) + rowBase + k0 + i, val, sys);
 				}
 			}
 			// nodes gMin .. gMax+1 of this row were touched - by the flush above or, for rings outside the window, by their own
@@ -461,8 +476,8 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 			if (tid == 0)
 				for (int pr = 0; pr < a.nRho; ++pr) {
 					unsigned int* bd = reinterpret_cast<unsigned int*>(reinterpret_cast<double*>(a.rho[pr]) + a.bndOffset) + 2 * seg.row;
-					atomicMax(bd, (unsigned int)(a.Nz + 2 - gMin));
-					atomicMax(bd + 1, (unsigned int)(gMax + 2));
+					grid_max(bd, (unsigned int)(a.Nz + 2 - gMin), sys);
+					grid_max(bd + 1, (unsigned int)(gMax + 2), sys);
 				}
 		}
 		if (a.nRho > 1 && a.pad1) {                      // remote adds performed before the grid can be declared complete:

@@ -80,9 +80,15 @@ constexpr int FWD_RP = 128;     // deposit rows handled per pass
 template <bool A_FIXED, int FWD_MB>
 __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ rho, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
 	const double* __restrict__ FT, const double* __restrict__ rowScale, double fixedInv,
-	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thLower,
-	double* __restrict__ spec, int Nr, int n1)
+	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thR, const double* __restrict__ thQ,
+	const double* __restrict__ thLower, double* __restrict__ spec, int Nr, int n1, int Jf, int rowsOut)
 {
+	// Jf: a row at or above the outermost deposit row (host-known: rings never change their row, so no deposit can land above
+	// the outermost populated row; Nr - 1 when nothing is known). The rows above Jf carry no deposit and are folded into the
+	// pivot of row Jf (thQ, "burn at both ends"): forward sweep over the touched rows below Jf, x_Jf from the folded pivot,
+	// back-substitution below, and above Jf the homogeneous recurrence x_j = thR_j x_{j-1} - only as far as rowsOut, the
+	// number of rows the caller wants (the push needs the potential in the populated rows only). With Jf = Nr - 1 this is the
+	// plain Thomas solve.
 	// Everything global is brought in with cp.async in a few large waves (the solve runs right after the push kernel
 	// has streamed gigabytes through L2, so every serial round trip costs a DRAM latency).
 	extern __shared__ double sB[];                              // [Nr][FWD_MB] beta -> alpha
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	double* sFT = sCp + (size_t)Nr * FWD_MB;                    // [FWD_KB][FWD_MB] chunk of the forward matrix
 	double* sRho = sFT + FWD_KB * FWD_MB;                       // [FWD_RP][FWD_KB] chunk of the deposit rows of this pass
 	int2* sBd = reinterpret_cast<int2*>(sRho + (size_t)FWD_RP * FWD_KB); // [Nr] non-zero range per row
-	__shared__ int sLo, sHi;
+	__shared__ int sLo, sHi, sJ0;
 	const int tid = threadIdx.x, mi = tid % FWD_MB, slot = tid / FWD_MB;
 	const int mBase = blockIdx.x * FWD_MB;
 	const int m = mBase + mi;
@@ -101,10 +107,15 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	const double* b = rho + (size_t)s * Nr * n1;
 	double* sLower = reinterpret_cast<double*>(sBd + Nr);       // [Nr] sub-diagonal of T_r
 	const int lane = tid & 31, warp = tid >> 5;
-	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; }
-	for (int j = slot; j < Nr; j += 256 / FWD_MB) {
-		cp_async8(&sInv[j * FWD_MB + mi], thInv + (size_t)j * n1 + (mOk ? m : 0), mOk);
-		cp_async8(&sCp[j * FWD_MB + mi], thCp + (size_t)j * n1 + (mOk ? m : 0), mOk);
+	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; sJ0 = Jf; }
+	const double q = (tid < FWD_MB && mOk) ? thQ[(size_t)Jf * n1 + m] : 0.0;
+	for (int j = slot; j < rowsOut || j <= Jf; j += 256 / FWD_MB) {
+		const size_t off = (size_t)j * n1 + (mOk ? m : 0);
+		if (j < Jf) {
+			cp_async8(&sInv[j * FWD_MB + mi], thInv + off, mOk);
+			cp_async8(&sCp[j * FWD_MB + mi], thCp + off, mOk);
+		}
+		else if (j > Jf) cp_async8(&sCp[j * FWD_MB + mi], thR + off, mOk);
 		sB[j * FWD_MB + mi] = 0.0;
 	}
 	for (int j = tid; j < Nr; j += 256) cp_async8(&sLower[j], thLower + j, true);
@@ -117,14 +128,15 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 			bd = e.y ? make_int2(n1 + 1 - (int)e.x, (int)e.y - 1) : make_int2(INT_MAX, INT_MIN);
 		}
 		else bd = bounds[s * Nr + j];
+		if (j > Jf) bd = make_int2(INT_MAX, INT_MIN);           // (cannot hold a deposit)
 		sBd[j] = bd;
-		if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); }
+		if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); atomicMin(&sJ0, j); }
 	}
 	__syncthreads();
 	const int kLo = sLo, kHi = sHi;
 	constexpr int SLOTS = 256 / FWD_MB, U = FWD_RP / SLOTS;     // this thread's rows of a pass: jp + slot + u * SLOTS
 	double acc[U];
-	for (int jp = 0; jp < Nr; jp += FWD_RP) {
+	for (int jp = 0; jp <= Jf; jp += FWD_RP) {
 #pragma unroll
 		for (int u = 0; u < U; ++u) acc[u] = 0.0;
 		for (int k0 = kLo; k0 <= kHi; k0 += FWD_KB) {
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 				cp_async8(&sFT[e], FT + (size_t)(k0 + kk) * n1 + (ok ? mBase + mm : 0), ok);
 			}
 			// deposit rows of this pass: one warp per row, only rows that have data in this chunk
-			for (int jj = warp; jj < FWD_RP && jp + jj < Nr; jj += 8) {
+			for (int jj = warp; jj < FWD_RP && jp + jj <= Jf; jj += 8) {
 				const int j = jp + jj;
 				const int2 bd = sBd[j];
 				if (bd.x > bd.y || bd.y < k0 || bd.x >= k0 + kn) continue;      // uniform per warp
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
 				const int jj = slot + u * SLOTS, j = jp + jj;
-				if (j >= Nr) continue;
+				if (j > Jf) continue;
 				const int2 bd = sBd[j];
 				const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
 				double t = acc[u];
@@ -162,34 +174,38 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
 			const int j = jp + slot + u * SLOTS;
-			if (j < Nr) sB[j * FWD_MB + mi] = acc[u] * scale;
+			if (j <= Jf) sB[j * FWD_MB + mi] = acc[u] * scale;
 		}
 	}
 	asm volatile("cp.async.wait_group 0;\n" ::);
 	__syncthreads();
 	if (tid < FWD_MB && mOk) {
-		// forward sweep y_j = g_j - (l_j inv_j) y_{j-1}; the coefficients of 8 rows are prepared off the chain, so the
-		// serial part is one dependent FMA per row
-		double y = sB[mi] * sInv[mi];
-		sB[mi] = y;
-		for (int j0 = 1; j0 < Nr; j0 += 8) {
+		// forward sweep over rows J0 .. Jf-1 (J0 = first touched row; below it y = 0):  y_j = g_j - (l_j inv_j) y_{j-1}; the
+		// coefficients of 8 rows are prepared off the chain, so the serial part is one dependent FMA per row
+		const int J0 = sJ0;
+		double y = 0.0;
+		for (int j0 = J0; j0 < Jf; j0 += 8) {
 			double c[8], g[8];
 #pragma unroll
 			for (int u = 0; u < 8; ++u) {
-				const int j = min(j0 + u, Nr - 1);
+				const int j = min(j0 + u, Jf - 1);
 				const double inv = sInv[j * FWD_MB + mi];
 				g[u] = sB[j * FWD_MB + mi] * inv;
 				c[u] = -(sLower[j] * inv);
 			}
 #pragma unroll
 			for (int u = 0; u < 8; ++u)
-				if (j0 + u < Nr) { y = fma(c[u], y, g[u]); g[u] = y; }
+				if (j0 + u < Jf) { y = fma(c[u], y, g[u]); g[u] = y; }
 #pragma unroll
 			for (int u = 0; u < 8; ++u)
-				if (j0 + u < Nr) sB[(j0 + u) * FWD_MB + mi] = g[u];
+				if (j0 + u < Jf) sB[(j0 + u) * FWD_MB + mi] = g[u];
 		}
-		// backward sweep x_j = y_j - cp_j x_{j+1}
-		for (int j0 = Nr - 2; j0 >= 0; j0 -= 8) {
+		// row Jf closes the system: the rows above it are folded into the pivot 1 / thQ
+		const double xJ = (sB[Jf * FWD_MB + mi] - sLower[Jf] * y) * q;
+		sB[Jf * FWD_MB + mi] = xJ;
+		// back-substitution below Jf:  x_j = y_j - cp_j x_{j+1}
+		y = xJ;
+		for (int j0 = Jf - 1; j0 >= 0; j0 -= 8) {
 			double c[8], g[8];
 #pragma unroll
 			for (int u = 0; u < 8; ++u) {
@@ -204,10 +220,20 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 			for (int u = 0; u < 8; ++u)
 				if (j0 - u >= 0) sB[(j0 - u) * FWD_MB + mi] = g[u];
 		}
+		// above Jf:  x_j = r_j x_{j-1}
+		y = xJ;
+		for (int j0 = Jf + 1; j0 < rowsOut; j0 += 8) {
+			double c[8];
+#pragma unroll
+			for (int u = 0; u < 8; ++u) c[u] = sCp[min(j0 + u, rowsOut - 1) * FWD_MB + mi];
+#pragma unroll
+			for (int u = 0; u < 8; ++u)
+				if (j0 + u < rowsOut) { y = c[u] * y; sB[(j0 + u) * FWD_MB + mi] = y; }
+		}
 	}
 	__syncthreads();
 	double* out = spec + (size_t)s * Nr * n1;
-	for (int j = slot; j < Nr; j += 256 / FWD_MB)
+	for (int j = slot; j < rowsOut; j += 256 / FWD_MB)
 		if (mOk) out[(size_t)j * n1 + m] = sB[j * FWD_MB + mi];
 }
 
@@ -729,13 +755,19 @@ int ptp_solver_reserve(ptp_trap* t, int nS)
 	return PTP_OK;
 }
 
-int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds, int rowLimit)
+int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, double* phi, bool withField, const uint2* encBounds, int rowLimit, int rowsWanted, int* rowsDone)
 {
+	if (rowsDone) *rowsDone = t->Nr;
 	if (nS <= 0) return PTP_OK;
 	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
 	PTP_TRY(ptp_solver_reserve(t, nS));
 	if (!encBounds) { k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds, Nr, rowLimit < 0 ? Nr : rowLimit); t->lastLaunches++; }
+	// Rows to produce: all of them, or - for the step, where only the populated rows are ever read by the push - the first
+	// rowsWanted, rounded up to whole blocks of the radial tables (a multiple of the inverse kernels' strip height too).
+	int rowsOut = Nr;
+	if (rowsWanted > 0 && rowsWanted < Nr) rowsOut = std::min(Nr, (rowsWanted + PTP_THOMAS_BLOCK - 1) / PTP_THOMAS_BLOCK * PTP_THOMAS_BLOCK);
+	if (rowLimit >= 0 && rowsOut < rowLimit) rowsOut = Nr;         // (a caller asking for fewer rows than may hold a deposit gets all)
 	auto smFwdBytes = [&](int mb) {
 		return ((size_t)3 * Nr * mb + (size_t)FWD_KB * mb + (size_t)FWD_RP * FWD_KB + (size_t)Nr) * sizeof(double) + (size_t)Nr * sizeof(int2);
 	};
@@ -748,23 +780,27 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= t->smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const size_t smField = smFieldBytes(ringStages);
 	const bool useFft = ptp_solver_fft_fits(t) && (t->solver == PTP_SOLVER_DIRECT_FFT || smField > t->smemMax);
+	if (!useFft && smField > t->smemMax) rowsOut = Nr;          // chunked inverse GEMM + separate node field: whole grids only
+	if (rowsDone) *rowsDone = rowsOut;
 	// large grids (many radial nodes or long rows): separate forward transform + streamed radial solves (ptp_solve_wide.cu)
 	const bool wide = mb == 4 || useFft || smFwd > t->smemMax;
 	if (wide) {
 		const bool formInInverse = useFft && ptp_solver_inverse_forms_rows(t);
-		PTP_TRY(ptp_solver_forward_wide(t, rho, rhoIsFixed, dScale, nS, spec, encBounds, !formInInverse));
+		PTP_TRY(ptp_solver_forward_wide(t, rho, rhoIsFixed, dScale, nS, spec, encBounds, !formInInverse, rowLimit, rowsOut));
 		if (useFft) {
-			PTP_TRY(ptp_solver_inverse_fft(t, spec, phi, nS, withField, !formInInverse));
+			PTP_TRY(ptp_solver_inverse_fft(t, spec, phi, nS, withField, !formInInverse, rowsOut));
 			if (withField) t->eNodesValid = true;
 			return PTP_OK;
 		}
 	}
 	else {
 		const dim3 gridFwd((n1 + mb - 1) / mb, nS);
+		// the fold row of the radial solves: the outermost row that can hold a deposit
+		const int Jf = rowLimit < 0 ? Nr - 1 : std::max(0, std::min(rowLimit, Nr) - 1);
 		auto launchFwd = [&](auto kern, double fInv) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd);
 			if (e != cudaSuccess) return e;
-			kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thLower, spec, Nr, n1);
+			kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thR, t->thQ, t->thLower, spec, Nr, n1, Jf, rowsOut);
 			return cudaGetLastError();
 		};
 		const cudaError_t ef = rhoIsFixed ? launchFwd(k_fwd_thomas<true, 16>, fixedInv) : launchFwd(k_fwd_thomas<false, 16>, 1.0);
@@ -776,7 +812,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		auto launchInv = [&](auto kern, bool field) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smField);
 			if (e != cudaSuccess) return e;
-			const dim3 grid(field ? (n1 + 1 + INV_TN - 3) / (INV_TN - 2) : (n1 + INV_TN - 1) / INV_TN, (Nr + INV_TM - 1) / INV_TM);
+			const dim3 grid(field ? (n1 + 1 + INV_TN - 3) / (INV_TN - 2) : (n1 + INV_TN - 1) / INV_TN, (rowsOut + INV_TM - 1) / INV_TM);
 			kern<<<grid, 256, smField, t->stream>>>(spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz, ringStages);
 			return cudaGetLastError();
 		};
@@ -788,6 +824,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		fieldDone = withField;
 	}
 	else {
+		// (rows that are not a power of two and too long for the fused kernel: all rows, one GEMM over the species)
 		const int kc = n1 < INV_KC ? n1 : INV_KC;
 		size_t smInv = ((size_t)INV_TM * (kc | 1) + (size_t)8 * INV_ST * INV_KS * INV_TN) * sizeof(double);
 		if (smInv < (size_t)8 * INV_TM * INV_TN * sizeof(double)) smInv = (size_t)8 * INV_TM * INV_TN * sizeof(double);

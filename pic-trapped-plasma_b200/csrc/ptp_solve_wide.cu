@@ -20,6 +20,7 @@
 
 #include <limits.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace {
@@ -201,7 +202,7 @@ constexpr int TW_RCAP = 160;    // rows of the compact path: 3 x 160 x 256 B = 1
 
 __global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAll, const int2* __restrict__ bounds, const uint2* __restrict__ encBounds,
 	const double* __restrict__ thInv, const double* __restrict__ thCp, const double* __restrict__ thR, const double* __restrict__ thQ,
-	const double* __restrict__ thP, const double* __restrict__ thLower, double* __restrict__ xbAll, int* __restrict__ wideJ, int Nr, int n1)
+	const double* __restrict__ thP, const double* __restrict__ thLower, double* __restrict__ xbAll, int* __restrict__ wideJ, int Nr, int n1, int rowsOut)
 {
 	extern __shared__ __align__(16) double smw[];
 	double* ring = smw;                                         // streamed: [TW_ST][2][TW_RS][32]; compact: sInv | sB | sC, [TW_RCAP][32] each
@@ -316,17 +317,18 @@ __global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAl
 	const int nB = (Nr + TW_BLK - 1) / TW_BLK, bFirst = J / TW_BLK + 1;
 	double* xb = xbAll + (size_t)s * nB * n1;
 	if (blockIdx.x == 0 && lane == 0) wideJ[s] = J;
-	for (int b0 = bFirst; b0 < nB; b0 += 16) {
+	const int nBOut = min(nB, (rowsOut + TW_BLK - 1) / TW_BLK);  // blocks the caller wants (the step: the populated rows only)
+	for (int b0 = bFirst; b0 < nBOut; b0 += 16) {
 		double pb[16];
 #pragma unroll
 		for (int u = 0; u < 16; ++u) {
 			const int b = b0 + u;
-			pb[u] = (b < nB && mOk) ? thP[(size_t)min(Nr - 1, b * TW_BLK + TW_BLK - 1) * n1 + m] : 0.0;
+			pb[u] = (b < nBOut && mOk) ? thP[(size_t)min(Nr - 1, b * TW_BLK + TW_BLK - 1) * n1 + m] : 0.0;
 		}
 #pragma unroll
 		for (int u = 0; u < 16; ++u) {
 			const int b = b0 + u;
-			if (b < nB && mOk) xb[(size_t)b * n1 + m] = x;
+			if (b < nBOut && mOk) xb[(size_t)b * n1 + m] = x;
 			x = pb[u] * x;
 		}
 	}
@@ -633,12 +635,14 @@ bool ptp_solver_fft_fits(const ptp_trap* t)
 }
 
 // beta -> alpha for nS grids: forward transform of the touched rows + radial solves. bounds / encBounds as in ptp_solver_run.
-int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand)
+int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand, int rowLimit, int rowsOut)
 {
 	const int n1 = t->Nz + 1, Nr = t->Nr;
+	if (rowsOut <= 0 || rowsOut > Nr) rowsOut = Nr;
+	const int rowsIn = rowLimit < 0 ? Nr : std::max(1, std::min(rowLimit, Nr));   // rows that can hold a deposit
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
 	const size_t smDct = (size_t)2 * (FD_K * FD_M + FD_K * FD_RP) * sizeof(double);
-	const dim3 gridDct((n1 + FD_M - 1) / FD_M, (Nr + FD_R - 1) / FD_R, nS);
+	const dim3 gridDct((n1 + FD_M - 1) / FD_M, (rowsIn + FD_R - 1) / FD_R, nS);
 	if (rhoIsFixed) {
 		PTP_CUDA(cudaFuncSetAttribute(k_fwd_dct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smDct));
 		k_fwd_dct<true><<<gridDct, 256, smDct, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fixedInv, spec, Nr, n1);
@@ -654,12 +658,12 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 	if (smTh > t->smemMax) { ptp_set_error("direct solver: Nr too large for the radial-solve kernel of this build"); return PTP_EINVAL; }
 	PTP_CUDA(cudaFuncSetAttribute(k_thomas_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smTh));
 	k_thomas_wide<<<dim3((n1 + 31) / 32, nS), 128, smTh, t->stream>>>(spec, t->rowBounds, encBounds, t->thInv, t->thCp, t->thR, t->thQ, t->thP, t->thLower,
-		t->wideXb, t->wideJ, Nr, n1);
+		t->wideXb, t->wideJ, Nr, n1, rowsOut);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_wide launch", __FILE__, __LINE__);
 	t->lastLaunches += 2;
 	if (!expand) return PTP_OK;                                 // the inverse transform forms the rows above the deposit itself
-	k_thomas_expand<<<dim3((n1 + 255) / 256, (Nr + 7) / 8, nS), 256, 0, t->stream>>>(spec, t->wideXb, t->wideJ, t->thP, Nr, n1);
+	k_thomas_expand<<<dim3((n1 + 255) / 256, (rowsOut + 7) / 8, nS), 256, 0, t->stream>>>(spec, t->wideXb, t->wideJ, t->thP, Nr, n1);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_expand launch", __FILE__, __LINE__);
 	t->lastLaunches += 1;
@@ -673,9 +677,10 @@ bool ptp_solver_inverse_forms_rows(const ptp_trap* t)
 	return t->Nz == R16_N && t->fftR16 && t->fftFormRows;
 }
 
-int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed)
+int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed, int rowsOut)
 {
 	const int N = t->Nz, Nr = t->Nr;
+	if (rowsOut <= 0 || rowsOut > Nr) rowsOut = Nr;
 	int bits = 0;
 	while ((1 << bits) < N) ++bits;
 	// N = 4096: three radix-16 rounds in registers (PTP_FFT_R16=0 at trap creation selects the radix-2 pass pairs instead)
@@ -683,12 +688,12 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 		const size_t sm16 = (size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
 		if (withField) {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-			k_idct_r16_field<true><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz,
+			k_idct_r16_field<true><<<rowsOut, 256, sm16, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz,
 				rowsFormed ? nullptr : t->wideXb, t->wideJ, t->thP, TW_BLK);
 		}
 		else {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-			k_idct_r16_field<false><<<Nr, 256, sm16, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, t->hz,
+			k_idct_r16_field<false><<<rowsOut, 256, sm16, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, t->hz,
 				rowsFormed ? nullptr : t->wideXb, t->wideJ, t->thP, TW_BLK);
 		}
 		const cudaError_t e16 = cudaGetLastError();
@@ -700,11 +705,11 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 	const int threads = N >= 1024 ? 256 : 128;
 	if (withField) {
 		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-		k_idct_fft_field<true><<<Nr, threads, sm, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, N, bits, t->hz);
+		k_idct_fft_field<true><<<rowsOut, threads, sm, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, N, bits, t->hz);
 	}
 	else {
 		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-		k_idct_fft_field<false><<<Nr, threads, sm, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, N, bits, t->hz);
+		k_idct_fft_field<false><<<rowsOut, threads, sm, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, N, bits, t->hz);
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_idct_fft_field launch", __FILE__, __LINE__);

@@ -31,11 +31,17 @@ int main(int argc, char** argv)
 	std::fclose(f);
 
 #include "tables_snippet.inc"
-	(void)thR; (void)thQ; (void)thP; (void)hr; (void)hr2;
+	(void)thP; (void)hr; (void)hr2;
 	const size_t smemMax = 232448;
 	std::vector<unsigned char> smem;                            // exactly the dynamic shared memory each launch requests (AddressSanitizer)
 	auto dynSmem = [&](size_t bytes) { smem.assign(bytes, 0); g_smem = smem.data(); };
 	const int nS = 1, M = nS * Nr;
+	// optional: rows that may hold a deposit (the outermost populated row + 1) and rows the caller wants, as ptp_solver_run gets them
+	const int rowLimit = argc > 3 ? std::atoi(argv[3]) : -1, rowsWanted = argc > 4 ? std::atoi(argv[4]) : 0;
+	int rowsOut = Nr;
+	if (rowsWanted > 0 && rowsWanted < Nr) rowsOut = std::min(Nr, (rowsWanted + PTP_THOMAS_BLOCK - 1) / PTP_THOMAS_BLOCK * PTP_THOMAS_BLOCK);
+	if (rowLimit >= 0 && rowsOut < rowLimit) rowsOut = Nr;
+	const int Jf = rowLimit < 0 ? Nr - 1 : std::max(0, std::min(rowLimit, Nr) - 1);
 
 	// ---- as ptp_solver_run ----
 	std::vector<int2> bounds(M);
@@ -46,17 +52,18 @@ int main(int argc, char** argv)
 	dynSmem(smFwdBytes(16));
 	emu_launch((n1 + 15) / 16, 256, [&] {
 		blockIdx.y = 0;
-		k_fwd_thomas<false, 16>(rho.data(), bounds.data(), nullptr, fwd.data(), nullptr, 1.0, thInv.data(), thCp.data(), lower.data(), spec.data(), Nr, n1);
+		k_fwd_thomas<false, 16>(rho.data(), bounds.data(), nullptr, fwd.data(), nullptr, 1.0, thInv.data(), thCp.data(), thR.data(), thQ.data(), lower.data(), spec.data(), Nr, n1, Jf, rowsOut);
 	});
 	const int stagesAll = ((n1 + 1) / 2 + 8 * INV_KS - 1) / (8 * INV_KS);
 	auto smFieldBytes = [&](int st) { return ((size_t)INV_TM * (n1 | 1) + (size_t)8 * st * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double); };
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const bool vec = n1 % 2 == 0;
 	const char* path;
+	if (smFieldBytes(ringStages) > smemMax && rowsOut < Nr) { std::printf("emu_solve: the chunked inverse produces whole grids only\n"); return 8; }
 	if (smFieldBytes(ringStages) <= smemMax) {
 		path = "k_inv_field";
 		dynSmem(smFieldBytes(ringStages));
-		const int gx = (n1 + 1 + INV_TN - 3) / (INV_TN - 2), gy = (Nr + INV_TM - 1) / INV_TM;
+		const int gx = (n1 + 1 + INV_TN - 3) / (INV_TN - 2), gy = (rowsOut + INV_TM - 1) / INV_TM;
 		for (int by = 0; by < gy; ++by)
 			emu_launch(gx, 256, [&] {
 				blockIdx.y = by;
@@ -93,6 +100,6 @@ int main(int argc, char** argv)
 	std::fwrite(Aphi.data(), 8, G, f);
 	std::fwrite(wallRhs.data(), 8, G, f);
 	std::fclose(f);
-	std::printf("emu_solve: %d x %d grid, inverse through %s (%d ring stages)\n", Nz, Nr, path, ringStages);
+	std::printf("emu_solve: %d x %d grid, inverse through %s (%d ring stages), fold row %d, %d rows produced\n", Nz, Nr, path, ringStages, Jf, rowsOut);
 	return 0;
 }

@@ -52,13 +52,19 @@ int main(int argc, char** argv)
 	std::vector<unsigned char> smem;
 	auto dynSmem = [&](size_t bytes) { smem.assign(bytes, 0); g_smem = smem.data(); fbw = reinterpret_cast<double2*>(g_smem); };
 	std::vector<double> spec(G, 0.0);
+	// optional: rows that may hold a deposit and rows the caller wants, as ptp_solver_run gets them
+	const int rowLimit = argc > 3 ? std::atoi(argv[3]) : -1, rowsWanted = argc > 4 ? std::atoi(argv[4]) : 0;
+	int rowsOut = Nr;
+	if (rowsWanted > 0 && rowsWanted < Nr) rowsOut = std::min(Nr, (rowsWanted + TW_BLK - 1) / TW_BLK * TW_BLK);
+	if (rowLimit >= 0 && rowsOut < rowLimit) rowsOut = Nr;
+	const int rowsIn = rowLimit < 0 ? Nr : std::max(1, std::min(rowLimit, Nr));
 	const int nB = (Nr + TW_BLK - 1) / TW_BLK;
 	std::vector<double> xb((size_t)nB * n1, 0.0);
 	std::vector<int> wideJ(1, -7);
 
 	// forward transform of the touched rows: grid (modes / 64, rows / 32, species)
 	dynSmem((size_t)2 * (FD_K * FD_M + FD_K * FD_RP) * sizeof(double));
-	for (int by = 0; by < (Nr + FD_R - 1) / FD_R; ++by)
+	for (int by = 0; by < (rowsIn + FD_R - 1) / FD_R; ++by)
 		emu_launch((n1 + FD_M - 1) / FD_M, 256, [&] {
 			blockIdx.y = by;
 			k_fwd_dct<false>(rho.data(), bounds.data(), nullptr, fwd.data(), nullptr, 1.0, spec.data(), Nr, n1);
@@ -68,10 +74,10 @@ int main(int argc, char** argv)
 	emu_launch((n1 + 31) / 32, 128, [&] {
 		blockIdx.y = 0;
 		k_thomas_wide(spec.data(), bounds.data(), nullptr, thInv.data(), thCp.data(), thR.data(), thQ.data(), thP.data(), lower.data(),
-			xb.data(), wideJ.data(), Nr, n1);
+			xb.data(), wideJ.data(), Nr, n1, rowsOut);
 	});
 	std::vector<double> specLazy = spec;                        // rows above the deposit's block still unset here
-	for (int by = 0; by < (Nr + 7) / 8; ++by)
+	for (int by = 0; by < (rowsOut + 7) / 8; ++by)
 		emu_launch((n1 + 255) / 256, 256, [&] {
 			blockIdx.y = by;
 			k_thomas_expand(spec.data(), xb.data(), wideJ.data(), thP.data(), Nr, n1);
@@ -81,15 +87,15 @@ int main(int argc, char** argv)
 	const int threads = N >= 1024 ? 256 : 128;
 	if (N == R16_N) {
 		dynSmem((size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double));
-		emu_launch(Nr, 256, [&] { k_idct_r16_field<true>(spec.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), 1, Nr, hz, nullptr, nullptr, nullptr, TW_BLK); });
+		emu_launch(rowsOut, 256, [&] { k_idct_r16_field<true>(spec.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), 1, Nr, hz, nullptr, nullptr, nullptr, TW_BLK); });
 		for (int j = 0; j < Nr; ++j)                            // rows the inverse must form itself: poison what expand would have written
 			if (wideJ[0] >= 0 && j > std::min(Nr - 1, (wideJ[0] / TW_BLK) * TW_BLK + TW_BLK - 1))
 				for (int k = 0; k < n1; ++k) specLazy[(size_t)j * n1 + k] = 1e300;
-		emu_launch(Nr, 256, [&] { k_idct_r16_field<true>(specLazy.data(), phiFormed.data(), tw.data(), phiTrap.data(), eN2.data(), 1, Nr, hz, xb.data(), wideJ.data(), thP.data(), TW_BLK); });
+		emu_launch(rowsOut, 256, [&] { k_idct_r16_field<true>(specLazy.data(), phiFormed.data(), tw.data(), phiTrap.data(), eN2.data(), 1, Nr, hz, xb.data(), wideJ.data(), thP.data(), TW_BLK); });
 	}
 	else {
 		dynSmem((size_t)N * sizeof(double2) + (size_t)(N + 1) * sizeof(double));
-		emu_launch(Nr, threads, [&] { k_idct_fft_field<true>(spec.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), 1, Nr, N, bits, hz); });
+		emu_launch(rowsOut, threads, [&] { k_idct_fft_field<true>(spec.data(), phi.data(), tw.data(), phiTrap.data(), eN.data(), 1, Nr, N, bits, hz); });
 		phiFormed = phi;
 	}
 	f = std::fopen(argv[2], "wb");
@@ -98,6 +104,6 @@ int main(int argc, char** argv)
 	std::fwrite(eN.data(), 8, G, f);
 	std::fwrite(phiFormed.data(), 8, G, f);
 	std::fclose(f);
-	std::printf("emu_wide: %d x %d grid, outermost deposit row %d, %s inverse\n", Nz, Nr, wideJ[0], N == R16_N ? "radix-16" : "radix-2");
+	std::printf("emu_wide: %d x %d grid, outermost deposit row %d, %s inverse, %d rows produced\n", Nz, Nr, wideJ[0], N == R16_N ? "radix-16" : "radix-2", rowsOut);
 	return 0;
 }

@@ -174,6 +174,18 @@ def test_large_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, 
     e = np.zeros_like(tot)
     e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * pt.hz)
     assert np.array_equal(en.reshape(Nr, n1), e)
+    # the step's form: only the populated rows (rounded up to blocks of 32) are produced - bit for bit the rows of the full solve
+    limit = max(rows) + 1
+    out2 = str(tmp_path / "out_rows.bin")
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_wide"), case, out2, str(limit), str(limit)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = (limit + 31) // 32 * 32
+    assert ("%d rows produced" % min(got, Nr)) in p.stdout
+    raw2 = np.fromfile(out2, np.float64)
+    keep = min(got, Nr) * n1
+    assert np.array_equal(raw2[:keep], phi[:keep]) and np.array_equal(raw2[G:G + keep], en[:keep]) and np.array_equal(raw2[2 * G:2 * G + keep], phi_formed[:keep])
+    if keep < G:
+        assert not raw2[keep:G].any()                                   # nothing written beyond
     pt.close()
 
 
@@ -223,6 +235,25 @@ def test_default_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz
     e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * pt.hz)
     assert np.array_equal(en.reshape(Nr, n1), e)
     assert np.array_equal(wall_rhs, pt.wall_rhs())
+    # rows above the outermost populated row folded into its pivot (the fold row is host knowledge: rings keep their row), whole
+    # grid produced: the same solution; and the step's form, which stops after the populated rows rounded up to blocks of 32
+    limit = max(rows) + 1
+    out2, out3 = str(tmp_path / "out_fold.bin"), str(tmp_path / "out_rows.bin")
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_solve"), case, out2, str(limit)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    fold = np.fromfile(out2, np.float64)
+    assert np.linalg.norm(fold[:G] - want) / np.linalg.norm(want) < 1e-10
+    assert np.linalg.norm(fold[:G] - phi) / np.linalg.norm(phi) < 1e-13
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_solve"), case, out3, str(limit), str(limit)], capture_output=True, text=True, timeout=900)
+    if "chunked inverse" in p.stdout:
+        assert p.returncode == 8                                        # (that path always produces whole grids)
+    else:
+        assert p.returncode == 0, p.stdout + p.stderr
+        part = np.fromfile(out3, np.float64)
+        keep = min((limit + 31) // 32 * 32, Nr) * n1
+        assert np.array_equal(part[:keep], fold[:keep]) and np.array_equal(part[G:G + keep], fold[G:G + keep])   # bit for bit
+        if keep < G:
+            assert not part[keep:G].any()
     pt.close()
 
 
