@@ -179,15 +179,15 @@ int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64)
 	return PTP_OK;
 }
 
-int ptp_comm_max_int(ptp_trap* t, int* value, int n)
+static int comm_reduce_int(ptp_trap* t, int* value, int n, ncclRedOp_t op)
 {
 	if (!t->comm || t->comm->nRanks == 1) return PTP_OK;
 	int* dV = nullptr;
 	PTP_CUDA(cudaMalloc(&dV, n * sizeof(int)));
 	cudaError_t e = cudaMemcpyAsync(dV, value, n * sizeof(int), cudaMemcpyHostToDevice, t->stream);
 	if (e != cudaSuccess) { cudaFree(dV); return ptp_cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__); }
-	ncclResult_t r = g_nccl.AllReduce(dV, dV, n, ncclInt32, ncclMax, t->comm->comm, t->stream);
-	if (r != ncclSuccess) { cudaFree(dV); return nccl_fail(r, "ncclAllReduce(max)"); }
+	ncclResult_t r = g_nccl.AllReduce(dV, dV, n, ncclInt32, op, t->comm->comm, t->stream);
+	if (r != ncclSuccess) { cudaFree(dV); return nccl_fail(r, "ncclAllReduce(int)"); }
 	e = cudaMemcpyAsync(value, dV, n * sizeof(int), cudaMemcpyDeviceToHost, t->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
 	cudaFree(dV);
@@ -195,11 +195,14 @@ int ptp_comm_max_int(ptp_trap* t, int* value, int n)
 	return PTP_OK;
 }
 
+int ptp_comm_max_int(ptp_trap* t, int* value, int n) { return comm_reduce_int(t, value, n, ncclMax); }
+int ptp_comm_sum_int(ptp_trap* t, int* value, int n) { return comm_reduce_int(t, value, n, ncclSum); }
+
 // Quantities every rank must agree on after a (re)load, settled by one small collective per load: the outermost populated
 // row (rows above it never receive a deposit) and the fixed-point scale 2^F of the deposit sums. F follows from the GLOBAL
-// ring count (F = min(40, 62 - ceil(log2(N + 1))): node sums stay below 2^62); shards are unequal, so every rank derives
-// its bit count from its own rings times the rank count and the maximum over the ranks decides - otherwise ranks near a power
-// of two would scale the same grid differently.
+// ring count (F = min(40, 62 - ceil(log2(N + 1))): node sums stay below 2^62); shards are unequal, so every rank gets the
+// ring count as the sum over the ranks - the same F as a single GPU holding the whole load would choose, so that results stay
+// bitwise independent of the rank count (a per-rank estimate would differ between ranks near a power of two).
 int ptp_layout_sync(ptp_trap* t)
 {
 	if (t->extentEpoch == t->layoutEpoch) return PTP_OK;
@@ -210,12 +213,15 @@ int ptp_layout_sync(ptp_trap* t)
 		for (int j = (int)p->rowLive.size() - 1; j >= ext; --j)
 			if (p->rowLive[j] > 0) { ext = j + 1; break; }
 	}
-	total *= ptp_comm_size(t);
+	if (t->comm && t->comm->nRanks > 1) {
+		PTP_TRY(ptp_comm_max_int(t, &ext));
+		// the global ring count as the sum of the shards (three 20-bit digits through the int32 collective)
+		int digit[3] = { (int)(total & 0xfffff), (int)((total >> 20) & 0xfffff), (int)(total >> 40) };
+		PTP_TRY(ptp_comm_sum_int(t, digit, 3));
+		total = ((long long)digit[2] << 40) + ((long long)digit[1] << 20) + (long long)digit[0];
+	}
 	int bits = 0;
 	while ((1LL << bits) < total + 1) ++bits;
-	int both[2] = { ext, bits };
-	PTP_TRY(ptp_comm_max_int(t, both, 2));
-	ext = both[0]; bits = both[1];
 	const int fixedBits = std::min(40, 62 - bits);
 	if (fixedBits != t->fixedBits) { t->fixedBits = fixedBits; ++t->cfgEpoch; }
 	t->rowExtent = ext;

@@ -218,6 +218,7 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p);
 
 // ---- ptp_comm.cu ---------------------------------------------------------------------------------
 int ptp_comm_allreduce(ptp_trap* t, void* buf, size_t count, bool isInt64);
+int ptp_comm_sum_int(ptp_trap* t, int* value, int n = 1);        // collective element-wise sum (the caller keeps the sums below 2^31)
 int ptp_comm_max_int(ptp_trap* t, int* value, int n = 1);        // collective element-wise max over the ranks (synchronises the stream)
 int ptp_row_extent(ptp_trap* t, int* extent);                    // collective on the first call after a (re)load, cached afterwards
 int ptp_layout_sync(ptp_trap* t);                                // row extent + fixed-point scale agreed between the ranks (same caching)

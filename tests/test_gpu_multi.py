@@ -53,3 +53,32 @@ def test_sharded_step_matches_single_gpu(world, exchange):
     res = _launch(world, "fixed", 2_000_000, 5, exchange)
     assert res["count_sharded"] == res["count_single"]
     assert res["replicas_identical"] and res["rhs_bitwise"] and res["phi_bitwise"]
+
+
+def test_fixed_point_scale_is_agreed_between_ranks_near_a_power_of_two():
+    """The fixed-point scale 2^F follows from the GLOBAL ring count. Shards are unequal (rank 0 gets the odd ring of every
+    row), so for a load just below 2^23 rings a per-rank estimate (own rings x ranks) puts rank 0 above the power of two and
+    rank 1 below it - two ranks scaling one grid differently. The scale is settled by a collective over the true total:
+    results stay bitwise equal to the single-GPU run."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import importlib
+    import numpy as np
+    from conftest import expected_density
+    ptp = importlib.import_module("pic-trapped-plasma_b200")
+    loaders = importlib.import_module("pic-trapped-plasma_b200.loaders")
+    dens = expected_density()
+    hz, hr = (4 * 0.0005 + 5 * 0.01322) / 585, 0.01488 / 128
+    pick = None
+    for num in range((1 << 23) - 1, (1 << 23) - 200, -1):
+        _, _, num_at_r = loaders.ring_counts(dens, 585, 128, hz, hr, num)
+        n = int(num_at_r.sum())
+        shard0 = int(((num_at_r + 1) // 2).sum())
+        if n + 1 <= (1 << 23) < 2 * shard0 + 1:
+            pick = num
+            break
+    assert pick is not None
+    for exchange in ("peer", "nccl"):
+        res = _launch(2, "fixed", pick, 3, exchange)
+        assert res["count_sharded"] == res["count_single"]
+        assert res["replicas_identical"] and res["rhs_bitwise"] and res["phi_bitwise"], (exchange, res)

@@ -589,7 +589,15 @@ def test_radix16_and_radix2_inverse_agree(monkeypatch):
         assert rel_l2(b, a) < 1e-13
 
 
-def _other_grid_case(Nz, Nr, solver, fixed):
+@pytest.mark.parametrize("Nz,Nr,solver", [(1024, 96, 0), (301, 130, 0), (48, 420, 0), (256, 24, 2), (4096, 12, 2)])
+def test_other_grids_exact_arithmetic_is_bit_exact(Nz, Nr, solver):
+    """The same lock-step comparison in EXACT arithmetic (true divisions, the reference's expression order): with the oracle's
+    potentials injected before every step the per-ring z and v, the cell indices and the loss flags are bit-identical -
+    no index may differ, on any solver path."""
+    _other_grid_case(Nz, Nr, solver, 0, exact=True)
+
+
+def _other_grid_case(Nz, Nr, solver, fixed, exact=False):
     """Grid shapes that take the other code paths of the solver against the CPU oracle: odd Nz+1 (8-byte copies), pipelined
     cosine ring (1024), chunked inverse GEMM + separate node field for long rows that are not a power of two (1500), and
     the large-grid organisation (ptp_solve_wide.cu): tiled forward transform + streamed radial solves for many radial
@@ -600,6 +608,8 @@ def _other_grid_case(Nz, Nr, solver, fixed):
     t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], Nz, Nr)
     if fixed:
         t.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64)
+    if exact:
+        t.set_arith_mode(ptp.PTP_ARITH_EXACT)
     if solver:
         t.set_solver(solver)
         t.solveLaplace()
@@ -635,12 +645,51 @@ def _other_grid_case(Nz, Nr, solver, fixed):
         assert np.max(np.abs(zz[og] - op.z[oo]) / op.z[oo]) < 1e-13
         k_g, _ = gp.cell_index()
         k_o, _ = op.cell_index()
+        if exact:
+            ov = np.lexsort((op.v, op.z, op.r))
+            gv = np.lexsort((vv, zz, rr))
+            assert np.array_equal(zz[gv], op.z[ov]) and np.array_equal(vv[gv], op.v[ov])     # bit for bit
+            assert np.array_equal(k_g[og], k_o[oo])                                           # every index
         assert np.mean(k_g[og] != k_o[oo]) < 1e-3          # identical unless a 1e-14 difference in z straddles a node
         assert rel_l2(gp.rhs(), op.rhs) < (1e-9 if fixed else 1e-12)
         assert rel_l2(gp.selfPotential(), op.self_potential) < 1e-9
         assert rel_l2(t.enodes(), pt.enodes()) < 1e-7
     t.close()
     pt.close()
+
+
+def test_step_solves_populated_rows_and_whole_grids_on_demand(c1_kat, monkeypatch):
+    """A step computes potentials and node field for the populated radial rows only (rings never change their row,
+    Source/Plasma.hpp:22-24); what the reference keeps on the whole grid (Plasma::selfPotential, the node field) is produced
+    when asked for. Against PTP_FULL_SOLVE=1 (every step solves the whole grid): per-ring state bit-identical after 20 steps,
+    the potentials and the node field of the whole grid bit-identical too, and equal to the oracle within the solver tolerance.
+    A species loaded later into rows the last step left out is pushed with the right field."""
+    res = []
+    for full in ("1", "0"):
+        monkeypatch.setenv("PTP_FULL_SOLVE", full)
+        t, el, ap = _fresh_c1(c1_kat, ptp.PTP_DEPOSIT_FIXED64)
+        el.solvePoisson()
+        ap.solvePoisson()
+        dt = float(c1_kat["dt"])
+        t.movePlasmas(dt, 20)
+        pe = el.getPotentialEnergy()
+        _, z, v, ids = el.download()
+        o = np.argsort(ids)
+        # a third species far out (row 100) joins: the next step needs the whole-grid potentials of the first two there
+        far = ptp.Plasma(t, "Far", ptp.massP, -ptp.ePos)
+        n = 5000
+        rng = np.random.default_rng(3)
+        far.upload(np.full(n, 100, np.int32), t.getLength() * (0.45 + 0.1 * rng.random(n)), rng.normal(0, 1e3, n), float(c1_kat["p_chargeMacro"]))
+        far.solvePoisson()
+        t.movePlasmas(dt, 3)
+        _, zf, vf, idf = far.download()
+        of = np.argsort(idf)
+        res.append((z[o], v[o], zf[of], vf[of], el.selfPotential(), ap.selfPotential(), far.selfPotential(), t.enodes(), el.rhs(), pe))
+        t.close()
+    a, b = res
+    for n, (x, y) in enumerate(zip(a[:9], b[:9])):
+        assert np.array_equal(x, y), n
+    assert a[9] == b[9]
 
 
 def test_graph_replay_is_bitwise_identical(c1_kat):
