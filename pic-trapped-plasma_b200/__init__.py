@@ -293,7 +293,9 @@ class PenningTrap:
         _check(lib().ptp_trap_set_tuning(self.h, threads, window, ctas, rings_per_thread))
 
     def set_graph(self, on=True):
-        _check(lib().ptp_trap_set_graph(self.h, 1 if on else 0))
+        """True / 1: replay every step as a CUDA graph; False / 0: never; -1 or None: automatic (the library's default policy)."""
+        mode = -1 if (on is None or (not isinstance(on, bool) and on < 0)) else (1 if on else 0)
+        _check(lib().ptp_trap_set_graph(self.h, mode))
 
     def set_sort_interval(self, interval):
         """> 0: re-sort every `interval` steps; 0: never; -1 (default): adaptive (see include/ptp.h)."""

@@ -103,38 +103,22 @@ int solve_species(ptp_trap* t, int first, int count, bool withField = false, int
 }
 
 // Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
+// The deposit grids are double-buffered by step parity: this step's sums go into the parity that the push kernels of the
+// previous step zeroed (their populated rows and touched-node ranges; begin_steps zeroes everything after a (re)load), and
+// this step's push kernels zero the other one - no memset between the kernels of a step, on one GPU as in peer-memory mode
+// (where the other ranks may add into the grid of the NEXT step as soon as they have passed this step's barrier).
 int push_deposit_all(ptp_trap* t, double dt)
 {
-	const int nS = (int)t->plasmas.size();
-	const size_t span = t->spanDoubles;
-	if (t->phiRows < t->rowExtent) PTP_TRY(ptp_materialize_fields(t));   // rings were loaded into rows the last solve left out
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
-	if (ptp_peer_mode(t)) {
-		// this step's target parity was zeroed one step ago (or at the start of the call); the other one - last step's
-		// sums, already consumed by its solve - is zeroed now, ahead of the step that will push into it
-		t->rhoParity ^= 1;
-		t->rhoAll = t->rhoStore + (size_t)t->rhoParity * span;
-		double* other = t->rhoStore + (size_t)(t->rhoParity ^ 1) * span;
-		if (t->G >= (1LL << 20) && t->extentEpoch == t->layoutEpoch) {
-			// large grid: begin_exchange cleared both parities in full, and no rank ever deposits above the (global) row extent
-			const size_t rowsBytes = (size_t)t->rowExtent * (t->Nz + 1) * sizeof(double);
-			for (int s = 0; s < nS; ++s) PTP_CUDA(cudaMemsetAsync(other + (size_t)s * t->G, 0, rowsBytes, t->stream));
-			PTP_CUDA(cudaMemsetAsync(other + (size_t)t->capS * t->G, 0, (size_t)t->capS * t->Nr * sizeof(double), t->stream));
-		}
-		else PTP_CUDA(cudaMemsetAsync(other, 0, span * sizeof(double), t->stream));
-	}
-	else if (t->G >= (1LL << 20) && t->cleanEpoch == t->layoutEpoch && t->extentEpoch == t->layoutEpoch) {
-		// large grid: only the rows that can hold a deposit, plus the row bounds (the rest is still zero from the last full clear)
-		const size_t rowsBytes = (size_t)t->rowExtent * (t->Nz + 1) * sizeof(double);
-		for (int s = 0; s < nS; ++s) PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)s * t->G, 0, rowsBytes, t->stream));
-		PTP_CUDA(cudaMemsetAsync(t->rhoAll + (size_t)t->capS * t->G, 0, (size_t)t->capS * t->Nr * sizeof(double), t->stream));
-	}
-	else {
-		PTP_CUDA(cudaMemsetAsync(t->rhoAll, 0, span * sizeof(double), t->stream));   // grids and row bounds of all species
-		t->cleanEpoch = t->layoutEpoch;
-	}
+	t->rhoParity ^= 1;
+	t->rhoAll = t->rhoStore + (size_t)t->rhoParity * t->spanDoubles;
 	for (ptp_plasma* p : t->plasmas) {
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+		if (p->cap == 0 || p->nCta == 0) {                       // no push kernel for an empty species: its slice of the other parity by hand
+			double* other = t->rhoStore + (size_t)(t->rhoParity ^ 1) * t->spanDoubles;
+			PTP_CUDA(cudaMemsetAsync(other + (size_t)p->index * t->G, 0, (size_t)t->G * sizeof(double), t->stream));
+			PTP_CUDA(cudaMemsetAsync(other + (size_t)t->capS * t->G + (size_t)p->index * t->Nr, 0, (size_t)t->Nr * sizeof(double), t->stream));
+		}
 		PTP_TRY(ptp_push_launch(t, p, dt, true));
 		p->encValid = true;
 	}
@@ -156,18 +140,24 @@ int reduce_rho(ptp_trap* t)
 	return PTP_OK;
 }
 
-// Peer-memory mode, at the start of every ptp_trap_step / ptp_trap_push_deposit call. The step keeps the invariant "the
-// parity that is not in use is zero on every rank" by itself (push_deposit_all), so the collective part - mapping the peers'
-// grids, clearing both parities and a barrier behind the clearing - runs only when the grids were (re)allocated or rings were
-// (re)loaded; per-step callers (the host classes call ptp_trap_step(dt, 1) from movePlasmas) pay nothing here.
-int begin_exchange(ptp_trap* t)
+// At the start of every stepping call (ptp_trap_step, ptp_trap_push_deposit, ptp_trap_step_programme). Cheap when nothing
+// has changed since the last call - per-step callers (the host classes call ptp_trap_step(dt, 1) from movePlasmas) pay for
+// two comparisons. After a (re)load or a (re)allocation: the ranks agree on row extent and fixed-point scale (a small
+// collective), potentials are completed where rings were loaded into rows the last solve left out, peer mappings are
+// exchanged, and both parities of the deposit grids are zeroed - in peer-memory mode with a barrier behind the zeroing, so
+// that no rank adds into a grid that its owner has not cleared yet. From then on the step keeps "the parity not in use is
+// zero" by itself.
+int begin_steps(ptp_trap* t)
 {
-	if (!ptp_peer_mode(t)) return PTP_OK;
-	PTP_TRY(ptp_peer_prepare(t));
-	if (t->peerCleanEpoch == t->layoutEpoch) return PTP_OK;
-	const size_t span = t->spanDoubles;
-	PTP_CUDA(cudaMemsetAsync(t->rhoStore, 0, 2 * span * sizeof(double), t->stream));
+	PTP_TRY(ptp_layout_sync(t));
+	if (t->phiRows < std::min(t->rowExtent, t->Nr)) PTP_TRY(ptp_materialize_fields(t));   // (reads the deposit grids: before they are zeroed)
+	const bool peer = ptp_peer_mode(t);
+	if (peer) PTP_TRY(ptp_peer_prepare(t));
+	if (t->cleanEpoch == t->layoutEpoch && (!peer || t->peerCleanEpoch == t->layoutEpoch)) return PTP_OK;
+	PTP_CUDA(cudaMemsetAsync(t->rhoStore, 0, 2 * t->spanDoubles * sizeof(double), t->stream));
 	for (ptp_plasma* p : t->plasmas) p->encValid = false;
+	t->cleanEpoch = t->layoutEpoch;
+	if (!peer) return PTP_OK;
 	t->peerCleanEpoch = t->layoutEpoch;
 	return ptp_peer_barrier(t);
 }
@@ -238,6 +228,10 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 		if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
 		if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));
 		if (const char* e = std::getenv("PTP_FULL_SOLVE")) t->lazyRows = std::atoi(e) == 0;
+		if (const char* e = std::getenv("PTP_PDL")) t->usePdl = std::atoi(e) != 0;
+		if (const char* e = std::getenv("PTP_INV_BULK")) t->invBulk = std::atoi(e);
+		if (const char* e = std::getenv("PTP_GRAPH")) t->useGraph = std::atoi(e);
+		if (const char* e = std::getenv("PTP_GRAPH_MAX_RINGS")) t->graphMaxRings = std::atoll(e);
 		PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
 		for (auto& ev : t->ev) PTP_CUDA(cudaEventCreate(&ev));
 		const size_t gb = (size_t)t->G * sizeof(double);
@@ -274,7 +268,7 @@ int ptp_trap_destroy(ptp_trap* t)
 	cudaFree(t->rhoStore); cudaFree(t->phiSelfAll); cudaFree(t->specAll); cudaFree(t->dScale);
 	for (auto& ev : t->ev) if (ev) cudaEventDestroy(ev);
 	for (auto& ev : t->evPool) cudaEventDestroy(ev);
-	if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
+	for (auto& g : t->graphExec) if (g) cudaGraphExecDestroy(g);
 	cudaFree(t->basisPhi); cudaFree(t->dWeights);
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
@@ -403,8 +397,7 @@ int ptp_trap_push_deposit(ptp_trap* t, double dt)
 	if (!t) { ptp_set_error("ptp_trap_push_deposit: null trap"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
-	PTP_TRY(ptp_layout_sync(t));
-	PTP_TRY(begin_exchange(t));
+	PTP_TRY(begin_steps(t));
 	PTP_TRY(push_deposit_all(t, dt));
 	PTP_TRY(reduce_rho(t));
 	return PTP_OK;
@@ -478,50 +471,60 @@ int maintain_order(ptp_trap* t)
 
 void drop_graph(ptp_trap* t)
 {
-	if (t->graphExec) cudaGraphExecDestroy(t->graphExec);
-	t->graphExec = nullptr;
+	for (auto& g : t->graphExec) {
+		if (g) cudaGraphExecDestroy(g);
+		g = nullptr;
+	}
 	t->graphCfg = -1;
 }
 
-// Capture one step (two in peer-memory mode, where consecutive steps use alternating grid parities) into a graph.
-// Everything a step would allocate or synchronise on lazily is settled before the capture starts.
-int capture_step_graph(ptp_trap* t, double dt)
+// Capture ONE step into a graph: the step that takes the deposit grids from parity (target ^ 1) to parity `target` - two
+// graphs, one per parity, so that any number of steps (also the one-step calls of PenningTrap::movePlasmas) can be
+// replayed. Everything a step would allocate or synchronise on lazily is settled before the capture starts.
+int capture_step_graph(ptp_trap* t, double dt, int target)
 {
-	drop_graph(t);
 	for (ptp_plasma* p : t->plasmas)
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	PTP_TRY(ptp_solver_reserve(t, (int)t->plasmas.size()));
-	PTP_TRY(ptp_layout_sync(t));                                  // may synchronise: not inside the capture
-	if (t->phiRows < t->rowExtent) PTP_TRY(ptp_materialize_fields(t));
-	const int unit = ptp_peer_mode(t) ? 2 : 1;
 	const int parity0 = t->rhoParity;
 	const long long steps0 = t->stepCount;
 	const int64_t launches0 = t->lastLaunches;
+	const int rows0 = t->phiRows;
 	PTP_CUDA(cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
-	int rc = PTP_OK;
-	for (int u = 0; u < unit && rc == PTP_OK; ++u) rc = one_step(t, dt, nullptr);
+	const int rc = one_step(t, dt, nullptr);
 	cudaGraph_t graph = nullptr;
 	cudaError_t e = cudaStreamEndCapture(t->stream, &graph);
-	t->stepCount = steps0;                                        // nothing has run yet
 	t->graphLaunches = t->lastLaunches - launches0;
+	t->graphRows = t->phiRows;
+	t->stepCount = steps0;                                        // nothing has run yet
 	t->lastLaunches = launches0;
+	t->phiRows = rows0;
+	t->rhoParity = parity0;
+	t->rhoAll = t->rhoStore + (size_t)parity0 * t->spanDoubles;
 	if (rc != PTP_OK || e != cudaSuccess || !graph) {
 		if (graph) cudaGraphDestroy(graph);
 		cudaGetLastError();
-		t->rhoParity = parity0;
-		t->rhoAll = t->rhoStore + (size_t)parity0 * t->spanDoubles;
 		if (rc == PTP_OK) return ptp_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
 		return rc;
 	}
-	e = cudaGraphInstantiate(&t->graphExec, graph, 0);
+	if (t->graphExec[target]) { cudaGraphExecDestroy(t->graphExec[target]); t->graphExec[target] = nullptr; }
+	e = cudaGraphInstantiate(&t->graphExec[target], graph, 0);
 	cudaGraphDestroy(graph);
-	if (e != cudaSuccess) { t->graphExec = nullptr; return ptp_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
-	t->graphCfg = t->cfgEpoch;
-	t->graphDt = dt;
-	t->graphParity = parity0;
-	t->graphUnit = unit;
+	if (e != cudaSuccess) { t->graphExec[target] = nullptr; return ptp_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
 	return PTP_OK;
+}
+
+// Replay policy. Forced on / off by ptp_trap_set_graph (or PTP_GRAPH); automatic otherwise: replay where the launches of a
+// step are not hidden behind its kernels - loads up to PTP_GRAPH_MAX_RINGS rings on this GPU (default 8 M: a step of a few tens
+// of microseconds) and multi-GPU runs (short per-GPU steps plus a barrier every rank waits on).
+bool want_graph(ptp_trap* t)
+{
+	if (t->solver == PTP_SOLVER_SOR || t->plasmas.empty() || t->useGraph == 0) return false;
+	if (t->useGraph > 0) return true;
+	long long rings = 0;
+	for (const ptp_plasma* p : t->plasmas) rings += p->nAlive;
+	return rings <= t->graphMaxRings || ptp_comm_size(t) > 1;
 }
 
 } // namespace
@@ -531,7 +534,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	if (!t || nSteps < 0) { ptp_set_error("ptp_trap_step: bad arguments"); return PTP_EINVAL; }
 	PTP_CUDA(cudaSetDevice(t->device));
 	t->lastLaunches = 0;
-	const bool graph = t->useGraph && t->sortInterval <= 0 && t->solver != PTP_SOLVER_SOR && !t->plasmas.empty();   // (no adaptive re-sort under replay)
+	const bool graph = want_graph(t);
 	// phase events for every step (up to a bound), so that callers can report the mean kernel time
 	const int timed = (!graph && nSteps <= 4096) ? nSteps : 0;
 	while ((int)t->evPool.size() < 4 * timed) {
@@ -540,26 +543,31 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 		t->evPool.push_back(e);
 	}
 	t->evSteps = timed;
-	PTP_TRY(ptp_layout_sync(t));                                 // collective on the first call after a (re)load, cached afterwards
-	PTP_TRY(begin_exchange(t));
-	int done = 0;
-	if (graph && nSteps > 0) {
-		if (!t->graphExec || t->graphCfg != t->cfgEpoch || t->graphDt != dt || t->graphParity != t->rhoParity)
-			PTP_TRY(capture_step_graph(t, dt));
-		if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));          // potentials were replaced since the last step (setPotential, parity hooks)
-		for (ptp_plasma* p : t->plasmas)
-			if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
-		PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
-		for (; done + t->graphUnit <= nSteps; done += t->graphUnit) {
-			PTP_CUDA(cudaGraphLaunch(t->graphExec, t->stream));
+	PTP_TRY(begin_steps(t));
+	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
+	for (int s = 0; s < nSteps; ++s) {
+		if (graph) {
+			if (t->graphCfg != t->cfgEpoch || t->graphDt != dt) {       // something a step launches has changed: both parities again
+				drop_graph(t);
+				t->graphCfg = t->cfgEpoch;
+				t->graphDt = dt;
+			}
+			const int target = t->rhoParity ^ 1;
+			if (!t->graphExec[target]) {
+				PTP_TRY(capture_step_graph(t, dt, target));
+				if (t->graphCfg != t->cfgEpoch) { drop_graph(t); t->graphCfg = t->cfgEpoch; t->graphDt = dt; PTP_TRY(capture_step_graph(t, dt, target)); }   // (the capture's own preparations planned segments)
+			}
+			if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));      // potentials were replaced since the last step (setPotential, parity hooks)
+			PTP_CUDA(cudaGraphLaunch(t->graphExec[target], t->stream));
+			t->rhoParity = target;
+			t->rhoAll = t->rhoStore + (size_t)target * t->spanDoubles;
 			t->lastLaunches += t->graphLaunches;
-			t->stepCount += t->graphUnit;
+			t->phiRows = t->graphRows;
+			t->eNodesValid = true;
+			for (ptp_plasma* p : t->plasmas) p->encValid = true;
+			++t->stepCount;
 		}
-		t->eNodesValid = true;
-	}
-	else PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
-	for (int s = done; s < nSteps; ++s) {
-		PTP_TRY(one_step(t, dt, s < timed ? &t->evPool[4 * s] : nullptr));
+		else PTP_TRY(one_step(t, dt, s < timed ? &t->evPool[4 * s] : nullptr));
 		PTP_TRY(maintain_order(t));
 	}
 	PTP_CUDA(cudaEventRecord(t->ev[4], t->stream));
@@ -574,8 +582,7 @@ int ptp_trap_step_programme(ptp_trap* t, double dt, int nSteps, const double* we
 	t->lastLaunches = 0;
 	t->evSteps = 0;
 	if (nSteps > 0) PTP_TRY(upload_weights(t, weights, (size_t)nSteps * t->nBasis));
-	PTP_TRY(ptp_layout_sync(t));
-	PTP_TRY(begin_exchange(t));
+	PTP_TRY(begin_steps(t));
 	PTP_CUDA(cudaEventRecord(t->ev[0], t->stream));
 	for (int s = 0; s < nSteps; ++s) {
 		PTP_TRY(combine_basis(t, t->dWeights + (size_t)s * t->nBasis));   // setPotential(...) of this step; the node field follows in the push
@@ -589,7 +596,7 @@ int ptp_trap_step_programme(ptp_trap* t, double dt, int nSteps, const double* we
 int ptp_trap_set_graph(ptp_trap* t, int on)
 {
 	if (!t) { ptp_set_error("ptp_trap_set_graph: null trap"); return PTP_EINVAL; }
-	t->useGraph = on != 0;
+	t->useGraph = on < 0 ? -1 : (on != 0 ? 1 : 0);             // 1: always replay, 0: never, -1: automatic (the default)
 	if (!on) drop_graph(t);
 	return PTP_OK;
 }

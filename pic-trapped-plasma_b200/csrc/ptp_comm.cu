@@ -69,6 +69,8 @@ struct PeerFlags { unsigned long long* f[8]; };
 __global__ void k_peer_barrier(PeerFlags flags, int rank, int nRanks, unsigned long long* dEpoch)
 {
 	__shared__ unsigned long long sEpoch;
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();                                             // this rank's push kernels (and their remote adds) are complete
 	if (threadIdx.x == 0) { sEpoch = *dEpoch + 1; *dEpoch = sEpoch; }
 	__syncthreads();
 	const unsigned long long epoch = sEpoch;
@@ -164,8 +166,7 @@ int ptp_peer_barrier(ptp_trap* t)
 	PtpComm* c = t->comm;
 	PeerFlags f{};
 	for (int p = 0; p < c->nRanks; ++p) f.f[p] = reinterpret_cast<unsigned long long*>(c->peerBase[p] + 2 * c->spanDoubles);
-	k_peer_barrier<<<1, 32, 0, t->stream>>>(f, c->rank, c->nRanks, c->dEpoch);
-	cudaError_t e = cudaGetLastError();
+	cudaError_t e = ptp_launch(k_peer_barrier, dim3(1), dim3(32), 0, t->stream, t->usePdl, f, c->rank, c->nRanks, c->dEpoch);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_peer_barrier launch", __FILE__, __LINE__);
 	t->lastLaunches++;
 	return PTP_OK;

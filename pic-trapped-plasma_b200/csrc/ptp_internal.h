@@ -146,6 +146,8 @@ struct ptp_trap {
 	// current; the whole grids are produced on demand from the deposit grids (ptp_materialize_fields) when a getter asks.
 	bool lazyRows = true;
 	int phiRows = 0;
+	bool usePdl = true;              // PTP_PDL=0: plain stream-ordered launches
+	int invBulk = 1;                 // PTP_INV_BULK=0: the cp.async form of the dense inverse transform also for even row lengths
 
 	PtpComm* comm = nullptr;
 	int allreduceKind = 0;
@@ -159,14 +161,15 @@ struct ptp_trap {
 	long long peerCleanEpoch = -1;   // peer-memory mode: layoutEpoch for which both parities were cleared collectively (the invariant
 	                                 // "the parity not in use is zero" then carries over from call to call)
 
-	// CUDA-graph replay of the step (ptp_trap_set_graph)
-	bool useGraph = false;
+	// CUDA-graph replay of the step (ptp_trap_set_graph): 1 on, 0 off, -1 automatic (small loads, where launch overhead counts)
+	int useGraph = -1;
 	long long cfgEpoch = 0;          // bumped by everything that changes what a step launches (uploads, modes, tuning, ...)
-	cudaGraphExec_t graphExec = nullptr;
+	long long graphMaxRings = 8000000;   // automatic policy: replay up to this many rings on this GPU (PTP_GRAPH_MAX_RINGS)
+	cudaGraphExec_t graphExec[2] = { nullptr, nullptr };   // one step each: [p] takes the deposit grids to parity p
 	long long graphCfg = -1;
 	double graphDt = 0;
-	int graphParity = 0, graphUnit = 1;
 	int64_t graphLaunches = 0;
+	int graphRows = 0;               // phiRows after a replayed step
 };
 
 // ---- error handling -------------------------------------------------------------------------
@@ -182,6 +185,36 @@ int ptp_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 		int rc_ = (call);               \
 		if (rc_ != PTP_OK) return rc_;  \
 	} while (0)
+
+// ---- programmatic dependent launch (sm_90+) ----------------------------------------------------
+// The kernels of a step form a chain on one stream: K1 per species -> [peer barrier] -> forward transform + radial solves ->
+// inverse transform + node field -> K1 of the next step. Launched with the programmatic-stream-serialization attribute, a
+// kernel's CTAs are scheduled as soon as every CTA of its predecessor has executed griddepcontrol.launch_dependents (all
+// kernels of the chain do so first thing), which takes the grid-launch latency and the predecessor's tail off the critical
+// path; griddepcontrol.wait then blocks until the predecessor has completed and its writes are visible. Every kernel of
+// the chain executes the wait before it touches anything an earlier kernel of the chain writes - which also keeps the
+// completion order transitive. What a kernel does before its wait reads only tables that no kernel writes (solver
+// constants, segment tables). Kernels launched without the attribute behave as before.
+#ifdef __CUDACC__
+__device__ __forceinline__ void ptp_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void ptp_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t ptp_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 // ---- ptp_solve.cu ------------------------------------------------------------------------------
 int ptp_solver_build(ptp_trap* t);

@@ -30,6 +30,7 @@
 
 #include <limits.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace {
@@ -54,6 +55,13 @@ struct PushArgs {
 	int nRho, pad1;
 	int mergeBins, pad2;        // consecutive rings of a thread that fall into the same cell share one read-modify-write of the bin
 	long long bndOffset;        // (uint2*)((double*)rho[r] + bndOffset) = this species' touched-node range per row (encoded maxima)
+	// The deposit grids are double-buffered by step parity. While this step's sums go into one parity, the kernel zeroes this
+	// species' part of the OTHER one (last step's sums, consumed by last step's solve), ready for the next step's deposits:
+	// the populated rows of its grid (no ring, hence no deposit, ever lands above them) and its touched-node ranges.
+	double* clearGrid;
+	long long clearGridWords;
+	double* clearBounds;
+	int clearBoundsWords, pad3;
 	unsigned long long* lost;   // [0] rings lost since upload, [1] deposits that missed the private window (re-sort trigger)
 };
 
@@ -177,6 +185,12 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 	const int n1 = a.Nz + 1;
 	const bool sys = a.nRho > 1;                 // remote grids are among the targets: system-scope atomics
 	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();                              // the node field of the last solve, the rings of the last push
+	if (PUSH) {
+		for (long long i = (long long)blockIdx.x * T + tid; i < a.clearGridWords; i += (long long)gridDim.x * T) a.clearGrid[i] = 0.0;
+		for (int i = blockIdx.x * T + tid; i < a.clearBoundsWords; i += gridDim.x * T) a.clearBounds[i] = 0.0;
+	}
 
 	for (int s = a.ctaSegBegin[blockIdx.x]; s < a.ctaSegBegin[blockIdx.x + 1]; ++s) {
 		const PtpSegment seg = a.segs[s];
@@ -541,32 +555,30 @@ __global__ void __launch_bounds__(256) k_tile_bounds(const PushArgs a, const Ptp
 }
 
 template <int T, int R, bool PUSH> struct Launcher {
-	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st)
+	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.mergeBins && PUSH && T == 512 && R == 4) {            // the variant exists for the default tuning only
 			auto kernM = k_push_deposit<512, 4, true, FIXED, EXACT, true>;
 			cudaError_t eM = cudaFuncSetAttribute(kernM, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eM != cudaSuccess) return eM;
-			kernM<<<grid, 512, smem, st>>>(a);
-			return cudaGetLastError();
+			return ptp_launch(kernM, dim3(grid), dim3(512), smem, st, pdl, a);
 		}
 		auto kern = k_push_deposit<T, R, PUSH, FIXED, EXACT>;
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
-		kern<<<grid, T, smem, st>>>(a);
-		return cudaGetLastError();
+		return ptp_launch(kern, dim3(grid), dim3(T), smem, st, pdl, a);
 	}
-	static cudaError_t dispatch(bool fixed, bool exact, const PushArgs& a, int grid, size_t smem, cudaStream_t st)
+	static cudaError_t dispatch(bool fixed, bool exact, const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
-		if (fixed) return exact ? go<true, true>(a, grid, smem, st) : go<true, false>(a, grid, smem, st);
-		return exact ? go<false, true>(a, grid, smem, st) : go<false, false>(a, grid, smem, st);
+		if (fixed) return exact ? go<true, true>(a, grid, smem, st, pdl) : go<true, false>(a, grid, smem, st, pdl);
+		return exact ? go<false, true>(a, grid, smem, st, pdl) : go<false, false>(a, grid, smem, st, pdl);
 	}
 };
 
-template <int T, int R> cudaError_t launch_tr(bool push, bool fixed, bool exact, const PushArgs& a, int grid, size_t smem, cudaStream_t st)
+template <int T, int R> cudaError_t launch_tr(bool push, bool fixed, bool exact, const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 {
-	return push ? Launcher<T, R, true>::dispatch(fixed, exact, a, grid, smem, st)
-	            : Launcher<T, R, false>::dispatch(fixed, exact, a, grid, smem, st);
+	return push ? Launcher<T, R, true>::dispatch(fixed, exact, a, grid, smem, st, pdl)
+	            : Launcher<T, R, false>::dispatch(fixed, exact, a, grid, smem, st, pdl);
 }
 
 PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
@@ -647,15 +659,23 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 	if (p->cap == 0 || p->nCta == 0) return PTP_OK;
 	PushArgs a = make_args(t, p, dt);
 	if (push && ptp_peer_mode(t)) ptp_peer_targets(t, t->rhoParity, (size_t)p->index * t->G, a.rho, &a.nRho);
+	if (push) {
+		double* other = t->rhoStore + (size_t)(t->rhoParity ^ 1) * t->spanDoubles;
+		a.clearGrid = other + (size_t)p->index * t->G;
+		a.clearGridWords = (long long)std::min(t->rowExtent, t->Nr) * (t->Nz + 1);
+		a.clearBounds = other + (size_t)t->capS * t->G + (size_t)p->index * t->Nr;
+		a.clearBoundsWords = t->Nr;
+	}
 	const size_t smem = ptp_push_smem_bytes(t, t->threads, t->window);
 	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64, exact = t->arithMode == PTP_ARITH_EXACT;
+	const bool pdl = t->usePdl;
 	cudaError_t e;
 	if (t->threads == 512)
-		e = t->ringsPerThread == 8 ? launch_tr<512, 8>(push, fixed, exact, a, p->nCta, smem, t->stream)
-		                           : launch_tr<512, 4>(push, fixed, exact, a, p->nCta, smem, t->stream);
+		e = t->ringsPerThread == 8 ? launch_tr<512, 8>(push, fixed, exact, a, p->nCta, smem, t->stream, pdl)
+		                           : launch_tr<512, 4>(push, fixed, exact, a, p->nCta, smem, t->stream, pdl);
 	else
-		e = t->ringsPerThread == 8 ? launch_tr<256, 8>(push, fixed, exact, a, p->nCta, smem, t->stream)
-		                           : launch_tr<256, 4>(push, fixed, exact, a, p->nCta, smem, t->stream);
+		e = t->ringsPerThread == 8 ? launch_tr<256, 8>(push, fixed, exact, a, p->nCta, smem, t->stream, pdl)
+		                           : launch_tr<256, 4>(push, fixed, exact, a, p->nCta, smem, t->stream, pdl);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_push_deposit launch", __FILE__, __LINE__);
 	t->lastLaunches++;
 	return PTP_OK;

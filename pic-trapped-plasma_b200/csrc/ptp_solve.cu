@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(256) k_row_bounds(const double* __restrict__ r
 {
 	const int lane = threadIdx.x & 31;
 	const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();
 	if (row >= rows) return;
 	if (row % Nr >= rowLimit) {                                 // no ring lives in this radial row: nothing to scan
 		if (lane == 0) bounds[row] = make_int2(INT_MAX, INT_MIN);
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 	}
 	for (int j = tid; j < Nr; j += 256) cp_async8(&sLower[j], thLower + j, true);
 	asm volatile("cp.async.commit_group;\n" ::);
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();                                             // the deposit (and its touched-node ranges) of this step; the tables above are constants
 	__syncthreads();
 	for (int j = tid; j < Nr; j += 256) {
 		int2 bd;
@@ -401,6 +405,26 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 	const bool upFront = ST >= (K2 + 8 * INV_KS - 1) / (8 * INV_KS);   // uniform over the CTA (warp 0 has the most rows)
 	const double* bBase = B + (size_t)warp * n1 + c0;
 
+	ptp_pdl_launch_dependents();
+	// The first species' slice of the cosine matrix (a constant) is requested before the wait, so that it streams in while
+	// the forward kernel is still finishing; alpha and the trap potential are read after it.
+	bool early = false;
+	if (upFront) {
+		for (int st = 0; st < nStages; ++st) {
+			double* dst = ring + (size_t)(st % ST) * INV_KS * INV_TN;
+#pragma unroll
+			for (int c = 0; c < EPL; ++c) {
+				const int i = st * INV_KS + cpRow[c];
+				const bool valid = cpOk[c] && i < rowsMine;
+				const double* src = valid ? bBase + (size_t)8 * i * n1 + cpCol[c] : B;
+				if (VEC) cp_async16(dst + cpRow[c] * INV_TN + cpCol[c], src, valid);
+				else cp_async8(dst + cpRow[c] * INV_TN + cpCol[c], src, valid);
+			}
+			asm volatile("cp.async.commit_group;\n" ::);
+		}
+		early = true;
+	}
+	ptp_pdl_wait();
 	if (FIELD) {
 		for (int o = tid; o < INV_TM * INV_TN; o += 256) {
 			const int r = o / INV_TN, c = o - r * INV_TN, col = c0 + c;
@@ -428,7 +452,9 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 			asm volatile("cp.async.commit_group;\n" ::);
 		};
 		__syncthreads();                                            // previous species' reduction buffers are free again
-		if (upFront) for (int st = 0; st < nStages; ++st) issue(st);
+		if (upFront) {
+			if (!(early && sp == 0)) for (int st = 0; st < nStages; ++st) issue(st);
+		}
 		else {
 #pragma unroll
 			for (int st = 0; st < INV_ST - 1; ++st) issue(st);      // B is in flight while A is staged
@@ -487,6 +513,175 @@ __global__ void __launch_bounds__(256) k_inv_field(const double* __restrict__ al
 			double v = 0.0;
 #pragma unroll
 			for (int w = 0; w < 8; ++w) v += ringAll[w * INV_TM * INV_TN + o];
+			const int r = o / INV_TN, c = o - r * INV_TN, col = c0 + c;
+			if (j0 + r < Nr && col >= 0 && col < n1) {
+				out[(size_t)(j0 + r) * n1 + col] = v;             // overlapping columns get the identical value from both tiles
+				if (FIELD) sTot[o] = __dadd_rn(sTot[o], v);
+			}
+		}
+	}
+	if (FIELD) {
+		__syncthreads();
+		for (int o = tid; o < INV_TM * (INV_TN - 2); o += 256) {
+			const int r = o / (INV_TN - 2), c = 1 + o % (INV_TN - 2), col = c0 + c;
+			if (j0 + r >= Nr || col < 0 || col >= n1) continue;     // the first tile starts at column -2
+			double e = 0.0;
+			if (col > 0 && col < n1 - 1)
+				e = __ddiv_rn(__dsub_rn(sTot[r * INV_TN + c - 1], sTot[r * INV_TN + c + 1]), __dmul_rn(2.0, hz));
+			eNodes[(size_t)(j0 + r) * n1 + col] = e;
+		}
+	}
+}
+
+// ---- bulk-async (TMA) staging -----------------------------------------------------------------------------------
+// cp.async.bulk moves a whole contiguous run with ONE instruction issued by one thread; completion is signalled on an
+// mbarrier through its transaction count. Source, destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@!p bra WAIT_%=;\n"
+		"}\n" ::"r"((unsigned int)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smemDst, const void* gmemSrc, unsigned int bytes, unsigned long long* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"((unsigned int)__cvta_generic_to_shared(smemDst)),
+		"l"(gmemSrc), "r"(bytes), "r"((unsigned int)__cvta_generic_to_shared(bar)) : "memory");
+}
+// generic-proxy accesses to shared memory (ordered by the preceding barrier) before the async proxy writes there again
+__device__ __forceinline__ void fence_proxy_async()
+{
+	asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+// k_inv_field for even row lengths (every grid row and every row of the cosine matrix then starts 16-byte aligned), staged
+// with bulk-async copies: the CTA's whole slice of the cosine matrix - K2 rows of 40 columns, 320 B each - and the 16 alpha
+// rows of the strip arrive through ~300 copy instructions instead of ~15 000 eight- and sixteen-byte cp.async, the cosine
+// slice once for all species and, being a constant, before the programmatic-launch wait (it streams in while the forward
+// kernel is still finishing). Same tiling, same paired modes, same arithmetic order per output value as k_inv_field, so
+// potentials and node field are bit-identical to it.
+// Shared memory: sA [16 rows] (row r at r * LDA + 2 (r >> 2): 16-byte aligned and the four rows a quarter-warp group reads
+// together fall into distinct banks) | sB [K2][40] | sTot [16][40]; the cross-warp reduction reuses sB.
+template <bool FIELD>
+__global__ void __launch_bounds__(256) k_inv_field_bulk(const double* __restrict__ alpha, const double* __restrict__ B,
+	double* __restrict__ phiSelf, const double* __restrict__ phiTrap, double* __restrict__ eNodes, int nS, int Nr, int n1, double hz, int LDA)
+{
+	extern __shared__ __align__(16) double sm[];
+	__shared__ unsigned long long bar[2];                           // [0] alpha tile (one phase per species), [1] cosine slice
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int la = lane >> 3, lb = lane & 7;                    // 4 row groups x 8 column groups
+	const int Nz = n1 - 1, K2 = (n1 + 1) / 2;
+	const int j0 = blockIdx.y * INV_TM;
+	const int c0 = FIELD ? (int)blockIdx.x * (INV_TN - 2) - 2 : (int)blockIdx.x * INV_TN;   // first column of the tile (even; may be -2)
+	double* sA = sm;
+	double* sB = sm + (size_t)INV_TM * LDA + 8;
+	double* sTot = sB + (size_t)K2 * INV_TN;
+	auto rowOff = [LDA](int r) { return r * LDA + 2 * (r >> 2); };
+	const int cFirst = max(c0, 0), cEnd = min(c0 + INV_TN, n1);  // valid columns of the tile: [cFirst, cEnd), both even
+	const unsigned int rowBytes = (unsigned int)(cEnd - cFirst) * 8u;
+	const int rowsValid = min(INV_TM, Nr - j0);
+	if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+	// columns outside the grid and rows below the strip's end are never stored; they get zeros once so that nothing undefined is computed
+	if (cEnd - cFirst < INV_TN)
+		for (int e = tid; e < K2 * INV_TN; e += 256) sB[e] = 0.0;
+	for (int e = tid; e < INV_TM * LDA + 8; e += 256) sA[e] = 0.0;
+	__syncthreads();
+	fence_proxy_async();
+	ptp_pdl_launch_dependents();
+	if (warp == 0) {
+		if (lane == 0) mbar_expect_tx(&bar[1], rowBytes * (unsigned int)K2);
+		__syncwarp();
+		for (int m = lane; m < K2; m += 32) bulk_g2s(sB + (size_t)m * INV_TN + (cFirst - c0), B + (size_t)m * n1 + cFirst, rowBytes, &bar[1]);
+	}
+	ptp_pdl_wait();                                             // alpha, the trap potential (constant in a step, but not a table)
+	if (FIELD) {
+		for (int o = tid; o < INV_TM * INV_TN; o += 256) {
+			const int r = o / INV_TN, c = o - r * INV_TN, col = c0 + c;
+			sTot[o] = (j0 + r < Nr && col >= 0 && col < n1) ? phiTrap[(size_t)(j0 + r) * n1 + col] : 0.0;
+		}
+	}
+	// parity of this lane's first column decides which variant (sum / difference) its even-j columns use
+	const bool firstEven = ((c0 + 5 * lb) & 1) == 0;
+	const int offE = firstEven ? 0 : Nz, sgnE = firstEven ? 1 : -1;  // index of the value for columns j = 0, 2, 4: offE + sgnE * m
+	const int offO = firstEven ? Nz : 0, sgnO = -sgnE;               // ... and for j = 1, 3
+	const int rowsMine = K2 > warp ? (K2 - warp + 7) / 8 : 0;        // this warp's modes: m = warp + 8 i
+	const double* a0 = sA + rowOff(4 * la), *a1 = sA + rowOff(4 * la + 1), *a2 = sA + rowOff(4 * la + 2), *a3 = sA + rowOff(4 * la + 3);
+	for (int sp = 0; sp < nS; ++sp) {
+		if (sp > 0) { __syncthreads(); fence_proxy_async(); }       // the last species' reads of sA and of the reduction buffer are done
+		if (warp == 1) {
+			const double* aSrc = alpha + ((size_t)sp * Nr + j0) * n1;
+			if (lane == 0) mbar_expect_tx(&bar[0], (unsigned int)rowsValid * (unsigned int)n1 * 8u);
+			__syncwarp();
+			if (lane < rowsValid) bulk_g2s(sA + rowOff(lane), aSrc + (size_t)lane * n1, (unsigned int)n1 * 8u, &bar[0]);
+		}
+		if (sp > 0 && warp == 0) {                                  // the reduction overwrote the head of the cosine slice: fetch those rows again
+			const int rowsDirty = min(K2, (8 * INV_TM * INV_TN + INV_TN - 1) / INV_TN);
+			if (lane == 0) mbar_expect_tx(&bar[1], rowBytes * (unsigned int)rowsDirty);
+			__syncwarp();
+			for (int m = lane; m < rowsDirty; m += 32) bulk_g2s(sB + (size_t)m * INV_TN + (cFirst - c0), B + (size_t)m * n1 + cFirst, rowBytes, &bar[1]);
+		}
+		mbar_wait(&bar[0], (unsigned int)(sp & 1));
+		for (int e = tid; e < INV_TM * K2; e += 256) {              // pair the modes: [m] <- a_m + a_{Nz-m}, [Nz-m] <- a_m - a_{Nz-m}
+			const int r = e / K2, m = e - r * K2;
+			if (m != Nz - m) {
+				double* row = sA + rowOff(r);
+				const double p = row[m], q = row[Nz - m];
+				row[m] = p + q;
+				row[Nz - m] = p - q;
+			}
+		}
+		mbar_wait(&bar[1], (unsigned int)(sp & 1));
+		__syncthreads();
+		double acc[4][5];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+#pragma unroll
+			for (int j = 0; j < 5; ++j) acc[i][j] = 0.0;
+		// the same order of accumulation per output value as k_inv_field: modes warp, warp + 8, ... in stages of INV_KS
+		for (int i0 = 0; i0 < rowsMine; i0 += INV_KS) {
+#pragma unroll
+			for (int rr = 0; rr < INV_KS; ++rr) {
+				const int i = i0 + rr;
+				const int m = min(warp + 8 * i, K2 - 1);
+				const double* bs = sB + (size_t)m * INV_TN + 5 * lb;
+				const int iE = offE + sgnE * m, iO = offO + sgnO * m;
+				double bv[5], ae[4], ao[4];
+#pragma unroll
+				for (int j = 0; j < 5; ++j) bv[j] = i < rowsMine ? bs[j] : 0.0;
+				ae[0] = a0[iE]; ae[1] = a1[iE]; ae[2] = a2[iE]; ae[3] = a3[iE];
+				ao[0] = a0[iO]; ao[1] = a1[iO]; ao[2] = a2[iO]; ao[3] = a3[iO];
+#pragma unroll
+				for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+					for (int j = 0; j < 5; ++j) acc[ii][j] = fma((j & 1) ? ao[ii] : ae[ii], bv[j], acc[ii][j]);
+			}
+		}
+		__syncthreads();                                            // every warp is done with the cosine slice: its head becomes [8][16][40]
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+#pragma unroll
+			for (int j = 0; j < 5; ++j) sB[(warp * INV_TM + 4 * la + i) * INV_TN + 5 * lb + j] = acc[i][j];
+		__syncthreads();
+		double* out = phiSelf + (size_t)sp * Nr * n1;
+		for (int o = tid; o < INV_TM * INV_TN; o += 256) {
+			double v = 0.0;
+#pragma unroll
+			for (int w = 0; w < 8; ++w) v += sB[w * INV_TM * INV_TN + o];
 			const int r = o / INV_TN, c = o - r * INV_TN, col = c0 + c;
 			if (j0 + r < Nr && col >= 0 && col < n1) {
 				out[(size_t)(j0 + r) * n1 + col] = v;             // overlapping columns get the identical value from both tiles
@@ -762,7 +957,11 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	const int n1 = t->Nz + 1, Nr = t->Nr, M = nS * Nr;
 	const double fixedInv = 1.0 / (double)(1ULL << t->fixedBits);
 	PTP_TRY(ptp_solver_reserve(t, nS));
-	if (!encBounds) { k_row_bounds<<<(M + 7) / 8, 256, 0, t->stream>>>(rho, M, n1, t->rowBounds, Nr, rowLimit < 0 ? Nr : rowLimit); t->lastLaunches++; }
+	if (!encBounds) {
+		const cudaError_t eb = ptp_launch(k_row_bounds, dim3((M + 7) / 8), dim3(256), 0, t->stream, t->usePdl, rho, M, n1, t->rowBounds, Nr, rowLimit < 0 ? Nr : rowLimit);
+		if (eb != cudaSuccess) return ptp_cuda_fail(eb, "k_row_bounds launch", __FILE__, __LINE__);
+		t->lastLaunches++;
+	}
 	// Rows to produce: all of them, or - for the step, where only the populated rows are ever read by the push - the first
 	// rowsWanted, rounded up to whole blocks of the radial tables (a multiple of the inverse kernels' strip height too).
 	int rowsOut = Nr;
@@ -779,8 +978,13 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	auto smFieldBytes = [&](int st) { return ((size_t)INV_TM * (n1 | 1) + (size_t)8 * st * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double); };
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= t->smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const size_t smField = smFieldBytes(ringStages);
-	const bool useFft = ptp_solver_fft_fits(t) && (t->solver == PTP_SOLVER_DIRECT_FFT || smField > t->smemMax);
-	if (!useFft && smField > t->smemMax) rowsOut = Nr;          // chunked inverse GEMM + separate node field: whole grids only
+	// even row length: every row of the grids and of the cosine matrix starts 16-byte aligned - bulk-async (TMA) staged form
+	const int ldaBulk = (n1 + 15) & ~15;
+	const size_t smBulk = ((size_t)INV_TM * ldaBulk + 8 + (size_t)((n1 + 1) / 2) * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
+	const bool bulkOk = n1 % 2 == 0 && t->invBulk && smBulk <= t->smemMax && (size_t)n1 * 8 * INV_TM < (1u << 20);
+	const bool fusedFits = bulkOk || smField <= t->smemMax;
+	const bool useFft = ptp_solver_fft_fits(t) && (t->solver == PTP_SOLVER_DIRECT_FFT || !fusedFits);
+	if (!useFft && !fusedFits) rowsOut = Nr;                    // chunked inverse GEMM + separate node field: whole grids only
 	if (rowsDone) *rowsDone = rowsOut;
 	// large grids (many radial nodes or long rows): separate forward transform + streamed radial solves (ptp_solve_wide.cu)
 	const bool wide = mb == 4 || useFft || smFwd > t->smemMax;
@@ -800,21 +1004,31 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		auto launchFwd = [&](auto kern, double fInv) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smFwd);
 			if (e != cudaSuccess) return e;
-			kern<<<gridFwd, 256, smFwd, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thR, t->thQ, t->thLower, spec, Nr, n1, Jf, rowsOut);
-			return cudaGetLastError();
+			return ptp_launch(kern, gridFwd, dim3(256), smFwd, t->stream, t->usePdl, rho, t->rowBounds, encBounds, t->dctFwd, dScale, fInv, t->thInv, t->thCp, t->thR, t->thQ,
+				t->thLower, spec, Nr, n1, Jf, rowsOut);
 		};
 		const cudaError_t ef = rhoIsFixed ? launchFwd(k_fwd_thomas<true, 16>, fixedInv) : launchFwd(k_fwd_thomas<false, 16>, 1.0);
 		if (ef != cudaSuccess) return ptp_cuda_fail(ef, "k_fwd_thomas launch", __FILE__, __LINE__);
 		t->lastLaunches++;
 	}
 	bool fieldDone = false;
-	if (smField <= t->smemMax) {
+	if (bulkOk) {
+		auto launchBulk = [&](auto kern, bool field) -> cudaError_t {
+			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smBulk);
+			if (e != cudaSuccess) return e;
+			const dim3 grid(field ? (n1 + 1 + INV_TN - 3) / (INV_TN - 2) : (n1 + INV_TN - 1) / INV_TN, (rowsOut + INV_TM - 1) / INV_TM);
+			return ptp_launch(kern, grid, dim3(256), smBulk, t->stream, t->usePdl, spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz, ldaBulk);
+		};
+		const cudaError_t eb = withField ? launchBulk(k_inv_field_bulk<true>, true) : launchBulk(k_inv_field_bulk<false>, false);
+		if (eb != cudaSuccess) return ptp_cuda_fail(eb, "k_inv_field_bulk launch", __FILE__, __LINE__);
+		fieldDone = withField;
+	}
+	else if (smField <= t->smemMax) {
 		auto launchInv = [&](auto kern, bool field) -> cudaError_t {
 			cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smField);
 			if (e != cudaSuccess) return e;
 			const dim3 grid(field ? (n1 + 1 + INV_TN - 3) / (INV_TN - 2) : (n1 + INV_TN - 1) / INV_TN, (rowsOut + INV_TM - 1) / INV_TM);
-			kern<<<grid, 256, smField, t->stream>>>(spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz, ringStages);
-			return cudaGetLastError();
+			return ptp_launch(kern, grid, dim3(256), smField, t->stream, t->usePdl, spec, t->dctInv, phi, t->phiTrap, t->eNodes, nS, Nr, n1, t->hz, ringStages);
 		};
 		const bool vec = n1 % 2 == 0;
 		cudaError_t ei;

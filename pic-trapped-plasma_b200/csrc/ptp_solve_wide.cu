@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(256, 2) k_fwd_dct(const double* __restrict__ r
 	__shared__ int sLo, sHi;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int mBase = blockIdx.x * FD_M, jBase = blockIdx.y * FD_R, s = blockIdx.z;
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();
 	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; }
 	__syncthreads();
 	if (tid < FD_R) {
@@ -213,6 +215,8 @@ __global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAl
 	const int m = blockIdx.x * 32 + lane;
 	const bool mOk = m < n1;
 	double* spec = specAll + (size_t)s * Nr * n1;
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();
 	if (tid == 0) { sJ0 = INT_MAX; sJ = INT_MIN; }
 	__syncthreads();
 	{
@@ -338,6 +342,8 @@ __global__ void __launch_bounds__(128) k_thomas_wide(double* __restrict__ specAl
 __global__ void __launch_bounds__(256) k_thomas_expand(double* __restrict__ specAll, const double* __restrict__ xbAll, const int* __restrict__ wideJ,
 	const double* __restrict__ thP, int Nr, int n1)
 {
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();
 	const int s = blockIdx.z, J = wideJ[s];
 	const int j0 = blockIdx.y * 8;
 	if (J < 0 || j0 <= min(Nr - 1, (J / TW_BLK) * TW_BLK + TW_BLK - 1)) return;   // TW_BLK is a multiple of 8: the whole group is on one side
@@ -369,6 +375,8 @@ __global__ void __launch_bounds__(256, 2) k_idct_fft_field(const double* __restr
 	double* tot = reinterpret_cast<double*>(fbw + N);           // [N+1] running total potential of the row (FIELD)
 	const int tid = threadIdx.x, T = blockDim.x, n1 = N + 1;
 	const int row = blockIdx.x;
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();
 	// Element p lives at p ^ f(p >> 3). 16-byte accesses are served a quarter-warp at a time, so the 8 lanes of a quarter
 	// must hit the 8 distinct 16-byte bank groups (p & 7). The late passes touch q-strided points with q < 8, which moves the
 	// lane index into bits 3..5 of p, and the bit-reversed read-out moves it into the top three bits: both fields are folded
@@ -532,12 +540,14 @@ __global__ void __launch_bounds__(256, 2) k_idct_r16_field(const double* __restr
 	extern __shared__ double2 fbw[];                            // [16][RS] exchange buffer; natural-order Z after the third round
 	double* tot = reinterpret_cast<double*>(fbw + 16 * RS);     // [N+1] running total potential of the row (FIELD)
 	const int t = threadIdx.x, row = blockIdx.x;
+	ptp_pdl_launch_dependents();
+	const double2 wA = __ldg(&tw[2 * t]);                       // W_N^t      (tw[j] = exp(-i pi j / N))   - constants, before the wait
+	const double2 wB = __ldg(&tw[32 * (t & 15)]);               // W_256^n0
+	ptp_pdl_wait();
 	if (FIELD) {                                                // asynchronous: needed only at the first read-out
 		for (int k = t; k <= N; k += 256) cpa8(&tot[k], phiTrap + (size_t)row * n1 + k, true);
 		cpa_commit();
 	}
-	const double2 wA = __ldg(&tw[2 * t]);                       // W_N^t      (tw[j] = exp(-i pi j / N))
-	const double2 wB = __ldg(&tw[32 * (t & 15)]);               // W_256^n0
 	for (int sp = 0; sp < nS; ++sp) {
 		const double* a = alphaAll + ((size_t)sp * Nr + row) * n1;
 		double2 x[16];
@@ -645,11 +655,13 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 	const dim3 gridDct((n1 + FD_M - 1) / FD_M, (rowsIn + FD_R - 1) / FD_R, nS);
 	if (rhoIsFixed) {
 		PTP_CUDA(cudaFuncSetAttribute(k_fwd_dct<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smDct));
-		k_fwd_dct<true><<<gridDct, 256, smDct, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, fixedInv, spec, Nr, n1);
+		const cudaError_t ed = ptp_launch(k_fwd_dct<true>, gridDct, dim3(256), smDct, t->stream, t->usePdl, rho, t->rowBounds, encBounds, t->dctFwd, dScale, fixedInv, spec, Nr, n1);
+		if (ed != cudaSuccess) return ptp_cuda_fail(ed, "k_fwd_dct launch", __FILE__, __LINE__);
 	}
 	else {
 		PTP_CUDA(cudaFuncSetAttribute(k_fwd_dct<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smDct));
-		k_fwd_dct<false><<<gridDct, 256, smDct, t->stream>>>(rho, t->rowBounds, encBounds, t->dctFwd, dScale, 1.0, spec, Nr, n1);
+		const cudaError_t ed = ptp_launch(k_fwd_dct<false>, gridDct, dim3(256), smDct, t->stream, t->usePdl, rho, t->rowBounds, encBounds, t->dctFwd, dScale, 1.0, spec, Nr, n1);
+		if (ed != cudaSuccess) return ptp_cuda_fail(ed, "k_fwd_dct launch", __FILE__, __LINE__);
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_fwd_dct launch", __FILE__, __LINE__);
@@ -657,14 +669,12 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 	const size_t smTh = (size_t)3 * TW_RCAP * 32 * sizeof(double) + (size_t)Nr * sizeof(double) + (size_t)Nr;
 	if (smTh > t->smemMax) { ptp_set_error("direct solver: Nr too large for the radial-solve kernel of this build"); return PTP_EINVAL; }
 	PTP_CUDA(cudaFuncSetAttribute(k_thomas_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smTh));
-	k_thomas_wide<<<dim3((n1 + 31) / 32, nS), 128, smTh, t->stream>>>(spec, t->rowBounds, encBounds, t->thInv, t->thCp, t->thR, t->thQ, t->thP, t->thLower,
+	e = ptp_launch(k_thomas_wide, dim3((n1 + 31) / 32, nS), dim3(128), smTh, t->stream, t->usePdl, spec, t->rowBounds, encBounds, t->thInv, t->thCp, t->thR, t->thQ, t->thP, t->thLower,
 		t->wideXb, t->wideJ, Nr, n1, rowsOut);
-	e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_wide launch", __FILE__, __LINE__);
 	t->lastLaunches += 2;
 	if (!expand) return PTP_OK;                                 // the inverse transform forms the rows above the deposit itself
-	k_thomas_expand<<<dim3((n1 + 255) / 256, (rowsOut + 7) / 8, nS), 256, 0, t->stream>>>(spec, t->wideXb, t->wideJ, t->thP, Nr, n1);
-	e = cudaGetLastError();
+	e = ptp_launch(k_thomas_expand, dim3((n1 + 255) / 256, (rowsOut + 7) / 8, nS), dim3(256), 0, t->stream, t->usePdl, spec, t->wideXb, t->wideJ, t->thP, Nr, n1);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_thomas_expand launch", __FILE__, __LINE__);
 	t->lastLaunches += 1;
 	return PTP_OK;
@@ -688,13 +698,15 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 		const size_t sm16 = (size_t)16 * R16_RS * sizeof(double2) + (size_t)(N + 1) * sizeof(double);
 		if (withField) {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-			k_idct_r16_field<true><<<rowsOut, 256, sm16, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz,
+			const cudaError_t el = ptp_launch(k_idct_r16_field<true>, dim3(rowsOut), dim3(256), sm16, t->stream, t->usePdl, spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, t->hz,
 				rowsFormed ? nullptr : t->wideXb, t->wideJ, t->thP, TW_BLK);
+			if (el != cudaSuccess) return ptp_cuda_fail(el, "k_idct_r16_field launch", __FILE__, __LINE__);
 		}
 		else {
 			PTP_CUDA(cudaFuncSetAttribute(k_idct_r16_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16));
-			k_idct_r16_field<false><<<rowsOut, 256, sm16, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, t->hz,
+			const cudaError_t el = ptp_launch(k_idct_r16_field<false>, dim3(rowsOut), dim3(256), sm16, t->stream, t->usePdl, spec, phi, t->fftTw, (const double*)nullptr, (double*)nullptr, nS, Nr, t->hz,
 				rowsFormed ? nullptr : t->wideXb, t->wideJ, t->thP, TW_BLK);
+			if (el != cudaSuccess) return ptp_cuda_fail(el, "k_idct_r16_field launch", __FILE__, __LINE__);
 		}
 		const cudaError_t e16 = cudaGetLastError();
 		if (e16 != cudaSuccess) return ptp_cuda_fail(e16, "k_idct_r16_field launch", __FILE__, __LINE__);
@@ -705,11 +717,13 @@ int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS,
 	const int threads = N >= 1024 ? 256 : 128;
 	if (withField) {
 		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-		k_idct_fft_field<true><<<rowsOut, threads, sm, t->stream>>>(spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, N, bits, t->hz);
+		const cudaError_t el = ptp_launch(k_idct_fft_field<true>, dim3(rowsOut), dim3(threads), sm, t->stream, t->usePdl, spec, phi, t->fftTw, t->phiTrap, t->eNodes, nS, Nr, N, bits, t->hz);
+		if (el != cudaSuccess) return ptp_cuda_fail(el, "k_idct_fft_field launch", __FILE__, __LINE__);
 	}
 	else {
 		PTP_CUDA(cudaFuncSetAttribute(k_idct_fft_field<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-		k_idct_fft_field<false><<<rowsOut, threads, sm, t->stream>>>(spec, phi, t->fftTw, nullptr, nullptr, nS, Nr, N, bits, t->hz);
+		const cudaError_t el = ptp_launch(k_idct_fft_field<false>, dim3(rowsOut), dim3(threads), sm, t->stream, t->usePdl, spec, phi, t->fftTw, (const double*)nullptr, (double*)nullptr, nS, Nr, N, bits, t->hz);
+		if (el != cudaSuccess) return ptp_cuda_fail(el, "k_idct_fft_field launch", __FILE__, __LINE__);
 	}
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_idct_fft_field launch", __FILE__, __LINE__);

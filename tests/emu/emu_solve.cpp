@@ -10,6 +10,17 @@
 static unsigned char* g_smem;
 static inline void cp_async8(void* dst, const void* src, bool valid) { if (valid) std::memcpy(dst, src, 8); else std::memset(dst, 0, 8); }
 static inline void cp_async16(void* dst, const void* src, bool valid) { if (valid) std::memcpy(dst, src, 16); else std::memset(dst, 0, 16); }
+// bulk-async copies complete at once here; the alignment rules of cp.async.bulk are checked
+static inline void mbar_init(unsigned long long*, int) {}
+static inline void mbar_fence_init() {}
+static inline void mbar_expect_tx(unsigned long long*, unsigned int) {}
+static inline void mbar_wait(unsigned long long*, unsigned int) { __syncthreads(); }   // every thread of the CTA waits on the same phase: a CTA barrier orders it behind the (synchronous) copies
+static inline void fence_proxy_async() {}
+static inline void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long*)
+{
+	if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15) || bytes == 0) { std::fprintf(stderr, "bulk_g2s: misaligned copy\n"); std::abort(); }
+	std::memcpy(dst, src, bytes);
+}
 #include "solve_snippet.inc"
 
 struct FakeTrap { int Nz, Nr; double hz, hr, radius, stDiag, stHz2, wallFactor; };
@@ -58,9 +69,25 @@ int main(int argc, char** argv)
 	auto smFieldBytes = [&](int st) { return ((size_t)INV_TM * (n1 | 1) + (size_t)8 * st * INV_KS * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double); };
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const bool vec = n1 % 2 == 0;
+	const int ldaBulk = (n1 + 15) & ~15;
+	const size_t smBulk = ((size_t)INV_TM * ldaBulk + 8 + (size_t)((n1 + 1) / 2) * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
+	const bool noBulk = std::getenv("PTP_INV_BULK") && std::atoi(std::getenv("PTP_INV_BULK")) == 0;
+	const bool bulkOk = vec && !noBulk && smBulk <= smemMax && (size_t)n1 * 8 * INV_TM < (1u << 20);
 	const char* path;
-	if (smFieldBytes(ringStages) > smemMax && rowsOut < Nr) { std::printf("emu_solve: the chunked inverse produces whole grids only\n"); return 8; }
-	if (smFieldBytes(ringStages) <= smemMax) {
+	if (!bulkOk && smFieldBytes(ringStages) > smemMax && rowsOut < Nr) { std::printf("emu_solve: the chunked inverse produces whole grids only\n"); return 8; }
+	if (bulkOk) {
+		path = "k_inv_field_bulk";
+		dynSmem(smBulk + 16);
+		// (the kernel's extern array is 16-byte aligned on the device; same here)
+		g_smem = reinterpret_cast<unsigned char*>(((uintptr_t)g_smem + 15) & ~(uintptr_t)15);
+		const int gx = (n1 + 1 + INV_TN - 3) / (INV_TN - 2), gy = (rowsOut + INV_TM - 1) / INV_TM;
+		for (int by = 0; by < gy; ++by)
+			emu_launch(gx, 256, [&] {
+				blockIdx.y = by;
+				k_inv_field_bulk<true>(spec.data(), inv.data(), phi.data(), phiTrap.data(), eN.data(), nS, Nr, n1, hz, ldaBulk);
+			});
+	}
+	else if (smFieldBytes(ringStages) <= smemMax) {
 		path = "k_inv_field";
 		dynSmem(smFieldBytes(ringStages));
 		const int gx = (n1 + 1 + INV_TN - 3) / (INV_TN - 2), gy = (rowsOut + INV_TM - 1) / INV_TM;

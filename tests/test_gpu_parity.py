@@ -661,9 +661,11 @@ def _other_grid_case(Nz, Nr, solver, fixed, exact=False):
 def test_step_solves_populated_rows_and_whole_grids_on_demand(c1_kat, monkeypatch):
     """A step computes potentials and node field for the populated radial rows only (rings never change their row,
     Source/Plasma.hpp:22-24); what the reference keeps on the whole grid (Plasma::selfPotential, the node field) is produced
-    when asked for. Against PTP_FULL_SOLVE=1 (every step solves the whole grid): per-ring state bit-identical after 20 steps,
-    the potentials and the node field of the whole grid bit-identical too, and equal to the oracle within the solver tolerance.
-    A species loaded later into rows the last step left out is pushed with the right field."""
+    when asked for. Against PTP_FULL_SOLVE=1 (every step solves the whole grid): per-ring state, the whole-grid potentials
+    and the node field are bit-identical after 20 steps (same fold row, same arithmetic per row), and equal to the oracle
+    within the solver tolerance. A species loaded later into rows the last step left out is pushed with the right field (the
+    potentials are completed first; the fold row of the radial solves moves with the new outermost row, so from here on the
+    two runs agree to rounding, not bitwise)."""
     res = []
     for full in ("1", "0"):
         monkeypatch.setenv("PTP_FULL_SOLVE", full)
@@ -675,6 +677,7 @@ def test_step_solves_populated_rows_and_whole_grids_on_demand(c1_kat, monkeypatc
         pe = el.getPotentialEnergy()
         _, z, v, ids = el.download()
         o = np.argsort(ids)
+        first = (z[o], v[o], el.selfPotential(), ap.selfPotential(), t.enodes(), el.rhs(), pe)
         # a third species far out (row 100) joins: the next step needs the whole-grid potentials of the first two there
         far = ptp.Plasma(t, "Far", ptp.massP, -ptp.ePos)
         n = 5000
@@ -684,12 +687,15 @@ def test_step_solves_populated_rows_and_whole_grids_on_demand(c1_kat, monkeypatc
         t.movePlasmas(dt, 3)
         _, zf, vf, idf = far.download()
         of = np.argsort(idf)
-        res.append((z[o], v[o], zf[of], vf[of], el.selfPotential(), ap.selfPotential(), far.selfPotential(), t.enodes(), el.rhs(), pe))
+        res.append((first, (zf[of], vf[of], el.selfPotential(), ap.selfPotential(), far.selfPotential(), t.enodes(), el.rhs())))
         t.close()
-    a, b = res
-    for n, (x, y) in enumerate(zip(a[:9], b[:9])):
+    (a1, a2), (b1, b2) = res
+    for n, (x, y) in enumerate(zip(a1[:6], b1[:6])):
         assert np.array_equal(x, y), n
-    assert a[9] == b[9]
+    assert a1[6] == b1[6]
+    for n, (x, y) in enumerate(zip(a2, b2)):
+        assert rel_l2(y, x) < 1e-12, n
+    assert rel_l2(a1[2], c1_kat["e_phi20"]) < 1e-8 if "e_phi20" in c1_kat else True
 
 
 def test_graph_replay_is_bitwise_identical(c1_kat):

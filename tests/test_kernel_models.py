@@ -235,6 +235,14 @@ def test_default_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz
     e[:, 1:-1] = (tot[:, :-2] - tot[:, 2:]) / (2 * pt.hz)
     assert np.array_equal(en.reshape(Nr, n1), e)
     assert np.array_equal(wall_rhs, pt.wall_rhs())
+    if n1 % 2 == 0 and "k_inv_field_bulk" in p.stdout:
+        # even row length: the bulk-async (TMA) staged inverse ran; the cp.async form of the same kernel gives the same bits
+        out0 = str(tmp_path / "out_cpasync.bin")
+        p0 = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_solve"), case, out0], capture_output=True, text=True, timeout=900,
+                            env=dict(os.environ, PTP_INV_BULK="0"))
+        assert p0.returncode == 0 and "k_inv_field_bulk" not in p0.stdout, p0.stdout + p0.stderr
+        raw0 = np.fromfile(out0, np.float64)
+        assert np.array_equal(raw0[:2 * G], raw[:2 * G])
     # rows above the outermost populated row folded into its pivot (the fold row is host knowledge: rings keep their row), whole
     # grid produced: the same solution; and the step's form, which stops after the populated rows rounded up to blocks of 32
     limit = max(rows) + 1
