@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(256) k_inv_field_bulk(const double* __restrict
 	const int c0 = FIELD ? (int)blockIdx.x * (INV_TN - 2) - 2 : (int)blockIdx.x * INV_TN;   // first column of the tile (even; may be -2)
 	double* sA = sm;
 	double* sB = sm + (size_t)INV_TM * LDA + 8;
-	double* sTot = sB + (size_t)K2 * INV_TN;
+	double* sTot = sB + (size_t)max(K2, 8 * INV_TM) * INV_TN;   // (the reduction needs [8][16][40] there, also on very short rows)
 	auto rowOff = [LDA](int r) { return r * LDA + 2 * (r >> 2); };
 	const int cFirst = max(c0, 0), cEnd = min(c0 + INV_TN, n1);  // valid columns of the tile: [cFirst, cEnd), both even
 	const unsigned int rowBytes = (unsigned int)(cEnd - cFirst) * 8u;
@@ -980,7 +980,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 	const size_t smField = smFieldBytes(ringStages);
 	// even row length: every row of the grids and of the cosine matrix starts 16-byte aligned - bulk-async (TMA) staged form
 	const int ldaBulk = (n1 + 15) & ~15;
-	const size_t smBulk = ((size_t)INV_TM * ldaBulk + 8 + (size_t)((n1 + 1) / 2) * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
+	const size_t smBulk = ((size_t)INV_TM * ldaBulk + 8 + (size_t)std::max((n1 + 1) / 2, 8 * INV_TM) * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
 	const bool bulkOk = n1 % 2 == 0 && t->invBulk && smBulk <= t->smemMax && (size_t)n1 * 8 * INV_TM < (1u << 20);
 	const bool fusedFits = bulkOk || smField <= t->smemMax;
 	const bool useFft = ptp_solver_fft_fits(t) && (t->solver == PTP_SOLVER_DIRECT_FFT || !fusedFits);

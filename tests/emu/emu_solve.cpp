@@ -70,7 +70,7 @@ int main(int argc, char** argv)
 	const int ringStages = smFieldBytes(std::max(stagesAll, 2)) <= smemMax ? std::max(stagesAll, 2) : INV_ST;
 	const bool vec = n1 % 2 == 0;
 	const int ldaBulk = (n1 + 15) & ~15;
-	const size_t smBulk = ((size_t)INV_TM * ldaBulk + 8 + (size_t)((n1 + 1) / 2) * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
+	const size_t smBulk = ((size_t)INV_TM * ldaBulk + 8 + (size_t)std::max((n1 + 1) / 2, 8 * INV_TM) * INV_TN + (size_t)INV_TM * INV_TN) * sizeof(double);
 	const bool noBulk = std::getenv("PTP_INV_BULK") && std::atoi(std::getenv("PTP_INV_BULK")) == 0;
 	const bool bulkOk = vec && !noBulk && smBulk <= smemMax && (size_t)n1 * 8 * INV_TM < (1u << 20);
 	const char* path;

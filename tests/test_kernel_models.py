@@ -192,6 +192,7 @@ def test_large_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
 @pytest.mark.parametrize("Nz,Nr,rows,k_lo,k_hi", [(585, 128, range(0, 12), 274, 311),     # the reference's default grid: fused inverse + node field
                                                   (300, 20, [0, 5, 19], 3, 297),           # odd row length: 8-byte copies
+                                                  (57, 9, [0, 2, 3], 20, 40),              # very short even rows: bulk-staged inverse, two column tiles
                                                   (1500, 12, range(0, 4), 700, 800)])      # long rows, not a power of two: chunked inverse GEMM + k_node_field
 def test_default_grid_solver_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, Nr, rows, k_lo, k_hi):
     """The shipped table builder and the kernels of ptp_solve.cu (row-bounds scan, forward DCT fused with the Thomas solves,
