@@ -184,6 +184,22 @@ int ptp_plasma_set_self_potential(ptp_plasma* p, const double* phi);/* parity ho
  * getNumMacroCentralWell (:151-162; limits = per-row [left,right] node indices, Source/PenningTrap.cpp:63-90). */
 int ptp_plasma_potential_energy(ptp_plasma* p, double chargeMacro, double* pe);
 int ptp_plasma_count_central_well(ptp_plasma* p, const int32_t* limitLeft, const int32_t* limitRight, int64_t* n);
+/* Plasma::getTemperature / getAverageTemperature / getstdDeviation (Source/Plasma.cpp:163-228) without histories on the host:
+ * over the live rings, *sumW = sum of w (w = 1 on the axis, 8 r elsewhere: ring mass = w massMacro, :169-170) and
+ * *sumWS2 = sum of w speed^2 with speed = mean of the ring's speeds at the last two save points (:180, :224) - the present
+ * speed when there is no earlier save point (*paired = 0). T = mass * sumWS2 / (KB * sumW). markSavePoint != 0 makes the
+ * present speeds the save point (what PenningTrap::saveStates does, Source/PenningTrap.cpp:364-385); the saved speeds
+ * follow their rings through re-sorts. Rings lost between two save points drop out of later sums, as in the reference. */
+int ptp_plasma_kinetic_sums(ptp_plasma* p, int markSavePoint, double* sumW, double* sumWS2, int* paired);
+/* Plasma::saveState(int indexR) (Source/Plasma.cpp:338-346): the live rings of ONE radial row - a contiguous slice of the
+ * row-bucketed storage, so only that slice crosses PCIe. z, v, id (any may be NULL) hold nMax entries; *n = rings in the row. */
+int ptp_plasma_download_row(ptp_plasma* p, int row, int64_t nMax, double* z, double* v, int64_t* id, int64_t* n);
+/* Loss log of Plasma::moveRings (Source/Plasma.cpp:108-118): the reference removes a lost ring at once by swapping it with
+ * the last one, step by step, which fixes the row order of its history files. The push kernel logs (ring id, step tag) for
+ * every ring that leaves the trap (step tag = pushes of this species since its load); entries [first, first + nMax) are
+ * copied out in the order they were logged (steps ascending), *total = entries logged so far, *overflowed = 1 when more
+ * rings were lost than the log holds (65536; the host classes then fall back to one sweep per refresh). */
+int ptp_plasma_loss_log(ptp_plasma* p, int64_t first, int64_t nMax, int64_t* ids, int64_t* steps, int64_t* total, int* overflowed);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,9 @@ SIGNATURES = {
     "ptp_plasma_set_self_potential": (_i, [_vp, _vp]),
     "ptp_plasma_potential_energy": (_i, [_vp, _d, C.POINTER(_d)]),
     "ptp_plasma_count_central_well": (_i, [_vp, _vp, _vp, C.POINTER(_i64)]),
+    "ptp_plasma_kinetic_sums": (_i, [_vp, _i, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i)]),
+    "ptp_plasma_download_row": (_i, [_vp, _i, _i64, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "ptp_plasma_loss_log": (_i, [_vp, _i64, _i64, _vp, _vp, C.POINTER(_i64), C.POINTER(_i)]),
 }
 
 
@@ -414,6 +417,35 @@ class Plasma:
         pe = C.c_double()
         _check(lib().ptp_plasma_potential_energy(self.h, self.chargeMacro, C.byref(pe)))
         return pe.value
+
+    def kineticSums(self, mark=False):
+        """(sum w, sum w speed^2, paired) of ptp_plasma_kinetic_sums; temperature = mass * s2 / (KB * sw)."""
+        sw, s2, paired = C.c_double(), C.c_double(), C.c_int()
+        _check(lib().ptp_plasma_kinetic_sums(self.h, 1 if mark else 0, C.byref(sw), C.byref(s2), C.byref(paired)))
+        return sw.value, s2.value, bool(paired.value)
+
+    def saveSpeeds(self):
+        """A save point of PenningTrap::saveStates for the temperature diagnostics; returns the temperature of the pair
+        (previous save point, this one) as Plasma::getTemperature would (Source/Plasma.cpp:212-228), None at the first."""
+        sw, s2, paired = self.kineticSums(mark=True)
+        return (self.mass * s2 / (KB * sw)) if (paired and sw > 0) else None
+
+    def downloadRow(self, row):
+        t = self.refTrap
+        n = C.c_int64()
+        cap = self.getNumMacro()
+        z, v, ids = np.empty(cap), np.empty(cap), np.empty(cap, np.int64)
+        _check(lib().ptp_plasma_download_row(self.h, int(row), cap, _ptr(z), _ptr(v), _ptr(ids), C.byref(n)))
+        return z[:n.value].copy(), v[:n.value].copy(), ids[:n.value].copy()
+
+    def lossLog(self, first=0):
+        total, over = C.c_int64(), C.c_int()
+        _check(lib().ptp_plasma_loss_log(self.h, int(first), 0, None, None, C.byref(total), C.byref(over)))
+        n = max(0, min(total.value, 1 << 16) - first)
+        ids, steps = np.empty(n, np.int64), np.empty(n, np.int64)
+        if n:
+            _check(lib().ptp_plasma_loss_log(self.h, int(first), n, _ptr(ids), _ptr(steps), C.byref(total), C.byref(over)))
+        return ids, steps, total.value, bool(over.value)
 
     def getNumMacroCentralWell(self, limitLeft, limitRight):  # Source/Plasma.cpp:151-162
         a = np.ascontiguousarray(limitLeft, dtype=np.int32)

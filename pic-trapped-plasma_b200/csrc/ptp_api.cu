@@ -751,6 +751,7 @@ int ptp_plasma_destroy(ptp_plasma* p)
 	t->eNodesValid = false;
 	cudaFree(p->z); cudaFree(p->v); cudaFree(p->id); cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->sortScratch); cudaFree(p->planScratch);
 	cudaFree(p->dRowOff); cudaFree(p->dSegs); cudaFree(p->dCtaSegBegin); cudaFree(p->dSegBounds); cudaFree(p->dLost);
+	cudaFree(p->dLossLog); cudaFree(p->vSaved); cudaFree(p->vSavedAlt);
 	delete p;
 	return PTP_OK;
 }

@@ -55,6 +55,11 @@ struct ptp_plasma {
 	size_t planScratchBytes = 0;
 	int nCta = 0;
 	unsigned long long* dLost = nullptr; // [2] device counters: rings lost since upload; deposits outside the private window since the last check
+	unsigned long long* dLossLog = nullptr; // loss log of the push kernel (header of 4 words + (id, step tag) pairs), reset by every (re)load
+	long long lossCap = 0;               // entries the log can hold
+	double* vSaved = nullptr;            // [cap] speed of every ring at the last save point (ptp_plasma_kinetic_sums), allocated on first use
+	double* vSavedAlt = nullptr;         // sort ping-pong
+	bool vSavedValid = false;
 	bool boundsValid = false;
 	bool encValid = false;       // the touched-node range per row kept next to this species' deposit grid (written by the push kernel's
 	                             // flush) describes the grid's present content

@@ -74,6 +74,32 @@ __global__ void k_central_well(const double* __restrict__ z, const PtpSegment* _
 	if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, (unsigned long long)n);
 }
 
+// Sums for Plasma::getTemperature / getAverageTemperature / getstdDeviation (Source/Plasma.cpp:163-228): over the live rings,
+// weight w = 1 on the axis, 8 r elsewhere (ring mass = w massMacro, Source/Plasma.cpp:169-170), speed = mean of the speeds at
+// the last two save points (positions and speeds are staggered by dt/2, :180,224) - or the present speed when there is no
+// earlier save point. out[0] += sum w, out[1] += sum w speed^2; T = mass out[1] / (KB out[0]). With mark, the present speed
+// becomes the save point.
+__global__ void __launch_bounds__(256) k_kinetic_sums(const double* __restrict__ z, const double* __restrict__ v, double* __restrict__ vSaved, bool paired, bool mark,
+	const PtpSegment* __restrict__ segs, int nSegs, double* __restrict__ out)
+{
+	double sw = 0.0, ss = 0.0;
+	for (int s = blockIdx.x; s < nSegs; s += gridDim.x) {
+		const PtpSegment seg = segs[s];
+		const double w = seg.row == 0 ? 1.0 : (double)(8 * seg.row);
+		for (long long i = seg.begin + threadIdx.x; i < seg.end; i += blockDim.x) {
+			const double zz = z[i];
+			if (!(zz == zz)) continue;
+			const double now = v[i];
+			const double speed = paired ? (vSaved[i] + now) / 2 : now;
+			sw += w;
+			ss += w * speed * speed;
+			if (mark) vSaved[i] = now;
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) { sw += __shfl_xor_sync(0xffffffffu, sw, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+	if ((threadIdx.x & 31) == 0 && sw != 0.0) { atomicAdd(out, sw); atomicAdd(out + 1, ss); }
+}
+
 // ---- K5: per-row counting sort by axial cell ---------------------------------------------------------
 // [emu-begin] (tests/emu/emu_sort.cpp runs the text between these markers on host threads)
 // The live prefix of every row bucket is cut into chunks of SORT_CHUNK slots (host table); one CTA per chunk. Rings arrive
@@ -140,7 +166,8 @@ __global__ void __launch_bounds__(256) k_sort_scan(const unsigned int* __restric
 // reserve the destination range.
 __global__ void __launch_bounds__(256) k_sort_scatter(const double* __restrict__ z, const double* __restrict__ v,
 	const long long* __restrict__ id, double* __restrict__ zOut, double* __restrict__ vOut, long long* __restrict__ idOut,
-	const long long* __restrict__ rowOff, const SortChunk* __restrict__ chunks, int Nz, double hz, unsigned long long* __restrict__ cursor)
+	const long long* __restrict__ rowOff, const SortChunk* __restrict__ chunks, int Nz, double hz, unsigned long long* __restrict__ cursor,
+	const double* __restrict__ vs, double* __restrict__ vsOut)
 {
 	extern __shared__ unsigned int sh[];                   // hist[Nz] then base (as 2 x u32 per cell)
 	unsigned int* hist = sh;
@@ -174,6 +201,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const double* __restrict__
 			zOut[dst] = zz;
 			vOut[dst] = v[i];
 			idOut[dst] = id[i];
+			if (vs) vsOut[dst] = vs[i];                          // speeds at the last save point travel with their rings
 		}
 	}
 }
@@ -378,7 +406,9 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 	const unsigned int nChunks = (unsigned int)chunks.size();
 	if (nChunks) k_sort_count<<<nChunks, 256, smCount, t->stream>>>(p->z, dChunks, Nz, t->hz, dCounts);
 	k_sort_scan<<<Nr, 256, 0, t->stream>>>(dCounts, Nz, dCursor, dLive);
-	if (nChunks) k_sort_scatter<<<nChunks, 256, smScatter, t->stream>>>(p->z, p->v, p->id, p->zAlt, p->vAlt, p->idAlt, p->dRowOff, dChunks, Nz, t->hz, dCursor);
+	if (p->vSaved && !p->vSavedAlt) PTP_CUDA(cudaMalloc(&p->vSavedAlt, p->cap * sizeof(double)));
+	if (nChunks) k_sort_scatter<<<nChunks, 256, smScatter, t->stream>>>(p->z, p->v, p->id, p->zAlt, p->vAlt, p->idAlt, p->dRowOff, dChunks, Nz, t->hz, dCursor,
+		p->vSaved, p->vSavedAlt);
 	// the alternate buffers hold the empty-slot pattern beyond altDirty (what they held when they were last the primary
 	// ones): only the slots between the new live prefix and that mark need it again
 	k_sort_pad<<<dim3(32, Nr), 256, 0, t->stream>>>(p->zAlt, p->vAlt, p->idAlt, p->dRowOff, dLive, dOldLive);
@@ -389,6 +419,7 @@ int ptp_sort_plasma(ptp_trap* t, ptp_plasma* p)
 	PTP_CUDA(cudaMemcpyAsync(live.data(), dLive, Nr * sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream));
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
 	std::swap(p->z, p->zAlt); std::swap(p->v, p->vAlt); std::swap(p->id, p->idAlt);
+	if (p->vSaved) std::swap(p->vSaved, p->vSavedAlt);
 	long long total = 0;
 	for (int r = 0; r < Nr; ++r) { p->altDirty[r] = p->rowLive[r]; p->rowLive[r] = (long long)live[r]; total += (long long)live[r]; }
 	p->nAlive = total;
@@ -418,8 +449,13 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 		cudaFree(p->z); cudaFree(p->v); cudaFree(p->id);
 		p->z = p->v = nullptr; p->id = nullptr;
 	}
-	cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff);
-	p->zAlt = p->vAlt = nullptr; p->idAlt = nullptr; p->dRowOff = nullptr;
+	cudaFree(p->zAlt); cudaFree(p->vAlt); cudaFree(p->idAlt); cudaFree(p->dRowOff); cudaFree(p->vSaved); cudaFree(p->vSavedAlt);
+	p->zAlt = p->vAlt = nullptr; p->idAlt = nullptr; p->dRowOff = nullptr; p->vSaved = p->vSavedAlt = nullptr; p->vSavedValid = false;
+	if (!p->dLossLog) {
+		p->lossCap = 1 << 16;
+		PTP_CUDA(cudaMalloc(&p->dLossLog, (4 + 2 * (size_t)p->lossCap) * sizeof(unsigned long long)));
+	}
+	PTP_CUDA(cudaMemsetAsync(p->dLossLog, 0, 4 * sizeof(unsigned long long), t->stream));
 	p->cap = newCap;
 	p->farBaseline = -1.0;
 	t->stepsSinceCheck = 0;
@@ -615,6 +651,84 @@ int ptp_plasma_potential_energy(ptp_plasma* p, double chargeMacro, double* pe)
 	PTP_CUDA(cudaStreamSynchronize(t->stream));
 	cudaFree(dOut);
 	*pe = h / 2;                                            // Source/Plasma.cpp:251
+	return PTP_OK;
+}
+
+int ptp_plasma_kinetic_sums(ptp_plasma* p, int markSavePoint, double* sumW, double* sumWS2, int* paired)
+{
+	if (!p || !sumW || !sumWS2) { ptp_set_error("ptp_plasma_kinetic_sums: null argument"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	*sumW = *sumWS2 = 0.0;
+	if (paired) *paired = p->vSavedValid ? 1 : 0;
+	if (p->segs.empty()) return PTP_OK;
+	if (markSavePoint && !p->vSaved) PTP_CUDA(cudaMalloc(&p->vSaved, p->cap * sizeof(double)));
+	double* dOut = nullptr;
+	PTP_CUDA(cudaMalloc(&dOut, 2 * sizeof(double)));
+	PTP_CUDA(cudaMemsetAsync(dOut, 0, 2 * sizeof(double), t->stream));
+	const int grid = std::min<int>((int)p->segs.size(), t->smCount * 4);
+	k_kinetic_sums<<<grid, 256, 0, t->stream>>>(p->z, p->v, p->vSaved, p->vSavedValid, markSavePoint != 0, p->dSegs, (int)p->segs.size(), dOut);
+	double h[2] = { 0, 0 };
+	cudaError_t e = cudaMemcpyAsync(h, dOut, sizeof(h), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+	cudaFree(dOut);
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_kinetic_sums", __FILE__, __LINE__);
+	if (markSavePoint) p->vSavedValid = true;
+	*sumW = h[0];
+	*sumWS2 = h[1];
+	return PTP_OK;
+}
+
+int ptp_plasma_download_row(ptp_plasma* p, int row, int64_t nMax, double* z, double* v, int64_t* id, int64_t* n)
+{
+	if (!p || !n || row < 0 || row >= p->trap->Nr || nMax < 0) { ptp_set_error("ptp_plasma_download_row: bad arguments"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	*n = 0;
+	const long long live = p->cap ? p->rowLive[row] : 0;           // slots of the bucket that may hold rings: one contiguous slice
+	if (live == 0) return PTP_OK;
+	const long long b = p->rowOff[row];
+	std::vector<double> zs((size_t)live), vs(v ? (size_t)live : 0);
+	std::vector<long long> ids(id ? (size_t)live : 0);
+	PTP_CUDA(cudaMemcpyAsync(zs.data(), p->z + b, (size_t)live * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	if (v) PTP_CUDA(cudaMemcpyAsync(vs.data(), p->v + b, (size_t)live * sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+	if (id) PTP_CUDA(cudaMemcpyAsync(ids.data(), p->id + b, (size_t)live * sizeof(long long), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	int64_t o = 0;
+	for (long long i = 0; i < live; ++i) {
+		if (!(zs[(size_t)i] == zs[(size_t)i])) continue;          // lost ring / empty slot
+		if (o < nMax) {
+			if (z) z[o] = zs[(size_t)i];
+			if (v) v[o] = vs[(size_t)i];
+			if (id) id[o] = ids[(size_t)i];
+		}
+		++o;
+	}
+	*n = o;
+	if (o > nMax) { ptp_set_error("ptp_plasma_download_row: buffers too small"); return PTP_EINVAL; }
+	return PTP_OK;
+}
+
+int ptp_plasma_loss_log(ptp_plasma* p, int64_t first, int64_t nMax, int64_t* ids, int64_t* steps, int64_t* total, int* overflowed)
+{
+	if (!p || !total || first < 0 || nMax < 0) { ptp_set_error("ptp_plasma_loss_log: bad arguments"); return PTP_EINVAL; }
+	ptp_trap* t = p->trap;
+	PTP_CUDA(cudaSetDevice(t->device));
+	*total = 0;
+	if (overflowed) *overflowed = 0;
+	if (!p->dLossLog) return PTP_OK;
+	unsigned long long count = 0;
+	PTP_CUDA(cudaMemcpyAsync(&count, p->dLossLog, sizeof(count), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	*total = (int64_t)count;
+	if (overflowed && (long long)count > p->lossCap) *overflowed = 1;
+	const int64_t have = std::min<int64_t>((int64_t)count, p->lossCap);
+	const int64_t take = std::max<int64_t>(0, std::min<int64_t>(nMax, have - first));
+	if (take == 0 || !ids || !steps) return PTP_OK;
+	std::vector<unsigned long long> h(2 * (size_t)take);
+	PTP_CUDA(cudaMemcpyAsync(h.data(), p->dLossLog + 4 + 2 * first, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	for (int64_t i = 0; i < take; ++i) { ids[i] = (int64_t)h[2 * (size_t)i]; steps[i] = (int64_t)h[2 * (size_t)i + 1]; }
 	return PTP_OK;
 }
 

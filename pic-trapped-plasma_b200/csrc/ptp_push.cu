@@ -63,6 +63,12 @@ struct PushArgs {
 	double* clearBounds;
 	int clearBoundsWords, pad3;
 	unsigned long long* lost;   // [0] rings lost since upload, [1] deposits that missed the private window (re-sort trigger)
+	// Loss log (nullptr: none): [0] entries written, [1] number of push launches of this species so far = the step tag, [2] CTA
+	// ticket of the current launch, [3] unused, then (ring id, step tag) pairs. The reference removes lost rings step by step
+	// (swap-with-back, Source/Plasma.cpp:114-118); the host classes replay that order from this log.
+	unsigned long long* lossLog;
+	const long long* id;        // [cap] ring ids (read for lost rings only)
+	long long lossCap;
 };
 
 // Axial cell of a position: bit-exact (int)floor(z / hz) (Source/Plasma.cpp:87, Source/PenningTrap.cpp:328).
@@ -187,6 +193,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
 	ptp_pdl_launch_dependents();
 	ptp_pdl_wait();                              // the node field of the last solve, the rings of the last push
+	const unsigned long long stepTag = (PUSH && a.lossLog) ? a.lossLog[1] : 0ULL;   // (advanced by the last CTA of this launch to finish)
 	if (PUSH) {
 		for (long long i = (long long)blockIdx.x * T + tid; i < a.clearGridWords; i += (long long)gridDim.x * T) a.clearGrid[i] = 0.0;
 		for (int i = blockIdx.x * T + tid; i < a.clearBoundsWords; i += gridDim.x * T) a.clearBounds[i] = 0.0;
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 				cells_of<R, EXACT>(z, live, a, k, w);
 				double eL[R], eR[R];
 				bool far = false;
+				unsigned int goneMask = 0;
 #pragma unroll
 				for (int i = 0; i < R; ++i) {
 					const unsigned int io = (unsigned int)(k[i] - kE0);
@@ -310,9 +318,22 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 					// a removed ring becomes a NaN tombstone instead of swap-with-back + pop (:116-117)
 					const bool keep = live[i] && (zN < a.length) && (zN > 0.0);
 					lost += (live[i] && !keep) ? 1u : 0u;
+					goneMask |= (live[i] && !keep) ? (1u << i) : 0u;
 					z[i] = keep ? zN : qNaN;
 					v[i] = keep ? vN : v[i];
 					live[i] = keep;
+				}
+				if (goneMask && a.lossLog) {                             // rare: which ring left the trap, and in which step
+#pragma unroll
+					for (int i = 0; i < R; ++i)
+						if ((goneMask >> i) & 1u) {
+							const long long slot = 2 * (p0 + (long long)(i >> 1) * T) + (i & 1);
+							const unsigned long long pos = atomicAdd(a.lossLog, 1ULL);
+							if ((long long)pos < a.lossCap) {
+								a.lossLog[4 + 2 * pos] = (unsigned long long)a.id[slot];
+								a.lossLog[5 + 2 * pos] = stepTag;
+							}
+						}
 				}
 			}
 
@@ -508,6 +529,15 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		}
 		__syncthreads();
 	}
+	if (PUSH && a.lossLog && tid == 0) {
+		// every CTA of the launch has read the step tag before the last one to finish advances it
+		__threadfence();
+		const unsigned long long ticket = atomicAdd(a.lossLog + 2, 1ULL);
+		if (ticket == (unsigned long long)gridDim.x - 1) {
+			a.lossLog[2] = 0ULL;
+			a.lossLog[1] = stepTag + 1;
+		}
+	}
 }
 
 // [emu-end]
@@ -616,6 +646,9 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
 	a.bndOffset = (long long)((size_t)t->capS * t->G - (size_t)p->index * t->G + (size_t)p->index * t->Nr);
 	a.lost = p->dLost;
+	a.lossLog = p->dLossLog;
+	a.id = p->id;
+	a.lossCap = p->lossCap;
 	return a;
 }
 

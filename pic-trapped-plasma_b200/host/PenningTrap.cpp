@@ -296,6 +296,11 @@ void PenningTrap::movePlasmas(double deltaT, int numSteps)
 	for (Plasma& p : plasmas) p.refreshAlive();
 }
 
+void PenningTrap::keepHistories(bool on)
+{
+	for (Plasma& p : plasmas) p.hostHistories = on;
+}
+
 void PenningTrap::saveStates(double aTime)
 {
 	timesSaved.push_back(aTime);

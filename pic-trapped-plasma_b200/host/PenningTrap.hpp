@@ -87,6 +87,10 @@ public:
 
 	// Extensions (not in the reference): several steps per call, device selection, raw handle.
 	void movePlasmas(double deltaT, int numSteps);
+	// keepHistories(false): saveStates keeps only what the temperature diagnostics need (sums formed on the device at every
+	// save point) and the potential energy - no ring crosses PCIe, getTemperature / getAverageTemperature / getstdDeviation
+	// work as before, extractPlasmasHistories has nothing to write. For loads whose histories would not fit on the host.
+	void keepHistories(bool on);
 	// Electrode programmes: keep one Laplace solution per electrode on the device; setPotential then costs one axpy
 	// kernel instead of a solve (also switched on by PTP_ELECTRODE_BASIS=1), and a schedule potentials[step][electrode]
 	// runs without returning to the host between steps.

@@ -103,14 +103,60 @@ void Plasma::getRings(std::vector<int>& r, std::vector<double>& z, std::vector<d
 	check(ptp_plasma_download(device, reinterpret_cast<int32_t*>(r.data()), z.data(), v.data(), reinterpret_cast<int64_t*>(id.data())));
 }
 
-// Bring `order` (ids of the live rings in the reference's ring order) up to date. The reference removes a
-// ring by swapping it with the last one and shrinking the vector, without advancing the index
-// (Source/Plasma.cpp:114-118); replaying exactly that on the id list reproduces its row order in the history files.
+// Bring `order` (ids of the live rings in the reference's ring order) up to date. The reference removes a ring at once,
+// in the step in which it leaves the trap, by swapping it with the last one and shrinking the vector without advancing the
+// index (Source/Plasma.cpp:114-118). The push kernel logs (ring id, step) for every lost ring; replaying the reference's
+// sweep once per logged step reproduces its ring order - hence the row order of the history files - also when rings were
+// lost in several steps since the last refresh (multi-step movePlasmas calls, electrode programmes). One sweep over the
+// rings lost in one step only moves rings from the back into the holes, so it is replayed from the position table in
+// O(lost) instead of O(live).
 void Plasma::refreshAlive()
 {
 	if (!device) return;
 	const std::size_t alive = (std::size_t)getNumMacro();
 	if (alive == order.size()) return;
+	std::int64_t total = 0;
+	int overflowed = 0;
+	check(ptp_plasma_loss_log(device, lossSeen, 0, nullptr, nullptr, &total, &overflowed));
+	const std::int64_t expected = (std::int64_t)order.size() - (std::int64_t)alive;
+	if (!overflowed && total - lossSeen == expected && posOf.size() == ringAlive.size()) {
+		std::vector<std::int64_t> ids((std::size_t)expected), steps((std::size_t)expected);
+		check(ptp_plasma_loss_log(device, lossSeen, expected, ids.data(), steps.data(), &total, &overflowed));
+		lossSeen += expected;
+		// entries arrive in step order (kernels of consecutive steps are stream-ordered); group by step
+		std::vector<std::size_t> idx((std::size_t)expected);
+		std::iota(idx.begin(), idx.end(), (std::size_t)0);
+		std::stable_sort(idx.begin(), idx.end(), [&](std::size_t a, std::size_t b) { return steps[a] < steps[b]; });
+		std::size_t g0 = 0;
+		std::vector<std::int64_t> holes;
+		while (g0 < idx.size()) {
+			std::size_t g1 = g0;
+			holes.clear();
+			while (g1 < idx.size() && steps[idx[g1]] == steps[idx[g0]]) {
+				const std::int64_t id = ids[idx[g1]];
+				ringAlive[(std::size_t)id] = 0;
+				holes.push_back(posOf[(std::size_t)id]);
+				++g1;
+			}
+			std::sort(holes.begin(), holes.end());
+			std::size_t n = order.size();
+			for (std::int64_t h : holes) {                        // the reference's sweep: ascending index, re-examine after a swap
+				const std::size_t i = (std::size_t)h;
+				while (i < n && !ringAlive[(std::size_t)order[i]]) {
+					posOf[(std::size_t)order[i]] = -1;
+					order[i] = order[n - 1];
+					if (i != n - 1) posOf[(std::size_t)order[i]] = (std::int64_t)i;
+					--n;
+				}
+			}
+			order.resize(n);
+			g0 = g1;
+		}
+		return;
+	}
+	// log not usable (more rings lost than it holds): one sweep over everything lost since the last refresh - the reference's
+	// order only if all of them left in the same step
+	lossSeen = total;
 	std::vector<int> r;
 	std::vector<double> z, v;
 	std::vector<std::int64_t> id;
@@ -124,19 +170,45 @@ void Plasma::refreshAlive()
 			order.pop_back();
 		}
 	}
+	posOf.assign(ringAlive.size(), -1);
+	for (std::size_t i = 0; i < order.size(); ++i) posOf[(std::size_t)order[i]] = (std::int64_t)i;
 }
 
+// PenningTrap::saveStates -> Plasma::saveState (Source/Plasma.cpp:330-346). Every save point also feeds the device-side
+// temperature sums (mean of the speeds at two consecutive save points, Source/Plasma.cpp:180,224). With histories on the host
+// (the default, what extractPlasmasHistories needs) the rings are downloaded - all of them, or for saveState(indexR) just
+// the contiguous slice of that radial row.
 void Plasma::saveSelected(int indexR, bool all)
 {
+	if (all) {
+		double sw = 0, s2 = 0;
+		int paired = 0;
+		check(ptp_plasma_kinetic_sums(device, 1, &sw, &s2, &paired));
+		if (paired && sw > 0) pairTemperature.push_back(mass * s2 / (KB * sw));
+	}
+	if (!hostHistories) return;
 	refreshAlive();
-	std::vector<int> r;
-	std::vector<double> z, v;
-	std::vector<std::int64_t> id;
-	getRings(r, z, v, id);
-	for (std::size_t i = 0; i < id.size(); ++i) {
-		if (!all && r[i] != indexR) continue;
-		historyZ[(std::size_t)id[i]].push_back(z[i]);
-		historySpeed[(std::size_t)id[i]].push_back(v[i]);
+	if (all) {
+		std::vector<int> r;
+		std::vector<double> z, v;
+		std::vector<std::int64_t> id;
+		getRings(r, z, v, id);
+		for (std::size_t i = 0; i < id.size(); ++i) {
+			historyZ[(std::size_t)id[i]].push_back(z[i]);
+			historySpeed[(std::size_t)id[i]].push_back(v[i]);
+		}
+		return;
+	}
+	if (indexR < 0 || indexR >= refTrap.Nr) return;
+	std::size_t cap = 0;
+	for (std::int64_t i : order) cap += ringR[(std::size_t)i] == indexR ? 1 : 0;
+	std::vector<double> z(cap), v(cap);
+	std::vector<std::int64_t> id(cap);
+	std::int64_t n = 0;
+	check(ptp_plasma_download_row(device, indexR, (std::int64_t)cap, z.data(), v.data(), reinterpret_cast<int64_t*>(id.data()), &n));
+	for (std::int64_t i = 0; i < n; ++i) {
+		historyZ[(std::size_t)id[(std::size_t)i]].push_back(z[(std::size_t)i]);
+		historySpeed[(std::size_t)id[(std::size_t)i]].push_back(v[(std::size_t)i]);
 	}
 }
 
@@ -182,6 +254,10 @@ double Plasma::getPotentialEnergy() const
 
 double Plasma::getTemperature() const
 {
+	if (!hostHistories) {                                       // from the device sums of the last two save points
+		if (pairTemperature.empty()) throw std::logic_error("getTemperature needs two saved states");
+		return pairTemperature.back();
+	}
 	double numParticles = 0, KE = 0;
 	for (std::int64_t i : order) {
 		const int r = ringR[(std::size_t)i];
@@ -200,6 +276,12 @@ double Plasma::getTemperature() const
 
 double Plasma::getAverageTemperature() const
 {
+	if (!hostHistories) {
+		if (pairTemperature.empty()) throw std::logic_error("getAverageTemperature needs two saved states");
+		double T = 0;
+		for (double x : pairTemperature) T += x;
+		return T / (double)pairTemperature.size();
+	}
 	const int times = (int)historySpeed[(std::size_t)order[0]].size() - 1;
 	double numParticles = 0;
 	for (std::int64_t i : order) {
@@ -223,6 +305,12 @@ double Plasma::getAverageTemperature() const
 
 double Plasma::getstdDeviation() const
 {
+	if (!hostHistories) {
+		const double m = getAverageTemperature();
+		double acc = 0;
+		for (double x : pairTemperature) acc += pow(x - m, 2);
+		return sqrt(acc / ((double)pairTemperature.size() - 1));
+	}
 	const double mean = getAverageTemperature();
 	const int times = (int)historySpeed[(std::size_t)order[0]].size() - 1;
 	double numParticles = 0;
@@ -269,6 +357,9 @@ void Plasma::loadRings(const std::vector<int>& r, const std::vector<double>& z, 
 	historySpeed.assign(r.size(), std::vector<double>());
 	order.resize(r.size());
 	std::iota(order.begin(), order.end(), (std::int64_t)0);
+	posOf = order;
+	lossSeen = 0;
+	pairTemperature.clear();
 	solvePoisson();
 }
 
@@ -298,6 +389,9 @@ void Plasma::placeRings(int numMacro)
 		historySpeed.assign(ringR.size(), std::vector<double>());
 		order.resize(ringR.size());
 		std::iota(order.begin(), order.end(), (std::int64_t)0);
+		posOf = order;
+		lossSeen = 0;
+		pairTemperature.clear();
 		std::cout << "Loading " << ringR.size() << " macro-particles from which " << perRowDevice[0] << " are at r=0.\n";
 		solvePoisson();
 		return;

@@ -34,6 +34,10 @@ private:
 	std::vector<char> ringAlive;
 	std::vector<std::vector<double>> historyZ, historySpeed; // per ring id, appended by saveState
 	std::vector<std::int64_t> order;                          // ids of the live rings in output order
+	std::vector<std::int64_t> posOf;                          // position of every ring id in `order` (-1: removed)
+	std::int64_t lossSeen = 0;                                // entries of the device's loss log already replayed
+	bool hostHistories = true;                                // false: save points keep only the temperature sums (PenningTrap::keepHistories)
+	std::vector<double> pairTemperature;                      // temperature of every pair of consecutive save points, from device sums
 
 	void placeRings(int numMacro);            // inverse-CDF placement + Maxwellian speeds, upload, first solve
 	void solvePoisson();

@@ -108,6 +108,7 @@ template <class T> static inline T atomicMin(T* p, T v)
 	while (old > v && !a.compare_exchange_weak(old, v, std::memory_order_relaxed)) {}
 	return old;
 }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void ptp_pdl_launch_dependents() {}
 static inline void ptp_pdl_wait() {}
 template <class T> static inline T atomicAdd_system(T* p, T v) { return atomicAdd(p, v); }

@@ -64,10 +64,16 @@ int main()
 		std::vector<unsigned long long> cursor((size_t)Nr * Nz, 0), live(Nr, 0);
 		emu_launch((int)chunks.size(), 256, [&] { k_sort_count(z.data(), chunks.data(), Nz, hz, counts.data()); });
 		emu_launch(Nr, 256, [&] { k_sort_scan(counts.data(), Nz, cursor.data(), live.data()); });
-		emu_launch((int)chunks.size(), 256, [&] { k_sort_scatter(z.data(), v.data(), id.data(), zA.data(), vA.data(), idA.data(), rowOff.data(), chunks.data(), Nz, hz, cursor.data()); });
+		// a fourth per-ring array (the speeds at the last save point) must travel with its ring: here twice the speed
+		std::vector<double> vs(v.size()), vsA(v.size(), -7.0);
+		for (size_t s = 0; s < v.size(); ++s) vs[s] = 2.0 * v[s];
+		emu_launch((int)chunks.size(), 256, [&] { k_sort_scatter(z.data(), v.data(), id.data(), zA.data(), vA.data(), idA.data(), rowOff.data(), chunks.data(), Nz, hz, cursor.data(), vs.data(), vsA.data()); });
 		emu_launch(4, 256, [&] { k_sort_pad(zA.data(), vA.data(), idA.data(), rowOff.data(), live.data(), altDirty.data()); }, Nr);
 		std::swap(z, zA); std::swap(v, vA); std::swap(id, idA);
 		for (int r = 0; r < Nr; ++r) { altDirty[r] = rowLive[r]; rowLive[r] = (long long)live[r]; }
+		for (int r = 0; r < Nr && rc == 0; ++r)
+			for (long long i = 0; i < (long long)live[r]; ++i)
+				if (vsA[rowOff[r] + i] != 2.0 * v[rowOff[r] + i]) { std::printf("round %d row %d slot %lld: saved speed did not travel with its ring\n", round, r, i); rc = 1; break; }
 		size_t seen = 0;
 		for (int r = 0; r < Nr && rc == 0; ++r) {
 			if ((long long)live[r] != wantLive[r]) { std::printf("round %d row %d: live %llu, expected %lld\n", round, r, live[r], wantLive[r]); rc = 1; }

@@ -73,4 +73,4 @@ def test_reference_drivers_compile_unchanged_against_host_classes():
     if not os.path.exists(os.path.join(ROOT, "pic-trapped-plasma_b200", "libptp_host.so")):
         pytest.skip("libptp_host.so not built")
     built = build_drivers.build()
-    assert [os.path.basename(b) for b in built] == ["driver_A", "driver_B", "driver_C", "driver_D"]
+    assert [os.path.basename(b) for b in built if "driver_" in b] == ["driver_A", "driver_B", "driver_C", "driver_D"]

@@ -134,3 +134,46 @@ def test_driver_d_with_electrode_basis(work, tmp_path):
     shutil.copytree(work, d)
     out = _run("D", d, PTP_ELECTRODE_BASIS="1")
     assert out.strip().endswith(_gold("driver_D_stdout.txt").strip())
+
+
+def test_history_row_order_after_losses_in_several_steps(tmp_path, c1_kat):
+    """Rings that leave the trap in DIFFERENT steps of one multi-step movePlasmas call: the reference removes each at once by
+    swap-with-back (Source/Plasma.cpp:108-118), which decides the row order of its history files. The host classes replay
+    that order from the push kernel's loss log (ring id + step), so the Positions file lists the survivors exactly in the
+    order the oracle's ring array ends up in when it is stepped one step at a time."""
+    from oracle import port
+    exe = os.path.join(DRV, "loss_order")
+    if not os.path.exists(exe):
+        pytest.skip("build/drivers/loss_order not built")
+    r, z, v, cm = c1_kat["e_r0"].astype(np.int32), c1_kat["e_z0"], c1_kat["e_v0"], float(c1_kat["e_chargeMacro"])
+    rings = str(tmp_path / "rings.bin")
+    with open(rings, "wb") as f:
+        f.write(np.array([len(r)], np.int64).tobytes())
+        f.write(np.array([cm], np.float64).tobytes())
+        f.write(r.tobytes())
+        f.write(np.ascontiguousarray(z).tobytes())
+        f.write(np.ascontiguousarray(v).tobytes())
+    steps, barrier = 150, -47.0            # the well gets shallow: ~2400 of 4001 rings leave, up to ~120 per step, over ~100 steps
+    p = subprocess.run([exe, rings, str(tmp_path / "out_"), str(steps), str(barrier)], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stdout + p.stderr
+    ot = port.default_trap()
+    op = ot.plasma("Electrons", 9.1093837015e-31, -1.602176634e-19)
+    op.set_rings(r, z, v, cm)
+    op.solve_poisson()
+    ot.set_potential(1, barrier)
+    lost_per_step = []
+    for _ in range(steps):
+        before = op.count()
+        ot.move_plasmas(2e-8 / 35, 1)
+        lost_per_step.append(before - op.count())
+    assert sum(1 for x in lost_per_step if x > 0) >= 3 and op.count() < len(r)       # the scenario does lose rings in several steps
+    assert int(p.stdout.strip().splitlines()[-1]) == op.count()
+    rows = [line.split(",") for line in open(str(tmp_path / "out_PositionsElectrons.csv")).read().splitlines()]
+    got_r = np.array([int(x[0]) for x in rows])
+    got_z = np.array([float(x[1]) for x in rows])
+    assert len(rows) == op.count()
+    assert np.array_equal(got_r, op.r)                                               # same rings in the same order ...
+    assert np.max(np.abs(got_z - op.z) / op.z) < 1e-9                                # ... at the same places
+    # a plain sort by id would not do: the order really is permuted
+    assert not np.array_equal(op.r, np.sort(op.r))
+    ot.close()

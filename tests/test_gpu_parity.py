@@ -692,10 +692,9 @@ def test_step_solves_populated_rows_and_whole_grids_on_demand(c1_kat, monkeypatc
     (a1, a2), (b1, b2) = res
     for n, (x, y) in enumerate(zip(a1[:6], b1[:6])):
         assert np.array_equal(x, y), n
-    assert a1[6] == b1[6]
+    assert a1[6] == pytest.approx(b1[6], rel=1e-13)       # (the reduction's atomic adds land in arbitrary order)
     for n, (x, y) in enumerate(zip(a2, b2)):
         assert rel_l2(y, x) < 1e-12, n
-    assert rel_l2(a1[2], c1_kat["e_phi20"]) < 1e-8 if "e_phi20" in c1_kat else True
 
 
 def test_graph_replay_is_bitwise_identical(c1_kat):
@@ -730,3 +729,76 @@ def test_graph_replay_is_bitwise_identical(c1_kat):
         assert np.array_equal(x, y), n
     assert b[8] == a[8]                            # same kernels launched, through the graph
     print("300 steps of C1: stream %.1f us/step, graph %.1f us/step" % (a[7] / 300 * 1e6, b[7] / 300 * 1e6))
+
+
+# ------------------------------------------------------------------------------------------ diagnostics on the device (f-2)
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_temperature_sums_match_reference_get_temperature(c1_kat):
+    """Plasma::getTemperature (Source/Plasma.cpp:212-228) from sums formed on the device at the save points - ring mass
+    massMacro (8 r), mean of the speeds at two consecutive save points - against the compiled reference run through the same
+    protocol (saveStates, steps, saveStates); also after a re-sort (the saved speeds travel with their rings) and for both
+    species of C1. rel <= 1e-12 at the first pair (identical inputs), <= 1e-6 free-running."""
+    rt = ref.default_trap()
+    t, el, ap = _fresh_c1(c1_kat)
+    pairs = []
+    for tag, name, mass, g in (("e", "Electrons", ptp.massE, el), ("p", "Antiprotons", ptp.massP, ap)):
+        o = rt.plasma(name, mass, -ref.E_POS)
+        o.set_rings(c1_kat[f"{tag}_r0"], c1_kat[f"{tag}_z0"], c1_kat[f"{tag}_v0"], float(c1_kat[f"{tag}_chargeMacro"]))
+        o.solve_poisson()
+        g.solvePoisson()
+        pairs.append((g, o))
+    dt = float(c1_kat["dt"])
+    rt.save_states(0.0)
+    assert all(g.saveSpeeds() is None for g, _ in pairs)         # first save point: no pair yet
+    for k in range(4):
+        rt.move_plasmas(dt, 3)
+        t.movePlasmas(dt, 3)
+        if k == 2:
+            t.sort()
+        rt.save_states((k + 1) * 3 * dt)
+        for g, o in pairs:
+            assert g.saveSpeeds() == pytest.approx(o.temperature(), rel=1e-12 if k == 0 else 1e-6)
+    t.close()
+    rt.close()
+
+
+def test_row_slice_download_and_loss_log(c1_kat):
+    """ptp_plasma_download_row = the rings of one radial row (what Plasma::saveState(int indexR) needs, Source/Plasma.cpp:338-346)
+    without moving the other rows; ptp_plasma_loss_log = which ring left in which step (Source/Plasma.cpp:108-118)."""
+    t, el, ap = _fresh_c1(c1_kat)
+    el.solvePoisson()
+    ap.solvePoisson()
+    dt = float(c1_kat["dt"])
+    t.movePlasmas(dt, 2)
+    r, z, v, ids = _by_id(el)
+    for row in (0, 3, 9, 50):
+        zr, vr, ir = el.downloadRow(row)
+        o = np.argsort(ir)
+        sel = r == row
+        assert np.array_equal(ir[o], ids[sel]) and np.array_equal(zr[o], z[sel]) and np.array_equal(vr[o], v[sel])
+    # losses: lower the barrier and compare the log with the oracle's per-step losses
+    ot = port.default_trap()
+    op = ot.plasma("Electrons", ptp.massE, -ptp.ePos)
+    op.set_rings(r, z, v, float(c1_kat["e_chargeMacro"]))
+    oa = ot.plasma("Antiprotons", ptp.massP, -ptp.ePos)
+    ra, za, va, _ = _by_id(ap)
+    oa.set_rings(ra, za, va, float(c1_kat["p_chargeMacro"]))
+    op.solve_poisson()
+    oa.solve_poisson()
+    ot.set_potential(1, -47.0)
+    t.setPotential(1, -47.0)
+    lost_per_step = []
+    for _ in range(70):
+        before = op.count()
+        ot.move_plasmas(dt, 1)
+        lost_per_step.append(before - op.count())
+    t.movePlasmas(dt, 70)
+    lids, lsteps, total, over = el.lossLog()
+    assert not over and total == len(lids) == sum(lost_per_step) > 100
+    first = int(lsteps.min()) - next(i for i, x in enumerate(lost_per_step) if x)      # tag of the first of the 70 steps
+    assert [int(np.sum(lsteps == first + i)) for i in range(70)] == lost_per_step
+    assert len(np.unique(lids)) == len(lids) and el.getNumMacro() == op.count()
+    _, _, _, alive = _by_id(el)
+    assert not np.intersect1d(alive, lids).size
+    t.close()
+    ot.close()

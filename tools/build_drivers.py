@@ -19,12 +19,21 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 def build(verbose=False):
     diag = os.path.join(REFERENCE, "Diagnostics")
-    if not os.path.isdir(diag):
-        return []
     out_dir = os.path.join(ROOT, "build", "drivers")
     os.makedirs(out_dir, exist_ok=True)
     pkg = os.path.join(ROOT, "pic-trapped-plasma_b200")
     built = []
+    # this repo's own test programs over the same class surface (tests/drivers/*.cpp)
+    for src in sorted(glob.glob(os.path.join(ROOT, "tests", "drivers", "*.cpp"))):
+        out = os.path.join(out_dir, os.path.splitext(os.path.basename(src))[0])
+        cmd = [CXX, "-std=c++17", "-O2", src, "-I" + os.path.join(pkg, "host"), "-I" + os.path.join(ROOT, "include"),
+               "-L" + pkg, "-lptp_host", "-lptp_b200", "-Wl,-rpath," + pkg, "-Wl,-rpath,$ORIGIN/../../pic-trapped-plasma_b200", "-o", out]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        built.append(out)
+    if not os.path.isdir(diag):
+        return built
     for letter in "ABCD":
         src = glob.glob(os.path.join(diag, letter + ")*.txt"))
         if not src:
