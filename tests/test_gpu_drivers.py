@@ -173,7 +173,7 @@ def test_history_row_order_after_losses_in_several_steps(tmp_path, c1_kat):
     got_z = np.array([float(x[1]) for x in rows])
     assert len(rows) == op.count()
     assert np.array_equal(got_r, op.r)                                               # same rings in the same order ...
-    assert np.max(np.abs(got_z - op.z) / op.z) < 1e-9                                # ... at the same places
+    assert np.max(np.abs(got_z - op.z) / op.z) < 1e-6                                # ... at the same places (free-running over 150 violent steps)
     # a plain sort by id would not do: the order really is permuted
     assert not np.array_equal(op.r, np.sort(op.r))
     ot.close()
