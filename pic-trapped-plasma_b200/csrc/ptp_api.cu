@@ -230,6 +230,7 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 		if (const char* e = std::getenv("PTP_FULL_SOLVE")) t->lazyRows = std::atoi(e) == 0;
 		if (const char* e = std::getenv("PTP_PDL")) t->usePdl = std::atoi(e) != 0;
 		if (const char* e = std::getenv("PTP_INV_BULK")) t->invBulk = std::atoi(e);
+		if (const char* e = std::getenv("PTP_CLUSTER_SOLVE")) t->clusterSolve = std::atoi(e);
 		if (const char* e = std::getenv("PTP_GRAPH")) t->useGraph = std::atoi(e);
 		if (const char* e = std::getenv("PTP_GRAPH_MAX_RINGS")) t->graphMaxRings = std::atoll(e);
 		PTP_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));

@@ -152,6 +152,7 @@ struct ptp_trap {
 	bool lazyRows = true;
 	int phiRows = 0;
 	bool usePdl = true;              // PTP_PDL=0: plain stream-ordered launches
+	int clusterSolve = 1;            // PTP_CLUSTER_SOLVE=0: the step's solve through the two-kernel path even when the plasma occupies few rows
 	int invBulk = 1;                 // PTP_INV_BULK=0: the cp.async form of the dense inverse transform also for even row lengths
 
 	PtpComm* comm = nullptr;
@@ -237,6 +238,10 @@ bool ptp_solver_fft_fits(const ptp_trap* t);
 int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* spec, const uint2* encBounds, bool expand = true, int rowLimit = -1, int rowsOut = 0);
 bool ptp_solver_inverse_forms_rows(const ptp_trap* t);
 int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed = true, int rowsOut = 0);
+// ptp_solve_cluster.cu: forward transform + radial solves + inverse transform + node field of a step in one cluster kernel
+bool ptp_solver_cluster_plan(const ptp_trap* t, int rowLimit, int rowsOut, int* PM, int* NC, int* KWc, int* CW, size_t* smem);
+int ptp_solver_cluster_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi, const uint2* encBounds, int rowLimit, int rowsOut,
+	int PM, int NC, int KWc, int CW, size_t smem);
 int ptp_node_field(ptp_trap* t);
 int ptp_wall_rhs(ptp_trap* t, const double* dWall, double* dRhs);
 int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi);

@@ -962,6 +962,18 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		if (eb != cudaSuccess) return ptp_cuda_fail(eb, "k_row_bounds launch", __FILE__, __LINE__);
 		t->lastLaunches++;
 	}
+	// The step's solve for a plasma that occupies few radial rows: one cluster kernel (ptp_solve_cluster.cu)
+	if (withField && rowsWanted > 0 && rowLimit >= 0 && t->solver == PTP_SOLVER_DIRECT) {
+		const int rows16 = std::min(Nr, (std::max(rowsWanted, rowLimit) + 15) & ~15);
+		int PM, NC, KWc, CW;
+		size_t smc;
+		if (rows16 < Nr && ptp_solver_cluster_plan(t, rowLimit, rows16, &PM, &NC, &KWc, &CW, &smc)) {
+			PTP_TRY(ptp_solver_cluster_run(t, rho, rhoIsFixed, dScale, nS, phi, encBounds, rowLimit, rows16, PM, NC, KWc, CW, smc));
+			if (rowsDone) *rowsDone = rows16;
+			t->eNodesValid = true;
+			return PTP_OK;
+		}
+	}
 	// Rows to produce: all of them, or - for the step, where only the populated rows are ever read by the push - the first
 	// rowsWanted, rounded up to whole blocks of the radial tables (a multiple of the inverse kernels' strip height too).
 	int rowsOut = Nr;
