@@ -146,19 +146,21 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 		__syncthreads();
 		const int kLo = sLo, kHi = sHi;
 		// ---- forward DCT-I of the touched nodes for the own modes: beta[j][slot] ----------------------------------
-		constexpr int UMAX = (CS_MAXROWS + 2) / 3;                  // rows per thread at the smallest lane count (NM <= 85 -> >= 3 lanes)
-		double acc[UMAX];
-#pragma unroll
-		for (int u = 0; u < UMAX; ++u) acc[u] = 0.0;
+		// (Every loop of this kernel is kept rolled: the code runs once per SM and step, so it is instruction-fetch bound -
+		// ncu shows "no instruction" as the top stall of every solve kernel - and short loops are what the fetch unit can keep up with.)
+		if (worker)
+			for (int j = lane6; j < rowsT; j += nLanes) sB[j * NM + slot] = 0.0;
 		for (int k0 = kLo; k0 <= kHi; k0 += CS_KB) {
 			const int kn = min(CS_KB, kHi - k0 + 1);
 			__syncthreads();                                        // the previous chunk has been consumed
+#pragma unroll 1
 			for (int e = tid; e < kn * NM; e += CS_T) {
 				const int kk = e / NM, s = e - kk * NM;
 				bool ok;
 				const int mm = modeOf(s, ok);
 				cs_cp8(&sFT[e], a.FT + (size_t)(k0 + kk) * n1 + mm, ok);
 			}
+#pragma unroll 1
 			for (int e = tid; e < rowsIn * kn; e += CS_T) {
 				const int j = e / kn, kk = e - j * kn;
 				const int2 bd = sBd[j];
@@ -169,35 +171,27 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 			cs_wait_all();
 			__syncthreads();
 			if (worker) {
-#pragma unroll
-				for (int u = 0; u < UMAX; ++u) {
-					const int j = lane6 + u * nLanes;
-					if (j >= rowsIn) break;
+#pragma unroll 1
+				for (int j = lane6; j < rowsIn; j += nLanes) {
 					const int2 bd = sBd[j];
 					const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
-					double t = acc[u];
+					double t = 0.0;
+#pragma unroll 2
 					for (int kk = a0; kk <= a1; ++kk) {
 						const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(sRho)[j * CS_KB + kk] : sRho[j * CS_KB + kk];
 						t = fma(val, sFT[kk * NM + slot], t);
 					}
-					acc[u] = t;
+					sB[j * NM + slot] += t * scale;                  // (own element)
 				}
 			}
 		}
 		cs_wait_all();                                              // (also the tables requested before the wait)
-		if (worker) {
-#pragma unroll
-			for (int u = 0; u < UMAX; ++u) {
-				const int j = lane6 + u * nLanes;
-				if (j < rowsIn) sB[j * NM + slot] = acc[u] * scale;
-			}
-		}
 		__syncthreads();
 		// ---- radial solves: forward sweep over the touched rows below Jf, folded pivot at Jf, back-substitution, rows above ----
 		if (tid < NM && mOk) {
 			const int J0 = sJ0;
 			double y = 0.0;
-#pragma unroll 4
+#pragma unroll 1
 			for (int j = J0; j < Jf; ++j) {
 				const double inv = sInv[j * NM + tid];
 				y = fma(-(sLower[j] * inv), y, sB[j * NM + tid] * inv);
@@ -206,13 +200,13 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 			const double xJ = (sB[Jf * NM + tid] - sLower[Jf] * y) * q;
 			sB[Jf * NM + tid] = xJ;
 			y = xJ;
-#pragma unroll 4
+#pragma unroll 1
 			for (int j = Jf - 1; j >= 0; --j) {
 				y = fma(-sCp[j * NM + tid], y, sB[j * NM + tid]);
 				sB[j * NM + tid] = y;
 			}
 			y = xJ;
-#pragma unroll 4
+#pragma unroll 1
 			for (int j = Jf + 1; j < rowsOut; ++j) {
 				y = sCp[j * NM + tid] * y;
 				sB[j * NM + tid] = y;
@@ -233,13 +227,21 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 		}
 		__syncthreads();
 		// ---- partial inverse transform of the own pairs for every node of the cluster's range ---------------------
-		for (int o = tid; o < rowsOut * KW; o += CS_T) {
-			const int j = o / KW, kk = o - j * KW;
-			const double* sv = sS + j * NM + (((kA + kk) & 1) ? PM : 0);
-			double t = 0.0;
-#pragma unroll 4
-			for (int s = 0; s < PM; ++s) t = fma(sv[s], sC[s * KWp + kk], t);
-			sPart[j * KWp + kk] = t;
+		{
+			const int ng = CS_T / KW;                               // row groups: thread -> (node kk, rows g, g + ng, ...)
+			const int g = tid / KW, kk = tid - g * KW;
+			if (g < ng) {
+				const double* cv = sC + kk;
+				const int sel = ((kA + kk) & 1) ? PM : 0;
+#pragma unroll 1
+				for (int j = g; j < rowsOut; j += ng) {
+					const double* sv = sS + j * NM + sel;
+					double t = 0.0;
+#pragma unroll 2
+					for (int s2 = 0; s2 < PM; ++s2) t = fma(sv[s2], cv[s2 * KWp], t);
+					sPart[j * KWp + kk] = t;
+				}
+			}
 		}
 		cluster.sync();                                             // every CTA's partials are in place
 		// ---- sum the 16 partials of this CTA's share (+ halo) out of the peers' shared memory --------------------
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 				if (k < 0 || k >= n1) continue;
 				const int kk = k - kA;
 				double v = 0.0;
-#pragma unroll
+#pragma unroll 4
 				for (int r = 0; r < CL; ++r) v += cluster.map_shared_rank(sPart, r)[j * KWp + kk];
 				if (x >= 1 && x <= myK1 - myK0) out[(size_t)j * n1 + k] = v;
 				sTot[j * CWp + x] = __dadd_rn(sTot[j * CWp + x], v);  // species added in registration order (Source/PenningTrap.cpp:226-232)
@@ -293,6 +295,7 @@ bool ptp_solver_cluster_plan(const ptp_trap* t, int rowLimit, int rowsOut, int* 
 	const int KWc = (n1 + NC - 1) / NC;
 	NC = (n1 + KWc - 1) / KWc;
 	const int CW = (KWc + CL - 1) / CL;
+	if (KWc + 2 > CS_T) return false;                           // (partial inverse: one thread per node of the cluster's range)
 	const int Jf = std::max(0, std::min(rowLimit, t->Nr) - 1);
 	const size_t smem = cluster_smem_bytes(n1, Jf, rowsOut, PM, KWc, CW);
 	if (smem > t->smemMax) return false;
