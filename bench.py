@@ -253,7 +253,8 @@ def main():
     ap.add_argument("--ctas", type=int, default=-1)
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=-1, help="> 0: re-sort every so many steps; 0: never; -1: adaptive (library default)")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer"], help="exchange step for N > 1 (auto: peer memory up to 2^20 grid nodes)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer", "gather"],
+                    help="exchange step for N > 1 (auto: peer-memory gather up to 2^20 grid nodes, NCCL above; peer = remote adds fused into the deposit flush)")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -273,7 +274,7 @@ def main():
     total = sum(n for _, _, _, n in species)
     config = {"workload": "%s: %s" % (args.workload, desc), "grid": "Nz=%d Nr=%d" % grid_of(args.workload), "dt_s": DT, "species": len(species),
               "rings_total": total, "deposit": args.deposit,
-              "exchange": ("peer-memory push fused into the deposit flush + flag barrier" if args.allreduce == "peer" else "NCCL all-reduce") if world > 1 else "none (1 GPU)",
+              "exchange": args.allreduce if world > 1 else "none (1 GPU)",
               "l2": "ring arrays %d MB per GPU vs 126 MB L2 (no flush needed)" % (total // world * 16 // 2**20) if total // world * 16 > 200e6
               else "ring arrays %d MB per GPU: L2-resident, NOT an HBM-bound measurement" % (total // world * 16 // 2**20)}
 
@@ -324,9 +325,11 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         trap.comm_init(uid[0], world, rank)
         if args.allreduce == "auto":
-            args.allreduce = "peer" if trap.G <= (1 << 20) else "nccl"
-        trap.set_allreduce(1 if args.allreduce == "peer" else 0)
-        config["exchange"] = "peer-memory push fused into the deposit flush + flag barrier" if args.allreduce == "peer" else "NCCL all-reduce"
+            args.allreduce = "gather" if trap.G <= (1 << 20) else "nccl"
+        trap.set_allreduce({"nccl": 0, "peer": 1, "gather": 3}[args.allreduce])
+        config["exchange"] = {"peer": "peer-memory adds fused into the deposit flush (system-scope atomics over NVLink) + flag barrier",
+                              "gather": "peer-memory gather: each rank stores its populated rows into every rank's gather area over NVLink, flags, local sum in rank order (one kernel)",
+                              "nccl": "NCCL all-reduce"}[args.allreduce]
     trap.set_deposit_mode(ptp.PTP_DEPOSIT_FIXED64 if args.deposit == "fixed" else ptp.PTP_DEPOSIT_FP64)
     if args.threads or args.window or args.ctas >= 0 or args.rings:
         trap.set_tuning(args.threads, args.window, args.ctas, args.rings)
@@ -402,12 +405,14 @@ def main():
     launches = int(local[med, 5])
     timing = {"batches": len(batches), "steps_per_batch": args.steps, "reported": "median batch", "timed_wall_s": wall,
               "batch_ms": {"min": float(mx[:, 0].min()), "median": ms_total, "max": float(mx[:, 0].max())}}
-    # Steps replayed as CUDA graphs carry no per-phase events: one more un-timed pass of K stream-launched steps with the phase
-    # events gives the kernel times for the roofline and the phase table (the headline value stays the replayed one).
+    # The timed steps carry no per-phase events (events between the kernels of a step cost the programmatic-launch overlap, and
+    # graph replay has none): one more un-timed pass of K stream-launched steps WITH the phase events gives the kernel times
+    # for the roofline and the phase table (the headline value stays the one measured above).
     phases = [float(mx[med, 1]), float(mx[med, 2]), float(mx[med, 3])]
-    timing["graph_replay"] = bool(ms_push == 0.0)
+    timing["graph_replay"] = bool(trap.last_launches() and args.graph != "off" and (args.graph == "on" or n_local <= 8_000_000 or world > 1))
     if ms_push == 0.0:
         trap.set_graph(False)
+        trap.set_phase_events(True)
         barrier()
         trap.movePlasmas(DT, args.steps)
         trap.sync()
@@ -417,6 +422,7 @@ def main():
         ms_push, phases = float(probe[1]), [float(probe[1]), float(probe[2]), float(probe[3])]
         timing["phase_probe"] = "separate un-timed pass of %d stream-launched steps (whole pass %.4f ms/step)" % (args.steps, float(probe[0]) / args.steps)
         trap.set_graph(None if args.graph == "auto" else args.graph == "on")
+        trap.set_phase_events(False)
         local_ph = [float(local[med, 0])] + tm[1:4]
     else:
         local_ph = local[med, :4].tolist()

@@ -102,8 +102,11 @@ int ptp_trap_solve_fields(ptp_trap* t);
 /* Block until all queued work of this trap has finished. */
 int ptp_trap_sync(ptp_trap* t);
 /* Device time in milliseconds of the last ptp_trap_step call: [0]=whole call; summed over its steps: [1]=push+deposit kernels,
- * [2]=all-reduce, [3]=solve + node field (CUDA events on the trap's stream). */
+ * [2]=all-reduce, [3]=solve + node field (CUDA events on the trap's stream). The per-phase entries are zero unless
+ * ptp_trap_set_phase_events(t, 1) was called and the steps were stream-launched (not replayed as a graph): events between
+ * the kernels of a step cost the programmatic-launch overlap, so they are recorded on request only. */
 int ptp_trap_last_times(ptp_trap* t, double* ms4);
+int ptp_trap_set_phase_events(ptp_trap* t, int on);
 /* Number of kernels the last ptp_trap_step / push_deposit / solve_fields call launched. */
 int64_t ptp_trap_last_launches(ptp_trap* t);
 
@@ -136,9 +139,16 @@ int ptp_trap_set_tuning(ptp_trap* t, int threads, int window, int ctas, int ring
 /* 128-byte NCCL unique id; rank 0 creates it, the launcher broadcasts it (torch.distributed / MPI / file). */
 int ptp_comm_unique_id(void* id128);
 int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank);
-/* Exchange of the deposit grids between the ranks (needs ptp_trap_comm_init): 0 = NCCL all-reduce; 1 = peer memory, the
- * push kernel's flush adds into every rank's grid over NVLink and a flag barrier replaces the collective; 2 = choose by
- * grid size (peer memory up to 2^20 nodes). */
+/* Exchange of the deposit grids between the ranks (needs ptp_trap_comm_init):
+ *   0 = NCCL all-reduce;
+ *   1 = peer memory, fused: the push kernel's flush adds into every rank's grid over NVLink (system-scope atomics) and a
+ *       flag barrier replaces the collective;
+ *   3 = peer memory, gather: one small kernel per step pushes this rank's populated rows into a slot of every rank's gather
+ *       area with plain stores, flags, and sums the slots in rank order - no remote atomics, every rank holds bitwise the
+ *       same sums also in fp64 mode;
+ *   2 = choose by grid size (gather up to 2^20 nodes, NCCL above).
+ * Multi-rank callers must issue the same sequence of calls on every rank (same species created in the same order): the
+ * peer mappings are exchanged collectively whenever the grids had to be reallocated. */
 int ptp_trap_set_allreduce(ptp_trap* t, int kind);
 
 /* ---- plasma ------------------------------------------------------------------------------- */

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ptp_trap_solve_fields": (_i, [_vp]),
     "ptp_trap_sync": (_i, [_vp]),
     "ptp_trap_last_times": (_i, [_vp, _vp]),
+    "ptp_trap_set_phase_events": (_i, [_vp, _i]),
     "ptp_trap_last_launches": (_i64, [_vp]),
     "ptp_trap_sort": (_i, [_vp]),
     "ptp_trap_set_sort_interval": (_i, [_vp, _i]),
@@ -249,6 +250,9 @@ class PenningTrap:
         out = np.zeros(4)
         _check(lib().ptp_trap_last_times(self.h, _ptr(out)))
         return out
+
+    def set_phase_events(self, on=True):
+        _check(lib().ptp_trap_set_phase_events(self.h, 1 if on else 0))
 
     def last_launches(self):
         return int(lib().ptp_trap_last_launches(self.h))

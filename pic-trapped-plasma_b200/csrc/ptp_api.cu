@@ -130,7 +130,8 @@ int push_deposit_all(ptp_trap* t, double dt)
 int reduce_rho(ptp_trap* t)
 {
 	const int nS = (int)t->plasmas.size();
-	if (ptp_peer_mode(t)) return ptp_peer_barrier(t);
+	if (ptp_peer_gather(t)) return ptp_peer_exchange(t);
+	if (ptp_peer_fused(t)) return ptp_peer_barrier(t);
 	if (ptp_comm_size(t) == 1) return PTP_OK;
 	int extent = t->Nr;
 	PTP_TRY(ptp_row_extent(t, &extent));
@@ -159,7 +160,7 @@ int begin_steps(ptp_trap* t)
 	t->cleanEpoch = t->layoutEpoch;
 	if (!peer) return PTP_OK;
 	t->peerCleanEpoch = t->layoutEpoch;
-	return ptp_peer_barrier(t);
+	return ptp_peer_fused(t) ? ptp_peer_barrier(t) : PTP_OK;   // (gather exchange: nobody else writes into this rank's grids)
 }
 
 int solve_all(ptp_trap* t)
@@ -537,7 +538,7 @@ int ptp_trap_step(ptp_trap* t, double dt, int nSteps)
 	t->lastLaunches = 0;
 	const bool graph = want_graph(t);
 	// phase events for every step (up to a bound), so that callers can report the mean kernel time
-	const int timed = (!graph && nSteps <= 4096) ? nSteps : 0;
+	const int timed = (!graph && t->phaseEvents && nSteps <= 4096) ? nSteps : 0;
 	while ((int)t->evPool.size() < 4 * timed) {
 		cudaEvent_t e;
 		PTP_CUDA(cudaEventCreate(&e));
@@ -599,6 +600,13 @@ int ptp_trap_set_graph(ptp_trap* t, int on)
 	if (!t) { ptp_set_error("ptp_trap_set_graph: null trap"); return PTP_EINVAL; }
 	t->useGraph = on < 0 ? -1 : (on != 0 ? 1 : 0);             // 1: always replay, 0: never, -1: automatic (the default)
 	if (!on) drop_graph(t);
+	return PTP_OK;
+}
+
+int ptp_trap_set_phase_events(ptp_trap* t, int on)
+{
+	if (!t) { ptp_set_error("ptp_trap_set_phase_events: null trap"); return PTP_EINVAL; }
+	t->phaseEvents = on != 0;
 	return PTP_OK;
 }
 

@@ -22,6 +22,12 @@ struct PtpComm {
 	size_t spanDoubles = 0;          // capS * G at mapping time
 	unsigned long long* dEpoch = nullptr; // barrier generation, kept on the device so that barrier launches can be replayed from a CUDA graph;
 	                                      // all ranks advance it in lock-step
+	// gather exchange (ptp_trap_set_allreduce(t, 3)): one allocation per rank, mapped by every rank:
+	//   [2 parities][nRanks][span] deposit grids as pushed by each rank | [nRanks][PTP_EXCHANGE_CTAS] flags | [2] exchange count, CTA ticket
+	double* gatherStore = nullptr;
+	size_t gatherSpan = 0;
+	double* peerGather[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool gatherMapped = false;
 };
 
 namespace {
@@ -89,6 +95,103 @@ __global__ void k_peer_barrier(PeerFlags flags, int rank, int nRanks, unsigned l
 	__threadfence_system();
 }
 
+// ---- gather exchange ---------------------------------------------------------------------------------------------
+// Every rank pushes its step's deposit grids (the populated rows and the touched-node ranges, local sums of its own rings)
+// into slot [rank] of EVERY rank's gather area with plain stores over NVLink, signals, waits for the other ranks' signals
+// and then sums the slots in rank order into its own grids: an all-gather + local reduction. Compared with adding into the
+// peers' grids from the push kernel's flush: no remote atomics at all (7 x 56 KB of posted stores per rank and step on the
+// default grid instead of ~70 000 contended remote adds), the push kernel is the single-GPU kernel, and the sum has a fixed
+// order - every rank holds bitwise the same grids in fp64 mode too. The work is cut into PTP_EXCHANGE_CTAS independent slices
+// (one CTA each, its own flags), so there is no grid-wide synchronisation inside the kernel.
+constexpr int PTP_EXCHANGE_CTAS = 8;
+constexpr int PTP_EXCHANGE_THREADS = 512;
+
+struct ExchangeArgs {
+	double* L;                       // this rank's deposit grids of the step: local sums on entry, global sums on exit
+	double* G[8];                    // gather area of every rank for this step's parity: [nRanks][span]
+	unsigned long long* flags[8];    // flag array of every rank: [nRanks][PTP_EXCHANGE_CTAS]
+	unsigned long long* epoch;       // own: [0] exchanges completed, [1] CTA ticket
+	long long span, gridDoubles, rowWords;   // doubles per slot; doubles per species grid; populated rows x (Nz + 1)
+	int rank, nRanks, nS, capS, Nr, fixed;
+};
+
+__global__ void __launch_bounds__(PTP_EXCHANGE_THREADS) k_peer_exchange(const ExchangeArgs a)
+{
+	ptp_pdl_launch_dependents();
+	ptp_pdl_wait();                                             // this rank's push kernels are complete
+	const int tid = threadIdx.x, b = blockIdx.x;
+	const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(a.epoch) + 1;
+	const long long perS = a.rowWords + a.Nr, total = (long long)a.nS * perS;
+	const long long chunk = (total + gridDim.x - 1) / gridDim.x, lo = (long long)b * chunk, hi = min(total, lo + chunk);
+	auto offsetOf = [&](long long it, bool& isGrid) {
+		const long long s = it / perS, w = it - s * perS;
+		isGrid = w < a.rowWords;
+		return isGrid ? s * a.gridDoubles + w : (long long)a.capS * a.gridDoubles + s * a.Nr + (w - a.rowWords);
+	};
+	// push this rank's slice into slot [rank] of every rank's gather area
+	const unsigned long long* L64 = reinterpret_cast<const unsigned long long*>(a.L);
+	for (long long it = lo + tid; it < hi; it += PTP_EXCHANGE_THREADS) {
+		bool isGrid;
+		const long long off = offsetOf(it, isGrid);
+		const unsigned long long v = L64[off];
+		for (int p = 0; p < a.nRanks; ++p) reinterpret_cast<unsigned long long*>(a.G[p] + (long long)a.rank * a.span)[off] = v;
+	}
+	__syncthreads();
+	if (tid < a.nRanks) {
+		__threadfence_system();                                 // the CTA's stores (ordered by the barrier) before the flag
+		unsigned long long* remote = a.flags[tid] + a.rank * PTP_EXCHANGE_CTAS + b;
+		asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(remote), "l"(epoch) : "memory");
+		const unsigned long long* mine = a.flags[a.rank] + tid * PTP_EXCHANGE_CTAS + b;
+		unsigned long long seen;
+		do {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(seen) : "l"(mine) : "memory");
+		} while (seen < epoch);
+	}
+	__syncthreads();
+	// sum the slots in rank order (L2 loads: the lines were written by the peers) into this rank's grids
+	const double* mineG = a.G[a.rank];
+	for (long long it = lo + tid; it < hi; it += PTP_EXCHANGE_THREADS) {
+		bool isGrid;
+		const long long off = offsetOf(it, isGrid);
+		unsigned long long out;
+		if (!isGrid) {                                          // touched-node range of a row: two encoded maxima
+			unsigned int x = 0, y = 0;
+			for (int r = 0; r < a.nRanks; ++r) {
+				const unsigned long long w = __ldcg(reinterpret_cast<const unsigned long long*>(mineG + (long long)r * a.span) + off);
+				x = max(x, (unsigned int)(w & 0xffffffffULL));
+				y = max(y, (unsigned int)(w >> 32));
+			}
+			out = ((unsigned long long)y << 32) | x;
+		}
+		else if (a.fixed) {
+			out = 0ULL;
+			for (int r = 0; r < a.nRanks; ++r) out += __ldcg(reinterpret_cast<const unsigned long long*>(mineG + (long long)r * a.span) + off);
+		}
+		else {
+			double sum = 0.0;
+			for (int r = 0; r < a.nRanks; ++r) sum = __dadd_rn(sum, __ldcg(mineG + (long long)r * a.span + off));
+			out = (unsigned long long)__double_as_longlong(sum);
+		}
+		reinterpret_cast<unsigned long long*>(a.L)[off] = out;
+	}
+	__syncthreads();
+	if (tid == 0) {                                             // every CTA has read the exchange count before the last one to finish advances it
+		__threadfence();
+		const unsigned long long ticket = atomicAdd(a.epoch + 1, 1ULL);
+		if (ticket == (unsigned long long)gridDim.x - 1) { a.epoch[1] = 0ULL; a.epoch[0] = epoch; }
+	}
+}
+
+void unmap_gather(ptp_trap* t)
+{
+	PtpComm* c = t->comm;
+	if (!c || !c->gatherMapped) return;
+	for (int r = 0; r < c->nRanks; ++r)
+		if (r != c->rank && c->peerGather[r]) cudaIpcCloseMemHandle(c->peerGather[r]);
+	for (auto& b : c->peerGather) b = nullptr;
+	c->gatherMapped = false;
+}
+
 void unmap_peers(ptp_trap* t)
 {
 	PtpComm* c = t->comm;
@@ -103,13 +206,81 @@ void unmap_peers(ptp_trap* t)
 int ptp_comm_size(ptp_trap* t) { return t->comm ? t->comm->nRanks : 1; }
 int ptp_comm_rank(ptp_trap* t) { return t->comm ? t->comm->rank : 0; }
 
-bool ptp_peer_mode(ptp_trap* t) { return t->comm && t->comm->nRanks > 1 && t->allreduceKind == 1; }
+bool ptp_peer_fused(ptp_trap* t) { return t->comm && t->comm->nRanks > 1 && t->allreduceKind == 1; }
+bool ptp_peer_gather(ptp_trap* t) { return t->comm && t->comm->nRanks > 1 && t->allreduceKind == 3; }
+bool ptp_peer_mode(ptp_trap* t) { return ptp_peer_fused(t) || ptp_peer_gather(t); }
+
+namespace {
+// Collective: (re)allocate this rank's gather area, exchange the IPC handles, map the peers' areas.
+int gather_prepare(ptp_trap* t)
+{
+	PtpComm* c = t->comm;
+	if (!t->peerStale && c->gatherMapped && c->gatherSpan == t->spanDoubles) return PTP_OK;
+	if (c->nRanks > 8) { ptp_set_error("peer-memory mode supports at most 8 ranks"); return PTP_EINVAL; }
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	unmap_gather(t);
+	cudaFree(c->gatherStore);
+	c->gatherStore = nullptr;
+	const size_t span = t->spanDoubles;
+	const size_t tailWords = (size_t)c->nRanks * PTP_EXCHANGE_CTAS + 2;
+	const size_t bytes = (2 * (size_t)c->nRanks * span + tailWords) * sizeof(double);
+	PTP_CUDA(cudaMalloc(&c->gatherStore, bytes));
+	PTP_CUDA(cudaMemsetAsync(c->gatherStore, 0, bytes, t->stream));
+	cudaIpcMemHandle_t mine;
+	PTP_CUDA(cudaIpcGetMemHandle(&mine, c->gatherStore));
+	unsigned char* dH = nullptr;
+	const size_t hs = sizeof(cudaIpcMemHandle_t);
+	PTP_CUDA(cudaMalloc(&dH, hs * c->nRanks));
+	PTP_CUDA(cudaMemcpyAsync(dH + hs * c->rank, &mine, hs, cudaMemcpyHostToDevice, t->stream));
+	ncclResult_t r = g_nccl.AllGather(dH + hs * c->rank, dH, hs, ncclChar, c->comm, t->stream);   // (behind the zeroing: nobody signals into a dirty flag array)
+	if (r != ncclSuccess) { cudaFree(dH); return nccl_fail(r, "ncclAllGather(ipc handles)"); }
+	std::vector<cudaIpcMemHandle_t> all(c->nRanks);
+	PTP_CUDA(cudaMemcpyAsync(all.data(), dH, hs * c->nRanks, cudaMemcpyDeviceToHost, t->stream));
+	PTP_CUDA(cudaStreamSynchronize(t->stream));
+	cudaFree(dH);
+	for (int p = 0; p < c->nRanks; ++p) {
+		if (p == c->rank) { c->peerGather[p] = c->gatherStore; continue; }
+		void* ptr = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[p], cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) return ptp_cuda_fail(e, "cudaIpcOpenMemHandle (peer-memory mode needs P2P-capable GPUs)", __FILE__, __LINE__);
+		c->peerGather[p] = static_cast<double*>(ptr);
+	}
+	c->gatherMapped = true;
+	c->gatherSpan = span;
+	t->peerStale = false;
+	t->peerCleanEpoch = -1;
+	return PTP_OK;
+}
+} // namespace
+
+int ptp_peer_exchange(ptp_trap* t)
+{
+	PtpComm* c = t->comm;
+	ExchangeArgs a{};
+	const size_t span = c->gatherSpan;
+	a.L = t->rhoAll;
+	for (int p = 0; p < c->nRanks; ++p) {
+		a.G[p] = c->peerGather[p] + (size_t)t->rhoParity * c->nRanks * span;
+		a.flags[p] = reinterpret_cast<unsigned long long*>(c->peerGather[p] + 2 * (size_t)c->nRanks * span);
+	}
+	a.epoch = reinterpret_cast<unsigned long long*>(c->gatherStore + 2 * (size_t)c->nRanks * span) + (size_t)c->nRanks * PTP_EXCHANGE_CTAS;
+	a.span = (long long)span;
+	a.gridDoubles = t->G;
+	a.rowWords = (long long)std::min(t->rowExtent, t->Nr) * (t->Nz + 1);
+	a.rank = c->rank; a.nRanks = c->nRanks; a.nS = (int)t->plasmas.size(); a.capS = t->capS; a.Nr = t->Nr;
+	a.fixed = t->depositMode == PTP_DEPOSIT_FIXED64 ? 1 : 0;
+	cudaError_t e = ptp_launch(k_peer_exchange, dim3(PTP_EXCHANGE_CTAS), dim3(PTP_EXCHANGE_THREADS), 0, t->stream, t->usePdl, a);
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_peer_exchange launch", __FILE__, __LINE__);
+	t->lastLaunches++;
+	return PTP_OK;
+}
 
 // Collective over all ranks: exchange the CUDA IPC handles of the rhoStore allocations (through an NCCL all-gather)
 // and map every peer's allocation. Needed once, and again whenever a rank had to reallocate (more species).
 int ptp_peer_prepare(ptp_trap* t)
 {
 	PtpComm* c = t->comm;
+	if (t->allreduceKind == 3) return gather_prepare(t);
 	// Remapping is a collective (all-gather of the IPC handles): ranks must agree on when it happens. They do when every rank
 	// issues the same sequence of calls (SPMD use: same species created in the same order), which include/ptp.h requires of
 	// multi-rank callers - the allocation is replaced only when a species is added beyond the reserved capacity.
@@ -241,6 +412,8 @@ void ptp_comm_free(ptp_trap* t)
 {
 	if (t->comm) {
 		unmap_peers(t);
+		unmap_gather(t);
+		cudaFree(t->comm->gatherStore);
 		cudaFree(t->comm->dEpoch);
 		if (t->comm->comm && g_nccl.ok) g_nccl.CommDestroy(t->comm->comm);
 		delete t->comm;
@@ -280,12 +453,13 @@ int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank)
 
 int ptp_trap_set_allreduce(ptp_trap* t, int kind)
 {
-	if (!t || kind < 0 || kind > 2) { ptp_set_error("ptp_trap_set_allreduce: bad arguments"); return PTP_EINVAL; }
+	if (!t || kind < 0 || kind > 3) { ptp_set_error("ptp_trap_set_allreduce: bad arguments"); return PTP_EINVAL; }
 	if (kind >= 1 && !t->comm) { ptp_set_error("ptp_trap_set_allreduce: peer-memory mode needs ptp_trap_comm_init first"); return PTP_ESTATE; }
 	// auto: the peer-memory exchange costs one remote atomic per flushed node and per out-of-window ring and peer, the
 	// collective costs the whole grid. Measured at 4 GPUs: 13 us vs 26 us per step on the default grid (75 k nodes), but
 	// 1.3 ms vs 0.13 ms on the 4096 x 1024 grid, whose long sparse plasma tails deposit outside the private windows.
-	if (kind == 2) kind = t->G <= (1LL << 20) ? 1 : 0;
+	if (kind == 2) kind = t->G <= (1LL << 20) ? 3 : 0;
+	if (kind != t->allreduceKind) { t->peerStale = true; t->peerCleanEpoch = -1; }
 	t->allreduceKind = kind;
 	++t->cfgEpoch;
 	return PTP_OK;

@@ -76,6 +76,8 @@ struct ptp_trap {
 	size_t smemMax = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	bool phaseEvents = false;        // ptp_trap_set_phase_events: record 4 events per step (they sit between the kernels of the
+	                                 // programmatic-launch chain and cost the overlap, so they are off unless a caller asks for phase times)
 	std::vector<cudaEvent_t> evPool; // 4 events per step of the last ptp_trap_step call (phase timing)
 	int evSteps = 0;
 	double lastMs[4] = { 0, 0, 0, 0 };
@@ -270,7 +272,10 @@ void ptp_comm_free(ptp_trap* t);
 int ptp_comm_size(ptp_trap* t);
 int ptp_comm_rank(ptp_trap* t);
 // peer-memory mode (ptp_trap_set_allreduce(t, 1)): the push kernel's flush adds into every rank's grid over NVLink
-bool ptp_peer_mode(ptp_trap* t);
+bool ptp_peer_mode(ptp_trap* t);                                  // either peer-memory exchange
+bool ptp_peer_fused(ptp_trap* t);                                 // kind 1: the push kernel's flush adds into every rank's grid
+bool ptp_peer_gather(ptp_trap* t);                                // kind 3: all-gather of the ranks' grids by stores + local sum in rank order
+int ptp_peer_exchange(ptp_trap* t);                               // the gather exchange of this step (one kernel)
 int ptp_peer_prepare(ptp_trap* t);                               // collective: (re)map the peers' rhoStore
 void ptp_peer_targets(ptp_trap* t, int parity, size_t offsetDoubles, void** out, int* n); // grid pointers of all ranks
 int ptp_peer_barrier(ptp_trap* t);                                // all ranks' pushes of this epoch have landed

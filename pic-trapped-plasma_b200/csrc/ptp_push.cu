@@ -691,7 +691,7 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 {
 	if (p->cap == 0 || p->nCta == 0) return PTP_OK;
 	PushArgs a = make_args(t, p, dt);
-	if (push && ptp_peer_mode(t)) ptp_peer_targets(t, t->rhoParity, (size_t)p->index * t->G, a.rho, &a.nRho);
+	if (push && ptp_peer_fused(t)) ptp_peer_targets(t, t->rhoParity, (size_t)p->index * t->G, a.rho, &a.nRho);
 	if (push) {
 		double* other = t->rhoStore + (size_t)(t->rhoParity ^ 1) * t->spanDoubles;
 		a.clearGrid = other + (size_t)p->index * t->G;

@@ -41,7 +41,7 @@ def main():
     uid = [ptp.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     trap.comm_init(uid[0], world, rank)
-    trap.set_allreduce(1 if exchange == "peer" else 0)
+    trap.set_allreduce({"nccl": 0, "peer": 1, "gather": 3}[exchange])
     r, z, cm, _ = loaders.place_rings(dens, 585, 128, trap.hz, trap.hr, n_total, rank, world)
     # speeds must not depend on the sharding: draw the full row-ordered sequence and take this rank's rings
     r_all, z_all, _, num_at_r = loaders.place_rings(dens, 585, 128, trap.hz, trap.hr, n_total)

@@ -38,18 +38,19 @@ def _launch(world, mode, n_total, steps, exchange="nccl"):
     return json.loads(line[len("RESULT "):])
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["nccl", "peer", "gather"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_step_matches_single_gpu(world, exchange):
     """exchange = "nccl": all-reduce of rank-local grids; "peer": the push kernel's flush adds into every rank's grid over
-    NVLink (CUDA IPC mappings) and a flag barrier replaces the collective."""
+    NVLink (CUDA IPC mappings, system-scope atomics) and a flag barrier replaces the collective; "gather": every rank stores
+    its populated rows into a slot of every rank's gather area and sums the slots in rank order (the default up to 2^20 nodes)."""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     res = _launch(world, "fp64", 2_000_000, 5, exchange)
     assert res["count_sharded"] == res["count_single"]
     assert res["rhs_rel"] < 1e-12 and res["phi_rel"] < 1e-10
-    if exchange == "nccl":
-        assert res["replicas_identical"]             # fp64 atomics from several ranks land in arbitrary order in peer mode
+    if exchange != "peer":
+        assert res["replicas_identical"]             # fp64 atomics from several ranks land in arbitrary order in the fused peer mode
     res = _launch(world, "fixed", 2_000_000, 5, exchange)
     assert res["count_sharded"] == res["count_single"]
     assert res["replicas_identical"] and res["rhs_bitwise"] and res["phi_bitwise"]
@@ -78,7 +79,7 @@ def test_fixed_point_scale_is_agreed_between_ranks_near_a_power_of_two():
             pick = num
             break
     assert pick is not None
-    for exchange in ("peer", "nccl"):
+    for exchange in ("gather", "peer", "nccl"):
         res = _launch(2, "fixed", pick, 3, exchange)
         assert res["count_sharded"] == res["count_single"]
         assert res["replicas_identical"] and res["rhs_bitwise"] and res["phi_bitwise"], (exchange, res)
