@@ -523,6 +523,7 @@ int capture_step_graph(ptp_trap* t, double dt, int target)
 bool want_graph(ptp_trap* t)
 {
 	if (t->solver == PTP_SOLVER_SOR || t->plasmas.empty() || t->useGraph == 0) return false;
+	if (ptp_comm_size(t) > 1 && !ptp_peer_mode(t)) return false;   // (an NCCL collective inside the step: not captured)
 	if (t->useGraph > 0) return true;
 	long long rings = 0;
 	for (const ptp_plasma* p : t->plasmas) rings += p->nAlive;

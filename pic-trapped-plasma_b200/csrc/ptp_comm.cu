@@ -10,6 +10,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <limits.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -112,29 +114,37 @@ struct ExchangeArgs {
 	unsigned long long* flags[8];    // flag array of every rank: [nRanks][PTP_EXCHANGE_CTAS]
 	unsigned long long* epoch;       // own: [0] exchanges completed, [1] CTA ticket
 	long long span, gridDoubles, rowWords;   // doubles per slot; doubles per species grid; populated rows x (Nz + 1)
-	int rank, nRanks, nS, capS, Nr, fixed;
+	int rank, nRanks, nS, capS, Nr, fixed, rows, pad;   // rows = populated rows
 };
 
+// One warp per (species, row) of the populated rows; a row travels as its touched node range only (the ranges the push
+// kernels publish: a few hundred of the 4097 nodes of a fine-grid row), together with the range itself.
 __global__ void __launch_bounds__(PTP_EXCHANGE_THREADS) k_peer_exchange(const ExchangeArgs a)
 {
 	ptp_pdl_launch_dependents();
 	ptp_pdl_wait();                                             // this rank's push kernels are complete
-	const int tid = threadIdx.x, b = blockIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, b = blockIdx.x;
+	const int warpsPerCta = PTP_EXCHANGE_THREADS / 32;
 	const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(a.epoch) + 1;
-	const long long perS = a.rowWords + a.Nr, total = (long long)a.nS * perS;
-	const long long chunk = (total + gridDim.x - 1) / gridDim.x, lo = (long long)b * chunk, hi = min(total, lo + chunk);
-	auto offsetOf = [&](long long it, bool& isGrid) {
-		const long long s = it / perS, w = it - s * perS;
-		isGrid = w < a.rowWords;
-		return isGrid ? s * a.gridDoubles + w : (long long)a.capS * a.gridDoubles + s * a.Nr + (w - a.rowWords);
+	const int n1 = (int)(a.rowWords / max(a.rows, 1)), rowsTotal = a.nS * a.rows;
+	auto decode = [n1](unsigned long long w, int& lo, int& hi) {    // encoded maxima (Nz + 2 - kmin, kmax + 1 + 1); 0 = untouched
+		const unsigned int x = (unsigned int)(w & 0xffffffffULL), y = (unsigned int)(w >> 32);
+		if (y == 0) { lo = 1; hi = 0; }
+		else { lo = n1 + 1 - (int)x; hi = (int)y - 1; }
 	};
-	// push this rank's slice into slot [rank] of every rank's gather area
-	const unsigned long long* L64 = reinterpret_cast<const unsigned long long*>(a.L);
-	for (long long it = lo + tid; it < hi; it += PTP_EXCHANGE_THREADS) {
-		bool isGrid;
-		const long long off = offsetOf(it, isGrid);
-		const unsigned long long v = L64[off];
-		for (int p = 0; p < a.nRanks; ++p) reinterpret_cast<unsigned long long*>(a.G[p] + (long long)a.rank * a.span)[off] = v;
+	unsigned long long* L64 = reinterpret_cast<unsigned long long*>(a.L);
+	// push this rank's rows (touched range + the range) into slot [rank] of every rank's gather area
+	for (int w = b * warpsPerCta + (tid >> 5); w < rowsTotal; w += gridDim.x * warpsPerCta) {
+		const int s = w / a.rows, j = w - s * a.rows;
+		const long long bOff = (long long)a.capS * a.gridDoubles + (long long)s * a.Nr + j, gOff = (long long)s * a.gridDoubles + (long long)j * n1;
+		const unsigned long long bnd = L64[bOff];
+		int lo, hi;
+		decode(bnd, lo, hi);
+		for (int p = 0; p < a.nRanks; ++p) {
+			unsigned long long* slot = reinterpret_cast<unsigned long long*>(a.G[p] + (long long)a.rank * a.span);
+			if (lane == 0) slot[bOff] = bnd;
+			for (int k = lo + lane; k <= hi; k += 32) slot[gOff + k] = L64[gOff + k];
+		}
 	}
 	__syncthreads();
 	if (tid < a.nRanks) {
@@ -149,30 +159,35 @@ __global__ void __launch_bounds__(PTP_EXCHANGE_THREADS) k_peer_exchange(const Ex
 	}
 	__syncthreads();
 	// sum the slots in rank order (L2 loads: the lines were written by the peers) into this rank's grids
-	const double* mineG = a.G[a.rank];
-	for (long long it = lo + tid; it < hi; it += PTP_EXCHANGE_THREADS) {
-		bool isGrid;
-		const long long off = offsetOf(it, isGrid);
-		unsigned long long out;
-		if (!isGrid) {                                          // touched-node range of a row: two encoded maxima
-			unsigned int x = 0, y = 0;
-			for (int r = 0; r < a.nRanks; ++r) {
-				const unsigned long long w = __ldcg(reinterpret_cast<const unsigned long long*>(mineG + (long long)r * a.span) + off);
-				x = max(x, (unsigned int)(w & 0xffffffffULL));
-				y = max(y, (unsigned int)(w >> 32));
+	const unsigned long long* mineG = reinterpret_cast<const unsigned long long*>(a.G[a.rank]);
+	for (int w = b * warpsPerCta + (tid >> 5); w < rowsTotal; w += gridDim.x * warpsPerCta) {
+		const int s = w / a.rows, j = w - s * a.rows;
+		const long long bOff = (long long)a.capS * a.gridDoubles + (long long)s * a.Nr + j, gOff = (long long)s * a.gridDoubles + (long long)j * n1;
+		int lo[8], hi[8], ulo = INT_MAX, uhi = INT_MIN;
+		unsigned int mx = 0, my = 0;
+		for (int r = 0; r < a.nRanks; ++r) {
+			const unsigned long long bw = __ldcg(mineG + (long long)r * a.span + bOff);
+			decode(bw, lo[r], hi[r]);
+			mx = max(mx, (unsigned int)(bw & 0xffffffffULL));
+			my = max(my, (unsigned int)(bw >> 32));
+			if (lo[r] <= hi[r]) { ulo = min(ulo, lo[r]); uhi = max(uhi, hi[r]); }
+		}
+		if (lane == 0) L64[bOff] = ((unsigned long long)my << 32) | mx;
+		for (int k = ulo + lane; k <= uhi; k += 32) {
+			unsigned long long out;
+			if (a.fixed) {
+				out = 0ULL;
+				for (int r = 0; r < a.nRanks; ++r)
+					if (k >= lo[r] && k <= hi[r]) out += __ldcg(mineG + (long long)r * a.span + gOff + k);
 			}
-			out = ((unsigned long long)y << 32) | x;
+			else {
+				double sum = 0.0;
+				for (int r = 0; r < a.nRanks; ++r)
+					if (k >= lo[r] && k <= hi[r]) sum = __dadd_rn(sum, __longlong_as_double((long long)__ldcg(mineG + (long long)r * a.span + gOff + k)));
+				out = (unsigned long long)__double_as_longlong(sum);
+			}
+			L64[gOff + k] = out;
 		}
-		else if (a.fixed) {
-			out = 0ULL;
-			for (int r = 0; r < a.nRanks; ++r) out += __ldcg(reinterpret_cast<const unsigned long long*>(mineG + (long long)r * a.span) + off);
-		}
-		else {
-			double sum = 0.0;
-			for (int r = 0; r < a.nRanks; ++r) sum = __dadd_rn(sum, __ldcg(mineG + (long long)r * a.span + off));
-			out = (unsigned long long)__double_as_longlong(sum);
-		}
-		reinterpret_cast<unsigned long long*>(a.L)[off] = out;
 	}
 	__syncthreads();
 	if (tid == 0) {                                             // every CTA has read the exchange count before the last one to finish advances it
@@ -268,6 +283,7 @@ int ptp_peer_exchange(ptp_trap* t)
 	a.gridDoubles = t->G;
 	a.rowWords = (long long)std::min(t->rowExtent, t->Nr) * (t->Nz + 1);
 	a.rank = c->rank; a.nRanks = c->nRanks; a.nS = (int)t->plasmas.size(); a.capS = t->capS; a.Nr = t->Nr;
+	a.rows = std::min(t->rowExtent, t->Nr);
 	a.fixed = t->depositMode == PTP_DEPOSIT_FIXED64 ? 1 : 0;
 	cudaError_t e = ptp_launch(k_peer_exchange, dim3(PTP_EXCHANGE_CTAS), dim3(PTP_EXCHANGE_THREADS), 0, t->stream, t->usePdl, a);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_peer_exchange launch", __FILE__, __LINE__);
@@ -458,7 +474,7 @@ int ptp_trap_set_allreduce(ptp_trap* t, int kind)
 	// auto: the peer-memory exchange costs one remote atomic per flushed node and per out-of-window ring and peer, the
 	// collective costs the whole grid. Measured at 4 GPUs: 13 us vs 26 us per step on the default grid (75 k nodes), but
 	// 1.3 ms vs 0.13 ms on the 4096 x 1024 grid, whose long sparse plasma tails deposit outside the private windows.
-	if (kind == 2) kind = t->G <= (1LL << 20) ? 3 : 0;
+	if (kind == 2) kind = 3;
 	if (kind != t->allreduceKind) { t->peerStale = true; t->peerCleanEpoch = -1; }
 	t->allreduceKind = kind;
 	++t->cfgEpoch;

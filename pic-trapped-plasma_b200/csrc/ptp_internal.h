@@ -241,7 +241,7 @@ int ptp_solver_forward_wide(ptp_trap* t, const double* rho, bool rhoIsFixed, con
 bool ptp_solver_inverse_forms_rows(const ptp_trap* t);
 int ptp_solver_inverse_fft(ptp_trap* t, const double* spec, double* phi, int nS, bool withField, bool rowsFormed = true, int rowsOut = 0);
 // ptp_solve_cluster.cu: forward transform + radial solves + inverse transform + node field of a step in one cluster kernel
-bool ptp_solver_cluster_plan(const ptp_trap* t, int rowLimit, int rowsOut, int* PM, int* NC, int* KWc, int* CW, size_t* smem);
+bool ptp_solver_cluster_plan(const ptp_trap* t, int nS, int rowLimit, int rowsOut, int* PM, int* NC, int* KWc, int* CW, size_t* smem);
 int ptp_solver_cluster_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* dScale, int nS, double* phi, const uint2* encBounds, int rowLimit, int rowsOut,
 	int PM, int NC, int KWc, int CW, size_t smem);
 int ptp_node_field(ptp_trap* t);

@@ -967,7 +967,7 @@ int ptp_solver_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double
 		const int rows16 = std::min(Nr, (std::max(rowsWanted, rowLimit) + 15) & ~15);
 		int PM, NC, KWc, CW;
 		size_t smc;
-		if (rows16 < Nr && ptp_solver_cluster_plan(t, rowLimit, rows16, &PM, &NC, &KWc, &CW, &smc)) {
+		if (rows16 < Nr && ptp_solver_cluster_plan(t, nS, rowLimit, rows16, &PM, &NC, &KWc, &CW, &smc)) {
 			PTP_TRY(ptp_solver_cluster_run(t, rho, rhoIsFixed, dScale, nS, phi, encBounds, rowLimit, rows16, PM, NC, KWc, CW, smc));
 			if (rowsDone) *rowsDone = rows16;
 			t->eNodesValid = true;

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 {
 	cg::cluster_group cluster = cg::this_cluster();
 	extern __shared__ __align__(16) double smc[];
-	__shared__ int sLo, sHi, sJ0;
+	__shared__ int sLo, sHi;
 	const int tid = threadIdx.x;
 	const int c = (int)cluster.block_rank();
 	const int cid = blockIdx.x / CL;
@@ -74,17 +74,22 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 	const int kA = max(kc0 - 1, 0), kB = min(kc1 + 1, n1), KW = kB - kA, KWp = a.KWc + 2;
 	const int CWp = a.CW + 2;
 
+	// All species go through every phase together (species x row = one longer row index), so that the phases - each a short
+	// dependent chain behind a barrier - are paid once per step, not once per species.
+	const int nS = a.nS;
 	double* sInv = smc;                                         // [rowsIn][NM] 1 / pivot          (rows < Jf)
 	double* sCp = sInv + (size_t)rowsIn * NM;                   // [rowsT][NM]  upper / pivot (rows < Jf), thR (rows > Jf)
-	double* sB = sCp + (size_t)rowsT * NM;                      // [rowsT][NM]  beta -> alpha
-	double* sS = sB + (size_t)rowsT * NM;                       // [rowsOut][NM] paired modes: sums at [s], differences at [PM + s]
-	double* sFT = sS + (size_t)rowsOut * NM;                    // [CS_KB][NM]  chunk of the forward matrix (own modes)
-	double* sRho = sFT + (size_t)CS_KB * NM;                    // [rowsIn][CS_KB] chunk of the deposit rows
-	double* sC = sRho + (size_t)rowsIn * CS_KB;                 // [PM][KWp]    cos(pi p k / Nz), own pairs x the cluster's nodes
-	double* sPart = sC + (size_t)PM * KWp;                      // [rowsOut][KWp] partial inverse transform of the own modes
-	double* sTot = sPart + (size_t)rowsOut * KWp;               // [rowsOut][CWp] total potential of this CTA's share (+ halo)
+	double* sB = sCp + (size_t)rowsT * NM;                      // [nS][rowsT][NM]  beta -> alpha
+	double* sS = sB + (size_t)nS * rowsT * NM;                  // [nS][rowsOut][NM] paired modes: sums at [s], differences at [PM + s]
+	double* sFT = sS + (size_t)nS * rowsOut * NM;               // [CS_KB][NM]  chunk of the forward matrix (own modes)
+	double* sRho = sFT + (size_t)CS_KB * NM;                    // [nS][rowsIn][CS_KB] chunk of the deposit rows
+	double* sC = sRho + (size_t)nS * rowsIn * CS_KB;            // [PM][KWp]    cos(pi p k / Nz), own pairs x the cluster's nodes
+	double* sPart = sC + (size_t)PM * KWp;                      // [nS][rowsOut][KWp] partial inverse transform of the own modes
+	double* sTot = sPart + (size_t)nS * rowsOut * KWp;          // [rowsOut][CWp] total potential of this CTA's share (+ halo)
 	double* sLower = sTot + (size_t)rowsOut * CWp;              // [rowsT]
-	int2* sBd = reinterpret_cast<int2*>(sLower + rowsT);        // [rowsIn]
+	double* sScale = sLower + rowsT;                            // [nS]
+	int2* sBd = reinterpret_cast<int2*>(sScale + nS);           // [nS][rowsIn]
+	int* sJ0 = reinterpret_cast<int*>(sBd + (size_t)nS * rowsIn); // [nS] first touched row
 
 	// mode of slot s: pair p = c PM + (s mod PM); slots [0, PM) hold mode p, slots [PM, 2 PM) hold mode Nz - p
 	const int slot = tid % NM, lane6 = tid / NM, nLanes = CS_T / NM;      // forward transform: thread -> (slot, rows lane6 + i nLanes)
@@ -116,151 +121,164 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 		cs_cp8(&sC[s * KWp + kk], a.C + (size_t)(p < K2 ? p : 0) * n1 + kA + kk, p < K2);
 	}
 	cs_commit();
-	const double q = (tid < NM && mOk) ? a.thQ[(size_t)Jf * n1 + m] : 0.0;
+	const double q = mOk ? a.thQ[(size_t)Jf * n1 + m] : 0.0;    // (by slot: every thread that may run a radial solve has it)
 	ptp_pdl_launch_dependents();
 	ptp_pdl_wait();                                             // this step's deposit and its touched-node ranges
 
-	// this CTA's share of the cluster's nodes: core [x0, x1) in cluster coordinates (k - kA), one halo node on either side
-	const int myK0 = kc0 + c * a.CW, myK1 = min(myK0 + a.CW, kc1);          // core nodes (may be empty for the last CTAs)
+	// this CTA's share of the cluster's nodes: core [myK0, myK1), one halo node on either side
+	const int myK0 = kc0 + c * a.CW, myK1 = min(myK0 + a.CW, kc1);          // (may be empty for the last CTAs)
 	if (myK0 < myK1)
 		for (int o = tid; o < rowsOut * CWp; o += CS_T) {
 			const int j = o / CWp, x = o - j * CWp, k = myK0 - 1 + x;
 			sTot[o] = (k >= 0 && k < n1 && x < myK1 - myK0 + 2) ? a.phiTrap[(size_t)j * n1 + k] : 0.0;
 		}
-
-	for (int sp = 0; sp < a.nS; ++sp) {
-		const double scale = (a.rowScale ? a.rowScale[sp] : 1.0) * (A_FIXED ? a.fixedInv : 1.0);
-		const double* b = a.rho + (size_t)sp * a.Nr * n1;
-		if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; sJ0 = Jf; }
-		__syncthreads();
-		for (int j = tid; j < rowsIn; j += CS_T) {
-			int2 bd;
-			if (a.encBounds) {                                      // maxima written by the push kernel's flush: (Nz+2-kmin, kmax+1), 0 = untouched
-				const uint2 e = a.encBounds[sp * a.Nr + j];
-				bd = e.y ? make_int2(n1 + 1 - (int)e.x, (int)e.y - 1) : make_int2(INT_MAX, INT_MIN);
-			}
-			else bd = a.bounds[sp * a.Nr + j];
-			sBd[j] = bd;
-			if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); atomicMin(&sJ0, j); }
+	if (tid == 0) { sLo = INT_MAX; sHi = INT_MIN; }
+	if (tid < nS) {
+		sJ0[tid] = Jf;
+		sScale[tid] = (a.rowScale ? a.rowScale[tid] : 1.0) * (A_FIXED ? a.fixedInv : 1.0);
+	}
+	__syncthreads();
+	for (int v = tid; v < nS * rowsIn; v += CS_T) {
+		const int sp = v / rowsIn, j = v - sp * rowsIn;
+		int2 bd;
+		if (a.encBounds) {                                      // maxima written by the push kernel's flush: (Nz+2-kmin, kmax+1), 0 = untouched
+			const uint2 e = a.encBounds[sp * a.Nr + j];
+			bd = e.y ? make_int2(n1 + 1 - (int)e.x, (int)e.y - 1) : make_int2(INT_MAX, INT_MIN);
 		}
+		else bd = a.bounds[sp * a.Nr + j];
+		sBd[v] = bd;
+		if (bd.x <= bd.y) { atomicMin(&sLo, bd.x); atomicMax(&sHi, bd.y); atomicMin(&sJ0[sp], j); }
+	}
+	__syncthreads();
+	const int kLo = sLo, kHi = sHi;
+	// ---- forward DCT-I of the touched nodes for the own modes: beta[sp][j][slot] ----------------------------------
+	// (Every loop of this kernel is kept rolled: the code runs once per SM and step, so it is instruction-fetch bound -
+	// ncu shows "no instruction" as the top stall of every solve kernel - and short loops are what the fetch unit can keep up with.)
+	if (worker)
+		for (int v = lane6; v < nS * rowsT; v += nLanes) sB[v * NM + slot] = 0.0;
+	for (int k0 = kLo; k0 <= kHi; k0 += CS_KB) {
+		const int kn = min(CS_KB, kHi - k0 + 1);
+		__syncthreads();                                        // the previous chunk has been consumed
+#pragma unroll 1
+		for (int e = tid; e < kn * NM; e += CS_T) {
+			const int kk = e / NM, s = e - kk * NM;
+			bool ok;
+			const int mm = modeOf(s, ok);
+			cs_cp8(&sFT[e], a.FT + (size_t)(k0 + kk) * n1 + mm, ok);
+		}
+#pragma unroll 1
+		for (int e = tid; e < nS * rowsIn * kn; e += CS_T) {
+			const int v = e / kn, kk = e - v * kn;
+			const int sp = v / rowsIn, j = v - sp * rowsIn;
+			const int2 bd = sBd[v];
+			const bool ok = bd.x <= bd.y && k0 + kk >= bd.x && k0 + kk <= bd.y;   // exact zeros elsewhere
+			cs_cp8(&sRho[v * CS_KB + kk], a.rho + ((size_t)sp * a.Nr + j) * n1 + k0 + kk, ok);
+		}
+		cs_commit();
+		cs_wait_all();
 		__syncthreads();
-		const int kLo = sLo, kHi = sHi;
-		// ---- forward DCT-I of the touched nodes for the own modes: beta[j][slot] ----------------------------------
-		// (Every loop of this kernel is kept rolled: the code runs once per SM and step, so it is instruction-fetch bound -
-		// ncu shows "no instruction" as the top stall of every solve kernel - and short loops are what the fetch unit can keep up with.)
-		if (worker)
-			for (int j = lane6; j < rowsT; j += nLanes) sB[j * NM + slot] = 0.0;
-		for (int k0 = kLo; k0 <= kHi; k0 += CS_KB) {
-			const int kn = min(CS_KB, kHi - k0 + 1);
-			__syncthreads();                                        // the previous chunk has been consumed
+		if (worker) {
 #pragma unroll 1
-			for (int e = tid; e < kn * NM; e += CS_T) {
-				const int kk = e / NM, s = e - kk * NM;
-				bool ok;
-				const int mm = modeOf(s, ok);
-				cs_cp8(&sFT[e], a.FT + (size_t)(k0 + kk) * n1 + mm, ok);
-			}
-#pragma unroll 1
-			for (int e = tid; e < rowsIn * kn; e += CS_T) {
-				const int j = e / kn, kk = e - j * kn;
-				const int2 bd = sBd[j];
-				const bool ok = bd.x <= bd.y && k0 + kk >= bd.x && k0 + kk <= bd.y;   // exact zeros elsewhere
-				cs_cp8(&sRho[j * CS_KB + kk], b + (size_t)j * n1 + k0 + kk, ok);
-			}
-			cs_commit();
-			cs_wait_all();
-			__syncthreads();
-			if (worker) {
-#pragma unroll 1
-				for (int j = lane6; j < rowsIn; j += nLanes) {
-					const int2 bd = sBd[j];
-					const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
-					double t = 0.0;
+			for (int v = lane6; v < nS * rowsIn; v += nLanes) {
+				const int sp = v / rowsIn, j = v - sp * rowsIn;
+				const int2 bd = sBd[v];
+				const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
+				double t = 0.0;
 #pragma unroll 2
-					for (int kk = a0; kk <= a1; ++kk) {
-						const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(sRho)[j * CS_KB + kk] : sRho[j * CS_KB + kk];
-						t = fma(val, sFT[kk * NM + slot], t);
-					}
-					sB[j * NM + slot] += t * scale;                  // (own element)
+				for (int kk = a0; kk <= a1; ++kk) {
+					const double val = A_FIXED ? (double)reinterpret_cast<const long long*>(sRho)[v * CS_KB + kk] : sRho[v * CS_KB + kk];
+					t = fma(val, sFT[kk * NM + slot], t);
 				}
+				sB[(sp * rowsT + j) * NM + slot] += t * sScale[sp];  // (own element)
 			}
 		}
-		cs_wait_all();                                              // (also the tables requested before the wait)
-		__syncthreads();
-		// ---- radial solves: forward sweep over the touched rows below Jf, folded pivot at Jf, back-substitution, rows above ----
-		if (tid < NM && mOk) {
-			const int J0 = sJ0;
+	}
+	cs_wait_all();                                              // (also the tables requested before the wait)
+	__syncthreads();
+	// ---- radial solves: forward sweep over the touched rows below Jf, folded pivot at Jf, back-substitution, rows above ----
+	if (worker && mOk) {
+#pragma unroll 1
+		for (int sp = lane6; sp < nS; sp += nLanes) {
+			double* bb = sB + (size_t)sp * rowsT * NM + slot;
+			const int J0 = sJ0[sp];
 			double y = 0.0;
 #pragma unroll 1
 			for (int j = J0; j < Jf; ++j) {
-				const double inv = sInv[j * NM + tid];
-				y = fma(-(sLower[j] * inv), y, sB[j * NM + tid] * inv);
-				sB[j * NM + tid] = y;
+				const double inv = sInv[j * NM + slot];
+				y = fma(-(sLower[j] * inv), y, bb[j * NM] * inv);
+				bb[j * NM] = y;
 			}
-			const double xJ = (sB[Jf * NM + tid] - sLower[Jf] * y) * q;
-			sB[Jf * NM + tid] = xJ;
+			const double xJ = (bb[Jf * NM] - sLower[Jf] * y) * q;
+			bb[Jf * NM] = xJ;
 			y = xJ;
 #pragma unroll 1
 			for (int j = Jf - 1; j >= 0; --j) {
-				y = fma(-sCp[j * NM + tid], y, sB[j * NM + tid]);
-				sB[j * NM + tid] = y;
+				y = fma(-sCp[j * NM + slot], y, bb[j * NM]);
+				bb[j * NM] = y;
 			}
 			y = xJ;
 #pragma unroll 1
 			for (int j = Jf + 1; j < rowsOut; ++j) {
-				y = sCp[j * NM + tid] * y;
-				sB[j * NM + tid] = y;
+				y = sCp[j * NM + slot] * y;
+				bb[j * NM] = y;
 			}
 		}
-		__syncthreads();
-		// ---- pair the modes: cos(pi (Nz - p) k / Nz) = (-1)^k cos(pi p k / Nz) -----------------------------------
-		for (int e = tid; e < rowsOut * PM; e += CS_T) {
-			const int j = e / PM, s = e - j * PM, p = c * PM + s;
-			double plus = 0.0, minus = 0.0;
-			if (p < K2) {
-				const double ap = sB[j * NM + s];
-				if (Nz - p == p) plus = minus = ap;
-				else { const double aq = sB[j * NM + PM + s]; plus = ap + aq; minus = ap - aq; }
-			}
-			sS[j * NM + s] = plus;
-			sS[j * NM + PM + s] = minus;
+	}
+	__syncthreads();
+	// ---- pair the modes: cos(pi (Nz - p) k / Nz) = (-1)^k cos(pi p k / Nz) -----------------------------------
+	for (int e = tid; e < nS * rowsOut * PM; e += CS_T) {
+		const int v = e / PM, s = e - v * PM, p = c * PM + s;   // v = sp * rowsOut + j
+		const int sp = v / rowsOut, j = v - sp * rowsOut;
+		const double* bb = sB + ((size_t)sp * rowsT + j) * NM;
+		double plus = 0.0, minus = 0.0;
+		if (p < K2) {
+			const double ap = bb[s];
+			if (Nz - p == p) plus = minus = ap;
+			else { const double aq = bb[PM + s]; plus = ap + aq; minus = ap - aq; }
 		}
-		__syncthreads();
-		// ---- partial inverse transform of the own pairs for every node of the cluster's range ---------------------
-		{
-			const int ng = CS_T / KW;                               // row groups: thread -> (node kk, rows g, g + ng, ...)
-			const int g = tid / KW, kk = tid - g * KW;
-			if (g < ng) {
-				const double* cv = sC + kk;
-				const int sel = ((kA + kk) & 1) ? PM : 0;
+		sS[v * NM + s] = plus;
+		sS[v * NM + PM + s] = minus;
+	}
+	__syncthreads();
+	// ---- partial inverse transform of the own pairs for every node of the cluster's range ---------------------
+	{
+		const int ng = CS_T / KW;                               // row groups: thread -> (node kk, rows g, g + ng, ...)
+		const int g = tid / KW, kk = tid - g * KW;
+		if (g < ng) {
+			const double* cv = sC + kk;
+			const int sel = ((kA + kk) & 1) ? PM : 0;
 #pragma unroll 1
-				for (int j = g; j < rowsOut; j += ng) {
-					const double* sv = sS + j * NM + sel;
-					double t = 0.0;
+			for (int v = g; v < nS * rowsOut; v += ng) {
+				const double* sv = sS + v * NM + sel;
+				double t = 0.0;
 #pragma unroll 2
-					for (int s2 = 0; s2 < PM; ++s2) t = fma(sv[s2], cv[s2 * KWp], t);
-					sPart[j * KWp + kk] = t;
-				}
+				for (int s2 = 0; s2 < PM; ++s2) t = fma(sv[s2], cv[s2 * KWp], t);
+				sPart[v * KWp + kk] = t;
 			}
 		}
-		cluster.sync();                                             // every CTA's partials are in place
-		// ---- sum the 16 partials of this CTA's share (+ halo) out of the peers' shared memory --------------------
-		if (myK0 < myK1) {
-			double* out = a.phiSelf + (size_t)sp * a.Nr * n1;
-			const int nx = myK1 - myK0 + 2;
-			for (int o = tid; o < rowsOut * nx; o += CS_T) {
-				const int j = o / nx, x = o - j * nx, k = myK0 - 1 + x;
-				if (k < 0 || k >= n1) continue;
-				const int kk = k - kA;
+	}
+	cluster.sync();                                             // every CTA's partials are in place
+	// ---- sum the 16 partials of this CTA's share (+ halo) out of the peers' shared memory --------------------
+	if (myK0 < myK1) {
+		const int nx = myK1 - myK0 + 2;
+		for (int o = tid; o < rowsOut * nx; o += CS_T) {
+			const int j = o / nx, x = o - j * nx, k = myK0 - 1 + x;
+			if (k < 0 || k >= n1) continue;
+			const int kk = k - kA;
+			double tot = sTot[j * CWp + x];
+#pragma unroll 1
+			for (int sp = 0; sp < nS; ++sp) {                       // species added in registration order (Source/PenningTrap.cpp:226-232)
+				const int off = (sp * rowsOut + j) * KWp + kk;
 				double v = 0.0;
 #pragma unroll 4
-				for (int r = 0; r < CL; ++r) v += cluster.map_shared_rank(sPart, r)[j * KWp + kk];
-				if (x >= 1 && x <= myK1 - myK0) out[(size_t)j * n1 + k] = v;
-				sTot[j * CWp + x] = __dadd_rn(sTot[j * CWp + x], v);  // species added in registration order (Source/PenningTrap.cpp:226-232)
+				for (int r = 0; r < CL; ++r) v += cluster.map_shared_rank(sPart, r)[off];
+				if (x >= 1 && x <= myK1 - myK0) a.phiSelf[((size_t)sp * a.Nr + j) * n1 + k] = v;
+				tot = __dadd_rn(tot, v);
 			}
+			sTot[j * CWp + x] = tot;
 		}
-		cluster.sync();                                             // the peers are done reading this CTA's partials
 	}
+	cluster.sync();                                             // the peers are done reading this CTA's partials
 	// ---- node field: E = (Phi[k-1] - Phi[k+1]) / (2 hz), zero at both ends (Source/PenningTrap.cpp:218-233) ----------
 	if (myK0 < myK1) {
 		const int nc = myK1 - myK0;
@@ -273,19 +291,18 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 	}
 }
 
-size_t cluster_smem_bytes(int n1, int Jf, int rowsOut, int PM, int KWc, int CW)
+size_t cluster_smem_bytes(int nS, int Jf, int rowsOut, int PM, int KWc, int CW)
 {
-	const size_t NM = 2 * (size_t)PM, rowsIn = (size_t)Jf + 1, rowsT = std::max<size_t>(rowsIn, rowsOut);
-	const size_t doubles = rowsIn * NM + 2 * rowsT * NM + (size_t)rowsOut * NM + (size_t)CS_KB * NM + rowsIn * CS_KB + (size_t)PM * (KWc + 2) +
-		(size_t)rowsOut * (KWc + 2) + (size_t)rowsOut * (CW + 2) + rowsT;
-	(void)n1;
-	return doubles * sizeof(double) + rowsIn * sizeof(int2) + 64;
+	const size_t S = (size_t)nS, NM = 2 * (size_t)PM, rowsIn = (size_t)Jf + 1, rowsT = std::max<size_t>(rowsIn, rowsOut);
+	const size_t doubles = rowsIn * NM + rowsT * NM + S * rowsT * NM + S * (size_t)rowsOut * NM + (size_t)CS_KB * NM + S * rowsIn * CS_KB + (size_t)PM * (KWc + 2) +
+		S * (size_t)rowsOut * (KWc + 2) + (size_t)rowsOut * (CW + 2) + rowsT + S;
+	return doubles * sizeof(double) + S * rowsIn * sizeof(int2) + S * sizeof(int) + 64;
 }
 
 } // namespace
 
 // Can (and should) this solve go through the cluster kernel? All species, node field wanted, few rows, tables fit.
-bool ptp_solver_cluster_plan(const ptp_trap* t, int rowLimit, int rowsOut, int* PMout, int* NCout, int* KWcOut, int* CWout, size_t* smemOut)
+bool ptp_solver_cluster_plan(const ptp_trap* t, int nS, int rowLimit, int rowsOut, int* PMout, int* NCout, int* KWcOut, int* CWout, size_t* smemOut)
 {
 	if (!t->clusterSolve || rowLimit < 0 || rowLimit > CS_MAXROWS || rowsOut > CS_MAXROWS || rowsOut < 1) return false;
 	const int n1 = t->Nz + 1, K2 = (n1 + 1) / 2;
@@ -297,7 +314,7 @@ bool ptp_solver_cluster_plan(const ptp_trap* t, int rowLimit, int rowsOut, int* 
 	const int CW = (KWc + CL - 1) / CL;
 	if (KWc + 2 > CS_T) return false;                           // (partial inverse: one thread per node of the cluster's range)
 	const int Jf = std::max(0, std::min(rowLimit, t->Nr) - 1);
-	const size_t smem = cluster_smem_bytes(n1, Jf, rowsOut, PM, KWc, CW);
+	const size_t smem = cluster_smem_bytes(nS, Jf, rowsOut, PM, KWc, CW);
 	if (smem > t->smemMax) return false;
 	*PMout = PM; *NCout = NC; *KWcOut = KWc; *CWout = CW; *smemOut = smem;
 	return true;

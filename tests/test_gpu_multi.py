@@ -32,7 +32,10 @@ def _free_port():
 def _launch(world, mode, n_total, steps, exchange="nccl"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "_multi_worker.py"), mode, str(n_total), str(steps), exchange]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=int(os.environ.get("PTP_TEST_LAUNCH_TIMEOUT", "300")), cwd=ROOT)
+    except subprocess.TimeoutExpired as e:
+        raise AssertionError("multi-GPU worker timed out: %s\n%s" % ((e.stdout or b"")[-3000:], (e.stderr or b"")[-3000:]))
     assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-3000:])
     line = [x for x in p.stdout.splitlines() if x.startswith("RESULT ")][-1]
     return json.loads(line[len("RESULT "):])
