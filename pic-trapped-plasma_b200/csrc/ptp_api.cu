@@ -112,6 +112,29 @@ int push_deposit_all(ptp_trap* t, double dt)
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	t->rhoParity ^= 1;
 	t->rhoAll = t->rhoStore + (size_t)t->rhoParity * t->spanDoubles;
+	// Several species: one launch for all of them (default tuning only), the SMs shared out by live rings.
+	const int nS = (int)t->plasmas.size();
+	bool multi = t->multiPush && nS >= 2 && nS <= 4 && t->threads == 512 && t->ringsPerThread == 4 && !t->mergeBins;
+	for (ptp_plasma* p : t->plasmas) multi = multi && p->cap > 0;
+	{
+		double total = 0;
+		for (ptp_plasma* p : t->plasmas) total += (double)std::max<int64_t>(p->nAlive, 1);
+		for (ptp_plasma* p : t->plasmas) {
+			const double share = multi ? (double)std::max<int64_t>(p->nAlive, 1) / total : 1.0;
+			if (std::abs(share - p->ctaShare) > 0.1 * std::max(share, p->ctaShare)) { p->ctaShare = share; p->boundsValid = false; }
+		}
+	}
+	if (multi) {
+		for (ptp_plasma* p : t->plasmas) {
+			if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+			multi = multi && p->nCta > 0;
+		}
+	}
+	if (multi) {
+		PTP_TRY(ptp_push_launch_multi(t, t->plasmas.data(), nS, dt));
+		for (ptp_plasma* p : t->plasmas) p->encValid = true;
+		return PTP_OK;
+	}
 	for (ptp_plasma* p : t->plasmas) {
 		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
 		if (p->cap == 0 || p->nCta == 0) {                       // no push kernel for an empty species: its slice of the other parity by hand
@@ -231,6 +254,7 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 		if (const char* e = std::getenv("PTP_FULL_SOLVE")) t->lazyRows = std::atoi(e) == 0;
 		if (const char* e = std::getenv("PTP_PDL")) t->usePdl = std::atoi(e) != 0;
 		if (const char* e = std::getenv("PTP_INV_BULK")) t->invBulk = std::atoi(e);
+		if (const char* e = std::getenv("PTP_MULTI_PUSH")) t->multiPush = std::atoi(e);
 		if (const char* e = std::getenv("PTP_CLUSTER_SOLVE")) t->clusterSolve = std::atoi(e);
 		if (const char* e = std::getenv("PTP_GRAPH")) t->useGraph = std::atoi(e);
 		if (const char* e = std::getenv("PTP_GRAPH_MAX_RINGS")) t->graphMaxRings = std::atoll(e);

@@ -61,6 +61,7 @@ struct ptp_plasma {
 	double* vSavedAlt = nullptr;         // sort ping-pong
 	bool vSavedValid = false;
 	bool boundsValid = false;
+	double ctaShare = 1.0;       // share of the SMs this species' push gets when all species run in one launch (by live rings)
 	bool encValid = false;       // the touched-node range per row kept next to this species' deposit grid (written by the push kernel's
 	                             // flush) describes the grid's present content
 };
@@ -155,6 +156,7 @@ struct ptp_trap {
 	int phiRows = 0;
 	bool usePdl = true;              // PTP_PDL=0: plain stream-ordered launches
 	int clusterSolve = 1;            // PTP_CLUSTER_SOLVE=0: the step's solve through the two-kernel path even when the plasma occupies few rows
+	int multiPush = 1;               // PTP_MULTI_PUSH=0: one push launch per species
 	int invBulk = 1;                 // PTP_INV_BULK=0: the cp.async form of the dense inverse transform also for even row lengths
 
 	PtpComm* comm = nullptr;
@@ -250,6 +252,7 @@ int ptp_sor_run(ptp_trap* t, const double* rho, bool rhoIsFixed, const double* d
 
 // ---- ptp_push.cu ---------------------------------------------------------------------------------
 int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push);
+int ptp_push_launch_multi(ptp_trap* t, ptp_plasma* const* ps, int n, double dt);   // K1 of up to 4 species in one launch
 int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p);
 int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& tiles, std::vector<int2>& tileBounds, int64_t* nLive);
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window);

@@ -245,6 +245,7 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 	p->nAlive = live;
 	const long long totalTiles = (long long)tiles.size();
 	int nCta = t->ctas > 0 ? t->ctas : t->smCount;
+	if (p->ctaShare < 1.0) nCta = std::max(1, (int)(nCta * p->ctaShare + 0.5));   // all species in one launch: SMs by live rings
 	if (totalTiles < nCta) nCta = (int)totalTiles;
 	const int W = t->window < t->Nz ? t->window : t->Nz;
 	// A row whose rings fit the window with a little room to spare is never split by cell range: wherever its rings drift

@@ -171,8 +171,10 @@ __device__ __forceinline__ void grid_max(unsigned int* p, unsigned int val, bool
 	else atomicMax(p, val);
 }
 
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE = false>
-__global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
+// The kernel body for CTA `bid` of `nb` CTAs working on one species (k_push_deposit: the launch's own grid;
+// k_push_deposit_multi: a sub-range of a launch that covers several species).
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE>
+__device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int bid, const int nb)
 {
 	constexpr int NV = R / 2;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -195,11 +197,11 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 	ptp_pdl_wait();                              // the node field of the last solve, the rings of the last push
 	const unsigned long long stepTag = (PUSH && a.lossLog) ? a.lossLog[1] : 0ULL;   // (advanced by the last CTA of this launch to finish)
 	if (PUSH) {
-		for (long long i = (long long)blockIdx.x * T + tid; i < a.clearGridWords; i += (long long)gridDim.x * T) a.clearGrid[i] = 0.0;
-		for (int i = blockIdx.x * T + tid; i < a.clearBoundsWords; i += gridDim.x * T) a.clearBounds[i] = 0.0;
+		for (long long i = (long long)bid * T + tid; i < a.clearGridWords; i += (long long)nb * T) a.clearGrid[i] = 0.0;
+		for (int i = bid * T + tid; i < a.clearBoundsWords; i += nb * T) a.clearBounds[i] = 0.0;
 	}
 
-	for (int s = a.ctaSegBegin[blockIdx.x]; s < a.ctaSegBegin[blockIdx.x + 1]; ++s) {
+	for (int s = a.ctaSegBegin[bid]; s < a.ctaSegBegin[bid + 1]; ++s) {
 		const PtpSegment seg = a.segs[s];
 		const int4 bounds = a.segBounds[s];
 		if (bounds.x > bounds.y) continue;           // no live ring in this segment (uniform per CTA)
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		}
 
 		// the CTA's next segment starts with cold loads: pull its first tiles into L2 while this segment's epilogue runs
-		if (PTP_L2_PREFETCH_TILES > 0 && s + 1 < a.ctaSegBegin[blockIdx.x + 1]) {
+		if (PTP_L2_PREFETCH_TILES > 0 && s + 1 < a.ctaSegBegin[bid + 1]) {
 			const PtpSegment nx = a.segs[s + 1];
 			for (int u = 0; u < PTP_L2_PREFETCH_TILES && nx.begin + u * tile < nx.end; ++u) {
 				const long long pf = ((nx.begin + u * tile) >> 1) + tid;
@@ -533,14 +535,38 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 		// every CTA of the launch has read the step tag before the last one to finish advances it
 		__threadfence();
 		const unsigned long long ticket = atomicAdd(a.lossLog + 2, 1ULL);
-		if (ticket == (unsigned long long)gridDim.x - 1) {
+		if (ticket == (unsigned long long)nb - 1) {
 			a.lossLog[2] = 0ULL;
 			a.lossLog[1] = stepTag + 1;
 		}
 	}
 }
 
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE = false>
+__global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
+{
+	push_deposit_body<T, R, PUSH, FIXED, EXACT, MERGE>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // [emu-end]
+
+// All species of a step in ONE launch: CTAs [ctaBegin[s], ctaBegin[s + 1]) work on species s. The species of the reference's
+// default configuration hold a few thousand rings each, the co-trapped 10 M-ring case 5 M each: one launch per species leaves
+// most SMs idle for most of a short kernel, and every launch pays its own ramp and tail. (The species are pushed with the
+// same pre-step field in the reference too, Source/PenningTrap.cpp:354-357, so their order is immaterial.)
+constexpr int PTP_MULTI_MAX = 4;
+struct PushArgsMulti {
+	int n, ctaBegin[PTP_MULTI_MAX + 1], pad[2];
+	PushArgs sp[PTP_MULTI_MAX];
+};
+
+template <int T, int R, bool FIXED, bool EXACT>
+__global__ void __launch_bounds__(T, 1) k_push_deposit_multi(const __grid_constant__ PushArgsMulti m)
+{
+	int si = 0;
+	while (si + 1 < m.n && (int)blockIdx.x >= m.ctaBegin[si + 1]) ++si;
+	push_deposit_body<T, R, true, FIXED, EXACT, false>(m.sp[si], (int)blockIdx.x - m.ctaBegin[si], m.ctaBegin[si + 1] - m.ctaBegin[si]);
+}
 
 // Axial cell range and live count of every tile (window planning at upload / after a sort) and validation of the
 // positions. One CTA per tile; tiles[] lists them as one-tile segments.
@@ -710,6 +736,42 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 		e = t->ringsPerThread == 8 ? launch_tr<256, 8>(push, fixed, exact, a, p->nCta, smem, t->stream, pdl)
 		                           : launch_tr<256, 4>(push, fixed, exact, a, p->nCta, smem, t->stream, pdl);
 	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_push_deposit launch", __FILE__, __LINE__);
+	t->lastLaunches++;
+	return PTP_OK;
+}
+
+// K1 for several species in one launch (same tuning and modes for all; at most PTP_MULTI_MAX species per launch).
+int ptp_push_launch_multi(ptp_trap* t, ptp_plasma* const* ps, int n, double dt)
+{
+	if (n < 1 || n > PTP_MULTI_MAX) { ptp_set_error("ptp_push_launch_multi: bad species count"); return PTP_EINVAL; }
+	PushArgsMulti m{};
+	m.n = n;
+	int total = 0;
+	for (int i = 0; i < n; ++i) {
+		ptp_plasma* p = ps[i];
+		PushArgs a = make_args(t, p, dt);
+		if (ptp_peer_fused(t)) ptp_peer_targets(t, t->rhoParity, (size_t)p->index * t->G, a.rho, &a.nRho);
+		double* other = t->rhoStore + (size_t)(t->rhoParity ^ 1) * t->spanDoubles;
+		a.clearGrid = other + (size_t)p->index * t->G;
+		a.clearGridWords = (long long)std::min(t->rowExtent, t->Nr) * (t->Nz + 1);
+		a.clearBounds = other + (size_t)t->capS * t->G + (size_t)p->index * t->Nr;
+		a.clearBoundsWords = t->Nr;
+		m.sp[i] = a;
+		m.ctaBegin[i] = total;
+		total += p->nCta;
+	}
+	for (int i = n; i <= PTP_MULTI_MAX; ++i) m.ctaBegin[i] = total;
+	const size_t smem = ptp_push_smem_bytes(t, t->threads, t->window);
+	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64, exact = t->arithMode == PTP_ARITH_EXACT;
+	auto go = [&](auto kern) -> cudaError_t {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		return ptp_launch(kern, dim3(total), dim3(512), smem, t->stream, t->usePdl, m);
+	};
+	cudaError_t e;
+	if (fixed) e = exact ? go(k_push_deposit_multi<512, 4, true, true>) : go(k_push_deposit_multi<512, 4, true, false>);
+	else e = exact ? go(k_push_deposit_multi<512, 4, false, true>) : go(k_push_deposit_multi<512, 4, false, false>);
+	if (e != cudaSuccess) return ptp_cuda_fail(e, "k_push_deposit_multi launch", __FILE__, __LINE__);
 	t->lastLaunches++;
 	return PTP_OK;
 }

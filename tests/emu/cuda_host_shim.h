@@ -34,6 +34,7 @@ static inline int4 make_int4(int x, int y, int z, int w) { return int4{ x, y, z,
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __grid_constant__
 #define __align__(n) alignas(n)
 
 struct EmuIdx { int x = 0, y = 0, z = 0; };
