@@ -102,6 +102,28 @@ int solve_species(ptp_trap* t, int first, int count, bool withField = false, int
 	return PTP_OK;
 }
 
+// Several species: one push launch for all of them (default tuning only), the SMs shared out by live rings; segment tables are
+// (re)planned where a species' share has changed. Idempotent - capture_step_graph runs it before the capture starts, so that
+// nothing is planned (a synchronising device pass) inside the capture.
+int plan_push(ptp_trap* t, bool* multiOut)
+{
+	const int nS = (int)t->plasmas.size();
+	bool multi = t->multiPush && nS >= 2 && nS <= 4 && t->threads == 512 && t->ringsPerThread == 4 && !t->mergeBins;
+	for (ptp_plasma* p : t->plasmas) multi = multi && p->cap > 0;
+	double total = 0;
+	for (ptp_plasma* p : t->plasmas) total += (double)std::max<int64_t>(p->nAlive, 1);
+	for (ptp_plasma* p : t->plasmas) {
+		const double share = multi ? (double)std::max<int64_t>(p->nAlive, 1) / total : 1.0;
+		if (std::abs(share - p->ctaShare) > 0.1 * std::max(share, p->ctaShare)) { p->ctaShare = share; p->boundsValid = false; }
+	}
+	for (ptp_plasma* p : t->plasmas) {
+		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+		multi = multi && p->nCta > 0;
+	}
+	*multiOut = multi;
+	return PTP_OK;
+}
+
 // Plasma::moveRings + Plasma::updateRHS of every species (push with the pre-step field, deposit at the new position).
 // The deposit grids are double-buffered by step parity: this step's sums go into the parity that the push kernels of the
 // previous step zeroed (their populated rows and touched-node ranges; begin_steps zeroes everything after a (re)load), and
@@ -112,24 +134,9 @@ int push_deposit_all(ptp_trap* t, double dt)
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	t->rhoParity ^= 1;
 	t->rhoAll = t->rhoStore + (size_t)t->rhoParity * t->spanDoubles;
-	// Several species: one launch for all of them (default tuning only), the SMs shared out by live rings.
+	bool multi = false;
+	PTP_TRY(plan_push(t, &multi));
 	const int nS = (int)t->plasmas.size();
-	bool multi = t->multiPush && nS >= 2 && nS <= 4 && t->threads == 512 && t->ringsPerThread == 4 && !t->mergeBins;
-	for (ptp_plasma* p : t->plasmas) multi = multi && p->cap > 0;
-	{
-		double total = 0;
-		for (ptp_plasma* p : t->plasmas) total += (double)std::max<int64_t>(p->nAlive, 1);
-		for (ptp_plasma* p : t->plasmas) {
-			const double share = multi ? (double)std::max<int64_t>(p->nAlive, 1) / total : 1.0;
-			if (std::abs(share - p->ctaShare) > 0.1 * std::max(share, p->ctaShare)) { p->ctaShare = share; p->boundsValid = false; }
-		}
-	}
-	if (multi) {
-		for (ptp_plasma* p : t->plasmas) {
-			if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
-			multi = multi && p->nCta > 0;
-		}
-	}
 	if (multi) {
 		PTP_TRY(ptp_push_launch_multi(t, t->plasmas.data(), nS, dt));
 		for (ptp_plasma* p : t->plasmas) p->encValid = true;
@@ -509,8 +516,7 @@ void drop_graph(ptp_trap* t)
 // replayed. Everything a step would allocate or synchronise on lazily is settled before the capture starts.
 int capture_step_graph(ptp_trap* t, double dt, int target)
 {
-	for (ptp_plasma* p : t->plasmas)
-		if (!p->boundsValid) PTP_TRY(ptp_bounds_launch(t, p));
+	{ bool multi; PTP_TRY(plan_push(t, &multi)); }
 	if (!t->eNodesValid) PTP_TRY(ptp_node_field(t));
 	PTP_TRY(ptp_solver_reserve(t, (int)t->plasmas.size()));
 	const int parity0 = t->rhoParity;
