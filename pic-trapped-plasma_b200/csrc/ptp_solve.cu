@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256) k_fwd_thomas(const double* __restrict__ r
 				const int jj = slot + u * SLOTS, j = jp + jj;
 				if (j > Jf) continue;
 				const int2 bd = sBd[j];
+				if (bd.x > bd.y) continue;                              // row without a deposit (the arithmetic below would overflow)
 				const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
 				double t = acc[u];
 				for (int kk = a0; kk <= a1; ++kk) {

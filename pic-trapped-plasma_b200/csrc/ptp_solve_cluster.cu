@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 			for (int v = lane6; v < nS * rowsIn; v += nLanes) {
 				const int sp = v / rowsIn, j = v - sp * rowsIn;
 				const int2 bd = sBd[v];
+				if (bd.x > bd.y) continue;                              // row without a deposit (the arithmetic below would overflow)
 				const int a0 = max(bd.x, k0) - k0, a1 = min(bd.y, k0 + kn - 1) - k0;
 				double t = 0.0;
 #pragma unroll 2

@@ -154,7 +154,10 @@ def test_history_row_order_after_losses_in_several_steps(tmp_path, c1_kat):
         f.write(np.ascontiguousarray(z).tobytes())
         f.write(np.ascontiguousarray(v).tobytes())
     steps, barrier = 150, -47.0            # the well gets shallow: ~2400 of 4001 rings leave, up to ~120 per step, over ~100 steps
-    p = subprocess.run([exe, rings, str(tmp_path / "out_"), str(steps), str(barrier)], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    wrap = os.environ.get("PTP_TEST_WRAP", "").split()          # e.g. "compute-sanitizer --tool memcheck"
+    p = subprocess.run(wrap + [exe, rings, str(tmp_path / "out_"), str(steps), str(barrier)], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    if wrap:
+        print(p.stdout[-6000:], p.stderr[-3000:])
     assert p.returncode == 0, p.stdout + p.stderr
     ot = port.default_trap()
     op = ot.plasma("Electrons", 9.1093837015e-31, -1.602176634e-19)
