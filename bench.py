@@ -409,7 +409,7 @@ def main():
     # graph replay has none): one more un-timed pass of K stream-launched steps WITH the phase events gives the kernel times
     # for the roofline and the phase table (the headline value stays the one measured above).
     phases = [float(mx[med, 1]), float(mx[med, 2]), float(mx[med, 3])]
-    timing["graph_replay"] = bool(trap.last_launches() and args.graph != "off" and (args.graph == "on" or n_local <= 8_000_000 or world > 1))
+    timing["graph_replay"] = bool(args.graph != "off" and not (world > 1 and args.allreduce == "nccl") and (args.graph == "on" or n_local <= 8_000_000 or world > 1))   # (the library's policy, ptp_api.cu want_graph)
     if ms_push == 0.0:
         trap.set_graph(False)
         trap.set_phase_events(True)
