@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--rings", type=int, default=0, help="rings per thread and tile (4 or 8)")
     ap.add_argument("--sort-interval", type=int, default=-1, help="> 0: re-sort every so many steps; 0: never; -1: adaptive (library default)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "peer", "gather"],
-                    help="exchange step for N > 1 (auto: peer-memory gather; peer = remote adds fused into the deposit flush)")
+                    help="exchange step for N > 1 (auto: the library's choice - remote adds fused into the deposit flush up to 2^20 grid nodes, peer-memory gather above)")
     ap.add_argument("--cpu-sample", type=int, default=10_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -325,7 +325,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         trap.comm_init(uid[0], world, rank)
         if args.allreduce == "auto":
-            args.allreduce = "gather"
+            args.allreduce = "peer" if trap.G <= (1 << 20) else "gather"      # the library's own choice (ptp_trap_set_allreduce(t, 2))
         trap.set_allreduce({"nccl": 0, "peer": 1, "gather": 3}[args.allreduce])
         config["exchange"] = {"peer": "peer-memory adds fused into the deposit flush (system-scope atomics over NVLink) + flag barrier",
                               "gather": "peer-memory gather: each rank stores its populated rows into every rank's gather area over NVLink, flags, local sum in rank order (one kernel)",

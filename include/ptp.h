@@ -146,7 +146,7 @@ int ptp_trap_comm_init(ptp_trap* t, const void* id128, int nRanks, int rank);
  *   3 = peer memory, gather: one small kernel per step pushes this rank's populated rows into a slot of every rank's gather
  *       area with plain stores, flags, and sums the slots in rank order - no remote atomics, every rank holds bitwise the
  *       same sums also in fp64 mode;
- *   2 = the default choice (gather).
+ *   2 = choose by grid size, as measured: fused up to 2^20 nodes, gather above.
  * Multi-rank callers must issue the same sequence of calls on every rank (same species created in the same order): the
  * peer mappings are exchanged collectively whenever the grids had to be reallocated. */
 int ptp_trap_set_allreduce(ptp_trap* t, int kind);

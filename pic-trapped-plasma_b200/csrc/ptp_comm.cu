@@ -491,10 +491,11 @@ int ptp_trap_set_allreduce(ptp_trap* t, int kind)
 {
 	if (!t || kind < 0 || kind > 3) { ptp_set_error("ptp_trap_set_allreduce: bad arguments"); return PTP_EINVAL; }
 	if (kind >= 1 && !t->comm) { ptp_set_error("ptp_trap_set_allreduce: peer-memory mode needs ptp_trap_comm_init first"); return PTP_ESTATE; }
-	// auto: the peer-memory exchange costs one remote atomic per flushed node and per out-of-window ring and peer, the
-	// collective costs the whole grid. Measured at 4 GPUs: 13 us vs 26 us per step on the default grid (75 k nodes), but
-	// 1.3 ms vs 0.13 ms on the 4096 x 1024 grid, whose long sparse plasma tails deposit outside the private windows.
-	if (kind == 2) kind = 3;
+	// auto, by measurement (8 x B200, profiles/r02_scale.txt): on the default grid the fused adds cost the push kernel ~7 us but the
+	// exchange is then one flag barrier (15 us with the skew between the ranks) against 23 us for the gather kernel - 0.109 vs
+	// 0.113 ms per step of c4 at 8 GPUs, equal at 2; on the 4096 x 1024 grid, whose sparse plasma tails deposit outside the
+	// private windows, every such ring would cost two remote atomics per peer (round 1: 1.3 ms per push) - gather there.
+	if (kind == 2) kind = t->G <= (1LL << 20) ? 1 : 3;
 	if (kind != t->allreduceKind) { t->peerStale = true; t->peerCleanEpoch = -1; }
 	t->allreduceKind = kind;
 	++t->cfgEpoch;
