@@ -30,3 +30,14 @@ def test_reference_arm_is_silent_on_other_ranks():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_k1_traffic_profile_belongs_to_the_shipped_push_kernel():
+    """bench.py reports roofline.traffic only while profiles/k1_traffic.json was taken from the push kernel source that ships
+    (hash of ptp_push.cu); a change to the kernel without a new ncu capture must show up here, not as a silently stale number."""
+    import hashlib
+    prof = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+    src = open(os.path.join(ROOT, "pic-trapped-plasma_b200", "csrc", "ptp_push.cu"), "rb").read()
+    assert prof["push_cu_sha16"] == hashlib.sha256(src).hexdigest()[:16]
+    for wl in ("c4", "c5"):
+        assert 28.0 < prof[wl]["dram_bytes_per_ring"] < 36.0        # 32 B algorithmic: no wasted re-reads
