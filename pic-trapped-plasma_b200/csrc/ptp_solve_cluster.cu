@@ -29,6 +29,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+// [cluster-begin] (tests/emu/emu_cluster.sh compiles the text up to [cluster-end] for the host: 16 CTAs of a cluster run
+// concurrently on CPU threads, cluster.sync is a barrier over all of them, map_shared_rank a pointer translation)
 constexpr int CL = 16;          // CTAs per cluster (non-portable size: needs cudaFuncAttributeNonPortableClusterSizeAllowed)
 constexpr int CS_KB = 64;       // axial nodes of the deposit staged per chunk
 constexpr int CS_T = 256;
@@ -63,7 +65,6 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 {
 	cg::cluster_group cluster = cg::this_cluster();
 	extern __shared__ __align__(16) double smc[];
-	__shared__ int sLo, sHi;
 	const int tid = threadIdx.x;
 	const int c = (int)cluster.block_rank();
 	const int cid = blockIdx.x / CL;
@@ -90,6 +91,8 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 	double* sScale = sLower + rowsT;                            // [nS]
 	int2* sBd = reinterpret_cast<int2*>(sScale + nS);           // [nS][rowsIn]
 	int* sJ0 = reinterpret_cast<int*>(sBd + (size_t)nS * rowsIn); // [nS] first touched row
+	int& sLo = sJ0[nS];                                         // union of the touched node ranges of all species and rows
+	int& sHi = sJ0[nS + 1];
 
 	// mode of slot s: pair p = c PM + (s mod PM); slots [0, PM) hold mode p, slots [PM, 2 PM) hold mode Nz - p
 	const int slot = tid % NM, lane6 = tid / NM, nLanes = CS_T / NM;      // forward transform: thread -> (slot, rows lane6 + i nLanes)
@@ -292,12 +295,14 @@ __global__ void __launch_bounds__(CS_T, 1) k_solve_cluster(const ClusterSolveArg
 	}
 }
 
+// [cluster-end]
+
 size_t cluster_smem_bytes(int nS, int Jf, int rowsOut, int PM, int KWc, int CW)
 {
 	const size_t S = (size_t)nS, NM = 2 * (size_t)PM, rowsIn = (size_t)Jf + 1, rowsT = std::max<size_t>(rowsIn, rowsOut);
 	const size_t doubles = rowsIn * NM + rowsT * NM + S * rowsT * NM + S * (size_t)rowsOut * NM + (size_t)CS_KB * NM + S * rowsIn * CS_KB + (size_t)PM * (KWc + 2) +
 		S * (size_t)rowsOut * (KWc + 2) + (size_t)rowsOut * (CW + 2) + rowsT + S;
-	return doubles * sizeof(double) + S * rowsIn * sizeof(int2) + S * sizeof(int) + 64;
+	return doubles * sizeof(double) + S * rowsIn * sizeof(int2) + (S + 2) * sizeof(int) + 64;
 }
 
 } // namespace

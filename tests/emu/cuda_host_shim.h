@@ -45,7 +45,7 @@ struct EmuWarp {
 	std::barrier<> bar{ 32 };
 	unsigned long long buf[32];
 };
-static std::barrier<>* g_ctaBarrier = nullptr;
+static thread_local std::barrier<>* g_ctaBarrier = nullptr;   // (thread-local: the cluster emulation runs several CTAs at once)
 static thread_local EmuWarp* g_warp = nullptr;
 static thread_local int g_lane = 0;
 static inline void __syncthreads() { g_ctaBarrier->arrive_and_wait(); }
@@ -155,13 +155,13 @@ static inline void emu_launch(int gridX, int threads, const std::function<void()
 	for (int by = 0; by < gridY; ++by)
 		for (int b = 0; b < gridX; ++b) {
 			std::barrier<> bar(threads);
-			g_ctaBarrier = &bar;
 			std::vector<std::unique_ptr<EmuWarp>> warps;
 			for (int w = 0; w < threads / 32; ++w) warps.emplace_back(new EmuWarp);
 			std::vector<std::thread> th;
 			for (int t = 0; t < threads; ++t)
 				th.emplace_back([&, t, b, by] {
 					threadIdx.x = t; blockIdx.x = b; blockIdx.y = by;
+					g_ctaBarrier = &bar;
 					g_warp = warps[t / 32].get(); g_lane = t & 31;
 					body();
 				});

@@ -322,3 +322,55 @@ def test_loader_text_on_host_threads_matches_reference_loader(tmp_path, density_
     assert n == int(mine.sum()) and np.array_equal(ids, np.arange(n))
     assert np.array_equal(r, r0[mine]) and np.array_equal(z, z0[mine]) and np.array_equal(v, v0[mine])
     rt.close()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+@pytest.mark.parametrize("Nz,Nr,rows,k_lo,k_hi,n_species", [(585, 128, range(0, 12), 274, 311, 2),    # the reference's default grid, two species
+                                                           (300, 24, [0, 5, 19], 3, 297, 1),          # odd row length, long touched range (5 chunks)
+                                                           (57, 9, [0, 2, 3], 20, 40, 3)])            # tiny grid: one cluster, mode pairs beyond K2 idle
+def test_cluster_solve_kernel_text_on_host_threads_matches_lu_oracle(tmp_path, Nz, Nr, rows, k_lo, k_hi, n_species):
+    """k_solve_cluster - the one-kernel step solve on thread-block clusters (ptp_solve_cluster.cu) - on host threads: the 16
+    CTAs of a cluster run concurrently, cluster.sync is a barrier over all of them, distributed shared memory a pointer
+    translation. All species at once; potentials of the populated rows against the oracle's LU solve (rel-L2 <= 1e-10), the
+    node field bit for bit the centred difference of phi_trap + sum of the species' potentials in registration order
+    (Source/PenningTrap.cpp:226-233); rows beyond the produced ones untouched."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    if not _BUILT.get("cluster"):
+        b = subprocess.run(["bash", os.path.join(ROOT, "tests", "emu", "emu_cluster.sh")], capture_output=True, text=True, timeout=900)
+        assert b.returncode == 0, b.stdout + b.stderr
+        _BUILT["cluster"] = True
+    pt = port.PortTrap(0.01488, [0.01322] * 5, [0, -70, -15, -70, 0], [0.0005] * 4, Nz, Nr)
+    n1 = Nz + 1
+    rng = np.random.default_rng(Nz + Nr)
+    rho = np.zeros((n_species, Nr, n1))
+    for s in range(n_species):
+        for j in rows:
+            lo = k_lo + int(rng.integers(0, 3))
+            rho[s, j, lo:k_hi + 1 - s] = -1e6 * rng.random(k_hi + 1 - s - lo)
+    case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
+    with open(case, "wb") as f:
+        f.write(np.array([Nz, Nr], np.int32).tobytes())
+        f.write(np.array([pt.hz, pt.hr, pt.radius], np.float64).tobytes())
+        f.write(rho.tobytes())
+        f.write(np.ascontiguousarray(pt.phi).tobytes())
+    limit = max(rows) + 1
+    p = subprocess.run([os.path.join(ROOT, "build", "emu", "emu_cluster"), case, out, str(limit), str(n_species)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    raw = np.fromfile(out, np.float64)
+    G = pt.G
+    got = min((limit + 15) // 16 * 16, Nr)
+    phi = raw[:n_species * G].reshape(n_species, Nr, n1)
+    en = raw[n_species * G:].reshape(Nr, n1)
+    tot = pt.phi.reshape(Nr, n1).copy()
+    for s in range(n_species):
+        want = pt.solve(rho[s].reshape(-1)).reshape(Nr, n1)
+        assert np.linalg.norm(phi[s, :got] - want[:got]) / np.linalg.norm(want[:got]) < 1e-10
+        assert not phi[s, got:].any()
+        tot[:got] = tot[:got] + phi[s, :got]
+    e = np.zeros((got, n1))
+    e[:, 1:-1] = (tot[:got, :-2] - tot[:got, 2:]) / (2 * pt.hz)
+    assert np.array_equal(en[:got], e)
+    assert np.all(en[got:] == -1.0)
+    pt.close()
