@@ -263,6 +263,8 @@ def main():
     ap.add_argument("--min-time", type=float, default=0.5, help="repeat the K-step batch until this many seconds are covered; the median batch is reported")
     ap.add_argument("--max-batches", type=int, default=400)
     ap.add_argument("--total", type=int, default=0, help="override the workload's ring count (experiments: shard-sized loads on one GPU)")
+    ap.add_argument("--hot", default="auto", choices=["auto", "on", "off"],
+                    help="per-warp-bin form of the push kernel for species that cannot be kept ordered by cell (auto: the re-sort policy decides)")
     ap.add_argument("--electrons", action="store_true", help="experiments: run the workload's species with the electron mass (fast rings: 0.23 cells/step on the default grid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -347,6 +349,8 @@ def main():
     plasmas = []
     for name, mkey, share, num in species:
         p = ptp.Plasma(trap, name, getattr(ptp, mkey), -ptp.ePos)
+        if args.hot != "auto":
+            p.set_hot(1 if args.hot == "on" else 0)
         p.loadDensity(dens * share, TEMPERATURE, num, shard=rank, nShards=world, solve=False)
         plasmas.append(p)
     trap.sync()
@@ -393,6 +397,7 @@ def main():
     alive_after = sum_over_ranks(float(sum(p.getNumMacro() for p in plasmas)))
     clocks = sampler.stop()
     sorts_timed = trap.sorts_done() - sorts_before
+    hot_after = [bool(p.is_hot()) for p in plasmas]
     local = np.array(batches)
     mx = np.array(max_over_ranks(local[:, :4].tolist())).reshape(-1, 4) if world > 1 else local[:, :4]
     alive = np.array(sum_over_ranks(local[:, 4].tolist())) if world > 1 else local[:, 4]
@@ -547,7 +552,8 @@ def main():
                 "phases_ms_per_step_per_rank[whole,push,exchange,solve]": per_rank,
                 "load": {"how": "ptp_plasma_load_density (device-side Plasma::loadDensityFile placement + deviate stream)", "seconds_rank0": t_load},
                 "tuning": {"threads": args.threads or 512, "window": args.window or 44, "ctas": args.ctas, "rings_per_thread": args.rings or 4,
-                           "sort_interval": args.sort_interval, "sorts_in_run_rank0": sorts_timed, "graph": args.graph}}
+                           "sort_interval": args.sort_interval, "sorts_in_run_rank0": sorts_timed, "graph": args.graph,
+                           "hot": args.hot, "hot_form_in_use_rank0": hot_after}}
         print(json.dumps(line))
     trap.close()
     if world > 1:

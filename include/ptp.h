@@ -122,6 +122,16 @@ int ptp_trap_sort(ptp_trap* t);
 int ptp_trap_set_sort_interval(ptp_trap* t, int interval);
 /* Number of per-species re-sorts either policy has triggered since the trap was created. */
 int64_t ptp_trap_sorts_done(ptp_trap* t);
+/* Hot species. Plasma::moveRings (Source/Plasma.cpp:100-120) is indifferent to the order of its rings; the default push kernel
+ * is not - it needs the rings of a segment within a 44-cell window, which re-sorts maintain. Rings that cross the whole plasma
+ * within a few dozen steps (electrons on a fine grid: more than a cell per step) cannot be kept ordered; for them the push
+ * kernel has a second form (per-warp bins over one window of up to ~1400 cells, no re-sorts). mode 1: always that form,
+ * 0: never, -1 (default; PTP_SCATTER overrides the default for new species): the adaptive re-sort policy switches a species
+ * over when two of its re-sorts fall less than PTP_HOT_SORT_STEPS (default 64) steps apart. Same results: identical bits in
+ * fixed-point deposit mode, rounding level in fp64 mode; positions and speeds do not depend on the form at all. */
+int ptp_plasma_set_hot(ptp_plasma* p, int mode);
+/* 1 while the per-warp-bin form of the push kernel is in use for this species (valid after the first step or deposit). */
+int ptp_plasma_is_hot(ptp_plasma* p);
 
 int ptp_trap_set_deposit_mode(ptp_trap* t, int mode);
 int ptp_trap_set_arith_mode(ptp_trap* t, int mode);

@@ -65,6 +65,8 @@ SIGNATURES = {
     "ptp_trap_sort": (_i, [_vp]),
     "ptp_trap_set_sort_interval": (_i, [_vp, _i]),
     "ptp_trap_sorts_done": (_i64, [_vp]),
+    "ptp_plasma_set_hot": (_i, [_vp, _i]),
+    "ptp_plasma_is_hot": (_i, [_vp]),
     "ptp_trap_set_deposit_mode": (_i, [_vp, _i]),
     "ptp_trap_set_arith_mode": (_i, [_vp, _i]),
     "ptp_trap_set_solver": (_i, [_vp, _i, _d, _i]),
@@ -350,6 +352,13 @@ class Plasma:
         _check(lib().ptp_plasma_create(trap.h, C.byref(h), self.mass, self.charge))
         self.h = h
         trap.plasmas.append(self)
+
+    def set_hot(self, mode):
+        """1: push this species with the per-warp-bin form of K1 (no re-sorts); 0: never; -1: let the re-sort policy decide."""
+        _check(lib().ptp_plasma_set_hot(self.h, int(mode)))
+
+    def is_hot(self):
+        return bool(lib().ptp_plasma_is_hot(self.h))
 
     def upload(self, r, z, v, chargeMacro):
         """Replace the rings (what both loaders end with); macro quantities as Source/Plasma.cpp:492-494."""

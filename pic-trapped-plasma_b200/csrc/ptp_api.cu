@@ -108,8 +108,8 @@ int solve_species(ptp_trap* t, int first, int count, bool withField = false, int
 int plan_push(ptp_trap* t, bool* multiOut)
 {
 	const int nS = (int)t->plasmas.size();
-	bool multi = t->multiPush && nS >= 2 && nS <= 4 && t->threads == 512 && t->ringsPerThread == 4 && !t->mergeBins;
-	for (ptp_plasma* p : t->plasmas) multi = multi && p->cap > 0;
+	bool multi = t->multiPush && nS >= 2 && nS <= 4 && t->threads == 512 && t->ringsPerThread == 4;
+	for (ptp_plasma* p : t->plasmas) multi = multi && p->cap > 0 && p->hot != 1;   // (a hot species has a launch of its own: other kernel variant)
 	double total = 0;
 	for (ptp_plasma* p : t->plasmas) total += (double)std::max<int64_t>(p->nAlive, 1);
 	for (ptp_plasma* p : t->plasmas) {
@@ -254,7 +254,8 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 		t->smemMax = prop.sharedMemPerBlockOptin;
 		if (const char* e = std::getenv("PTP_FFT_R16")) t->fftR16 = std::atoi(e);
 		if (const char* e = std::getenv("PTP_FFT_FORM_ROWS")) t->fftFormRows = std::atoi(e);
-		if (const char* e = std::getenv("PTP_MERGE_BINS")) t->mergeBins = std::atoi(e);
+		if (const char* e = std::getenv("PTP_SCATTER")) t->scatterPolicy = std::atoi(e);
+		if (const char* e = std::getenv("PTP_HOT_SORT_STEPS")) t->hotSortSteps = std::max(1, std::atoi(e));
 		if (const char* e = std::getenv("PTP_PLAN_SLACK")) t->planSlack = std::atoi(e);
 		if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));
 		if (const char* e = std::getenv("PTP_SORT_FAR_FRACTION")) t->sortFarFraction = std::max(0.0, std::atof(e));
@@ -492,9 +493,20 @@ int maintain_order(ptp_trap* t)
 			if (!sort) p->farBaseline = rate;
 		}
 		else sort = rate > p->farBaseline + std::max(t->sortFarFraction, 0.5 * p->farBaseline);
-		if (sort) {
+		if (p->scatter) sort = false;                           // (the wide window has no order to restore; misses there are rings beyond it)
+		if (sort && p->hot < 0 && p->lastSortStep >= 0 && t->stepCount - p->lastSortStep < t->hotSortSteps && ptp_push_scatter_usable(t)) {
+			// the order of the last re-sort did not survive hotSortSteps steps: the rings of this species cross the plasma faster
+			// than sorting can follow (each sort costs about ten steps). From here on the SCATTER variant of K1 pushes it.
+			p->hot = 1;
+			p->hotAuto = true;
+			PTP_TRY(ptp_build_segments(t, p));
+			PTP_CUDA(cudaMemsetAsync(p->dLost + 1, 0, sizeof(unsigned long long), t->stream));
+			sort = false;
+		}
+		else if (sort) {
 			PTP_TRY(ptp_sort_plasma(t, p));                     // clears the counters and the baseline
 			++t->sortsDone;
+			p->lastSortStep = t->stepCount;
 			t->nextCheckSteps = 4;
 		}
 		else if (far) PTP_CUDA(cudaMemsetAsync(p->dLost + 1, 0, sizeof(unsigned long long), t->stream));
@@ -701,6 +713,25 @@ int ptp_trap_set_sort_interval(ptp_trap* t, int interval)
 
 int64_t ptp_trap_sorts_done(ptp_trap* t) { return t ? t->sortsDone : 0; }
 
+int ptp_plasma_set_hot(ptp_plasma* p, int mode)
+{
+	if (!p || mode < -1 || mode > 1) { ptp_set_error("ptp_plasma_set_hot: bad arguments"); return PTP_EINVAL; }
+	if (mode == 1 && !ptp_push_scatter_usable(p->trap)) {
+		ptp_set_error("ptp_plasma_set_hot: the per-warp-bin push kernel needs the default tuning (512 threads x 4 rings per thread)");
+		return PTP_EINVAL;
+	}
+	if (mode != p->hot) {
+		p->hot = mode;
+		p->hotAuto = false;
+		p->lastSortStep = -1;
+		p->boundsValid = false;                                  // segment tables are planned per kernel form
+		++p->trap->cfgEpoch;
+	}
+	return PTP_OK;
+}
+
+int ptp_plasma_is_hot(ptp_plasma* p) { return p && p->scatter ? 1 : 0; }
+
 int ptp_trap_set_deposit_mode(ptp_trap* t, int mode)
 {
 	if (t) ++t->cfgEpoch;
@@ -760,6 +791,7 @@ int ptp_plasma_create(ptp_trap* t, ptp_plasma** out, double mass, double charge)
 	p->charge = charge;
 	p->rowOff.assign(t->Nr + 1, 0);
 	p->rowLive.assign(t->Nr, 0);
+	p->hot = t->scatterPolicy < -1 || t->scatterPolicy > 1 ? -1 : t->scatterPolicy;
 	PTP_CUDA(cudaMalloc(&p->dLost, 2 * sizeof(unsigned long long)));
 	PTP_CUDA(cudaMemset(p->dLost, 0, 2 * sizeof(unsigned long long)));
 	const size_t gb = (size_t)t->G * sizeof(double);

@@ -62,6 +62,12 @@ struct ptp_plasma {
 	bool vSavedValid = false;
 	bool boundsValid = false;
 	double ctaShare = 1.0;       // share of the SMs this species' push gets when all species run in one launch (by live rings)
+	// Hot species: rings that cross the whole plasma within a few dozen steps (electrons on a fine grid) cannot be kept ordered
+	// by cell; they are pushed by the SCATTER variant of K1 (per-warp bins over one wide window, no re-sorts).
+	int hot = -1;                // ptp_plasma_set_hot: -1 decided by the re-sort policy, 0 never, 1 always
+	bool hotAuto = false;        // hot was set by the policy, not by the caller: a reload starts undecided again
+	bool scatter = false;        // the variant in use (segment tables are planned for it)
+	long long lastSortStep = -1; // trap step count at the last miss-triggered re-sort (-1: none since the load)
 	bool encValid = false;       // the touched-node range per row kept next to this species' deposit grid (written by the push kernel's
 	                             // flush) describes the grid's present content
 };
@@ -143,7 +149,8 @@ struct ptp_trap {
 	// kernel variants, read from the environment once, when the trap is created
 	int fftR16 = 1;                  // PTP_FFT_R16: rows of 4096 nodes go through the radix-16 inverse (0: radix-2 pass pairs)
 	int fftFormRows = 1;             // PTP_FFT_FORM_ROWS: the radix-16 inverse forms the rows above the plasma itself (0: k_thomas_expand)
-	int mergeBins = 0;               // PTP_MERGE_BINS: push kernel variant that merges a thread's same-cell rings (never timed: off)
+	int scatterPolicy = -1;          // PTP_SCATTER: default of ptp_plasma::hot for new species (-1 automatic, 0 never, 1 always)
+	int hotSortSteps = 64;           // automatic policy: a species that needs two re-sorts less than this many steps apart is hot (PTP_HOT_SORT_STEPS)
 	int planSlack = -1;              // rows whose rings span more cells than the deposit window are cut into segments that leave this many
 	                                 // cells of the window free (room for the rings' drift until the next re-sort); -1: window / 2 (PTP_PLAN_SLACK)
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)
@@ -256,6 +263,9 @@ int ptp_push_launch_multi(ptp_trap* t, ptp_plasma* const* ps, int n, double dt);
 int ptp_bounds_launch(ptp_trap* t, ptp_plasma* p);
 int ptp_tile_bounds(ptp_trap* t, ptp_plasma* p, const std::vector<PtpSegment>& tiles, std::vector<int2>& tileBounds, int64_t* nLive);
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window);
+int ptp_push_scatter_window(const ptp_trap* t);                  // cells of the SCATTER variant's window (0: does not fit)
+size_t ptp_push_scatter_smem_bytes(const ptp_trap* t);
+bool ptp_push_scatter_usable(const ptp_trap* t);                 // default tuning (512 x 4) and a window of a useful size
 int ptp_push_field_window(const ptp_trap* t);
 int ptp_push_configure(ptp_trap* t);
 

@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(256) k_sort_pad(double* __restrict__ z, double
 int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 {
 	const long long tile = (long long)t->ringsPerThread * t->threads;
-	const long long maxSegTiles = 4095 / t->ringsPerThread;     // 12-bit per-thread count field of the packed bins
+	// which variant of K1 pushes this species (ptp_plasma::hot; the automatic policy sets it in maintain_order)
+	p->scatter = p->hot == 1 && ptp_push_scatter_usable(t);
+	// 12-bit count field of the packed bins: per thread, or - SCATTER variant - per warp
+	const long long maxSegTiles = p->scatter ? 4095 / (32 * t->ringsPerThread) : 4095 / t->ringsPerThread;
 	std::vector<PtpSegment> tiles;
 	for (int r = 0; r < t->Nr; ++r)
 		for (long long b = 0; b < p->rowLive[r]; b += tile) {
@@ -275,7 +278,7 @@ int ptp_build_segments(ptp_trap* t, ptp_plasma* p)
 		auto isWide = [&](long long q) { return tb[q].x <= tb[q].y && tb[q].y - tb[q].x + 1 > limit; };
 		long long wide = 0;
 		for (long long q = 0; q < totalTiles; ++q) wide += isWide(q) ? 1 : 0;
-		const bool mostlyWide = 2 * wide > totalTiles;
+		const bool mostlyWide = p->scatter || 2 * wide > totalTiles;   // (SCATTER variant: the window covers the whole plasma, rows are not split by cell range)
 		std::vector<std::pair<long long, long long>> runs;      // [first tile, end tile)
 		for (long long i = 0; i < totalTiles;) {
 			int lo = tb[i].x, hi = tb[i].y;
@@ -459,6 +462,8 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 	PTP_CUDA(cudaMemsetAsync(p->dLossLog, 0, 4 * sizeof(unsigned long long), t->stream));
 	p->cap = newCap;
 	p->farBaseline = -1.0;
+	p->lastSortStep = -1;
+	if (p->hotAuto) { p->hot = -1; p->hotAuto = false; }         // new rings: the policy decides again
 	t->stepsSinceCheck = 0;
 	t->nextCheckSteps = 4;
 	p->nUploaded = n;

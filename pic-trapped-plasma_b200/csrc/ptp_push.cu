@@ -53,7 +53,7 @@ struct PushArgs {
 	int4* segBounds;            // per segment: (min cell, max cell, mean cell, -) of its live rings, updated every step
 	void* rho[8];               // [G] double weights or int64 fixed point: this rank's grid, or every rank's (peer-memory mode)
 	int nRho, pad1;
-	int mergeBins, pad2;        // consecutive rings of a thread that fall into the same cell share one read-modify-write of the bin
+	int scatter, pad2;          // SCATTER variant of the kernel: per-warp bins over a wide window (hot species; see push_deposit_body)
 	long long bndOffset;        // (uint2*)((double*)rho[r] + bndOffset) = this species' touched-node range per row (encoded maxima)
 	// The deposit grids are double-buffered by step parity. While this step's sums go into one parity, the kernel zeroes this
 	// species' part of the OTHER one (last step's sums, consumed by last step's solve), ready for the next step's deposits:
@@ -69,6 +69,7 @@ struct PushArgs {
 	unsigned long long* lossLog;
 	const long long* id;        // [cap] ring ids (read for lost rings only)
 	long long lossCap;
+	double invFixedScale;       // 2^-fixedBits (SCATTER variant, fp64 deposit mode)
 };
 
 // Axial cell of a position: bit-exact (int)floor(z / hz) (Source/Plasma.cpp:87, Source/PenningTrap.cpp:328).
@@ -171,9 +172,45 @@ __device__ __forceinline__ void grid_max(unsigned int* p, unsigned int val, bool
 	else atomicMax(p, val);
 }
 
+// SCATTER variant of the deposit: the rings of the 32 lanes (cell io, packed word = count 1 | weight) go into the warp's own
+// bins wb[] by plain read-modify-write. Lanes that share a cell must not write in the same instruction; match.any finds the
+// groups of lanes with the same cell, and then
+//  * turns: the lanes of every group write one after the other, by their rank in the group - as many rounds as the largest
+//    group has lanes: 2-3 for 32 rings spread over a few hundred cells (rings in arbitrary order, the case this variant
+//    exists for), up to 32 when the rings are still ordered by cell (after a load or a sort);
+//  * sums: every group adds its weights as integers with warp reductions (three 18-bit digits: 32 x 2^18 fits a u32, three
+//    digits cover the 52-bit sum field) and its first lane writes once. The reductions of different groups run one after the
+//    other (WARPSYNC.EXCLUSIVE), so the cost grows with the number of groups.
+// The cheaper of the two is taken stage by stage: sums when there are no more groups than the largest group has lanes.
+// Either way the bins receive exact integer sums - the result does not depend on the path.
+__device__ __forceinline__ void scatter_add(unsigned long long* wb, bool in, unsigned int io, unsigned long long word, int lane)
+{
+	const unsigned int full = 0xffffffffu;
+	const unsigned int peers = __match_any_sync(full, in ? (int)io : -1);
+	const unsigned int rank = (unsigned int)__popc(peers & ((1u << lane) - 1u));
+	const unsigned int largest = __reduce_max_sync(full, in ? (unsigned int)__popc(peers) : 0u);
+	if (largest == 0u) return;                                           // (warp-uniform) no lane has a deposit in the window
+	const unsigned int groups = (unsigned int)__popc(__ballot_sync(full, in && rank == 0u));
+	if (largest > 1u && groups <= largest) {
+		const unsigned long long q = in ? (word & kSumMask) : 0ULL;
+		const unsigned int d0 = __reduce_add_sync(peers, (unsigned int)(q & 0x3ffffULL));
+		const unsigned int d1 = __reduce_add_sync(peers, (unsigned int)((q >> 18) & 0x3ffffULL));
+		const unsigned int d2 = __reduce_add_sync(peers, (unsigned int)(q >> 36));
+		if (in && rank == 0u)
+			wb[io] += ((unsigned long long)__popc(peers) << 52) + ((unsigned long long)d2 << 36) + ((unsigned long long)d1 << 18) + d0;
+		__syncwarp();                                                    // the next writer of a bin may be another lane
+	}
+	else {
+		for (unsigned int r = 0; r < largest; ++r) {
+			if (in && rank == r) wb[io] += word;
+			__syncwarp();
+		}
+	}
+}
+
 // The kernel body for CTA `bid` of `nb` CTAs working on one species (k_push_deposit: the launch's own grid;
 // k_push_deposit_multi: a sub-range of a launch that covers several species).
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool SCATTER>
 __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int bid, const int nb)
 {
 	constexpr int NV = R / 2;
@@ -184,12 +221,21 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 	unsigned long long* redS = redC + W;                                     // [W] u64 (fixed) or double bits
 	unsigned long long* bins = redS + W;                                     // [W][T] packed words / double sums
 	unsigned short* cnts = reinterpret_cast<unsigned short*>(bins + (size_t)W * T); // [W][T] fp64 mode only (a thread sees < 4096 rings per segment)
+	// SCATTER variant - for species whose rings mix over the whole plasma length within a few steps (electrons on a fine
+	// grid: 1.6 cells per step, a bounce every ~35 steps), so that no cell sort survives and thread-private windows of 44
+	// cells cannot hold them. Bins are private to a WARP instead ([T/32][W] packed words: 8 B per cell and warp, so the window
+	// is ~30 x wider and serves as field window too: W == WE), and the 32 rings a warp handles in one instruction are put into
+	// the warp's bins by plain read-modify-write in conflict-free rounds (scatter_add) - no atomics (shared 64-bit atomics are
+	// CAS loops, 32-bit ones cost ~2 cycles per lane), no sorts, whatever the order of the rings. The sums are kept in fixed
+	// point in BOTH deposit modes (exact integers: the fixed-point mode gets bitwise the sums of the thread-private kernel;
+	// the fp64 mode converts when the segment is flushed).
 	__shared__ int sKmin, sKmax;
 	__shared__ unsigned int sLost, sFar;
 	__shared__ long long sKsum[T / 32];
 	__shared__ unsigned int sNdep[T / 32];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	unsigned long long* wbins = bins + (size_t)warp * W;                     // SCATTER: this warp's [W] packed words (count:12 | sum:52)
 	const int n1 = a.Nz + 1;
 	const bool sys = a.nRho > 1;                 // remote grids are among the targets: system-scope atomics
 	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
@@ -213,7 +259,19 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 		k0 = max(0, min(k0, a.Nz - W));
 		// the field window is wider than the deposit window (16 B per cell instead of 10 B per cell and thread): rings that
 		// have drifted out of the deposit window still gather from shared memory - a global load there would stall the warp
-		const int kE0 = max(0, min(k0 + (W >> 1) - (WE >> 1), a.Nz - WE));
+		int kE0 = max(0, min(k0 + (W >> 1) - (WE >> 1), a.Nz - WE));
+		// SCATTER: one window for field and deposit, and only the part of it that this step can reach is loaded, cleared and
+		// reduced - the cell range of the segment's rings and a margin on either side for the step's drift; a ring that flies
+		// further in one step takes the global path
+		int Wuse = W;
+		if constexpr (SCATTER) {
+			constexpr int kScatterMargin = 48;
+			k0 = max(0, bounds.x - kScatterMargin);
+			Wuse = min(a.Nz, bounds.y + kScatterMargin + 1) - k0;
+			if (Wuse > W) { Wuse = W; k0 = max(0, min(bounds.z - (W >> 1), a.Nz - W)); }
+			kE0 = k0;
+		}
+		const unsigned int weUse = SCATTER ? (unsigned int)Wuse : (unsigned int)WE;
 		// The segment's first global loads go out before anything else - the first tile of rings and this thread's entry of
 		// the field window (WE <= 256 <= T) - so that their latency overlaps the clearing of the bins.
 		const double2* z2 = reinterpret_cast<const double2*>(a.z);
@@ -232,16 +290,26 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 			}
 		}
 		double eL0 = 0.0, eR0 = 0.0;
-		if (PUSH && tid < WE) {
+		if (!SCATTER && PUSH && tid < WE) {
 			const int node = kE0 + tid;
 			if (node <= a.Nz) eL0 = a.eNodes[rowBase + node];
 			if (node + 1 <= a.Nz) eR0 = a.eNodes[rowBase + node + 1];
 		}
-		for (int i = 0; i < W; ++i) {
-			bins[(size_t)i * T + tid] = 0ULL;
-			if (!FIXED) cnts[(size_t)i * T + tid] = 0;
+		if constexpr (!SCATTER) {
+			for (int i = 0; i < W; ++i) {
+				bins[(size_t)i * T + tid] = 0ULL;
+				if (!FIXED) cnts[(size_t)i * T + tid] = 0;
+			}
+			if (PUSH && tid < WE) eTile[tid] = make_double2(eL0, eR0);
 		}
-		if (PUSH && tid < WE) eTile[tid] = make_double2(eL0, eR0);
+		else {
+			for (int c = lane; c < Wuse; c += 32) wbins[c] = 0ULL;
+			if (PUSH)
+				for (int i = tid; i < Wuse; i += T) {                    // (k0 + i <= Nz - 1: both nodes of the cell exist)
+					const long long node = rowBase + k0 + i;
+					eTile[i] = make_double2(a.eNodes[node], a.eNodes[node + 1]);
+				}
+		}
 		if (tid == 0) { sKmin = INT_MAX; sKmax = INT_MIN; sLost = 0u; sFar = 0u; }
 		__syncthreads();
 
@@ -293,7 +361,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 #pragma unroll
 				for (int i = 0; i < R; ++i) {
 					const unsigned int io = (unsigned int)(k[i] - kE0);
-					const bool in = io < (unsigned int)WE;
+					const bool in = io < weUse;
 					far |= live[i] && !in;
 					const double2 e = eTile[in ? io : 0u];
 					eL[i] = e.x; eR[i] = e.y;
@@ -301,7 +369,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 				if (far) {
 #pragma unroll
 					for (int i = 0; i < R; ++i)
-						if (live[i] && (unsigned int)(k[i] - kE0) >= (unsigned int)WE) {
+						if (live[i] && (unsigned int)(k[i] - kE0) >= weUse) {
 							eL[i] = a.eNodes[rowBase + k[i]];
 							eR[i] = a.eNodes[rowBase + k[i] + 1];
 						}
@@ -342,7 +410,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 			// ---- deposit at the (new) position: Plasma::updateRHS body (Source/Plasma.cpp:86-92) -----------
 			cells_of<R, EXACT>(z, live, a, k, w);
 			bool farD = false;
-			if constexpr (!MERGE) {
+			if constexpr (!SCATTER) {
 #pragma unroll
 				for (int i = 0; i < R; ++i) {
 					const unsigned int io = (unsigned int)(k[i] - k0);
@@ -365,45 +433,24 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 				}
 			}
 			else {
-				// MERGE (PTP_MERGE_BINS=1, 512 x 4 push kernels; off by default until measured): a thread's rings are neighbours in a
-				// z-ordered row and mostly share a cell; their weights are summed in registers and the bin sees one read-modify-write
-				// per run instead of one per ring (a dependent shared-memory round trip each). Same sums in fixed point; in fp64 the
-				// association changes at rounding level.
-				unsigned int pendIo = 0xffffffffu, pendC = 0;
-				double pendW = 0.0;
-				unsigned long long pendWord = 0ULL;
-				auto flushPending = [&]() {
-					if (pendIo == 0xffffffffu) return;
-					if (FIXED) bins[(size_t)pendIo * T + tid] += pendWord;
-					else {
-						double* b = reinterpret_cast<double*>(bins) + (size_t)pendIo * T + tid;
-						*b = __dadd_rn(*b, pendW);
-						cnts[(size_t)pendIo * T + tid] += (unsigned short)pendC;
-					}
-				};
+				// SCATTER: the warp's 32 rings of this stage into the warp's bins
 #pragma unroll
 				for (int i = 0; i < R; ++i) {
 					const unsigned int io = (unsigned int)(k[i] - k0);
-					const bool in = live[i] && io < (unsigned int)W;
-					farD |= live[i] && io >= (unsigned int)W;
-					nFar += (live[i] && io >= (unsigned int)W) ? 1u : 0u;
+					const bool in = live[i] && io < (unsigned int)Wuse;
+					farD |= live[i] && io >= (unsigned int)Wuse;
+					nFar += (live[i] && io >= (unsigned int)Wuse) ? 1u : 0u;
 					if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
-					if (in) {
-						if (io != pendIo) { flushPending(); pendIo = io; pendC = 0; pendW = 0.0; pendWord = 0ULL; }
-						if (FIXED) {
-							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
-							pendWord += (unsigned long long)__double_as_longlong(t) - kPackBias;
-						}
-						else { pendW = pendC ? __dadd_rn(pendW, w[i]) : w[i]; ++pendC; }
-					}
+					// the packed word of the thread-private path: (1 << 52) | round(w * 2^F)
+					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
+					scatter_add(wbins, in, io, (unsigned long long)__double_as_longlong(t) - kPackBias, lane);
 				}
-				flushPending();
 			}
 			if (farD) {
 				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
 #pragma unroll
 				for (int i = 0; i < R; ++i)
-					if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)W) {
+					if (live[i] && (unsigned int)(k[i] - k0) >= (unsigned int)Wuse) {
 						// (the row's touched node range is widened to the segment's whole cell range in the epilogue)
 						if (FIXED) {
 							const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
@@ -465,7 +512,21 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 		__syncthreads();
 		const int gMin = sKmin, gMax = sKmax;
 		if (gMin <= gMax) {
-			const int lo = max(gMin, k0) - k0, hi = min(gMax, k0 + W - 1) - k0;
+			const int lo = max(gMin, k0) - k0, hi = min(gMax, k0 + Wuse - 1) - k0;
+			if constexpr (SCATTER) {
+				for (int b = lo + tid; b <= hi; b += T) {               // one thread per cell: the T/32 warps' words
+					unsigned long long c = 0, sm = 0;
+					for (int wq = 0; wq < T / 32; ++wq) {
+						const unsigned long long word = bins[(size_t)wq * W + b];
+						c += word >> 52;
+						sm += word & kSumMask;
+					}
+					redC[b] = c;
+					// fp64 mode: the exact integer sum (< 2^16 rings x 2^F per warp, 2^20 x 2^F per CTA and segment) back to units of one ring
+					redS[b] = FIXED ? sm : (unsigned long long)__double_as_longlong(__dmul_rn((double)sm, a.invFixedScale));
+				}
+			}
+			else
 			for (int b = lo + warp; b <= hi; b += T / 32) {
 				if (FIXED) {
 					unsigned long long c = 0, sm = 0;
@@ -542,10 +603,10 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 	}
 }
 
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool MERGE = false>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool SCATTER = false>
 __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
-	push_deposit_body<T, R, PUSH, FIXED, EXACT, MERGE>(a, (int)blockIdx.x, (int)gridDim.x);
+	push_deposit_body<T, R, PUSH, FIXED, EXACT, SCATTER>(a, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // [emu-end]
@@ -613,11 +674,11 @@ __global__ void __launch_bounds__(256) k_tile_bounds(const PushArgs a, const Ptp
 template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
-		if (a.mergeBins && PUSH && T == 512 && R == 4) {            // the variant exists for the default tuning only
-			auto kernM = k_push_deposit<512, 4, true, FIXED, EXACT, true>;
-			cudaError_t eM = cudaFuncSetAttribute(kernM, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (eM != cudaSuccess) return eM;
-			return ptp_launch(kernM, dim3(grid), dim3(512), smem, st, pdl, a);
+		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
+			auto kernS = k_push_deposit<512, 4, PUSH, FIXED, EXACT, true>;
+			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (eS != cudaSuccess) return eS;
+			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);
 		}
 		auto kern = k_push_deposit<T, R, PUSH, FIXED, EXACT>;
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -644,6 +705,11 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.W = t->window < t->Nz ? t->window : t->Nz;
 	a.WE = ptp_push_field_window(t);
 	a.fixedBits = t->fixedBits;
+	a.scatter = p->scatter ? 1 : 0;
+	if (p->scatter) {
+		a.W = a.WE = ptp_push_scatter_window(t);
+		if (t->depositMode != PTP_DEPOSIT_FIXED64) a.fixedBits = 40;     // the warps' bins hold fixed-point sums in fp64 mode too
+	}
 	a.hz = t->hz;
 	a.invHz = 1.0 / t->hz;
 	a.eps = (t->Nz + 2) * 1e-15;
@@ -653,7 +719,8 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.charge = p->charge;
 	a.mass = p->mass;
 	a.invMass = 1.0 / p->mass;
-	a.fixedScale = (double)(1ULL << t->fixedBits);
+	a.fixedScale = (double)(1ULL << a.fixedBits);
+	a.invFixedScale = 1.0 / a.fixedScale;
 	a.eNodes = t->eNodes;
 	a.z = p->z;
 	a.v = p->v;
@@ -667,7 +734,6 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 		// adds one system fence per CTA after the flush anyway (measured cost: ~12 us per step at 4 GPUs).
 		static const int fence = std::getenv("PTP_PEER_FENCE") ? 1 : 0;
 		a.pad1 = fence;
-		a.mergeBins = t->mergeBins;
 	}
 	a.rho[0] = t->rhoAll + (size_t)p->index * t->G;
 	a.bndOffset = (long long)((size_t)t->capS * t->G - (size_t)p->index * t->G + (size_t)p->index * t->Nr);
@@ -692,6 +758,24 @@ int ptp_push_field_window(const ptp_trap* t)
 	if (we < w) we = w;
 	return (int)we;
 }
+
+// SCATTER variant (hot species): cells of the one window that serves as field window and deposit window - 16 B of field,
+// 16 B of reduction rows and one 8-byte word per warp and cell (512 threads).
+int ptp_push_scatter_window(const ptp_trap* t)
+{
+	const size_t perCell = 16 + 16 + 8 * (512 / 32);
+	size_t w = t->smemMax > 2048 ? (t->smemMax - 2048) / perCell : 0;
+	if (w > (size_t)t->Nz) w = (size_t)t->Nz;
+	return (int)w;
+}
+
+bool ptp_push_scatter_usable(const ptp_trap* t)
+{
+	const int w = ptp_push_scatter_window(t);
+	return t->threads == 512 && t->ringsPerThread == 4 && (w >= 128 || w == t->Nz);
+}
+
+size_t ptp_push_scatter_smem_bytes(const ptp_trap* t) { return (size_t)ptp_push_scatter_window(t) * (16 + 16 + 8 * (512 / 32)); }
 
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window)
 {
@@ -725,7 +809,7 @@ int ptp_push_launch(ptp_trap* t, ptp_plasma* p, double dt, bool push)
 		a.clearBounds = other + (size_t)t->capS * t->G + (size_t)p->index * t->Nr;
 		a.clearBoundsWords = t->Nr;
 	}
-	const size_t smem = ptp_push_smem_bytes(t, t->threads, t->window);
+	const size_t smem = p->scatter ? ptp_push_scatter_smem_bytes(t) : ptp_push_smem_bytes(t, t->threads, t->window);
 	const bool fixed = t->depositMode == PTP_DEPOSIT_FIXED64, exact = t->arithMode == PTP_ARITH_EXACT;
 	const bool pdl = t->usePdl;
 	cudaError_t e;

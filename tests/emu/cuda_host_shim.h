@@ -78,6 +78,35 @@ static inline unsigned int __match_any_sync(unsigned, int key)
 	g_warp->bar.arrive_and_wait();
 	return m;
 }
+static inline unsigned int __ballot_sync(unsigned, bool pred)
+{
+	g_warp->buf[g_lane] = pred ? 1ULL : 0ULL;
+	g_warp->bar.arrive_and_wait();
+	unsigned int m = 0;
+	for (int l = 0; l < 32; ++l) m |= (unsigned int)g_warp->buf[l] << l;
+	g_warp->bar.arrive_and_wait();
+	return m;
+}
+// redux.sync over the lanes named in `mask`. On the device the lanes of a warp may name different (disjoint) masks in one
+// instruction - the groups then execute one after the other (WARPSYNC.EXCLUSIVE); here all 32 lanes arrive together and each
+// takes the sum / maximum over its own mask, checking that its partners named the same one.
+static inline unsigned int emu_redux(unsigned int mask, unsigned int x, bool isMax)
+{
+	if (!((mask >> g_lane) & 1u)) { std::fprintf(stderr, "redux: calling lane not in its mask\n"); std::abort(); }
+	g_warp->buf[g_lane] = ((unsigned long long)mask << 32) | x;
+	g_warp->bar.arrive_and_wait();
+	unsigned int r = 0;
+	for (int l = 0; l < 32; ++l)
+		if ((mask >> l) & 1u) {
+			if ((unsigned int)(g_warp->buf[l] >> 32) != mask) { std::fprintf(stderr, "redux: lanes of one group name different masks\n"); std::abort(); }
+			const unsigned int v = (unsigned int)g_warp->buf[l];
+			r = isMax ? (v > r ? v : r) : r + v;
+		}
+	g_warp->bar.arrive_and_wait();
+	return r;
+}
+static inline unsigned int __reduce_add_sync(unsigned int mask, unsigned int x) { return emu_redux(mask, x, false); }
+static inline unsigned int __reduce_max_sync(unsigned int mask, unsigned int x) { return emu_redux(mask, x, true); }
 static inline unsigned int __brev(unsigned int x)
 {
 	unsigned int r = 0;

@@ -17,14 +17,14 @@ static unsigned char* g_smem;
 #include "push_snippet.inc"
 
 struct CaseHeader {
-	int Nz, Nr, W, WE, fixed, exact, fixedBits, segTiles, nCta, mergeBins;
+	int Nz, Nr, W, WE, fixed, exact, fixedBits, segTiles, nCta, scatter;
 	long long n;
 	double hz, length, dt, charge, mass;
 };
 
 template <bool FIXED, bool EXACT> static void run(const PushArgs& a, int nCta)
 {
-	if (a.mergeBins) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, true>(a); });
+	if (a.scatter) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, true>(a); });
 	else emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT>(a); });
 }
 
@@ -78,7 +78,8 @@ int main(int argc, char** argv)
 	std::vector<double> rho(G + h.Nr, 0.0);                  // grid + per-row touched-node range (two u32 per row)
 	unsigned long long lost[2] = { 0, 0 };
 	const size_t perBin = h.fixed ? 8 : 10;
-	std::vector<unsigned char> smem((size_t)h.WE * 16 + (size_t)h.W * 16 + (size_t)h.W * 512 * perBin);   // = ptp_push_smem_bytes, to the byte (AddressSanitizer)
+	// = ptp_push_smem_bytes / ptp_push_scatter_smem_bytes, to the byte (AddressSanitizer)
+	std::vector<unsigned char> smem(h.scatter ? (size_t)h.W * (16 + 16 + 8 * (512 / 32)) : (size_t)h.WE * 16 + (size_t)h.W * 16 + (size_t)h.W * 512 * perBin);
 	g_smem = smem.data();
 
 	PushArgs a{};
@@ -86,9 +87,10 @@ int main(int argc, char** argv)
 	a.hz = h.hz; a.invHz = 1.0 / h.hz; a.eps = (h.Nz + 2) * 1e-15; a.epsHi = 1.0 - a.eps; a.length = h.length;
 	a.dt = h.dt; a.charge = h.charge; a.mass = h.mass; a.invMass = 1.0 / h.mass;
 	a.fixedScale = (double)(1ULL << h.fixedBits);
+	a.invFixedScale = 1.0 / a.fixedScale;
 	a.eNodes = eNodes.data(); a.z = bz.data(); a.v = bv.data();
 	a.segs = segs.data(); a.ctaSegBegin = ctaSegBegin.data(); a.segBounds = bounds.data();
-	a.rho[0] = rho.data(); a.nRho = 1; a.pad1 = 0; a.mergeBins = h.mergeBins; a.bndOffset = G; a.lost = lost;
+	a.rho[0] = rho.data(); a.nRho = 1; a.pad1 = 0; a.scatter = h.scatter; a.bndOffset = G; a.lost = lost;
 	if (h.fixed) { if (h.exact) run<true, true>(a, nCta); else run<true, false>(a, nCta); }
 	else { if (h.exact) run<false, true>(a, nCta); else run<false, false>(a, nCta); }
 

@@ -286,8 +286,10 @@ def test_electrode_programme_matches_per_step_solves(c1_kat):
     tb.close()
 
 
-def test_losses_match_oracle_ring_by_ring():
-    """Small odd grid, hot rings: loss flags and survivors bit-exact against the restated swap-pop loop."""
+@pytest.mark.parametrize("hot", [0, 1])
+def test_losses_match_oracle_ring_by_ring(hot):
+    """Small odd grid, hot rings: loss flags and survivors bit-exact against the restated swap-pop loop.
+    hot = 1: through the per-warp-bin form of the push kernel (ptp_plasma_set_hot) - rings in arbitrary order."""
     args = (0.02, [0.01, 0.02, 0.015], [5.0, -40.0, 3.0], [0.002, 0.001], 57, 9)
     pt = port.PortTrap(*args)
     t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], args[4], args[5])
@@ -301,9 +303,11 @@ def test_losses_match_oracle_ring_by_ring():
     op = pt.plasma("Electrons", ptp.massE, -ptp.ePos)
     op.set_rings(r, z, v, -1e-16)
     gp = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+    gp.set_hot(hot)
     gp.upload(r, z, v, -1e-16)
     op.solve_poisson()
     gp.solvePoisson()
+    assert gp.is_hot() == bool(hot)
     ids_alive = np.arange(n)
     for step in range(6):
         # lock-step: oracle potentials in
@@ -483,6 +487,77 @@ def test_adaptive_resort_keeps_results_and_triggers(monkeypatch, c1_kat):
     assert res[0][7] == res[1][7]
     for a, b in zip(res[0][:6], res[1][:6]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_hot_species_form_of_push_kernel(c1_kat, exact):
+    """ptp_plasma_set_hot: the per-warp-bin form of K1 (one wide window, no re-sorts) against the thread-private form.
+    Electrons on a fine grid (1.6 cells per step: after 40 steps the load order is gone), fixed-point deposits: positions,
+    speeds, deposit grid and potential identical bit for bit at every check point, with and without re-sorts of the
+    thread-private run; stand-alone deposit (K2) too. fp64 deposits: grid within the fp64 tier (1e-12), and the
+    trajectories stay together at rounding level."""
+    from bench import density_on
+    Nz, Nr = 4096, 64
+    el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
+    dens = density_on(Nz, Nr)
+    dt = float(c1_kat["dt"])
+
+    def run(hot, mode, check_steps):
+        t = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
+        t.set_deposit_mode(mode)
+        t.set_arith_mode(ptp.PTP_ARITH_EXACT if exact else ptp.PTP_ARITH_FAST)
+        p = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
+        p.set_hot(hot)
+        n, _ = p.loadDensity(dens, 150.0, 300_000)
+        assert p.is_hot() == bool(hot)
+        out = [(p.rhs(), p.selfPotential())]                    # the loader's first deposit (K2) and solve
+        for k in check_steps:
+            t.movePlasmas(dt, k)
+            out.append(_by_id(p) + (p.rhs(), p.selfPotential()))
+        out.append((t.sorts_done(), p.getNumMacro(), p.is_hot()))
+        t.close()
+        return out
+
+    a = run(0, ptp.PTP_DEPOSIT_FIXED64, (1, 7, 40))
+    b = run(1, ptp.PTP_DEPOSIT_FIXED64, (1, 7, 40))
+    assert a[-1][2] is False and b[-1] == (0, a[-1][1], True)          # no re-sort of the hot form, same survivors
+    for x, y in zip(a[:-1], b[:-1]):
+        for u, w in zip(x, y):
+            assert np.array_equal(u, w)
+    c = run(0, ptp.PTP_DEPOSIT_FP64, (1, 12))
+    d = run(1, ptp.PTP_DEPOSIT_FP64, (1, 12))
+    assert rel_l2(d[0][0], c[0][0]) < 1e-12 and rel_l2(d[0][1], c[0][1]) < 1e-11
+    assert rel_l2(d[1][1], c[1][1]) < 1e-14 and rel_l2(d[1][2], c[1][2]) < 1e-12    # (the fields of the first step differ at rounding level)
+    assert rel_l2(d[1][4], c[1][4]) < 1e-12
+    assert rel_l2(d[2][1], c[2][1]) < 1e-12 and rel_l2(d[2][4], c[2][4]) < 1e-9 and rel_l2(d[2][5], c[2][5]) < 1e-9
+
+
+def test_hot_species_are_found_by_the_resort_policy(monkeypatch, c1_kat):
+    """Adaptive policy: electrons on a fine grid need a re-sort every ~20 steps; after the second one within
+    PTP_HOT_SORT_STEPS the species is handed to the per-warp-bin form and the re-sorts stop. Antiprotons on the same grid
+    (0.04 cells per step) stay with the thread-private form. PTP_SCATTER=0 keeps the old behaviour (re-sorts go on)."""
+    from bench import density_on
+    monkeypatch.setenv("PTP_SORT_CHECK_STEPS", "8")
+    Nz, Nr = 4096, 64
+    el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
+    dens = density_on(Nz, Nr)
+    dt = float(c1_kat["dt"])
+    res = {}
+    for tag, mass, env in (("e", ptp.massE, None), ("p", ptp.massP, None), ("e0", ptp.massE, "0")):
+        if env is not None:
+            monkeypatch.setenv("PTP_SCATTER", env)
+        t = ptp.PenningTrap(0.01488, el, [0.0005] * 4, Nz, Nr)
+        p = ptp.Plasma(t, "Species", mass, -ptp.ePos)
+        n, _ = p.loadDensity(dens, 150.0, 400_000)
+        t.movePlasmas(dt, 70)
+        mid = (t.sorts_done(), p.is_hot())
+        t.movePlasmas(dt, 80)
+        res[tag] = mid + (t.sorts_done(), p.is_hot(), p.getNumMacro(), n)
+        t.close()
+    assert res["e"][1] and res["e"][3] and 1 <= res["e"][0] <= 3 and res["e"][2] == res["e"][0], res
+    assert not res["p"][3] and res["p"][2] <= 1, res
+    assert not res["e0"][3] and res["e0"][2] > res["e"][2], res
+    assert res["e"][4] == res["e"][5] and res["e0"][4] == res["e0"][5]
 
 
 def test_edge_cases():

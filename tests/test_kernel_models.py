@@ -25,7 +25,7 @@ def test_radix16_kernel_text_on_host_threads():
 
 
 # ------------------------------------------------------------------------------------------ K1 on host threads
-def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, fixed_bits=40, seg_tiles=2, n_cta=3, merge=0):
+def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, fixed_bits=40, seg_tiles=2, n_cta=3, scatter=0):
     import numpy as np
     exe = os.path.join(ROOT, "build", "emu", "emu_push")
     if not _BUILT.get("push"):
@@ -34,7 +34,7 @@ def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixe
         _BUILT["push"] = True
     case, out = str(tmp_path / "case.bin"), str(tmp_path / "out.bin")
     with open(case, "wb") as f:
-        f.write(np.array([trap.Nz, trap.Nr, W, WE, fixed, exact, fixed_bits, seg_tiles, n_cta, merge], np.int32).tobytes())
+        f.write(np.array([trap.Nz, trap.Nr, W, WE, fixed, exact, fixed_bits, seg_tiles, n_cta, scatter], np.int32).tobytes())
         f.write(np.array([len(r)], np.int64).tobytes())
         f.write(np.array([trap.hz, trap.length, dt, charge, mass], np.float64).tobytes())
         for a, t in ((enodes, np.float64), (r, np.int32), (z, np.float64), (v, np.float64)):
@@ -54,13 +54,17 @@ def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixe
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
-@pytest.mark.parametrize("W,WE,fixed,exact,merge", [(44, 256, 0, 1, 0), (44, 256, 0, 0, 0), (44, 256, 1, 1, 0), (6, 12, 0, 1, 0), (6, 6, 1, 0, 0),
-                                                    (44, 256, 0, 1, 1), (44, 256, 1, 0, 1), (6, 12, 0, 0, 1)])
-def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed, exact, merge):
+@pytest.mark.parametrize("W,WE,fixed,exact,scatter,shuffle", [(44, 256, 0, 1, 0, 0), (44, 256, 0, 0, 0, 0), (44, 256, 1, 1, 0, 0), (6, 12, 0, 1, 0, 0), (6, 6, 1, 0, 0, 0),
+                                                              (300, 300, 0, 1, 1, 0), (300, 300, 0, 0, 1, 1), (300, 300, 1, 0, 1, 1), (300, 300, 1, 1, 1, 0),
+                                                              (24, 24, 0, 0, 1, 1), (24, 24, 1, 0, 1, 0)])
+def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed, exact, scatter, shuffle):
     """The source text of k_push_deposit (pic-trapped-plasma_b200/csrc/ptp_push.cu) compiled for the host and run CTA by CTA
     on 512 threads, against the oracle on the C1 electrons plus fast rings near both trap ends (losses): positions / speeds
     ring by ring (EXACT arithmetic: bit for bit; FAST: 1e-14), loss count, deposit (fp64 1e-12; fixed point 2^-40 per ring),
-    the touched node range per row. W = 6 forces most rings through the out-of-window paths (global gather / atomics)."""
+    the touched node range per row. W = 6 forces most rings through the out-of-window paths (global gather / atomics).
+    scatter = 1: the per-warp-bin form of the kernel (hot species) - rings in load order (few distinct cells per warp: the
+    warp-reduction path) and shuffled within their rows (many distinct cells: the rounds path); W = 24 leaves part of the
+    plasma outside the window; in fixed-point mode the deposit grid equals the thread-private form's bit for bit."""
     import numpy as np
     sys.path.insert(0, ROOT)
     from oracle import port
@@ -75,11 +79,13 @@ def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed,
     z = np.concatenate([kat["e_z0"], np.where(rng.random(extra) < 0.5, edge, trap.length - edge)])
     v = np.concatenate([kat["e_v0"], rng.normal(0, 2e5, extra)])
     order = np.argsort(r, kind="stable")
+    if shuffle:
+        order = np.lexsort((rng.random(len(r)), r))
     r, z, v = r[order], z[order], v[order]
     pl.set_rings(r, z, v, float(kat["e_chargeMacro"]))
     pl.solve_poisson()
     enodes = trap.enodes()
-    zo, vo, grid, bnd, lost, seg_bounds = _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, merge=merge)
+    zo, vo, grid, bnd, lost, seg_bounds = _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixed, exact, scatter=scatter)
     # the reference's ring update, expression by expression (Source/PenningTrap.cpp:328-333, Source/Plasma.cpp:105-108)
     hz, n1 = trap.hz, trap.Nz + 1
     k = np.floor(z / hz).astype(np.int64)
@@ -119,6 +125,12 @@ def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed,
     # out-of-window counter: nothing misses a 44-cell window around a 37-cell plasma except the rings parked at the trap ends
     if W == 6:
         assert int(lost[1]) > 1000
+    if scatter:
+        # rings beyond the window: only (some of) those parked at the trap ends when the window covers the plasma with its margin
+        assert (int(lost[1]) > 300) == (W == 24), int(lost[1])
+        if fixed:
+            ref = _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, 44, 256, fixed, exact)
+            assert ref[2] == grid and np.array_equal(ref[0], zo, equal_nan=True) and np.array_equal(ref[1], vo)
     trap.close()
 
 
