@@ -240,6 +240,39 @@ def push_source_sha():
         return hashlib.sha256(f.read()).hexdigest()[:16]
 
 
+K1_PROFILED = "k_push_depositILi512ELi4ELb1ELb0ELb0ELb0EE"       # k_push_deposit<512, 4, PUSH, fp64, FAST, thread-private bins>
+
+
+def k1_sass_sha(path=None):
+    """Hash of the machine code of the profiled instantiation of K1 inside the shipped library (cuobjdump -sass; addresses,
+    encodings and the link-time addresses of the static shared variables masked): ties profiles/k1_traffic.json to the
+    kernel that runs even when other parts of ptp_push.cu have changed since the capture. None without cuobjdump."""
+    import hashlib
+    import re
+    import shutil
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    path = path or os.path.join(ROOT, "pic-trapped-plasma_b200", "libptp_b200.so")
+    try:
+        out = subprocess.run([exe, "-sass", path], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    cur, body = None, []
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        if cur and K1_PROFILED in cur:
+            if re.match(r"^\s*/\* 0x[0-9a-f]+ \*/\s*$", line):
+                continue
+            line = re.sub(r"/\*[0-9a-f]{4,}\*/", "", line)
+            line = re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line).strip()
+            line = re.sub(r"^(U?MOV U?R\d+), 0x[0-9a-f]+ ;", r"\1, IMM ;", line)
+            if line:
+                body.append(line)
+    return hashlib.sha256("\n".join(body).encode()).hexdigest()[:16] if body else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -456,11 +489,12 @@ def main():
         try:
             tr = json.load(open(prof))
             entry = tr.get(args.workload)
-            if entry and tr.get("push_cu_sha16") == push_source_sha():
+            same = tr.get("push_cu_sha16") == push_source_sha() or (rank == 0 and tr.get("k1_sass_sha16") and tr.get("k1_sass_sha16") == k1_sass_sha())
+            if entry and same:
                 roofline["traffic"] = entry["dram_bytes_per_ring"] * units
                 roofline["traffic_source"] = "%s: %s, %.2f B/ring x rings of this launch" % (tr.get("report"), entry.get("kernel"), entry["dram_bytes_per_ring"])
             elif entry:
-                roofline["traffic_source"] = "profiles/k1_traffic.json is from another version of ptp_push.cu: not reported"
+                roofline["traffic_source"] = "profiles/k1_traffic.json is from another version of the push kernel (source and machine code differ): not reported"
         except Exception:
             pass
 

@@ -127,7 +127,7 @@ int64_t ptp_trap_sorts_done(ptp_trap* t);
  * within a few dozen steps (electrons on a fine grid: more than a cell per step) cannot be kept ordered; for them the push
  * kernel has a second form (per-warp bins over one window of up to ~1400 cells, no re-sorts). mode 1: always that form,
  * 0: never, -1 (default; PTP_SCATTER overrides the default for new species): the adaptive re-sort policy switches a species
- * over when two of its re-sorts fall less than PTP_HOT_SORT_STEPS (default 64) steps apart. Same results: identical bits in
+ * over when a third re-sort in a row is due less than PTP_HOT_SORT_STEPS (default 64) steps after the one before. Same results: identical bits in
  * fixed-point deposit mode, rounding level in fp64 mode; positions and speeds do not depend on the form at all. */
 int ptp_plasma_set_hot(ptp_plasma* p, int mode);
 /* 1 while the per-warp-bin form of the push kernel is in use for this species (valid after the first step or deposit). */

@@ -494,9 +494,11 @@ int maintain_order(ptp_trap* t)
 		}
 		else sort = rate > p->farBaseline + std::max(t->sortFarFraction, 0.5 * p->farBaseline);
 		if (p->scatter) sort = false;                           // (the wide window has no order to restore; misses there are rings beyond it)
-		if (sort && p->hot < 0 && p->lastSortStep >= 0 && t->stepCount - p->lastSortStep < t->hotSortSteps && ptp_push_scatter_usable(t)) {
-			// the order of the last re-sort did not survive hotSortSteps steps: the rings of this species cross the plasma faster
-			// than sorting can follow (each sort costs about ten steps). From here on the SCATTER variant of K1 pushes it.
+		const bool quick = sort && p->lastSortStep >= 0 && t->stepCount - p->lastSortStep < t->hotSortSteps;
+		if (quick && p->quickSorts >= 1 && p->hot < 0 && ptp_push_scatter_usable(t)) {
+			// the third re-sort in a row that is due less than hotSortSteps steps after the one before: the rings of this species
+			// cross the plasma faster than sorting can follow (each sort costs about ten steps). From here on the per-warp-bin
+			// form of K1 pushes it (ptp_plasma_set_hot).
 			p->hot = 1;
 			p->hotAuto = true;
 			PTP_TRY(ptp_build_segments(t, p));
@@ -506,6 +508,7 @@ int maintain_order(ptp_trap* t)
 		else if (sort) {
 			PTP_TRY(ptp_sort_plasma(t, p));                     // clears the counters and the baseline
 			++t->sortsDone;
+			p->quickSorts = quick ? p->quickSorts + 1 : 0;
 			p->lastSortStep = t->stepCount;
 			t->nextCheckSteps = 4;
 		}
@@ -724,6 +727,7 @@ int ptp_plasma_set_hot(ptp_plasma* p, int mode)
 		p->hot = mode;
 		p->hotAuto = false;
 		p->lastSortStep = -1;
+		p->quickSorts = 0;
 		p->boundsValid = false;                                  // segment tables are planned per kernel form
 		++p->trap->cfgEpoch;
 	}

@@ -68,6 +68,7 @@ struct ptp_plasma {
 	bool hotAuto = false;        // hot was set by the policy, not by the caller: a reload starts undecided again
 	bool scatter = false;        // the variant in use (segment tables are planned for it)
 	long long lastSortStep = -1; // trap step count at the last miss-triggered re-sort (-1: none since the load)
+	int quickSorts = 0;          // re-sorts in a row that came less than hotSortSteps steps after the one before
 	bool encValid = false;       // the touched-node range per row kept next to this species' deposit grid (written by the push kernel's
 	                             // flush) describes the grid's present content
 };
@@ -150,7 +151,7 @@ struct ptp_trap {
 	int fftR16 = 1;                  // PTP_FFT_R16: rows of 4096 nodes go through the radix-16 inverse (0: radix-2 pass pairs)
 	int fftFormRows = 1;             // PTP_FFT_FORM_ROWS: the radix-16 inverse forms the rows above the plasma itself (0: k_thomas_expand)
 	int scatterPolicy = -1;          // PTP_SCATTER: default of ptp_plasma::hot for new species (-1 automatic, 0 never, 1 always)
-	int hotSortSteps = 64;           // automatic policy: a species that needs two re-sorts less than this many steps apart is hot (PTP_HOT_SORT_STEPS)
+	int hotSortSteps = 64;           // automatic policy: a species whose re-sorts keep coming less than this many steps apart is hot (PTP_HOT_SORT_STEPS)
 	int planSlack = -1;              // rows whose rings span more cells than the deposit window are cut into segments that leave this many
 	                                 // cells of the window free (room for the rings' drift until the next re-sort); -1: window / 2 (PTP_PLAN_SLACK)
 	long long sortsDone = 0;         // re-sorts triggered by either policy (ptp_trap_sorts_done)

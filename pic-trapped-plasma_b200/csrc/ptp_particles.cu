@@ -463,6 +463,7 @@ int ptp_plasma_set_layout(ptp_plasma* p, const std::vector<long long>& count, in
 	p->cap = newCap;
 	p->farBaseline = -1.0;
 	p->lastSortStep = -1;
+	p->quickSorts = 0;
 	if (p->hotAuto) { p->hot = -1; p->hotAuto = false; }         // new rings: the policy decides again
 	t->stepsSinceCheck = 0;
 	t->nextCheckSteps = 4;

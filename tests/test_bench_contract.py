@@ -33,11 +33,19 @@ def test_reference_arm_is_silent_on_other_ranks():
 
 
 def test_k1_traffic_profile_belongs_to_the_shipped_push_kernel():
-    """bench.py reports roofline.traffic only while profiles/k1_traffic.json was taken from the push kernel source that ships
-    (hash of ptp_push.cu); a change to the kernel without a new ncu capture must show up here, not as a silently stale number."""
+    """bench.py reports roofline.traffic only while profiles/k1_traffic.json was taken from the push kernel that ships: same
+    source file (hash of ptp_push.cu), or - when other parts of the file have changed since the capture - the same machine code of
+    the profiled instantiation inside libptp_b200.so (cuobjdump -sass). A change to the kernel without a new ncu capture must show
+    up here, not as a silently stale number."""
     import hashlib
+    sys.path.insert(0, ROOT)
+    import bench
     prof = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
     src = open(os.path.join(ROOT, "pic-trapped-plasma_b200", "csrc", "ptp_push.cu"), "rb").read()
-    assert prof["push_cu_sha16"] == hashlib.sha256(src).hexdigest()[:16]
+    if prof["push_cu_sha16"] != hashlib.sha256(src).hexdigest()[:16]:
+        so = os.path.join(ROOT, "pic-trapped-plasma_b200", "libptp_b200.so")
+        assert os.path.exists(so), "library not built: cannot compare the profiled kernel's machine code"
+        sha = bench.k1_sass_sha(so)
+        assert sha is not None and prof.get("k1_sass_sha16") == sha
     for wl in ("c4", "c5"):
         assert 28.0 < prof[wl]["dram_bytes_per_ring"] < 36.0        # 32 B algorithmic: no wasted re-reads
