@@ -240,7 +240,7 @@ def push_source_sha():
         return hashlib.sha256(f.read()).hexdigest()[:16]
 
 
-K1_PROFILED = "k_push_depositILi512ELi4ELb1ELb0ELb0ELb0EE"       # k_push_deposit<512, 4, PUSH, fp64, FAST, thread-private bins>
+K1_PROFILED = r"k_push_depositILi512ELi4ELb1ELb0ELb0EL[bi]0EE"   # k_push_deposit<512, 4, PUSH, fp64, FAST, thread-private bins>
 
 
 def k1_sass_sha(path=None):
@@ -262,7 +262,7 @@ def k1_sass_sha(path=None):
         if m:
             cur = m.group(1)
             continue
-        if cur and K1_PROFILED in cur:
+        if cur and re.search(K1_PROFILED, cur):
             if re.match(r"^\s*/\* 0x[0-9a-f]+ \*/\s*$", line):
                 continue
             line = re.sub(r"/\*[0-9a-f]{4,}\*/", "", line)

@@ -208,9 +208,38 @@ __device__ __forceinline__ void scatter_add(unsigned long long* wb, bool in, uns
 	}
 }
 
+// The same without match.any (SCATTER = 2): the lanes find out who may write by trying - every lane that still has a deposit
+// puts its lane number into a tag next to the bin it wants, the lane whose number survived writes the bin, the others try again.
+// As many rounds as the largest group of lanes with the same cell, each round one byte store, one byte load and a vote more than
+// a turn of scatter_add. Rings still ordered by cell (all 32 lanes in one cell: up to 32 rounds) are caught by a shuffle and a
+// vote and summed by full-warp reductions.
+__device__ __forceinline__ void scatter_add_tags(unsigned long long* wb, unsigned char* tag, bool in, unsigned int io, unsigned long long word, int lane)
+{
+	const unsigned int full = 0xffffffffu;
+	const int key = in ? (int)io : -1;
+	const int key0 = __shfl_sync(full, key, 0);
+	if (__all_sync(full, key == key0)) {
+		if (key0 < 0) return;
+		const unsigned long long q = word & kSumMask;
+		const unsigned int d0 = __reduce_add_sync(full, (unsigned int)(q & 0x3ffffULL));
+		const unsigned int d1 = __reduce_add_sync(full, (unsigned int)((q >> 18) & 0x3ffffULL));
+		const unsigned int d2 = __reduce_add_sync(full, (unsigned int)(q >> 36));
+		if (lane == 0) wb[io] += (32ULL << 52) + ((unsigned long long)d2 << 36) + ((unsigned long long)d1 << 18) + d0;
+		__syncwarp();
+		return;
+	}
+	bool pending = in;
+	do {
+		if (pending) tag[io] = (unsigned char)lane;
+		__syncwarp();
+		if (pending && tag[io] == (unsigned char)lane) { wb[io] += word; pending = false; }
+		__syncwarp();
+	} while (__any_sync(full, pending));
+}
+
 // The kernel body for CTA `bid` of `nb` CTAs working on one species (k_push_deposit: the launch's own grid;
 // k_push_deposit_multi: a sub-range of a launch that covers several species).
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool SCATTER>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, int SCATTER>
 __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int bid, const int nb)
 {
 	constexpr int NV = R / 2;
@@ -236,6 +265,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	unsigned long long* wbins = bins + (size_t)warp * W;                     // SCATTER: this warp's [W] packed words (count:12 | sum:52)
+	unsigned char* wtags = reinterpret_cast<unsigned char*>(bins + (size_t)(T / 32) * W) + (size_t)warp * W;   // SCATTER = 2: this warp's [W] tags
 	const int n1 = a.Nz + 1;
 	const bool sys = a.nRho > 1;                 // remote grids are among the targets: system-scope atomics
 	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
@@ -443,7 +473,8 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 					if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
 					// the packed word of the thread-private path: (1 << 52) | round(w * 2^F)
 					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
-					scatter_add(wbins, in, io, (unsigned long long)__double_as_longlong(t) - kPackBias, lane);
+					if constexpr (SCATTER == 2) scatter_add_tags(wbins, wtags, in, io, (unsigned long long)__double_as_longlong(t) - kPackBias, lane);
+					else scatter_add(wbins, in, io, (unsigned long long)__double_as_longlong(t) - kPackBias, lane);
 				}
 			}
 			if (farD) {
@@ -603,7 +634,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 	}
 }
 
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool SCATTER = false>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, int SCATTER = 0>
 __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
 	push_deposit_body<T, R, PUSH, FIXED, EXACT, SCATTER>(a, (int)blockIdx.x, (int)gridDim.x);
@@ -626,7 +657,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit_multi(const __grid_consta
 {
 	int si = 0;
 	while (si + 1 < m.n && (int)blockIdx.x >= m.ctaBegin[si + 1]) ++si;
-	push_deposit_body<T, R, true, FIXED, EXACT, false>(m.sp[si], (int)blockIdx.x - m.ctaBegin[si], m.ctaBegin[si + 1] - m.ctaBegin[si]);
+	push_deposit_body<T, R, true, FIXED, EXACT, 0>(m.sp[si], (int)blockIdx.x - m.ctaBegin[si], m.ctaBegin[si + 1] - m.ctaBegin[si]);
 }
 
 // Axial cell range and live count of every tile (window planning at upload / after a sort) and validation of the
@@ -675,7 +706,7 @@ template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
-			auto kernS = k_push_deposit<512, 4, PUSH, FIXED, EXACT, true>;
+			auto kernS = a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
 			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eS != cudaSuccess) return eS;
 			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);
@@ -705,7 +736,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.W = t->window < t->Nz ? t->window : t->Nz;
 	a.WE = ptp_push_field_window(t);
 	a.fixedBits = t->fixedBits;
-	a.scatter = p->scatter ? 1 : 0;
+	a.scatter = p->scatter ? t->scatterForm : 0;
 	if (p->scatter) {
 		a.W = a.WE = ptp_push_scatter_window(t);
 		if (t->depositMode != PTP_DEPOSIT_FIXED64) a.fixedBits = 40;     // the warps' bins hold fixed-point sums in fp64 mode too
@@ -760,10 +791,11 @@ int ptp_push_field_window(const ptp_trap* t)
 }
 
 // SCATTER variant (hot species): cells of the one window that serves as field window and deposit window - 16 B of field,
-// 16 B of reduction rows and one 8-byte word per warp and cell (512 threads).
+// 16 B of reduction rows and one 8-byte word + one tag byte per warp and cell (512 threads).
+constexpr size_t kScatterBytesPerCell = 16 + 16 + (8 + 1) * (512 / 32);
 int ptp_push_scatter_window(const ptp_trap* t)
 {
-	const size_t perCell = 16 + 16 + 8 * (512 / 32);
+	const size_t perCell = kScatterBytesPerCell;
 	size_t w = t->smemMax > 2048 ? (t->smemMax - 2048) / perCell : 0;
 	if (w > (size_t)t->Nz) w = (size_t)t->Nz;
 	return (int)w;
@@ -775,7 +807,7 @@ bool ptp_push_scatter_usable(const ptp_trap* t)
 	return t->threads == 512 && t->ringsPerThread == 4 && (w >= 128 || w == t->Nz);
 }
 
-size_t ptp_push_scatter_smem_bytes(const ptp_trap* t) { return (size_t)ptp_push_scatter_window(t) * (16 + 16 + 8 * (512 / 32)); }
+size_t ptp_push_scatter_smem_bytes(const ptp_trap* t) { return (size_t)ptp_push_scatter_window(t) * kScatterBytesPerCell; }
 
 size_t ptp_push_smem_bytes(const ptp_trap* t, int threads, int window)
 {

@@ -87,6 +87,8 @@ static inline unsigned int __ballot_sync(unsigned, bool pred)
 	g_warp->bar.arrive_and_wait();
 	return m;
 }
+static inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
 // redux.sync over the lanes named in `mask`. On the device the lanes of a warp may name different (disjoint) masks in one
 // instruction - the groups then execute one after the other (WARPSYNC.EXCLUSIVE); here all 32 lanes arrive together and each
 // takes the sum / maximum over its own mask, checking that its partners named the same one.
