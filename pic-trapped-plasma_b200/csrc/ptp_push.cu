@@ -208,6 +208,17 @@ __device__ __forceinline__ void scatter_add(unsigned long long* wb, bool in, uns
 	}
 }
 
+// Several lanes of a warp store to the same byte in one instruction and exactly one of the stores takes effect - defined on the
+// device; on the host emulation (one std::thread per lane) the same is said with a relaxed atomic.
+__device__ __forceinline__ void st_one_wins(unsigned char* p, unsigned char v)
+{
+#ifndef PTP_HOST_EMU
+	*p = v;
+#else
+	std::atomic_ref<unsigned char>(*p).store(v, std::memory_order_relaxed);
+#endif
+}
+
 // The same without match.any (SCATTER = 2): the lanes find out who may write by trying - every lane that still has a deposit
 // puts its lane number into a tag next to the bin it wants, the lane whose number survived writes the bin, the others try again.
 // As many rounds as the largest group of lanes with the same cell, each round one byte store, one byte load and a vote more than
@@ -230,11 +241,82 @@ __device__ __forceinline__ void scatter_add_tags(unsigned long long* wb, unsigne
 	}
 	bool pending = in;
 	do {
-		if (pending) tag[io] = (unsigned char)lane;
+		if (pending) st_one_wins(tag + io, (unsigned char)lane);
 		__syncwarp();
 		if (pending && tag[io] == (unsigned char)lane) { wb[io] += word; pending = false; }
 		__syncwarp();
 	} while (__any_sync(full, pending));
+}
+
+// SCATTER = 3: no match.any (measured on the B200: ~500 cycles until its result arrives with 16 warps of an SM asking, whatever
+// the data) and no turns (their number depends on the order of the rings). The warp sorts its 32 (cell, lane) keys with a
+// bitonic network of 15 shuffle steps, fetches each ring's packed word to its sorted position, adds up the runs of equal cells
+// with a segmented scan (5 shuffle steps) - the last lane of every run then holds (rings in the cell | sum of their weights) -
+// and returns; the caller lets those lanes write, one plain read-modify-write per distinct cell, conflict-free by
+// construction. The cost is the same for any order of the rings.
+// (volatile: the compiler keeps these shuffles in program order, i.e. R of them back to back - left to itself it runs one
+// network after the other to save three registers)
+__device__ __forceinline__ unsigned int shfl_xor_ordered(unsigned int x, int laneMask)
+{
+#ifndef PTP_HOST_EMU
+	unsigned int y;
+	asm volatile("shfl.sync.bfly.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(y) : "r"(x), "r"(laneMask));
+	return y;
+#else
+	return __shfl_xor_sync(0xffffffffu, x, laneMask);
+#endif
+}
+
+template <int R>
+__device__ __forceinline__ void scatter_group_sorted(const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane,
+	unsigned int (&cellOut)[R], unsigned long long (&sumOut)[R], bool (&writeOut)[R])
+{
+	const unsigned int full = 0xffffffffu;
+	constexpr unsigned int kNone = 0x3ffffffu;                            // lanes without a deposit sort to the end
+	// (the R networks advance in lock step - every loop below runs over the rings innermost - so that R shuffles are in flight
+	// at any time instead of one)
+	unsigned int x[R];
+#pragma unroll
+	for (int i = 0; i < R; ++i) x[i] = ((in[i] ? io[i] : kNone) << 5) | (unsigned int)lane;   // (distinct keys: no ties)
+	// Bitonic network in the form where the lower lane of a pair always keeps the smaller key: the first step of every merge
+	// pairs lane l with its mirror image in the block of k lanes (l ^ (k - 1)), the others with l ^ j. One shuffle, one
+	// compare (the lane's side of the pair folded into it) and one select per step.
+#pragma unroll
+	for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			const bool upper = (lane & j) != 0;                            // this lane keeps the larger key of the pair
+			unsigned int y[R];
+#pragma unroll
+			for (int i = 0; i < R; ++i) y[i] = shfl_xor_ordered(x[i], j == (k >> 1) ? k - 1 : j);
+#pragma unroll
+			for (int i = 0; i < R; ++i) x[i] = ((y[i] < x[i]) != upper) ? y[i] : x[i];
+		}
+	}
+	unsigned int prev[R];
+	int first[R];
+#pragma unroll
+	for (int i = 0; i < R; ++i) {
+		cellOut[i] = x[i] >> 5;
+		sumOut[i] = __shfl_sync(full, word[i], (int)(x[i] & 31u));
+		prev[i] = __shfl_up_sync(full, cellOut[i], 1);
+	}
+#pragma unroll
+	for (int i = 0; i < R; ++i) {
+		if (cellOut[i] == kNone) sumOut[i] = 0ULL;
+		const unsigned int heads = __ballot_sync(full, lane == 0 || cellOut[i] != prev[i]);
+		first[i] = 31 - __clz((int)(heads & (full >> (31 - lane))));      // first lane of this lane's run
+		writeOut[i] = cellOut[i] != kNone && (lane == 31 || ((heads >> (lane + 1)) & 1u));
+	}
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		unsigned long long up[R];
+#pragma unroll
+		for (int i = 0; i < R; ++i) up[i] = __shfl_up_sync(full, sumOut[i], d);
+#pragma unroll
+		for (int i = 0; i < R; ++i)
+			if (lane - d >= first[i]) sumOut[i] += up[i];
+	}
 }
 
 // The kernel body for CTA `bid` of `nb` CTAs working on one species (k_push_deposit: the launch's own grid;
@@ -439,6 +521,18 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 
 			// ---- deposit at the (new) position: Plasma::updateRHS body (Source/Plasma.cpp:86-92) -----------
 			cells_of<R, EXACT>(z, live, a, k, w);
+			if constexpr (SCATTER != 0) {
+				// the rings go back to memory before the deposit: z and v are dead from here on, which leaves registers for the
+				// sorting networks of the deposit to run side by side
+				if (PUSH) {
+#pragma unroll
+					for (int j = 0; j < NV; ++j)
+						if (liveIn[j]) {
+							st_ring(z2w + p0 + (long long)j * T, make_double2(z[2 * j], z[2 * j + 1]));
+							st_ring(v2w + p0 + (long long)j * T, make_double2(v[2 * j], v[2 * j + 1]));
+						}
+				}
+			}
 			bool farD = false;
 			if constexpr (!SCATTER) {
 #pragma unroll
@@ -464,17 +558,32 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 			}
 			else {
 				// SCATTER: the warp's 32 rings of this stage into the warp's bins
+				unsigned int ioS[R];
+				unsigned long long wordS[R];
+				bool inS[R];
 #pragma unroll
 				for (int i = 0; i < R; ++i) {
-					const unsigned int io = (unsigned int)(k[i] - k0);
-					const bool in = live[i] && io < (unsigned int)Wuse;
-					farD |= live[i] && io >= (unsigned int)Wuse;
-					nFar += (live[i] && io >= (unsigned int)Wuse) ? 1u : 0u;
+					ioS[i] = (unsigned int)(k[i] - k0);
+					inS[i] = live[i] && ioS[i] < (unsigned int)Wuse;
+					farD |= live[i] && ioS[i] >= (unsigned int)Wuse;
+					nFar += (live[i] && ioS[i] >= (unsigned int)Wuse) ? 1u : 0u;
 					if (live[i]) { kMin = min(kMin, k[i]); kMax = max(kMax, k[i]); kSum += k[i]; ++nDep; }
 					// the packed word of the thread-private path: (1 << 52) | round(w * 2^F)
 					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
-					if constexpr (SCATTER == 2) scatter_add_tags(wbins, wtags, in, io, (unsigned long long)__double_as_longlong(t) - kPackBias, lane);
-					else scatter_add(wbins, in, io, (unsigned long long)__double_as_longlong(t) - kPackBias, lane);
+					wordS[i] = (unsigned long long)__double_as_longlong(t) - kPackBias;
+					if constexpr (SCATTER == 2) scatter_add_tags(wbins, wtags, inS[i], ioS[i], wordS[i], lane);
+					else if constexpr (SCATTER == 1) scatter_add(wbins, inS[i], ioS[i], wordS[i], lane);
+				}
+				if constexpr (SCATTER == 3) {
+					unsigned int cellS[R];
+					unsigned long long sumS[R];
+					bool writeS[R];
+					scatter_group_sorted<R>(inS, ioS, wordS, lane, cellS, sumS, writeS);
+#pragma unroll
+					for (int i = 0; i < R; ++i) {
+						if (writeS[i]) wbins[cellS[i]] += sumS[i];
+						__syncwarp();                                    // the same cell may be written by another lane for the next ring
+					}
 				}
 			}
 			if (farD) {
@@ -501,7 +610,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 						}
 					}
 			}
-			if (PUSH) {
+			if (PUSH && SCATTER == 0) {
 #pragma unroll
 				for (int j = 0; j < NV; ++j)
 					if (liveIn[j]) {
@@ -706,7 +815,7 @@ template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
-			auto kernS = a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
+			auto kernS = a.scatter == 3 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 3> : a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
 			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eS != cudaSuccess) return eS;
 			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);

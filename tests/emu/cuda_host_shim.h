@@ -117,6 +117,7 @@ static inline unsigned int __brev(unsigned int x)
 }
 static inline int __ffs(unsigned int x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned int)x) : 32; }
 
 template <class T> static inline T atomicAdd(T* p, T v) { return std::atomic_ref<T>(*p).fetch_add(v, std::memory_order_relaxed); }
 static inline double atomicAdd(double* p, double v)
