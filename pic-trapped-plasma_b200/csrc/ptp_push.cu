@@ -172,88 +172,17 @@ __device__ __forceinline__ void grid_max(unsigned int* p, unsigned int val, bool
 	else atomicMax(p, val);
 }
 
-// SCATTER variant of the deposit: the rings of the 32 lanes (cell io, packed word = count 1 | weight) go into the warp's own
-// bins wb[] by plain read-modify-write. Lanes that share a cell must not write in the same instruction; match.any finds the
-// groups of lanes with the same cell, and then
-//  * turns: the lanes of every group write one after the other, by their rank in the group - as many rounds as the largest
-//    group has lanes: 2-3 for 32 rings spread over a few hundred cells (rings in arbitrary order, the case this variant
-//    exists for), up to 32 when the rings are still ordered by cell (after a load or a sort);
-//  * sums: every group adds its weights as integers with warp reductions (three 18-bit digits: 32 x 2^18 fits a u32, three
-//    digits cover the 52-bit sum field) and its first lane writes once. The reductions of different groups run one after the
-//    other (WARPSYNC.EXCLUSIVE), so the cost grows with the number of groups.
-// The cheaper of the two is taken stage by stage: sums when there are no more groups than the largest group has lanes.
-// Either way the bins receive exact integer sums - the result does not depend on the path.
-__device__ __forceinline__ void scatter_add(unsigned long long* wb, bool in, unsigned int io, unsigned long long word, int lane)
-{
-	const unsigned int full = 0xffffffffu;
-	const unsigned int peers = __match_any_sync(full, in ? (int)io : -1);
-	const unsigned int rank = (unsigned int)__popc(peers & ((1u << lane) - 1u));
-	const unsigned int largest = __reduce_max_sync(full, in ? (unsigned int)__popc(peers) : 0u);
-	if (largest == 0u) return;                                           // (warp-uniform) no lane has a deposit in the window
-	const unsigned int groups = (unsigned int)__popc(__ballot_sync(full, in && rank == 0u));
-	if (largest > 1u && groups <= largest) {
-		const unsigned long long q = in ? (word & kSumMask) : 0ULL;
-		const unsigned int d0 = __reduce_add_sync(peers, (unsigned int)(q & 0x3ffffULL));
-		const unsigned int d1 = __reduce_add_sync(peers, (unsigned int)((q >> 18) & 0x3ffffULL));
-		const unsigned int d2 = __reduce_add_sync(peers, (unsigned int)(q >> 36));
-		if (in && rank == 0u)
-			wb[io] += ((unsigned long long)__popc(peers) << 52) + ((unsigned long long)d2 << 36) + ((unsigned long long)d1 << 18) + d0;
-		__syncwarp();                                                    // the next writer of a bin may be another lane
-	}
-	else {
-		for (unsigned int r = 0; r < largest; ++r) {
-			if (in && rank == r) wb[io] += word;
-			__syncwarp();
-		}
-	}
-}
-
-// Several lanes of a warp store to the same byte in one instruction and exactly one of the stores takes effect - defined on the
-// device; on the host emulation (one std::thread per lane) the same is said with a relaxed atomic.
-__device__ __forceinline__ void st_one_wins(unsigned char* p, unsigned char v)
-{
-#ifndef PTP_HOST_EMU
-	*p = v;
-#else
-	std::atomic_ref<unsigned char>(*p).store(v, std::memory_order_relaxed);
-#endif
-}
-
-// The same without match.any (SCATTER = 2): the lanes find out who may write by trying - every lane that still has a deposit
-// puts its lane number into a tag next to the bin it wants, the lane whose number survived writes the bin, the others try again.
-// As many rounds as the largest group of lanes with the same cell, each round one byte store, one byte load and a vote more than
-// a turn of scatter_add. Rings still ordered by cell (all 32 lanes in one cell: up to 32 rounds) are caught by a shuffle and a
-// vote and summed by full-warp reductions.
-__device__ __forceinline__ void scatter_add_tags(unsigned long long* wb, unsigned char* tag, bool in, unsigned int io, unsigned long long word, int lane)
-{
-	const unsigned int full = 0xffffffffu;
-	const int key = in ? (int)io : -1;
-	const int key0 = __shfl_sync(full, key, 0);
-	if (__all_sync(full, key == key0)) {
-		if (key0 < 0) return;
-		const unsigned long long q = word & kSumMask;
-		const unsigned int d0 = __reduce_add_sync(full, (unsigned int)(q & 0x3ffffULL));
-		const unsigned int d1 = __reduce_add_sync(full, (unsigned int)((q >> 18) & 0x3ffffULL));
-		const unsigned int d2 = __reduce_add_sync(full, (unsigned int)(q >> 36));
-		if (lane == 0) wb[io] += (32ULL << 52) + ((unsigned long long)d2 << 36) + ((unsigned long long)d1 << 18) + d0;
-		__syncwarp();
-		return;
-	}
-	bool pending = in;
-	do {
-		if (pending) st_one_wins(tag + io, (unsigned char)lane);
-		__syncwarp();
-		if (pending && tag[io] == (unsigned char)lane) { wb[io] += word; pending = false; }
-		__syncwarp();
-	} while (__any_sync(full, pending));
-}
-
-// SCATTER = 3: no match.any (measured on the B200: ~500 cycles until its result arrives with 16 warps of an SM asking, whatever
-// the data) and no turns (their number depends on the order of the rings). The warp sorts its 32 (cell, lane) keys with a
-// bitonic network of 15 shuffle steps, fetches each ring's packed word to its sorted position, adds up the runs of equal cells
-// with a segmented scan (5 shuffle steps) - the last lane of every run then holds (rings in the cell | sum of their weights) -
-// and returns; the caller lets those lanes write, one plain read-modify-write per distinct cell, conflict-free by
-// construction. The cost is the same for any order of the rings.
+// SCATTER forms of the deposit (hot species): the rings of the 32 lanes of a warp (cell io, packed word = count 1 | weight) go
+// into the warp's own bins by plain read-modify-write, so lanes that share a cell must be found and their words added up first.
+// Measured on the B200 and dropped (profiles/r02_hot_species.txt): match.any + turns by rank in the group (~500 cycles until the
+// result of match.any arrives with 16 warps of an SM asking; as many turns as the largest group, so the time depends on the order
+// of the rings: 0.70 ms per step for 50 M mixed electrons, 1.0 ms after a re-sort, 3.5 ms for 100 M on the default grid), and
+// "try and see" with one tag byte per bin (no faster).
+//
+// SCATTER = 1, warp sort: the warp sorts its 32 (cell, lane) keys with a bitonic network of 15 shuffle steps, fetches each ring's
+// packed word to its sorted position, adds up the runs of equal cells with a segmented scan (5 shuffle steps) - the last lane of
+// every run then holds (rings in the cell | sum of their weights) - and those lanes write, one plain read-modify-write per
+// distinct cell, conflict-free by construction. The cost is the same for any order of the rings.
 // (volatile: the compiler keeps these shuffles in program order, i.e. R of them back to back - left to itself it runs one
 // network after the other to save three registers)
 __device__ __forceinline__ unsigned int shfl_xor_ordered(unsigned int x, int laneMask)
@@ -319,6 +248,72 @@ __device__ __forceinline__ void scatter_group_sorted(const bool (&in)[R], const 
 	}
 }
 
+// The deposit of the SCATTER forms for the R rings of a thread.
+// SCATTER = 2, hybrid: rings in arbitrary order over a few hundred cells put at most a handful of a warp's 32 rings into one cell,
+// and then the sort is more than is needed. The lanes that share a cell are found with one vote per bit of the cell index (the
+// votes are independent of each other: no chain of 15 dependent shuffles); if no cell holds more than kGatherMax of the warp's
+// rings, the first lane of every group fetches the words of its partners one shuffle at a time and writes. Otherwise (rings still
+// ordered by cell: up to 32 lanes per cell) the warp sort does the job at its fixed cost.
+constexpr int kScatterCellBits = 11;                // cells of the window < 2048 (ptp_push_scatter_window)
+constexpr unsigned int kGatherMax = 5;
+template <int R, int FORM>
+__device__ __forceinline__ void scatter_deposit(unsigned long long* wb, const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane)
+{
+	const unsigned int full = 0xffffffffu;
+	if constexpr (FORM == 2) {
+		unsigned int peers[R];
+#pragma unroll
+		for (int i = 0; i < R; ++i) peers[i] = __ballot_sync(full, in[i]);
+#pragma unroll
+		for (int b = 0; b < kScatterCellBits; ++b) {
+#pragma unroll
+			for (int i = 0; i < R; ++i) {
+				const bool bit = ((io[i] >> b) & 1u) != 0u;
+				const unsigned int m = __ballot_sync(full, bit);
+				peers[i] &= bit ? m : ~m;                                  // lanes with a deposit and the same cell index, bit by bit
+			}
+		}
+		unsigned int n = 0;
+#pragma unroll
+		for (int i = 0; i < R; ++i) n = max(n, in[i] ? (unsigned int)__popc(peers[i]) : 0u);
+		const unsigned int largest = __reduce_max_sync(full, n);
+		if (largest == 0u) return;                                       // (warp-uniform) nothing to deposit in the window
+		if (largest <= kGatherMax) {
+			unsigned long long sum[R];
+			unsigned int rest[R];
+#pragma unroll
+			for (int i = 0; i < R; ++i) {
+				sum[i] = word[i];
+				rest[i] = in[i] ? peers[i] & ~(1u << lane) : 0u;             // partners still to be added
+			}
+			for (unsigned int r = 1; r < largest; ++r) {
+#pragma unroll
+				for (int i = 0; i < R; ++i) {
+					const int src = rest[i] ? __ffs((int)rest[i]) - 1 : lane;
+					const unsigned long long got = __shfl_sync(full, word[i], src);
+					if (rest[i]) sum[i] += got;
+					rest[i] &= rest[i] - 1u;
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < R; ++i) {
+				if (in[i] && (peers[i] & ((1u << lane) - 1u)) == 0u) wb[io[i]] += sum[i];   // the first lane of the group
+				__syncwarp();                                            // the same cell may be written by another lane for the next ring
+			}
+			return;
+		}
+	}
+	unsigned int cellS[R];
+	unsigned long long sumS[R];
+	bool writeS[R];
+	scatter_group_sorted<R>(in, io, word, lane, cellS, sumS, writeS);
+#pragma unroll
+	for (int i = 0; i < R; ++i) {
+		if (writeS[i]) wb[cellS[i]] += sumS[i];
+		__syncwarp();                                                    // the same cell may be written by another lane for the next ring
+	}
+}
+
 // The kernel body for CTA `bid` of `nb` CTAs working on one species (k_push_deposit: the launch's own grid;
 // k_push_deposit_multi: a sub-range of a launch that covers several species).
 template <int T, int R, bool PUSH, bool FIXED, bool EXACT, int SCATTER>
@@ -336,9 +331,9 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 	// grid: 1.6 cells per step, a bounce every ~35 steps), so that no cell sort survives and thread-private windows of 44
 	// cells cannot hold them. Bins are private to a WARP instead ([T/32][W] packed words: 8 B per cell and warp, so the window
 	// is ~30 x wider and serves as field window too: W == WE), and the 32 rings a warp handles in one instruction are put into
-	// the warp's bins by plain read-modify-write in conflict-free rounds (scatter_add) - no atomics (shared 64-bit atomics are
-	// CAS loops, 32-bit ones cost ~2 cycles per lane), no sorts, whatever the order of the rings. The sums are kept in fixed
-	// point in BOTH deposit modes (exact integers: the fixed-point mode gets bitwise the sums of the thread-private kernel;
+	// the warp's bins by plain read-modify-write, one lane per distinct cell (scatter_group_sorted / scatter_deposit) - no
+	// atomics (shared 64-bit atomics are CAS loops, 32-bit ones cost ~2 cycles per lane), no re-sorts, whatever the order of the
+	// rings. The sums are kept in fixed point in BOTH deposit modes (exact integers: the fixed-point mode gets bitwise the sums of the thread-private kernel;
 	// the fp64 mode converts when the segment is flushed).
 	__shared__ int sKmin, sKmax;
 	__shared__ unsigned int sLost, sFar;
@@ -347,7 +342,6 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	unsigned long long* wbins = bins + (size_t)warp * W;                     // SCATTER: this warp's [W] packed words (count:12 | sum:52)
-	unsigned char* wtags = reinterpret_cast<unsigned char*>(bins + (size_t)(T / 32) * W) + (size_t)warp * W;   // SCATTER = 2: this warp's [W] tags
 	const int n1 = a.Nz + 1;
 	const bool sys = a.nRho > 1;                 // remote grids are among the targets: system-scope atomics
 	const double qNaN = __longlong_as_double(0x7ff8000000000000LL);
@@ -571,20 +565,8 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 					// the packed word of the thread-private path: (1 << 52) | round(w * 2^F)
 					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 					wordS[i] = (unsigned long long)__double_as_longlong(t) - kPackBias;
-					if constexpr (SCATTER == 2) scatter_add_tags(wbins, wtags, inS[i], ioS[i], wordS[i], lane);
-					else if constexpr (SCATTER == 1) scatter_add(wbins, inS[i], ioS[i], wordS[i], lane);
 				}
-				if constexpr (SCATTER == 3) {
-					unsigned int cellS[R];
-					unsigned long long sumS[R];
-					bool writeS[R];
-					scatter_group_sorted<R>(inS, ioS, wordS, lane, cellS, sumS, writeS);
-#pragma unroll
-					for (int i = 0; i < R; ++i) {
-						if (writeS[i]) wbins[cellS[i]] += sumS[i];
-						__syncwarp();                                    // the same cell may be written by another lane for the next ring
-					}
-				}
+				scatter_deposit<R, SCATTER>(wbins, inS, ioS, wordS, lane);
 			}
 			if (farD) {
 				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
@@ -815,7 +797,7 @@ template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
-			auto kernS = a.scatter == 3 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 3> : a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
+			auto kernS = a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
 			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eS != cudaSuccess) return eS;
 			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);
@@ -900,13 +882,14 @@ int ptp_push_field_window(const ptp_trap* t)
 }
 
 // SCATTER variant (hot species): cells of the one window that serves as field window and deposit window - 16 B of field,
-// 16 B of reduction rows and one 8-byte word + one tag byte per warp and cell (512 threads).
-constexpr size_t kScatterBytesPerCell = 16 + 16 + (8 + 1) * (512 / 32);
+// 16 B of reduction rows and one 8-byte word per warp and cell (512 threads). Fewer than 2048 cells (kScatterCellBits).
+constexpr size_t kScatterBytesPerCell = 16 + 16 + 8 * (512 / 32);
 int ptp_push_scatter_window(const ptp_trap* t)
 {
 	const size_t perCell = kScatterBytesPerCell;
 	size_t w = t->smemMax > 2048 ? (t->smemMax - 2048) / perCell : 0;
 	if (w > (size_t)t->Nz) w = (size_t)t->Nz;
+	if (w > 2047) w = 2047;
 	return (int)w;
 }
 

@@ -169,6 +169,8 @@ static inline double __longlong_as_double(long long v) { double r; std::memcpy(&
 static inline int __double2loint(double d) { return (int)(unsigned int)((unsigned long long)__double_as_longlong(d) & 0xffffffffULL); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned int min(unsigned int a, unsigned int b) { return a < b ? a : b; }
+static inline unsigned int max(unsigned int a, unsigned int b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
 static inline long long max(long long a, long long b) { return a > b ? a : b; }
 using std::floor;

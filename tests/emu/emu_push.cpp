@@ -24,8 +24,7 @@ struct CaseHeader {
 
 template <bool FIXED, bool EXACT> static void run(const PushArgs& a, int nCta)
 {
-	if (a.scatter == 3) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, 3>(a); });
-	else if (a.scatter == 2) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, 2>(a); });
+	if (a.scatter == 2) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, 2>(a); });
 	else if (a.scatter) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, 1>(a); });
 	else emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT>(a); });
 }
@@ -81,7 +80,7 @@ int main(int argc, char** argv)
 	unsigned long long lost[2] = { 0, 0 };
 	const size_t perBin = h.fixed ? 8 : 10;
 	// = ptp_push_smem_bytes / ptp_push_scatter_smem_bytes, to the byte (AddressSanitizer)
-	std::vector<unsigned char> smem(h.scatter ? (size_t)h.W * (16 + 16 + (8 + 1) * (512 / 32)) : (size_t)h.WE * 16 + (size_t)h.W * 16 + (size_t)h.W * 512 * perBin);
+	std::vector<unsigned char> smem(h.scatter ? (size_t)h.W * (16 + 16 + 8 * (512 / 32)) : (size_t)h.WE * 16 + (size_t)h.W * 16 + (size_t)h.W * 512 * perBin);
 	g_smem = smem.data();
 
 	PushArgs a{};
