@@ -248,61 +248,13 @@ __device__ __forceinline__ void scatter_group_sorted(const bool (&in)[R], const 
 	}
 }
 
-// The deposit of the SCATTER forms for the R rings of a thread.
-// SCATTER = 2, hybrid: rings in arbitrary order over a few hundred cells put at most a handful of a warp's 32 rings into one cell,
-// and then the sort is more than is needed. The lanes that share a cell are found with one vote per bit of the cell index (the
-// votes are independent of each other: no chain of 15 dependent shuffles); if no cell holds more than kGatherMax of the warp's
-// rings, the first lane of every group fetches the words of its partners one shuffle at a time and writes. Otherwise (rings still
-// ordered by cell: up to 32 lanes per cell) the warp sort does the job at its fixed cost.
-constexpr int kScatterCellBits = 11;                // cells of the window < 2048 (ptp_push_scatter_window)
-constexpr unsigned int kGatherMax = 5;
-template <int R, int FORM>
+// The deposit of the SCATTER form for the R rings of a thread.
+// (Also measured and dropped, profiles/r02_hot_species.txt: finding the lanes that share a cell with one vote per bit of the cell
+// index and letting the first lane of every small group fetch its partners' words shuffle by shuffle, with this sort as the
+// fall-back for large groups - 0.86 ms per step where the sort alone takes 0.75.)
+template <int R>
 __device__ __forceinline__ void scatter_deposit(unsigned long long* wb, const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane)
 {
-	const unsigned int full = 0xffffffffu;
-	if constexpr (FORM == 2) {
-		unsigned int peers[R];
-#pragma unroll
-		for (int i = 0; i < R; ++i) peers[i] = __ballot_sync(full, in[i]);
-#pragma unroll
-		for (int b = 0; b < kScatterCellBits; ++b) {
-#pragma unroll
-			for (int i = 0; i < R; ++i) {
-				const bool bit = ((io[i] >> b) & 1u) != 0u;
-				const unsigned int m = __ballot_sync(full, bit);
-				peers[i] &= bit ? m : ~m;                                  // lanes with a deposit and the same cell index, bit by bit
-			}
-		}
-		unsigned int n = 0;
-#pragma unroll
-		for (int i = 0; i < R; ++i) n = max(n, in[i] ? (unsigned int)__popc(peers[i]) : 0u);
-		const unsigned int largest = __reduce_max_sync(full, n);
-		if (largest == 0u) return;                                       // (warp-uniform) nothing to deposit in the window
-		if (largest <= kGatherMax) {
-			unsigned long long sum[R];
-			unsigned int rest[R];
-#pragma unroll
-			for (int i = 0; i < R; ++i) {
-				sum[i] = word[i];
-				rest[i] = in[i] ? peers[i] & ~(1u << lane) : 0u;             // partners still to be added
-			}
-			for (unsigned int r = 1; r < largest; ++r) {
-#pragma unroll
-				for (int i = 0; i < R; ++i) {
-					const int src = rest[i] ? __ffs((int)rest[i]) - 1 : lane;
-					const unsigned long long got = __shfl_sync(full, word[i], src);
-					if (rest[i]) sum[i] += got;
-					rest[i] &= rest[i] - 1u;
-				}
-			}
-#pragma unroll
-			for (int i = 0; i < R; ++i) {
-				if (in[i] && (peers[i] & ((1u << lane) - 1u)) == 0u) wb[io[i]] += sum[i];   // the first lane of the group
-				__syncwarp();                                            // the same cell may be written by another lane for the next ring
-			}
-			return;
-		}
-	}
 	unsigned int cellS[R];
 	unsigned long long sumS[R];
 	bool writeS[R];
@@ -566,7 +518,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 					wordS[i] = (unsigned long long)__double_as_longlong(t) - kPackBias;
 				}
-				scatter_deposit<R, SCATTER>(wbins, inS, ioS, wordS, lane);
+				scatter_deposit<R>(wbins, inS, ioS, wordS, lane);
 			}
 			if (farD) {
 				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
@@ -797,7 +749,7 @@ template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
-			auto kernS = a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
+			auto kernS = k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
 			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eS != cudaSuccess) return eS;
 			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);
@@ -827,7 +779,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.W = t->window < t->Nz ? t->window : t->Nz;
 	a.WE = ptp_push_field_window(t);
 	a.fixedBits = t->fixedBits;
-	a.scatter = p->scatter ? t->scatterForm : 0;
+	a.scatter = p->scatter ? 1 : 0;
 	if (p->scatter) {
 		a.W = a.WE = ptp_push_scatter_window(t);
 		if (t->depositMode != PTP_DEPOSIT_FIXED64) a.fixedBits = 40;     // the warps' bins hold fixed-point sums in fp64 mode too
@@ -882,7 +834,7 @@ int ptp_push_field_window(const ptp_trap* t)
 }
 
 // SCATTER variant (hot species): cells of the one window that serves as field window and deposit window - 16 B of field,
-// 16 B of reduction rows and one 8-byte word per warp and cell (512 threads). Fewer than 2048 cells (kScatterCellBits).
+// 16 B of reduction rows and one 8-byte word per warp and cell (512 threads).
 constexpr size_t kScatterBytesPerCell = 16 + 16 + 8 * (512 / 32);
 int ptp_push_scatter_window(const ptp_trap* t)
 {

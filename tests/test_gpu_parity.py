@@ -286,12 +286,10 @@ def test_electrode_programme_matches_per_step_solves(c1_kat):
     tb.close()
 
 
-@pytest.mark.parametrize("hot", [0, 1, 2])
-def test_losses_match_oracle_ring_by_ring(hot, monkeypatch):
+@pytest.mark.parametrize("hot", [0, 1])
+def test_losses_match_oracle_ring_by_ring(hot):
     """Small odd grid, hot rings: loss flags and survivors bit-exact against the restated swap-pop loop.
-    hot = 1 / 2: through the per-warp-bin form of the push kernel (ptp_plasma_set_hot) - rings in arbitrary order; the lanes
-    of a warp that share a cell found by a warp sort (1) or by votes with the sort as fall-back (2) - PTP_SCATTER_FORM."""
-    monkeypatch.setenv("PTP_SCATTER_FORM", str(max(hot, 1)))
+    hot = 1: through the per-warp-bin form of the push kernel (ptp_plasma_set_hot) - rings in arbitrary order."""
     args = (0.02, [0.01, 0.02, 0.015], [5.0, -40.0, 3.0], [0.002, 0.001], 57, 9)
     pt = port.PortTrap(*args)
     t = ptp.PenningTrap(args[0], [ptp.Electrode(a, b) for a, b in zip(args[1], args[2])], args[3], args[4], args[5])
@@ -305,7 +303,7 @@ def test_losses_match_oracle_ring_by_ring(hot, monkeypatch):
     op = pt.plasma("Electrons", ptp.massE, -ptp.ePos)
     op.set_rings(r, z, v, -1e-16)
     gp = ptp.Plasma(t, "Electrons", ptp.massE, -ptp.ePos)
-    gp.set_hot(min(hot, 1))
+    gp.set_hot(hot)
     gp.upload(r, z, v, -1e-16)
     op.solve_poisson()
     gp.solvePoisson()
@@ -491,15 +489,14 @@ def test_adaptive_resort_keeps_results_and_triggers(monkeypatch, c1_kat):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("exact,form", [(False, 1), (True, 1), (False, 2), (True, 2)])
-def test_hot_species_form_of_push_kernel(c1_kat, exact, form, monkeypatch):
+@pytest.mark.parametrize("exact", [False, True])
+def test_hot_species_form_of_push_kernel(c1_kat, exact):
     """ptp_plasma_set_hot: the per-warp-bin form of K1 (one wide window, no re-sorts) against the thread-private form.
     Electrons on a fine grid (1.6 cells per step: after 40 steps the load order is gone), fixed-point deposits: positions,
     speeds, deposit grid and potential identical bit for bit at every check point, with and without re-sorts of the
     thread-private run; stand-alone deposit (K2) too. fp64 deposits: grid within the fp64 tier (1e-12), and the
-    trajectories stay together at rounding level. form: how the lanes of a warp share its bins (PTP_SCATTER_FORM)."""
+    trajectories stay together at rounding level."""
     from bench import density_on
-    monkeypatch.setenv("PTP_SCATTER_FORM", str(form))
     Nz, Nr = 4096, 64
     el = [ptp.Electrode(0.01322, v) for v in (0, -70, -15, -70, 0)]
     dens = density_on(Nz, Nr)
