@@ -136,6 +136,33 @@ def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed,
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
+def test_hot_form_count_field_holds_the_longest_segment(tmp_path):
+    """The per-warp bins of the hot form pack (rings : 12 bits | weight sum : 52 bits). The planner caps a segment of a hot
+    species at 31 tiles (ptp_build_segments: 4095 / (32 lanes x 4 rings per tile)); the worst case for the count field is a
+    segment of that length whose rings ALL sit in one cell: 31 x 128 = 3968 rings per warp and bin. One CTA, one such segment,
+    fixed-point deposits: the grid must equal the thread-private form's bit for bit and hold every ring."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle import port
+    trap = port.default_trap()
+    n = 31 * 2048
+    rng = np.random.default_rng(5)
+    r = np.zeros(n, np.int32)
+    z = (300 + rng.random(n)) * trap.hz                                  # all in cell 300
+    v = np.zeros(n)
+    enodes = np.zeros(trap.G)
+    args = (trap, enodes, r, z, v, 1e-10, -1.602176634e-19, 9.1093837015e-31)
+    hot = _run_emu_push(tmp_path, *args, 200, 200, 1, 0, seg_tiles=31, n_cta=1, scatter=1)
+    (tmp_path / "ref").mkdir()
+    ref = _run_emu_push(tmp_path / "ref", *args, 44, 256, 1, 0, seg_tiles=31, n_cta=1)
+    assert hot[2] == ref[2]
+    grid = np.frombuffer(hot[2], np.int64)
+    assert grid.sum() == n << 40 and np.count_nonzero(grid) == 2        # nodes 300 and 301 of row 0
+    assert np.array_equal(hot[0], z) and int(hot[4][0]) == 0 and int(hot[4][1]) == 0
+    trap.close()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
 def test_sort_kernel_text_on_host_threads():
     """K5's four kernels (count / scan / scatter / pad, pic-trapped-plasma_b200/csrc/ptp_particles.cu) on host threads, driven
     like ptp_sort_plasma over three rounds with losses in between: rows ordered by axial cell, ring multiset intact (z, v
