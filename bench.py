@@ -489,7 +489,12 @@ def main():
         try:
             tr = json.load(open(prof))
             entry = tr.get(args.workload)
-            same = tr.get("push_cu_sha16") == push_source_sha() or (rank == 0 and tr.get("k1_sass_sha16") and tr.get("k1_sass_sha16") == k1_sass_sha())
+            # same source file as profiled, or a later version of the file whose K1 machine code was found identical to the profiled
+            # one (listed in the profile; tests/test_bench_contract.py re-checks the shipped library with cuobjdump), or - for a
+            # version not listed - the same machine code as seen right now
+            src = push_source_sha()
+            same = tr.get("push_cu_sha16") == src or src in tr.get("same_k1_sass_sources", []) or \
+                (rank == 0 and tr.get("k1_sass_sha16") and tr.get("k1_sass_sha16") == k1_sass_sha())
             if entry and same:
                 roofline["traffic"] = entry["dram_bytes_per_ring"] * units
                 roofline["traffic_source"] = "%s: %s, %.2f B/ring x rings of this launch" % (tr.get("report"), entry.get("kernel"), entry["dram_bytes_per_ring"])
