@@ -248,17 +248,95 @@ __device__ __forceinline__ void scatter_group_sorted(const bool (&in)[R], const 
 	}
 }
 
+// SCATTER = 2, the same with half the shuffles. A key is 16 bits (cell < 2047 in 11 bits | lane in 5), so the keys of two rings
+// share a register and one network sorts both: one shuffle per step, the per-halfword minimum / maximum (VIMNMX.U16x2) does the
+// two compare-exchanges. The segmented scan stops at the longest run of equal cells among the rings of the tile - the heads of
+// the runs are a vote, the same in every lane, so the test is warp-uniform: two steps instead of five when the rings are mixed.
+#ifdef PTP_HOST_EMU
+static inline unsigned int __vminu2(unsigned int a, unsigned int b)
+{
+	const unsigned int lo = (a & 0xffffu) < (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu), hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+	return (hi << 16) | lo;
+}
+static inline unsigned int __vmaxu2(unsigned int a, unsigned int b)
+{
+	const unsigned int lo = (a & 0xffffu) > (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu), hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+	return (hi << 16) | lo;
+}
+#endif
+template <int R>
+__device__ __forceinline__ void scatter_group_sorted_packed(const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane,
+	unsigned int (&cellOut)[R], unsigned long long (&sumOut)[R], bool (&writeOut)[R])
+{
+	static_assert(R % 2 == 0, "rings are sorted in pairs");
+	const unsigned int full = 0xffffffffu;
+	constexpr unsigned int kNone = 0x7ffu;                                // lanes without a deposit sort to the end
+	unsigned int x[R / 2];
+#pragma unroll
+	for (int h = 0; h < R / 2; ++h)
+		x[h] = ((((in[2 * h] ? io[2 * h] : kNone) << 5) | (unsigned int)lane) << 16) | ((in[2 * h + 1] ? io[2 * h + 1] : kNone) << 5) | (unsigned int)lane;
+#pragma unroll
+	for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			const bool upper = (lane & j) != 0;                            // this lane keeps the larger key of each pair
+#pragma unroll
+			for (int h = 0; h < R / 2; ++h) {
+				const unsigned int y = __shfl_xor_sync(full, x[h], j == (k >> 1) ? k - 1 : j);
+				x[h] = upper ? __vmaxu2(x[h], y) : __vminu2(x[h], y);
+			}
+		}
+	}
+	unsigned int heads[R];
+	int first[R];
+	unsigned int longer[5] = { 0u, 0u, 0u, 0u, 0u };                    // [s]: some ring of the tile has a run of more than 2^s equal cells
+#pragma unroll
+	for (int h = 0; h < R / 2; ++h) {
+		const unsigned int prev = __shfl_up_sync(full, x[h], 1);
+#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			const int i = 2 * h + q;
+			const unsigned int key = q == 0 ? x[h] >> 16 : x[h] & 0xffffu, keyPrev = q == 0 ? prev >> 16 : prev & 0xffffu;
+			cellOut[i] = key >> 5;
+			sumOut[i] = __shfl_sync(full, word[i], (int)(key & 31u));
+			if (cellOut[i] == kNone) sumOut[i] = 0ULL;
+			// (lanes without a deposit are runs of their own: a tile's padding must not look like one long run)
+			heads[i] = __ballot_sync(full, lane == 0 || cellOut[i] != (keyPrev >> 5) || cellOut[i] == kNone);
+			first[i] = 31 - __clz((int)(heads[i] & (full >> (31 - lane))));  // first lane of this lane's run
+			writeOut[i] = cellOut[i] != kNone && (lane == 31 || ((heads[i] >> (lane + 1)) & 1u));
+			unsigned int c = ~heads[i];                                    // lanes that continue a run; c & (c >> 1): two in a row, ...
+			longer[0] |= c;
+			c &= c >> 1; longer[1] |= c;
+			c &= c >> 2; longer[2] |= c;
+			c &= c >> 4; longer[3] |= c;
+			c &= c >> 8; longer[4] |= c;
+		}
+	}
+#pragma unroll
+	for (int st = 0; st < 5; ++st) {
+		if (longer[st] == 0u) break;                                     // (warp-uniform: votes)
+		const int d = 1 << st;
+		unsigned long long up[R];
+#pragma unroll
+		for (int i = 0; i < R; ++i) up[i] = __shfl_up_sync(full, sumOut[i], d);
+#pragma unroll
+		for (int i = 0; i < R; ++i)
+			if (lane - d >= first[i]) sumOut[i] += up[i];
+	}
+}
+
 // The deposit of the SCATTER form for the R rings of a thread.
 // (Also measured and dropped, profiles/r02_hot_species.txt: finding the lanes that share a cell with one vote per bit of the cell
 // index and letting the first lane of every small group fetch its partners' words shuffle by shuffle, with this sort as the
 // fall-back for large groups - 0.86 ms per step where the sort alone takes 0.75.)
-template <int R>
+template <int R, int FORM>
 __device__ __forceinline__ void scatter_deposit(unsigned long long* wb, const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane)
 {
 	unsigned int cellS[R];
 	unsigned long long sumS[R];
 	bool writeS[R];
-	scatter_group_sorted<R>(in, io, word, lane, cellS, sumS, writeS);
+	if constexpr (FORM == 2) scatter_group_sorted_packed<R>(in, io, word, lane, cellS, sumS, writeS);
+	else scatter_group_sorted<R>(in, io, word, lane, cellS, sumS, writeS);
 #pragma unroll
 	for (int i = 0; i < R; ++i) {
 		if (writeS[i]) wb[cellS[i]] += sumS[i];
@@ -518,7 +596,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 					wordS[i] = (unsigned long long)__double_as_longlong(t) - kPackBias;
 				}
-				scatter_deposit<R>(wbins, inS, ioS, wordS, lane);
+				scatter_deposit<R, SCATTER>(wbins, inS, ioS, wordS, lane);
 			}
 			if (farD) {
 				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
@@ -749,7 +827,7 @@ template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
-			auto kernS = k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
+			auto kernS = a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
 			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eS != cudaSuccess) return eS;
 			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);
@@ -779,7 +857,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.W = t->window < t->Nz ? t->window : t->Nz;
 	a.WE = ptp_push_field_window(t);
 	a.fixedBits = t->fixedBits;
-	a.scatter = p->scatter ? 1 : 0;
+	a.scatter = p->scatter ? t->scatterForm : 0;
 	if (p->scatter) {
 		a.W = a.WE = ptp_push_scatter_window(t);
 		if (t->depositMode != PTP_DEPOSIT_FIXED64) a.fixedBits = 40;     // the warps' bins hold fixed-point sums in fp64 mode too
