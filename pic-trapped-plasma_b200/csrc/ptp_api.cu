@@ -255,7 +255,6 @@ int ptp_trap_create(ptp_trap** out, int Nz, int Nr, double hz, double hr, double
 		if (const char* e = std::getenv("PTP_FFT_R16")) t->fftR16 = std::atoi(e);
 		if (const char* e = std::getenv("PTP_FFT_FORM_ROWS")) t->fftFormRows = std::atoi(e);
 		if (const char* e = std::getenv("PTP_SCATTER")) t->scatterPolicy = std::atoi(e);
-		if (const char* e = std::getenv("PTP_SCATTER_FORM")) t->scatterForm = std::atoi(e) == 2 ? 2 : 1;
 		if (const char* e = std::getenv("PTP_HOT_SORT_STEPS")) t->hotSortSteps = std::max(1, std::atoi(e));
 		if (const char* e = std::getenv("PTP_PLAN_SLACK")) t->planSlack = std::atoi(e);
 		if (const char* e = std::getenv("PTP_SORT_CHECK_STEPS")) t->sortCheckSteps = std::max(1, std::atoi(e));

@@ -151,7 +151,6 @@ struct ptp_trap {
 	int fftR16 = 1;                  // PTP_FFT_R16: rows of 4096 nodes go through the radix-16 inverse (0: radix-2 pass pairs)
 	int fftFormRows = 1;             // PTP_FFT_FORM_ROWS: the radix-16 inverse forms the rows above the plasma itself (0: k_thomas_expand)
 	int scatterPolicy = -1;          // PTP_SCATTER: default of ptp_plasma::hot for new species (-1 automatic, 0 never, 1 always)
-	int scatterForm = 1;             // PTP_SCATTER_FORM: 1 = one sorting network per ring, 2 = two rings' 16-bit keys per network + scan cut short
 	int hotSortSteps = 64;           // automatic policy: a species whose re-sorts keep coming less than this many steps apart is hot (PTP_HOT_SORT_STEPS)
 	int planSlack = -1;              // rows whose rings span more cells than the deposit window are cut into segments that leave this many
 	                                 // cells of the window free (room for the rings' drift until the next re-sort); -1: window / 2 (PTP_PLAN_SLACK)

@@ -172,86 +172,24 @@ __device__ __forceinline__ void grid_max(unsigned int* p, unsigned int val, bool
 	else atomicMax(p, val);
 }
 
-// SCATTER forms of the deposit (hot species): the rings of the 32 lanes of a warp (cell io, packed word = count 1 | weight) go
+// SCATTER form of the deposit (hot species): the rings of the 32 lanes of a warp (cell io, packed word = count 1 | weight) go
 // into the warp's own bins by plain read-modify-write, so lanes that share a cell must be found and their words added up first.
-// Measured on the B200 and dropped (profiles/r02_hot_species.txt): match.any + turns by rank in the group (~500 cycles until the
-// result of match.any arrives with 16 warps of an SM asking; as many turns as the largest group, so the time depends on the order
-// of the rings: 0.70 ms per step for 50 M mixed electrons, 1.0 ms after a re-sort, 3.5 ms for 100 M on the default grid), and
-// "try and see" with one tag byte per bin (no faster).
-//
-// SCATTER = 1, warp sort: the warp sorts its 32 (cell, lane) keys with a bitonic network of 15 shuffle steps, fetches each ring's
-// packed word to its sorted position, adds up the runs of equal cells with a segmented scan (5 shuffle steps) - the last lane of
-// every run then holds (rings in the cell | sum of their weights) - and those lanes write, one plain read-modify-write per
-// distinct cell, conflict-free by construction. The cost is the same for any order of the rings.
-// (volatile: the compiler keeps these shuffles in program order, i.e. R of them back to back - left to itself it runs one
-// network after the other to save three registers)
-__device__ __forceinline__ unsigned int shfl_xor_ordered(unsigned int x, int laneMask)
-{
-#ifndef PTP_HOST_EMU
-	unsigned int y;
-	asm volatile("shfl.sync.bfly.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(y) : "r"(x), "r"(laneMask));
-	return y;
-#else
-	return __shfl_xor_sync(0xffffffffu, x, laneMask);
-#endif
-}
-
-template <int R>
-__device__ __forceinline__ void scatter_group_sorted(const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane,
-	unsigned int (&cellOut)[R], unsigned long long (&sumOut)[R], bool (&writeOut)[R])
-{
-	const unsigned int full = 0xffffffffu;
-	constexpr unsigned int kNone = 0x3ffffffu;                            // lanes without a deposit sort to the end
-	// (the R networks advance in lock step - every loop below runs over the rings innermost - so that R shuffles are in flight
-	// at any time instead of one)
-	unsigned int x[R];
-#pragma unroll
-	for (int i = 0; i < R; ++i) x[i] = ((in[i] ? io[i] : kNone) << 5) | (unsigned int)lane;   // (distinct keys: no ties)
-	// Bitonic network in the form where the lower lane of a pair always keeps the smaller key: the first step of every merge
-	// pairs lane l with its mirror image in the block of k lanes (l ^ (k - 1)), the others with l ^ j. One shuffle, one
-	// compare (the lane's side of the pair folded into it) and one select per step.
-#pragma unroll
-	for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-		for (int j = k >> 1; j > 0; j >>= 1) {
-			const bool upper = (lane & j) != 0;                            // this lane keeps the larger key of the pair
-			unsigned int y[R];
-#pragma unroll
-			for (int i = 0; i < R; ++i) y[i] = shfl_xor_ordered(x[i], j == (k >> 1) ? k - 1 : j);
-#pragma unroll
-			for (int i = 0; i < R; ++i) x[i] = ((y[i] < x[i]) != upper) ? y[i] : x[i];
-		}
-	}
-	unsigned int prev[R];
-	int first[R];
-#pragma unroll
-	for (int i = 0; i < R; ++i) {
-		cellOut[i] = x[i] >> 5;
-		sumOut[i] = __shfl_sync(full, word[i], (int)(x[i] & 31u));
-		prev[i] = __shfl_up_sync(full, cellOut[i], 1);
-	}
-#pragma unroll
-	for (int i = 0; i < R; ++i) {
-		if (cellOut[i] == kNone) sumOut[i] = 0ULL;
-		const unsigned int heads = __ballot_sync(full, lane == 0 || cellOut[i] != prev[i]);
-		first[i] = 31 - __clz((int)(heads & (full >> (31 - lane))));      // first lane of this lane's run
-		writeOut[i] = cellOut[i] != kNone && (lane == 31 || ((heads >> (lane + 1)) & 1u));
-	}
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		unsigned long long up[R];
-#pragma unroll
-		for (int i = 0; i < R; ++i) up[i] = __shfl_up_sync(full, sumOut[i], d);
-#pragma unroll
-		for (int i = 0; i < R; ++i)
-			if (lane - d >= first[i]) sumOut[i] += up[i];
-	}
-}
-
-// SCATTER = 2, the same with half the shuffles. A key is 16 bits (cell < 2047 in 11 bits | lane in 5), so the keys of two rings
-// share a register and one network sorts both: one shuffle per step, the per-halfword minimum / maximum (VIMNMX.U16x2) does the
-// two compare-exchanges. The segmented scan stops at the longest run of equal cells among the rings of the tile - the heads of
-// the runs are a vote, the same in every lane, so the test is warp-uniform: two steps instead of five when the rings are mixed.
+// The warp SORTS its (cell, lane) keys with a bitonic network of 15 shuffle steps, fetches each ring's packed word to its sorted
+// position, adds up the runs of equal cells with a segmented scan - the last lane of every run then holds (rings in the cell |
+// sum of their weights) - and those lanes write, one plain read-modify-write per distinct cell, conflict-free by construction.
+// The cost hardly depends on the order of the rings.
+// A key is 16 bits (cell < 2047 in 11 bits | lane in 5), so the keys of two rings share a register and one network sorts both:
+// one shuffle per step, the per-halfword minimum / maximum (VIMNMX.U16x2) does the two compare-exchanges; the network is in the
+// form where the lower lane of a pair always keeps the smaller key (the first step of every merge pairs lane l with its mirror
+// image in the block of k lanes, l ^ (k - 1), the others with l ^ j). The segmented scan stops at the longest run of equal cells
+// among the rings of the tile - the heads of the runs are a vote, the same in every lane, so the test is warp-uniform: two steps
+// instead of five when the rings are mixed.
+// Measured on the B200 and dropped (profiles/r02_hot_species.txt, 50 M electrons on the 4096 x 1024 grid, ms per step; this
+// form: 0.63): one network per ring on 32-bit keys with all five scan steps (0.77; ptxas runs the four networks of a tile one
+// after the other); match.any + turns by rank in the group (0.77 for rings in load order, 1.16 after a re-sort, 3.5 for 100 M
+// electrons on the default grid: ~500 cycles until the result of match.any arrives with 16 warps of an SM asking, and as many
+// turns as the largest group); one tag byte per bin, "try and see" (0.81); one vote per bit of the cell index + gather by the
+// first lane of small groups, sort as fall-back (0.86).
 #ifdef PTP_HOST_EMU
 static inline unsigned int __vminu2(unsigned int a, unsigned int b)
 {
@@ -265,7 +203,7 @@ static inline unsigned int __vmaxu2(unsigned int a, unsigned int b)
 }
 #endif
 template <int R>
-__device__ __forceinline__ void scatter_group_sorted_packed(const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane,
+__device__ __forceinline__ void scatter_group_sorted(const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane,
 	unsigned int (&cellOut)[R], unsigned long long (&sumOut)[R], bool (&writeOut)[R])
 {
 	static_assert(R % 2 == 0, "rings are sorted in pairs");
@@ -326,17 +264,13 @@ __device__ __forceinline__ void scatter_group_sorted_packed(const bool (&in)[R],
 }
 
 // The deposit of the SCATTER form for the R rings of a thread.
-// (Also measured and dropped, profiles/r02_hot_species.txt: finding the lanes that share a cell with one vote per bit of the cell
-// index and letting the first lane of every small group fetch its partners' words shuffle by shuffle, with this sort as the
-// fall-back for large groups - 0.86 ms per step where the sort alone takes 0.75.)
-template <int R, int FORM>
+template <int R>
 __device__ __forceinline__ void scatter_deposit(unsigned long long* wb, const bool (&in)[R], const unsigned int (&io)[R], const unsigned long long (&word)[R], int lane)
 {
 	unsigned int cellS[R];
 	unsigned long long sumS[R];
 	bool writeS[R];
-	if constexpr (FORM == 2) scatter_group_sorted_packed<R>(in, io, word, lane, cellS, sumS, writeS);
-	else scatter_group_sorted<R>(in, io, word, lane, cellS, sumS, writeS);
+	scatter_group_sorted<R>(in, io, word, lane, cellS, sumS, writeS);
 #pragma unroll
 	for (int i = 0; i < R; ++i) {
 		if (writeS[i]) wb[cellS[i]] += sumS[i];
@@ -346,7 +280,7 @@ __device__ __forceinline__ void scatter_deposit(unsigned long long* wb, const bo
 
 // The kernel body for CTA `bid` of `nb` CTAs working on one species (k_push_deposit: the launch's own grid;
 // k_push_deposit_multi: a sub-range of a launch that covers several species).
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, int SCATTER>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool SCATTER>
 __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int bid, const int nb)
 {
 	constexpr int NV = R / 2;
@@ -545,7 +479,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 
 			// ---- deposit at the (new) position: Plasma::updateRHS body (Source/Plasma.cpp:86-92) -----------
 			cells_of<R, EXACT>(z, live, a, k, w);
-			if constexpr (SCATTER != 0) {
+			if constexpr (SCATTER) {
 				// the rings go back to memory before the deposit: z and v are dead from here on, which leaves registers for the
 				// sorting networks of the deposit to run side by side
 				if (PUSH) {
@@ -596,7 +530,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 					const double t = __fma_rn(w[i], a.fixedScale, 4503599627370496.0);
 					wordS[i] = (unsigned long long)__double_as_longlong(t) - kPackBias;
 				}
-				scatter_deposit<R, SCATTER>(wbins, inS, ioS, wordS, lane);
+				scatter_deposit<R>(wbins, inS, ioS, wordS, lane);
 			}
 			if (farD) {
 				// outside the private window: straight to the global grid (REDG.E.ADD.F64 / .64)
@@ -622,7 +556,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 						}
 					}
 			}
-			if (PUSH && SCATTER == 0) {
+			if (PUSH && !SCATTER) {
 #pragma unroll
 				for (int j = 0; j < NV; ++j)
 					if (liveIn[j]) {
@@ -755,7 +689,7 @@ __device__ __forceinline__ void push_deposit_body(const PushArgs& a, const int b
 	}
 }
 
-template <int T, int R, bool PUSH, bool FIXED, bool EXACT, int SCATTER = 0>
+template <int T, int R, bool PUSH, bool FIXED, bool EXACT, bool SCATTER = false>
 __global__ void __launch_bounds__(T, 1) k_push_deposit(const PushArgs a)
 {
 	push_deposit_body<T, R, PUSH, FIXED, EXACT, SCATTER>(a, (int)blockIdx.x, (int)gridDim.x);
@@ -778,7 +712,7 @@ __global__ void __launch_bounds__(T, 1) k_push_deposit_multi(const __grid_consta
 {
 	int si = 0;
 	while (si + 1 < m.n && (int)blockIdx.x >= m.ctaBegin[si + 1]) ++si;
-	push_deposit_body<T, R, true, FIXED, EXACT, 0>(m.sp[si], (int)blockIdx.x - m.ctaBegin[si], m.ctaBegin[si + 1] - m.ctaBegin[si]);
+	push_deposit_body<T, R, true, FIXED, EXACT, false>(m.sp[si], (int)blockIdx.x - m.ctaBegin[si], m.ctaBegin[si + 1] - m.ctaBegin[si]);
 }
 
 // Axial cell range and live count of every tile (window planning at upload / after a sort) and validation of the
@@ -827,7 +761,7 @@ template <int T, int R, bool PUSH> struct Launcher {
 	template <bool FIXED, bool EXACT> static cudaError_t go(const PushArgs& a, int grid, size_t smem, cudaStream_t st, bool pdl)
 	{
 		if (a.scatter) {                                             // per-warp bins (hot species); default tuning only
-			auto kernS = a.scatter == 2 ? k_push_deposit<512, 4, PUSH, FIXED, EXACT, 2> : k_push_deposit<512, 4, PUSH, FIXED, EXACT, 1>;
+			auto kernS = k_push_deposit<512, 4, PUSH, FIXED, EXACT, true>;
 			cudaError_t eS = cudaFuncSetAttribute(kernS, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (eS != cudaSuccess) return eS;
 			return ptp_launch(kernS, dim3(grid), dim3(512), smem, st, pdl, a);
@@ -857,7 +791,7 @@ PushArgs make_args(ptp_trap* t, ptp_plasma* p, double dt)
 	a.W = t->window < t->Nz ? t->window : t->Nz;
 	a.WE = ptp_push_field_window(t);
 	a.fixedBits = t->fixedBits;
-	a.scatter = p->scatter ? t->scatterForm : 0;
+	a.scatter = p->scatter ? 1 : 0;
 	if (p->scatter) {
 		a.W = a.WE = ptp_push_scatter_window(t);
 		if (t->depositMode != PTP_DEPOSIT_FIXED64) a.fixedBits = 40;     // the warps' bins hold fixed-point sums in fp64 mode too

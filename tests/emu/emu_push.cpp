@@ -24,8 +24,7 @@ struct CaseHeader {
 
 template <bool FIXED, bool EXACT> static void run(const PushArgs& a, int nCta)
 {
-	if (a.scatter == 2) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, 2>(a); });
-	else if (a.scatter) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, 1>(a); });
+	if (a.scatter) emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT, true>(a); });
 	else emu_launch(nCta, 512, [&] { k_push_deposit<512, 4, true, FIXED, EXACT>(a); });
 }
 

@@ -56,15 +56,14 @@ def _run_emu_push(tmp_path, trap, enodes, r, z, v, dt, charge, mass, W, WE, fixe
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
 @pytest.mark.parametrize("W,WE,fixed,exact,scatter,shuffle", [(44, 256, 0, 1, 0, 0), (44, 256, 0, 0, 0, 0), (44, 256, 1, 1, 0, 0), (6, 12, 0, 1, 0, 0), (6, 6, 1, 0, 0, 0),
                                                               (300, 300, 0, 1, 1, 0), (300, 300, 0, 0, 1, 1), (300, 300, 1, 0, 1, 1), (300, 300, 1, 1, 1, 0),
-                                                              (24, 24, 0, 0, 1, 1), (24, 24, 1, 0, 1, 0),
-                                                              (300, 300, 0, 1, 2, 0), (300, 300, 0, 0, 2, 1), (300, 300, 1, 0, 2, 1), (300, 300, 1, 1, 2, 0), (24, 24, 0, 0, 2, 1)])
+                                                              (24, 24, 0, 0, 1, 1), (24, 24, 1, 0, 1, 0)])
 def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed, exact, scatter, shuffle):
     """The source text of k_push_deposit (pic-trapped-plasma_b200/csrc/ptp_push.cu) compiled for the host and run CTA by CTA
     on 512 threads, against the oracle on the C1 electrons plus fast rings near both trap ends (losses): positions / speeds
     ring by ring (EXACT arithmetic: bit for bit; FAST: 1e-14), loss count, deposit (fp64 1e-12; fixed point 2^-40 per ring),
     the touched node range per row. W = 6 forces most rings through the out-of-window paths (global gather / atomics).
-    scatter = 1 / 2: the per-warp-bin form of the kernel (hot species; the rings of a warp grouped by a warp sort - one network per
-    ring / two rings' 16-bit keys per network and a scan cut short at the longest run) - rings in load order (few distinct cells per warp: the
+    scatter = 1: the per-warp-bin form of the kernel (hot species; the rings of a warp grouped by a warp sort, two rings' 16-bit keys
+    per network, the scan cut short at the longest run) - rings in load order (few distinct cells per warp: the
     warp-reduction path) and shuffled within their rows (many distinct cells: the rounds path); W = 24 leaves part of the
     plasma outside the window; in fixed-point mode the deposit grid equals the thread-private form's bit for bit."""
     import numpy as np
@@ -138,8 +137,7 @@ def test_push_kernel_text_on_host_threads_matches_oracle(tmp_path, W, WE, fixed,
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
-@pytest.mark.parametrize("form", [1, 2])
-def test_hot_form_count_field_holds_the_longest_segment(tmp_path, form):
+def test_hot_form_count_field_holds_the_longest_segment(tmp_path):
     """The per-warp bins of the hot form pack (rings : 12 bits | weight sum : 52 bits). The planner caps a segment of a hot
     species at 31 tiles (ptp_build_segments: 4095 / (32 lanes x 4 rings per tile)); the worst case for the count field is a
     segment of that length whose rings ALL sit in one cell: 31 x 128 = 3968 rings per warp and bin. One CTA, one such segment,
@@ -155,7 +153,7 @@ def test_hot_form_count_field_holds_the_longest_segment(tmp_path, form):
     v = np.zeros(n)
     enodes = np.zeros(trap.G)
     args = (trap, enodes, r, z, v, 1e-10, -1.602176634e-19, 9.1093837015e-31)
-    hot = _run_emu_push(tmp_path, *args, 200, 200, 1, 0, seg_tiles=31, n_cta=1, scatter=form)
+    hot = _run_emu_push(tmp_path, *args, 200, 200, 1, 0, seg_tiles=31, n_cta=1, scatter=1)
     (tmp_path / "ref").mkdir()
     ref = _run_emu_push(tmp_path / "ref", *args, 44, 256, 1, 0, seg_tiles=31, n_cta=1)
     assert hot[2] == ref[2]
@@ -166,10 +164,9 @@ def test_hot_form_count_field_holds_the_longest_segment(tmp_path, form):
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20 std::barrier)")
-@pytest.mark.parametrize("form", [1, 2])
-def test_hot_form_widest_window_on_host_threads(tmp_path, form):
+def test_hot_form_widest_window_on_host_threads(tmp_path):
     """The widest window the hot form can be given (1440 cells: ptp_push_scatter_window on a 227 KB SM) on a row of 2000 cells
-    with rings all over it: cell offsets up to 1439 (all 11 bits of the packed sort keys of form 2), rings beyond the window on
+    with rings all over it: cell offsets up to 1439 (all 11 bits of the packed sort keys), rings beyond the window on
     the global path, rings in arbitrary order. Fixed point: bit for bit the grid of the thread-private form."""
     import types
     import numpy as np
@@ -182,7 +179,7 @@ def test_hot_form_widest_window_on_host_threads(tmp_path, form):
     v = rng.normal(0, 3e4, n)                                            # up to ~1 cell per step
     enodes = rng.normal(0, 50.0, trap.G)
     args = (trap, enodes, r, z, v, 2e-10, -1.602176634e-19, 9.1093837015e-31)
-    hot = _run_emu_push(tmp_path, *args, 1440, 1440, 1, 0, seg_tiles=2, n_cta=2, scatter=form)
+    hot = _run_emu_push(tmp_path, *args, 1440, 1440, 1, 0, seg_tiles=2, n_cta=2, scatter=1)
     (tmp_path / "ref").mkdir()
     ref = _run_emu_push(tmp_path / "ref", *args, 44, 256, 1, 0, seg_tiles=2, n_cta=2)
     assert hot[2] == ref[2] and np.array_equal(hot[0], ref[0]) and np.array_equal(hot[1], ref[1])

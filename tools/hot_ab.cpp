@@ -1,8 +1,9 @@
-// A/B of the two sorting forms of the hot-species push kernel through the C ABI, without Python (a few seconds of GPU time):
-//  * validation: 20 M electrons on the c5 grid (4096 x 1024), fixed-point deposits, 40 steps - the per-warp-bin form
-//    (PTP_SCATTER_FORM=1 and 2) against the thread-private form without re-sorts: deposit grid bit for bit, rings (id, z, v)
-//    bit for bit (order-independent checksum), alive counts;
-//  * timing: 50 M electrons, fp64 deposits, hot from the load, 100 steps after 60 of warm-up, both forms.
+// Check of the hot-species form of the push kernel through the C ABI, without Python (a few seconds of GPU time):
+//  * validation: 20 M electrons on the c5 grid (4096 x 1024), fixed-point deposits, 40 steps - the per-warp-bin form against
+//    the thread-private form without re-sorts: deposit grid bit for bit, rings (id, z, v) bit for bit (order-independent
+//    checksum), alive counts;
+//  * timing: 50 M electrons, fp64 deposits, hot from the load, 100 steps after 60 of warm-up.
+// (profiles/r02_hot_ab_harness.txt: the run that decided between two sorting forms, selected by PTP_SCATTER_FORM then.)
 // Inputs: build/hot_ab/c5.bin (tools/hot_ab_prepare.py: wall potentials and the non-zero nodes of the expected density).
 // Build: g++ -O2 -std=c++17 tools/hot_ab.cpp -Iinclude -Lpic-trapped-plasma_b200 -lptp_b200 -Wl,-rpath,'$ORIGIN/../../pic-trapped-plasma_b200' -o build/hot_ab/hot_ab
 #include <cstdint>
@@ -59,9 +60,8 @@ struct Result {
 	double msPerStep = 0;
 };
 
-static Result run(const Inputs& in, const char* form, int hot, int mode, int64_t rings, int warm, int steps, bool check)
+static Result run(const Inputs& in, int hot, int mode, int64_t rings, int warm, int steps, bool check)
 {
-	setenv("PTP_SCATTER_FORM", form, 1);
 	ptp_trap* t = nullptr;
 	CK(ptp_trap_create(&t, (int)in.Nz, (int)in.Nr, in.hz, in.hr, in.length, in.radius, 0));
 	CK(ptp_trap_set_wall(t, in.wall.data()));
@@ -97,7 +97,7 @@ static Result run(const Inputs& in, const char* form, int hot, int mode, int64_t
 			r.ringSum += mix((uint64_t)id[i] * 0x9e3779b97f4a7c15ULL ^ mix(zb) ^ mix(vb + 0x1234567ULL) ^ (uint64_t)rr[i] << 48);
 		}
 	}
-	std::printf("  form %s hot %d (in use %d) mode %s rings %lld alive %lld sorts %lld: %.4f ms per step over %d steps\n", form, hot, r.hot, mode ? "fixed" : "fp64",
+	std::printf("  hot %d (in use %d) mode %s rings %lld alive %lld sorts %lld: %.4f ms per step over %d steps\n", hot, r.hot, mode ? "fixed" : "fp64",
 		(long long)loaded, (long long)r.alive, (long long)r.sorts, r.msPerStep, steps);
 	std::fflush(stdout);
 	CK(ptp_plasma_destroy(p));
@@ -110,17 +110,13 @@ int main(int argc, char** argv)
 	const Inputs in = load(argc > 1 ? argv[1] : "build/hot_ab/c5.bin");
 	std::printf("hot_ab: grid %lld x %lld, dt %.3e\n", (long long)in.Nz, (long long)in.Nr, in.dt);
 	std::printf("validation (20 M electrons, fixed point, 40 steps):\n");
-	const Result w = run(in, "1", 0, PTP_DEPOSIT_FIXED64, 20000000, 0, 40, true);
-	const Result a = run(in, "1", 1, PTP_DEPOSIT_FIXED64, 20000000, 0, 40, true);
-	const Result b = run(in, "2", 1, PTP_DEPOSIT_FIXED64, 20000000, 0, 40, true);
-	auto same = [&](const Result& x) {
-		return x.alive == w.alive && x.ringSum == w.ringSum && x.rhs.size() == w.rhs.size() && std::memcmp(x.rhs.data(), w.rhs.data(), w.rhs.size() * 8) == 0;
-	};
-	std::printf("  form 1 == thread-private form, bit for bit (grid, rings, counts): %s\n", same(a) ? "yes" : "NO");
-	std::printf("  form 2 == thread-private form, bit for bit (grid, rings, counts): %s\n", same(b) ? "yes" : "NO");
+	const Result w = run(in, 0, PTP_DEPOSIT_FIXED64, 20000000, 0, 40, true);
+	const Result a = run(in, 1, PTP_DEPOSIT_FIXED64, 20000000, 0, 40, true);
+	const bool same = a.alive == w.alive && a.ringSum == w.ringSum && a.rhs.size() == w.rhs.size() && std::memcmp(a.rhs.data(), w.rhs.data(), w.rhs.size() * 8) == 0;
+	std::printf("  hot form == thread-private form, bit for bit (grid, rings, counts): %s\n", same ? "yes" : "NO");
 	std::printf("timing (50 M electrons, fp64 deposits, hot from the load, 60 warm-up + 100 timed steps):\n");
-	const Result t1 = run(in, "1", 1, PTP_DEPOSIT_FP64, 50000000, 60, 100, false);
-	const Result t2 = run(in, "2", 1, PTP_DEPOSIT_FP64, 50000000, 60, 100, false);
-	std::printf("RESULT form1 %.4f form2 %.4f ms/step; valid1 %d valid2 %d\n", t1.msPerStep, t2.msPerStep, (int)same(a), (int)same(b));
-	return same(a) && same(b) ? 0 : 5;
+	const Result t1 = run(in, 1, PTP_DEPOSIT_FP64, 50000000, 60, 100, false);
+	const Result t2 = run(in, 1, PTP_DEPOSIT_FP64, 50000000, 60, 100, false);
+	std::printf("RESULT hot form %.4f %.4f ms/step; valid %d\n", t1.msPerStep, t2.msPerStep, (int)same);
+	return same ? 0 : 5;
 }
