@@ -22,7 +22,9 @@ for SAN in thread address; do
   done
   for H in push wide solve place; do
     case $H in place) pat="test_loader_text_on_host_threa[0-9]";; push) pat="test_push_kernel_text_on_host_[0-9]*";; wide) pat="test_large_grid_solver_text_on[0-9]";; solve) pat="test_default_grid_solver_text_[0-9]";; esac
-    for d in $CASES/$pat; do
+    EXTRA=""
+    [ $H = push ] && EXTRA="$CASES/test_hot_form_*[0-9]"          # the hot form's own cases (longest segment, widest window)
+    for d in $CASES/$pat $EXTRA; do
       [ -f "$d/case.bin" ] || continue
       if ! TSAN_OPTIONS="exitcode=66" ASAN_OPTIONS="exitcode=66:detect_leaks=0" build/emu/emu_${H}_$SAN "$d/case.bin" build/emu/san_out.bin > build/emu/san_${H}_$SAN.log 2>&1; then echo "$SAN $H $(basename $d): FAILED"; tail -20 build/emu/san_${H}_$SAN.log; rc=1; else echo "$SAN $H $(basename $d): clean"; fi
     done

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: PTP_SCATTER_FORM selected between variants of the hot form that existed when this ran; one form is shipped, the switch is gone)
 # Final single-GPU check of the round-2 tree after the hot-species work: all GPU tests (both hot forms are parametrised inside),
 # smoke, the driver's default bench line + reference arm, every named configuration, the hot-species workloads with both ways
 # of grouping a warp's rings (PTP_SCATTER_FORM), one full ncu capture of each hot form.

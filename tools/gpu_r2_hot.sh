@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: PTP_SCATTER_FORM selected between variants of the hot form that existed when this ran; one form is shipped, the switch is gone)
 # Hot species (electrons on the fine grid): parity tests of the per-warp-bin form of K1, then timings of the three ways to
 # push them - thread-private bins + re-sorts, per-warp bins with match.any groups (form 1), per-warp bins with tags (form 2) -
 # launch list and one full ncu capture of the hot form.

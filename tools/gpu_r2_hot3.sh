@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: PTP_SCATTER_FORM selected between variants of the hot form that existed when this ran; one form is shipped, the switch is gone)
 # Hot species, third way of sharing a warp's bins (warp sort + segmented sums, PTP_SCATTER_FORM=3): parity tests of all forms,
 # timings on electrons (fine grid, default grid) and on ordered antiprotons, one full ncu capture.
 mkdir -p gpurun_out/r2hot3
