@@ -53,6 +53,28 @@ def test_no_cpu_fallback_without_gpu():
         ptp.default_trap()
 
 
+def test_c_host_program_builds_against_the_abi_and_fails_loudly_without_a_gpu(tmp_path):
+    """tools/hot_ab.cpp is a complete host program on the C ABI alone (trap from wall potentials, device-side load, steps,
+    read-backs): it must build with nothing but include/ptp.h and the library, and - on a machine without a GPU - stop at
+    ptp_trap_create with the library's error text instead of computing anything."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    exe = str(tmp_path / "hot_ab")
+    pkg = os.path.join(ROOT, "pic-trapped-plasma_b200")
+    b = subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tools", "hot_ab.cpp"), "-I" + os.path.join(ROOT, "include"),
+                        "-L" + pkg, "-lptp_b200", "-Wl,-rpath," + pkg, "-o", exe], capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr
+    if ptp.lib().ptp_device_count() > 0:
+        pytest.skip("a GPU is present: the program itself is run by tools/gpu_*.sh")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "hot_ab_prepare.py")], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stdout + p.stderr
+    r = subprocess.run([exe, os.path.join(ROOT, "build", "hot_ab", "c5.bin")], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert r.returncode == 1 and "no CPU fallback" in r.stdout and "ms per step" not in r.stdout
+
+
 def test_product_does_not_touch_the_oracle():
     """The product path may not import, link or execute anything under oracle/."""
     pkg = os.path.join(ROOT, "pic-trapped-plasma_b200")
