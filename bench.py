@@ -32,8 +32,11 @@ WORKLOADS = {
     "c3": ([("Electrons", "massE", 0.5, 5_000_000), ("Antiprotons", "massP", 0.5, 5_000_000)], "e- + pbar co-trapped, 10M macro-rings (BASELINE configs[2])"),
     "c4": ([("Antiprotons", "massP", 1.0, 100_000_000)], "single-species 100M macro-rings, default trap 585x128 (BASELINE configs[3])"),
     "c5": ([("Antiprotons", "massP", 1.0, 50_000_000)], "fine-grid stress: 4096x1024 trap grid, 50M macro-rings (BASELINE configs[4])"),
+    # not a BASELINE configuration: c5 with the electron mass (1.6 cells per step - rings that no re-sort can keep ordered; the
+    # step hands them to the order-free form of the push kernel). Same as --workload c5 --electrons.
+    "c5e": ([("Electrons", "massE", 1.0, 50_000_000)], "hot species: electrons on the 4096x1024 grid, 50M macro-rings (c5 with the electron mass; not a BASELINE configuration)"),
 }
-GRIDS = {"c5": (4096, 1024)}          # (Nz, Nr); everything else runs on the reference's default 585 x 128
+GRIDS = {"c5": (4096, 1024), "c5e": (4096, 1024)}          # (Nz, Nr); everything else runs on the reference's default 585 x 128
 DT = 2e-8 / 35            # Diagnostics/C) Visualise Evolution.txt:34-36
 TEMPERATURE = 150.0
 
@@ -500,6 +503,11 @@ def main():
                 roofline["traffic_source"] = "%s: %s, %.2f B/ring x rings of this launch" % (tr.get("report"), entry.get("kernel"), entry["dram_bytes_per_ring"])
             elif entry:
                 roofline["traffic_source"] = "profiles/k1_traffic.json is from another version of the push kernel (source and machine code differ): not reported"
+            if any(hot_after):
+                # the capture is of the default (thread-private) form; a species in the order-free form runs other instantiations
+                roofline["traffic"] = None
+                roofline["kernel"] = "k_push_deposit (order-free form: per-warp bins, warp sort)"
+                roofline["traffic_source"] = "no ncu capture of the shipped order-free form of K1 (profiles/r02_ncu_hot_form.txt holds its first version: 30.9 B/ring)"
         except Exception:
             pass
 
@@ -565,7 +573,7 @@ def main():
                                    "%d x (movePlasmas + read back of the alive counts) + read back of the density grid" % e2e_steps}
 
     cpu = None
-    if args.workload == "c5":
+    if args.workload in GRIDS:
         args.no_cpu_baseline = True       # the stand-in LU cannot factorise the 4.2 M-node grid in reasonable time
     if not args.no_cpu_baseline:
         # rank 0's host cores, beside every N; at N > 1 the sample is taken from rank 0's shard (rings i = 0 mod N of every row)
